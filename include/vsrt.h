@@ -1,0 +1,228 @@
+/*
+ * vsrt.h -- C-ABI of the B200-native functional ray-traversal path of Vulkan-Sim
+ * (ubc-aamodt-group/treelet-prefetching-for-rt).
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface
+ * it replaces (paths relative to the reference tree).  The library behind it is
+ * hand-written sm_100a CUDA; there is no CPU fallback: without a usable CUDA device
+ * vsrt_create() fails with VSRT_E_NO_DEVICE and nothing else can be called.
+ *
+ * Conventions: plain C types only; int return codes (0 = ok, <0 = error, never abort --
+ * the reference asserts/aborts instead, vulkan_ray_tracing.cc:1568,893,2108); output
+ * buffers are caller-owned with an explicit capacity and the required size is always
+ * reported; a context is not thread-safe, distinct contexts are independent.
+ */
+#ifndef VSRT_H
+#define VSRT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSRT_VERSION 1
+
+/* ---- error codes ---- */
+enum {
+  VSRT_OK = 0,
+  VSRT_E_INVALID = -1,       /* bad argument / bad state */
+  VSRT_E_NO_DEVICE = -2,     /* no CUDA device / CUDA runtime failure at init (no CPU fallback) */
+  VSRT_E_CUDA = -3,          /* CUDA error while running; see vsrt_last_error() */
+  VSRT_E_CAPACITY = -4,      /* caller buffer too small; required size reported */
+  VSRT_E_UNKNOWN_AS = -5,    /* TLAS/BLAS address not registered (reference: abort(), :1568) */
+  VSRT_E_BAD_BVH = -6,       /* arena violates an invariant the reference asserts on */
+  VSRT_E_STACK_OVERFLOW = -7,/* a ray exceeded the traversal stack capacity (raise stack_entries) */
+  VSRT_E_BUDGET = -8,        /* treelet byte budget too small (reference: assert(remaining_bytes >= 0)) */
+  VSRT_E_UNSUPPORTED = -9    /* feature of the reference path not built yet (procedural leaves, remap in traces) */
+};
+
+/* ---- transaction record ABI: abstract_hardware_model.h:201-216, 315-321 ---- */
+enum {
+  VSRT_TXN_BVH_STRUCTURE = 0,
+  VSRT_TXN_BVH_INTERNAL_NODE = 1,
+  VSRT_TXN_BVH_INSTANCE_LEAF = 2,
+  VSRT_TXN_BVH_PRIMITIVE_LEAF_DESCRIPTOR = 3,
+  VSRT_TXN_BVH_QUAD_LEAF = 4,
+  VSRT_TXN_BVH_QUAD_LEAF_HIT = 5,
+  VSRT_TXN_BVH_PROCEDURAL_LEAF = 6,
+  VSRT_TXN_INTERSECTION_TABLE_LOAD = 7,
+  VSRT_TXN_UNDEFINED = 8
+};
+
+/* == MemoryTransactionRecord {void* address; uint32_t size; TransactionType type;} (16 B) */
+typedef struct vsrt_txn {
+  uint64_t address;   /* simulated-device address, host address + the offset the reference applies */
+  uint32_t size;      /* 64 / 128 / 8 bytes */
+  uint32_t type;      /* VSRT_TXN_* */
+} vsrt_txn;
+
+/* ---- traversal variant: instructions.cc:7235-7254 (-treelet_based_traversal) ---- */
+enum {
+  VSRT_MODE_DFS = 0,      /* VulkanRayTracing::traceRay, vulkan_ray_tracing.cc:2309 */
+  VSRT_MODE_TREELET = 1   /* VulkanRayTracing::traceRayWithTreelets, :1522 */
+};
+
+/* ray flags honoured by the reference (SPIR-V values) */
+#define VSRT_RAY_FLAG_OPAQUE 0x1u                  /* skipAnyHitShader, :2413 */
+#define VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT 0x4u  /* :1650, :2411 */
+#define VSRT_RAY_FLAG_SKIP_CLOSEST_HIT 0x8u        /* read, unused by traversal */
+
+/* One trace_ray operand set: instructions.cc:7157-7227 (14 PTX operands, minus the AS handle). */
+typedef struct vsrt_ray {
+  float origin[3];
+  float tmin;
+  float direction[3];
+  float tmax;
+  uint32_t ray_flags;
+  uint32_t cull_mask;          /* ignored by the reference traversal */
+  uint32_t sbt_record_offset;  /* echoed into Traversal_data */
+  uint32_t sbt_record_stride;
+  uint32_t miss_index;
+} vsrt_ray;                    /* 52 bytes */
+
+/* The fields of Traversal_data / Hit_data that traversal itself writes
+ * (vulkan_rt_thread_data.h:29-58; vulkan_ray_tracing.cc:2211-2245, :2990-3033). */
+typedef struct vsrt_hit {
+  uint32_t hit_geometry;        /* Traversal_data.hit_geometry */
+  float world_min_thit;         /* closest_hit.world_min_thit */
+  uint32_t primitive_index;     /* closest_hit.primitive_index  (PrimitiveIndex0) */
+  uint32_t geometry_index;      /* closest_hit.geometry_index */
+  uint32_t instance_index;      /* closest_hit.instance_index   (InstanceID) */
+  float barycentric[3];         /* closest_hit.barycentric_coordinates {v,w,u} */
+  float intersection_point[3];  /* closest_hit.intersection_point */
+  uint32_t n_all_hits;          /* Traversal_data.n_all_hits (DFS mode, non-opaque rays) */
+  uint64_t instance_leaf_address; /* host address of the closest instance leaf: the two 4x4 matrices of
+                                     Hit_data are a pure function of its bytes (util.h:210-224) */
+} vsrt_hit;                     /* 56 bytes */
+
+/* Functional counters: cuda-sim.h:155-166, vulkan_ray_tracing.cc:1658,1687,2214,2260,2269-2282 */
+typedef struct vsrt_counters {
+  uint64_t mem_access_type[9];  /* g_rt_mem_access_type[TransactionType] */
+  uint64_t num_hits;            /* g_rt_num_hits */
+  uint64_t num_any_hits;        /* g_rt_num_any_hits */
+  uint64_t n_anyhit_rays;       /* g_n_anyhit_rays (TerminateOnFirstHit rays) */
+  uint64_t n_closesthit_rays;   /* g_n_closesthit_rays */
+  uint64_t tot_nodes_per_ray;   /* g_tot_nodes_per_ray */
+  uint64_t accessed_data_size;  /* accessedDataSize: sum of txn.size (64-bit here; the reference's is 32-bit) */
+  uint64_t ray_count;           /* rayCount (global 1-based ray id of the last ray) */
+  uint64_t max_nodes_per_ray;   /* g_max_nodes_per_ray */
+  uint64_t max_tree_depth;      /* g_max_tree_depth */
+} vsrt_counters;
+#define VSRT_COUNTERS_N_SUM 16  /* leading uint64 fields reduced with SUM across ranks; the last 2 with MAX */
+#define VSRT_COUNTERS_N_MAX 2
+
+/* The RT options of gpgpusim.config this path honours (gpu-sim.cc:446-463,797,910). */
+typedef struct vsrt_config {
+  int32_t device;                   /* CUDA device ordinal; -1 = current device */
+  uint32_t max_treelet_size;        /* -max_treelet_size (default 49152; shipped config 512) */
+  uint32_t treelet_based_traversal; /* -treelet_based_traversal: default mode of vsrt_trace_ray_warp */
+  uint32_t remap_to_treelet_layout; /* -remap_to_treelet_layout */
+  uint32_t treelet_remap_stride;    /* -treelet_remap_stride */
+  uint32_t load_treelet_metadata;   /* -load_treelet_metadata */
+  uint32_t stack_entries;           /* per-ray traversal stack capacity (0 = default 96) */
+  uint32_t reserved;
+} vsrt_config;
+
+typedef struct vsrt_context vsrt_context;
+
+/* ---- lifetime ---- */
+void vsrt_default_config(vsrt_config* cfg);
+int vsrt_create(const vsrt_config* cfg, vsrt_context** out);
+void vsrt_destroy(vsrt_context* ctx);
+const char* vsrt_last_error(const vsrt_context* ctx);   /* ctx may be NULL: last create() failure */
+/* Parse "-flag value" lines of a gpgpusim.config (option_parser.cc) into cfg; unknown flags are skipped. */
+int vsrt_config_parse(vsrt_config* cfg, const char* text);
+
+/* ---- acceleration-structure registration ----
+ * Same 3-argument shape as gpgpusim_allocTLAS / gpgpusim_allocBLAS
+ * (gpgpusim_calls_from_mesa.cc:168-176 -> vulkan_ray_tracing.cc:4891-4899): host address of the
+ * GEN_RT_BVH header, size of the buffer that starts there, simulated-device address.  The bytes
+ * are read when the next trace/form call uploads the arena (vsrt_commit), not here. */
+int vsrt_alloc_tlas(vsrt_context* ctx, const void* root_addr, uint64_t buffer_size, uint64_t gpgpusim_addr);
+int vsrt_alloc_blas(vsrt_context* ctx, const void* root_addr, uint64_t buffer_size, uint64_t gpgpusim_addr);
+/* Upload (or re-upload after the host bytes changed) all registered buffers into the device arena and
+ * validate what the reference asserts on.  Called implicitly by the first form/trace. */
+int vsrt_commit(vsrt_context* ctx);
+
+/* ---- treelet formation: VulkanRayTracing::createTreelets (:823-1470) + buildNodeToRootMap (:475) ----
+ * Formed once per (context, tlas, budget); the reference forms lazily on the first ray (:1593). */
+int vsrt_form_treelets(vsrt_context* ctx, const void* tlas, uint32_t max_bytes_per_treelet);
+typedef struct vsrt_treelet_info {
+  uint64_t n_treelets;       /* treelet_roots_addr_only.size() */
+  uint64_t n_list_entries;   /* sum of de-duplicated node-list lengths */
+  uint64_t n_mapped_nodes;   /* node_map_addr_only.size() */
+  uint64_t total_bvh_size;   /* "Total BVH Size" the reference prints (:1364), 64-bit */
+  double form_ms;            /* device time of the formation kernels */
+} vsrt_treelet_info;
+int vsrt_treelet_info_get(vsrt_context* ctx, vsrt_treelet_info* out);
+/* Treelet table in ascending root device-address order (== iteration order of the reference's std::map,
+ * index == treelet_addr_to_metadata_idx).  list_offsets has n_treelets+1 entries; node_addr/node_size give
+ * each treelet's node list in the reference's (BFS) order.  Any pointer may be NULL. */
+int vsrt_treelet_table(vsrt_context* ctx, uint64_t* roots, uint64_t* list_offsets,
+                       uint64_t* node_addr, uint32_t* node_size);
+/* node_map_addr_only in ascending node device-address order. */
+int vsrt_node_map(vsrt_context* ctx, uint64_t* node_addr, uint64_t* root_addr);
+/* remapBVHToTreeletLayout (:1473-1509): original device address -> address in the treelet layout, ascending
+ * original order; base = where the reference's gpgpusim_malloc would have put treelet_layout_bvh. */
+int vsrt_treelet_remap(vsrt_context* ctx, uint64_t base, uint64_t* n_out, uint64_t* orig_addr, uint64_t* new_addr);
+/* addrToTreeletID (:468): device address of the treelet root owning `addr`; VSRT_E_INVALID if unknown
+ * (the reference asserts). */
+int vsrt_addr_to_treelet(vsrt_context* ctx, uint64_t addr, uint64_t* root);
+/* isTreeletRoot(uint8_t*) (:462): 1 / 0, <0 on error. */
+int vsrt_is_treelet_root(vsrt_context* ctx, uint64_t addr);
+/* treelet_addr_to_metadata_idx (:1332) */
+int vsrt_treelet_metadata_idx(vsrt_context* ctx, uint64_t root, uint32_t* idx);
+
+/* ---- traversal: traceRay / traceRayWithTreelets over a batch of lanes ----
+ * Replaces the per-lane loop core_t::execute_warp_inst_t -> trace_ray_impl -> traceRay*
+ * (abstract_hardware_model.cc:3052-3063, instructions.cc:7135-7254).  Ray i gets the reference's global
+ * 1-based ray id rayCount+i+1 (:1665).  Outputs, all host pointers, any may be NULL:
+ *   hits[n]            what traversal writes into Traversal_data
+ *   trace_offsets[n+1] CSR offsets into txns / treelet_ids
+ *   txns[]             thread->set_rt_transactions() contents, in the reference's order
+ *   treelet_ids[]      addrToTreeletID(txn.address) (the values of the "RayID,..." line, :2256-2262, 64-bit)
+ * txn_capacity counts records; *n_txn gets the number the batch produced.  If it exceeds the capacity the
+ * call returns VSRT_E_CAPACITY after filling hits/trace_offsets; the trace stays on the device and
+ * vsrt_trace_fetch() can still copy it out. */
+int vsrt_trace_rays(vsrt_context* ctx, const void* tlas, int mode, uint64_t n_rays, const vsrt_ray* rays,
+                    vsrt_hit* hits, uint64_t* trace_offsets, vsrt_txn* txns, uint64_t txn_capacity,
+                    uint64_t* treelet_ids, uint64_t* n_txn);
+int vsrt_trace_fetch(vsrt_context* ctx, vsrt_txn* txns, uint64_t txn_capacity, uint64_t* treelet_ids);
+/* One warp instruction worth of lanes (n <= 32, active_mask selects lanes), mode from the config. */
+int vsrt_trace_ray_warp(vsrt_context* ctx, const void* tlas, uint32_t active_mask, const vsrt_ray rays[32],
+                        vsrt_hit hits[32], uint32_t txn_counts[32], vsrt_txn* txns, uint64_t txn_capacity,
+                        uint64_t* n_txn);
+
+/* Device-resident variant: rays_dev is a device pointer to n_rays vsrt_ray; results stay on the device.
+ * `stream` is a cudaStream_t (NULL = the context's stream).  vsrt_trace_device_results returns the device
+ * pointers of the last batch (valid until the next trace call on this context). */
+int vsrt_trace_rays_device(vsrt_context* ctx, const void* tlas, int mode, uint64_t n_rays,
+                           const void* rays_dev, void* stream, uint64_t* n_txn);
+typedef struct vsrt_device_results {
+  const void* hits;          /* vsrt_hit[n_rays] */
+  const void* trace_offsets; /* uint64_t[n_rays+1] */
+  const void* txns;          /* vsrt_txn[n_txn] */
+  const void* treelet_ids;   /* uint64_t[n_txn] */
+  uint64_t n_rays, n_txn;
+  uint64_t algorithmic_bytes; /* sum of txn.size over the batch == accessedDataSize delta */
+  float traverse_ms, scan_ms, compact_ms; /* device time of the three stages of the last batch */
+  uint32_t kernel_launches;  /* kernels launched by the last batch */
+  uint32_t reserved;
+} vsrt_device_results;
+int vsrt_trace_device_results(vsrt_context* ctx, vsrt_device_results* out);
+
+/* ---- counters and histograms ---- */
+int vsrt_get_counters(vsrt_context* ctx, vsrt_counters* out);
+int vsrt_reset_counters(vsrt_context* ctx);
+/* Device copy of the counters as uint64[VSRT_COUNTERS_N_SUM + VSRT_COUNTERS_N_MAX] followed by the
+ * per-treelet visit histogram uint64[n_treelets] (metadata-index order): the buffers a multi-GPU run
+ * all-reduces (SUM over the first part and the histogram, MAX over the 2 max fields).
+ * vsrt_set_counters_device writes reduced values back. */
+int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_hist_dev, uint64_t* n_treelets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSRT_H */

@@ -1,0 +1,188 @@
+"""Test-side bindings of the two CPU oracles (TEST INFRASTRUCTURE; never imported by the product):
+
+  RefOracle  -- oracle/_ref/libvsrt_ref.so, the reference's own function bodies compiled from /root/reference
+                by oracle/build_ref.sh (process-global state: one instance at a time, reset() between scenes);
+  PortOracle -- oracle/libvsrt_oracle.so, the plain-C restatement (oracle/vsrt_oracle.c).
+
+Both expose: register(arena, delta), form(budget), tables(), trace(mode, rays) -> dict of numpy arrays.
+"""
+import ctypes
+import os
+import numpy as np
+from vsrt import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvsrt_ref.so")
+PORT_SO = os.path.join(ROOT, "oracle", "libvsrt_oracle.so")
+
+OHIT = np.dtype([("hit", "<u4"), ("t", "<f4"), ("prim", "<u4"), ("geom", "<u4"), ("instance_id", "<u4"),
+                 ("bary", "<f4", 3), ("point", "<f4", 3), ("n_all_hits", "<u4")])
+assert OHIT.itemsize == 48
+OCNT_FIELDS = (["mem_access_type_%d" % i for i in range(9)] +
+               ["num_hits", "num_any_hits", "n_anyhit_rays", "n_closesthit_rays", "max_nodes_per_ray",
+                "tot_nodes_per_ray", "max_tree_depth", "accessed_data_size", "ray_count"])
+
+c_u64, c_vp = ctypes.c_uint64, ctypes.c_void_p
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class _Base:
+    def _finish_trace(self, n, total, hits, counts, txns, tids):
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(counts, out=offsets[1:])
+        return {"hits": hits, "offsets": offsets, "txns": txns[:total], "treelet_ids": tids[:total]}
+
+
+class RefOracle(_Base):
+    kind = "reference"
+
+    def __init__(self):
+        L = ctypes.CDLL(REF_SO)
+        L.ref_alloc_tlas.argtypes = [c_vp, c_u64, c_vp]
+        L.ref_alloc_blas.argtypes = [c_vp, c_u64, c_vp]
+        L.ref_form_treelets.argtypes = [c_vp]
+        for f in ("ref_treelet_count", "ref_treelet_total_nodes", "ref_node_map_size", "ref_remap_size", "ref_remap_base"):
+            getattr(L, f).restype = c_u64
+        L.ref_treelet_table.argtypes = [c_vp] * 5
+        L.ref_node_map.argtypes = [c_vp] * 2
+        L.ref_remap.argtypes = [c_vp] * 2
+        L.ref_trace.restype = ctypes.c_int64
+        L.ref_trace.argtypes = [c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.c_int]
+        L.ref_get_counters.argtypes = [c_vp]
+        L.ref_config.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int]
+        self.L = L
+        self.tlas = None
+
+    def register(self, arena, delta=0, blas_delta=None, remap=False, stride=0):
+        """delta: device address - host address for the TLAS (and every BLAS unless blas_delta is given)."""
+        self.L.ref_reset()
+        self._remap, self._stride = remap, stride
+        self.arena, self.delta = arena, delta
+        self.L.ref_alloc_tlas(arena.tlas, arena.size - arena.tlas_offset, arena.tlas + delta)
+        for i, (off, size) in enumerate(arena.blas):
+            d = delta if blas_delta is None else blas_delta[i]
+            self.L.ref_alloc_blas(arena.base + off, size, arena.base + off + d)
+        self.tlas = arena.tlas
+
+    def form(self, budget):
+        self.L.ref_config(budget, 1 if self._remap else 0, self._stride, 0)
+        self.L.ref_form_treelets(self.tlas)
+
+    def tables(self):
+        L = self.L
+        nt, nn, nm = L.ref_treelet_count(), L.ref_treelet_total_nodes(), L.ref_node_map_size()
+        roots = np.zeros(nt, np.uint64); counts = np.zeros(nt, np.uint32); meta = np.zeros(nt, np.uint32)
+        na = np.zeros(nn, np.uint64); ns = np.zeros(nn, np.uint32)
+        L.ref_treelet_table(_abi.ptr(roots), _abi.ptr(counts), _abi.ptr(meta), _abi.ptr(na), _abi.ptr(ns))
+        mk = np.zeros(nm, np.uint64); mv = np.zeros(nm, np.uint64)
+        L.ref_node_map(_abi.ptr(mk), _abi.ptr(mv))
+        return {"roots": roots, "counts": counts, "meta_idx": meta, "node_addr": na, "node_size": ns,
+                "map_nodes": mk, "map_roots": mv}
+
+    def remap_table(self):
+        n = self.L.ref_remap_size()
+        o = np.zeros(n, np.uint64); m = np.zeros(n, np.uint64)
+        self.L.ref_remap(_abi.ptr(o), _abi.ptr(m))
+        return self.L.ref_remap_base(), o, m
+
+    def trace(self, mode, rays, cap_per_ray=512, keep_stdout=False):
+        n = len(rays)
+        hits = np.zeros(n, OHIT); counts = np.zeros(n, np.uint32)
+        cap = max(1024, n * cap_per_ray)
+        txns = np.zeros(cap, _abi.TXN); tids = np.zeros(cap, np.uint64)
+        total = self.L.ref_trace(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(counts), _abi.ptr(txns), cap,
+                                 _abi.ptr(tids), 1 if keep_stdout else 0)
+        if total < 0:
+            return self.trace(mode, rays, cap_per_ray * 4)   # NB: re-runs the rays (counters double count)
+        return self._finish_trace(n, total, hits, counts, txns, tids)
+
+    def counters(self):
+        a = np.zeros(len(OCNT_FIELDS), np.uint64)
+        self.L.ref_get_counters(_abi.ptr(a))
+        return dict(zip(OCNT_FIELDS, (int(x) for x in a)))
+
+
+class PortOracle(_Base):
+    kind = "port"
+
+    def __init__(self):
+        L = ctypes.CDLL(PORT_SO)
+        L.vo_create.restype = c_vp
+        L.vo_destroy.argtypes = [c_vp]
+        L.vo_alloc_tlas.argtypes = [c_vp, c_vp, c_u64, c_u64]
+        L.vo_alloc_blas.argtypes = [c_vp, c_vp, c_u64, c_u64]
+        L.vo_form_treelets.argtypes = [c_vp, c_vp, ctypes.c_int]
+        for f in ("vo_treelet_count", "vo_treelet_total_nodes", "vo_node_map_size", "vo_total_bvh_size"):
+            getattr(L, f).restype = c_u64; getattr(L, f).argtypes = [c_vp]
+        L.vo_treelet_table.argtypes = [c_vp] * 6
+        L.vo_node_map.argtypes = [c_vp] * 3
+        L.vo_treelet_remap.restype = c_u64
+        L.vo_treelet_remap.argtypes = [c_vp, c_u64, ctypes.c_uint32, c_vp, c_vp]
+        L.vo_trace.restype = ctypes.c_int64
+        L.vo_trace.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.c_int]
+        L.vo_get_counters.argtypes = [c_vp, c_vp]
+        L.vo_reset_counters.argtypes = [c_vp]
+        self.L = L
+        self.h = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.vo_destroy(self.h); self.h = None
+
+    def register(self, arena, delta=0, blas_delta=None, remap=False, stride=0):
+        if self.h:
+            self.L.vo_destroy(self.h)
+        self.h = self.L.vo_create()
+        self.arena, self.delta = arena, delta
+        self.L.vo_alloc_tlas(self.h, arena.tlas, arena.size - arena.tlas_offset, arena.tlas + delta)
+        for i, (off, size) in enumerate(arena.blas):
+            d = delta if blas_delta is None else blas_delta[i]
+            self.L.vo_alloc_blas(self.h, arena.base + off, size, arena.base + off + d)
+        self.tlas = arena.tlas
+
+    def form(self, budget):
+        rc = self.L.vo_form_treelets(self.h, self.tlas, budget)
+        if rc != 0:
+            raise RuntimeError("vo_form_treelets: %d" % rc)
+
+    def tables(self):
+        L, h = self.L, self.h
+        nt, nn, nm = L.vo_treelet_count(h), L.vo_treelet_total_nodes(h), L.vo_node_map_size(h)
+        roots = np.zeros(nt, np.uint64); counts = np.zeros(nt, np.uint32); meta = np.zeros(nt, np.uint32)
+        na = np.zeros(nn, np.uint64); ns = np.zeros(nn, np.uint32)
+        L.vo_treelet_table(h, _abi.ptr(roots), _abi.ptr(counts), _abi.ptr(meta), _abi.ptr(na), _abi.ptr(ns))
+        mk = np.zeros(nm, np.uint64); mv = np.zeros(nm, np.uint64)
+        L.vo_node_map(h, _abi.ptr(mk), _abi.ptr(mv))
+        return {"roots": roots, "counts": counts, "meta_idx": meta, "node_addr": na, "node_size": ns,
+                "map_nodes": mk, "map_roots": mv}
+
+    def remap_table(self, base, stride):
+        n = self.L.vo_treelet_remap(self.h, base, stride, None, None)
+        o = np.zeros(n, np.uint64); m = np.zeros(n, np.uint64)
+        self.L.vo_treelet_remap(self.h, base, stride, _abi.ptr(o), _abi.ptr(m))
+        order = np.argsort(o, kind="stable")
+        return o[order], m[order]
+
+    def trace(self, mode, rays, cap_per_ray=512, nthreads=1, want_trace=True):
+        n = len(rays)
+        hits = np.zeros(n, OHIT); counts = np.zeros(n, np.uint32)
+        if not want_trace:
+            total = self.L.vo_trace(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(counts), None, 0, None, nthreads)
+            return {"hits": hits, "counts": counts, "total": total}
+        cap = max(1024, n * cap_per_ray)
+        txns = np.zeros(cap, _abi.TXN); tids = np.zeros(cap, np.uint64)
+        total = self.L.vo_trace(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(counts), _abi.ptr(txns), cap,
+                                _abi.ptr(tids), nthreads)
+        if total < -(1 << 62):
+            raise RuntimeError("vo_trace error %d" % (-(total + (1 << 63))))
+        if total < 0:
+            return self.trace(mode, rays, cap_per_ray * 4, nthreads)
+        return self._finish_trace(n, total, hits, counts, txns, tids)
+
+    def counters(self):
+        a = np.zeros(len(OCNT_FIELDS), np.uint64)
+        self.L.vo_get_counters(self.h, _abi.ptr(a))
+        return dict(zip(OCNT_FIELDS, (int(x) for x in a)))

@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libvsrt.so), against the oracle on the same seeded
+inputs.  Oracle = oracle/_ref (the reference's own code) when it travelled with the snapshot, else the C port.
+Bit-exact on node-visit sequence, record size/type, treelet ids, hit ids AND on t / barycentrics."""
+import numpy as np
+import pytest
+from vsrt import scene as sc, _abi
+import helpers
+import oracles
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import __graft_entry__ as g
+    g.build()
+    import vsrt.api as api
+    return api
+
+
+def all_oracles():
+    out = [oracles.PortOracle()]
+    if oracles.have_ref():
+        out.insert(0, oracles.RefOracle())
+    return out
+
+
+def run_case(api, arena, rays, budget, delta=0, blas_delta=None, modes=(0, 1), check_counters=True, stack_entries=96):
+    for orc in all_oracles():
+        orc.register(arena, delta, blas_delta)
+        orc.form(budget)
+        ctx = api.Context(max_treelet_size=budget, device=0, stack_entries=stack_entries)
+        try:
+            ctx.register(arena, delta, blas_delta)
+            ctx.form_treelets()
+            helpers.assert_tables_equal(orc.tables(), ctx.tables(), "%s budget %d" % (orc.kind, budget))
+            for mode in modes:
+                o = orc.trace(mode, rays)
+                g = ctx.trace(mode, rays)
+                helpers.assert_trace_equal(o, g, "%s mode %d budget %d delta %x" % (orc.kind, mode, budget, delta))
+            if check_counters:
+                co, cg = orc.counters(), ctx.counters()
+                for i in range(9):
+                    assert co["mem_access_type_%d" % i] == cg["mem_access_type_%d" % i], "type histogram bin %d" % i
+                for ko, kg in helpers.COUNTER_MAP.items():
+                    assert co[ko] == cg[kg], "counter %s: oracle %d cuda %d" % (ko, co[ko], cg[kg])
+        finally:
+            ctx.close()
+
+
+def test_kat_vector(api):
+    """SURVEY.md 8(c) worked vector, including the DFS/TREELET divergence when the two quads swap depth."""
+    for z in ((1.0, 2.0), (2.0, 1.0)):
+        for budget in (512, 256):
+            a = helpers.kat_arena(*z)
+            ctx = api.Context(max_treelet_size=budget, device=0)
+            ctx.register(a)
+            info = ctx.form_treelets()
+            assert info.n_treelets == (1 if budget == 512 else 4)
+            for mode in (0, 1):
+                g = ctx.trace(mode, helpers.kat_ray(1 if mode == 0 else 0))
+                rec = [(int(t["address"]) - a.base, int(t["size"]), int(t["type"])) for t in g["txns"]]
+                last = 5 if (mode == 0 or z == (1.0, 2.0)) else 4
+                assert rec == [(0, 64, 0), (64, 64, 1), (192, 128, 2), (320, 64, 0), (384, 64, 1), (512, 8, 3), (512, 64, 5), (448, 8, 3), (448, 64, last)]
+                h = g["hits"][0]
+                assert h["hit_geometry"] == 1 and h["geometry_index"] == 3 and h["instance_index"] == 7
+                assert h["primitive_index"] == (101 if (mode == 1 and z == (2.0, 1.0)) else 100)
+                assert h["world_min_thit"] == 6.0 and list(h["barycentric"]) == [0.25, 0.5, 0.25]
+                tid = [int(x) - a.base for x in g["treelet_ids"]]
+                assert tid == ([0] * 9 if budget == 512 else [0, 0, 192, 192, 192, 512, 512, 448, 448])
+            ctx.close()
+    run_case(api, helpers.kat_arena(), helpers.kat_ray(1), 256)
+
+
+@pytest.mark.parametrize("ntri,nb,ni,flags,fan", [
+    (300, 1, 1, 0, 6),
+    (2000, 2, 3, sc.F_TRANSFORMS | sc.F_HOLES, 6),
+    (5000, 3, 7, sc.F_TRANSFORMS, 4),
+    (20000, 1, 2, sc.F_TRANSFORMS | sc.F_HOLES, 6),
+])
+@pytest.mark.parametrize("budget", [192, 512, 4096, 49152])
+def test_random_scenes(api, ntri, nb, ni, flags, fan, budget):
+    s = sc.Scene(ntri, seed=ntri, n_blas=nb, n_instances=ni, flags=flags, max_fanout=fan)
+    run_case(api, s, helpers.mixed_rays(1500, ntri), budget)
+
+
+@pytest.mark.parametrize("budget", [256, 1024])
+def test_host_device_offset_quirk(api, budget):
+    """Non-zero host->device offset: traceRayWithTreelets stores a HOST address in current_treelet_root
+    (vulkan_ray_tracing.cc:1752), so after the first switch every child goes to the `other` stack."""
+    s = sc.Scene(5000, seed=11, n_blas=2, n_instances=4, flags=sc.F_TRANSFORMS)
+    run_case(api, s, helpers.mixed_rays(1000, 5), budget, delta=0x100000)
+
+
+def test_non_uniform_blas_offsets(api):
+    """BLAS buffers registered at their own device offsets: traceRay switches device_offset inside a BLAS (:2640),
+    traceRayWithTreelets only for the BLAS header record (:1908-1913)."""
+    s = sc.Scene(3000, seed=21, n_blas=3, n_instances=5, flags=sc.F_TRANSFORMS)
+    run_case(api, s, helpers.mixed_rays(800, 9), 512, delta=0x4000, blas_delta=[0x4000, 0x900000, 0x40], check_counters=False)
+
+
+def test_clustered_scene_and_bounces(api):
+    s = sc.Scene(30000, seed=5, kind=sc.CLUSTERED)
+    prim = sc.rays_primary(96, 64, flags=_abi.FLAG_OPAQUE)
+    orc = all_oracles()[0]
+    orc.register(s); orc.form(2048)
+    ctx = api.Context(max_treelet_size=2048, device=0)
+    ctx.register(s); ctx.form_treelets()
+    rays = prim
+    for bounce in range(3):
+        o = orc.trace(1, rays); g = ctx.trace(1, rays)
+        helpers.assert_trace_equal(o, g, "bounce %d" % bounce)
+        rays = s.bounce(rays, g["hits"], 77, bounce, 0)
+        if len(rays) == 0:
+            break
+    ctx.close()
+
+
+def test_empty_and_ragged_batches(api):
+    s = sc.Scene(1000, seed=3)
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.register(s); ctx.form_treelets()
+    g = ctx.trace(1, np.zeros(0, _abi.RAY))
+    assert len(g["txns"]) == 0 and list(g["offsets"]) == [0]
+    orc = oracles.PortOracle(); orc.register(s); orc.form(512)
+    for n in (1, 31, 33, 257):
+        rays = sc.rays_random(n, seed=n)
+        helpers.assert_trace_equal(orc.trace(1, rays), ctx.trace(1, rays), "n=%d" % n)
+    # rays that miss the scene box entirely: exactly one record (the TLAS header) and no hit
+    far = sc.rays_random(64, seed=1); far["origin"] += 100.0; far["direction"][:] = (1, 0, 0)
+    g = ctx.trace(0, far)
+    assert np.all(np.diff(g["offsets"]) == 1) and not g["hits"]["hit_geometry"].any()
+    helpers.assert_trace_equal(orc.trace(0, far), g, "far rays")
+    ctx.close()
+
+
+def test_warp_call_and_queries(api):
+    s = sc.Scene(4000, seed=8, n_blas=2, n_instances=2)
+    orc = oracles.PortOracle(); orc.register(s); orc.form(512)
+    ctx = api.Context(max_treelet_size=512, device=0, treelet_based_traversal=1)
+    ctx.register(s); ctx.form_treelets()
+    rays = sc.rays_random(32, seed=4)
+    mask = 0xF0F0FFFF
+    w = ctx.trace_warp(rays, mask)
+    act = [l for l in range(32) if mask >> l & 1]
+    o = orc.trace(1, rays[act])
+    assert list(w["counts"][act]) == list(np.diff(o["offsets"])) and w["counts"].sum() == len(o["txns"])
+    assert np.array_equal(w["txns"], o["txns"])
+    t = orc.tables()
+    for node, root in list(zip(t["map_nodes"], t["map_roots"]))[::97]:
+        assert ctx.addr_to_treelet(int(node)) == int(root)
+    for i, r in enumerate(t["roots"][::53]):
+        assert ctx.is_treelet_root(int(r)) and ctx.metadata_idx(int(r)) == i * 53
+    assert not ctx.is_treelet_root(int(t["roots"][0]) + 8)
+    with pytest.raises(api.VsrtError):
+        ctx.addr_to_treelet(12345)
+    ctx.close()
+
+
+def test_error_paths(api):
+    s = sc.Scene(500, seed=2)
+    ctx = api.Context(max_treelet_size=128, device=0)
+    ctx.register(s)
+    with pytest.raises(api.VsrtError) as e:
+        ctx.form_treelets()
+    assert e.value.code == -8                      # budget below what the reference's asserts allow
+    ctx.close()
+    # BLAS never registered -> the reference asserts on blas_addr_map (:973); we return UNKNOWN_AS
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.alloc_tlas(s.tlas, s.size, s.tlas)
+    with pytest.raises(api.VsrtError) as e:
+        ctx.form_treelets()
+    assert e.value.code == -5
+    ctx.close()
+    # PrimitiveIndex1Delta != 0 -> reference assert :2108
+    a = helpers.kat_arena()
+    a.bytes[448 + 12] = 1
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.register(a)
+    with pytest.raises(api.VsrtError) as e:
+        ctx.form_treelets()
+    assert e.value.code == -6
+    ctx.close()
+    # unknown TLAS handle -> reference abort() (:1568)
+    ctx = api.Context(device=0)
+    ctx.register(s); ctx.tlas = s.tlas + 64
+    with pytest.raises(api.VsrtError) as e:
+        ctx.trace(0, sc.rays_random(4))
+    assert e.value.code == -5
+    ctx.close()
+
+
+def test_remap_table(api):
+    if not oracles.have_ref():
+        pytest.skip("needs oracle/_ref")
+    s = sc.Scene(3000, seed=13, n_blas=2, n_instances=3)
+    ref = oracles.RefOracle()
+    ref.register(s, remap=True, stride=256); ref.form(1024)
+    base, o, m = ref.remap_table()
+    ctx = api.Context(max_treelet_size=1024, device=0, treelet_remap_stride=256)
+    ctx.register(s); ctx.form_treelets()
+    go, gm = ctx.remap_table(base)
+    assert np.array_equal(o, go) and np.array_equal(m, gm)
+    ctx.close()
+
+
+def test_large_scene_properties(api):
+    """Full-size style check through size-independent properties (no oracle): both variants agree on hit t
+    for opaque closest-hit rays; per-ray records start with the TLAS header; counters equal the trace."""
+    s = sc.Scene(200000, seed=99)
+    rays = sc.rays_primary(320, 240, flags=_abi.FLAG_OPAQUE)
+    ctx = api.Context(max_treelet_size=4096, device=0)
+    ctx.register(s); ctx.form_treelets()
+    a = ctx.trace(0, rays); b = ctx.trace(1, rays)
+    assert np.array_equal(a["hits"]["hit_geometry"], b["hits"]["hit_geometry"])
+    assert np.array_equal(a["hits"]["world_min_thit"].view(np.uint32), b["hits"]["world_min_thit"].view(np.uint32))
+    for g in (a, b):
+        first = g["txns"][g["offsets"][:-1].astype(np.int64)]
+        assert np.all(first["address"] == s.tlas) and np.all(first["type"] == 0)
+    c = ctx.counters()
+    total = sum(c["mem_access_type_%d" % i] for i in range(9))
+    assert total == len(a["txns"]) + len(b["txns"])
+    assert c["accessed_data_size"] == int(a["txns"]["size"].sum()) + int(b["txns"]["size"].sum())
+    assert c["ray_count"] == 2 * len(rays)
+    # every treelet id is the root of the treelet owning the record's node
+    t = ctx.tables()
+    idx = np.searchsorted(t["map_nodes"], b["txns"]["address"])
+    assert np.array_equal(t["map_roots"][idx], b["treelet_ids"])
+    ctx.close()
+
+
+import golden_util  # noqa: E402
+
+
+@pytest.mark.parametrize("path", golden_util.fixtures(), ids=lambda p: p.split("golden_")[-1][:-4])
+def test_cuda_matches_golden(api, path):
+    """CUDA path against the fixtures recorded from the reference's own code (tests/golden/make_golden.py)."""
+    z, arena, rays = golden_util.load(path)
+    delta = int(z["delta"])
+    for b in (int(x) for x in z["budgets"]):
+        ctx = api.Context(max_treelet_size=b, device=0)
+        ctx.register(arena, delta); ctx.form_treelets()
+        helpers.assert_tables_equal(golden_util.expected_tables(z, b, arena.base), ctx.tables(), "golden budget %d" % b)
+        for mode in (0, 1):
+            helpers.assert_trace_equal(golden_util.expected_trace(z, b, mode, arena.base), ctx.trace(mode, rays), "golden b%d m%d" % (b, mode))
+        ctx.close()

@@ -1,0 +1,109 @@
+"""CPU tests of the oracle itself (no GPU): the plain-C restatement against (1) the golden fixtures recorded
+from the reference's own code and (2), when oracle/_ref was built here, the compiled reference live."""
+import numpy as np
+import pytest
+from vsrt import scene as sc, _abi
+import helpers
+import oracles
+import golden_util
+
+
+def same_hits(a, b):
+    return all(np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)) for f in a.dtype.names)
+
+
+@pytest.mark.parametrize("path", golden_util.fixtures(), ids=lambda p: p.split("golden_")[-1][:-4])
+def test_port_matches_golden(path):
+    z, arena, rays = golden_util.load(path)
+    delta = int(z["delta"])
+    port = oracles.PortOracle()
+    for b in (int(x) for x in z["budgets"]):
+        port.register(arena, delta); port.form(b)
+        exp = golden_util.expected_tables(z, b, arena.base)
+        got = port.tables()
+        for k in exp:
+            assert np.array_equal(exp[k], got[k]), "budget %d table %s" % (b, k)
+        for mode in (0, 1):
+            e = golden_util.expected_trace(z, b, mode, arena.base)
+            g = port.trace(mode, rays)
+            assert np.array_equal(e["offsets"], g["offsets"])
+            assert np.array_equal(e["txns"], g["txns"])
+            assert np.array_equal(e["treelet_ids"], g["treelet_ids"])
+            assert same_hits(e["hits"], g["hits"])
+        c = port.counters()
+        assert [c[k] for k in oracles.OCNT_FIELDS] == [int(x) for x in z["b%d_counters" % b]]
+
+
+def test_golden_fixtures_exist():
+    assert len(golden_util.fixtures()) >= 4
+
+
+def test_kat_vector_port():
+    """SURVEY.md 8(c) worked vector on the port oracle."""
+    a = helpers.kat_arena(2.0, 1.0)
+    port = oracles.PortOracle(); port.register(a); port.form(256)
+    t = port.tables()
+    assert [int(r) - a.base for r in t["roots"]] == [0, 192, 448, 512] and list(t["counts"]) == [2, 3, 1, 1]
+    d = port.trace(0, helpers.kat_ray(1)); tr = port.trace(1, helpers.kat_ray(0))
+    assert int(d["hits"]["prim"][0]) == 100 and int(tr["hits"]["prim"][0]) == 101
+    assert int(d["txns"]["type"][-1]) == 5 and int(tr["txns"]["type"][-1]) == 4
+    assert float(d["hits"]["t"][0]) == 6.0 and float(tr["hits"]["t"][0]) == 6.0
+
+
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+@pytest.mark.parametrize("ntri,nb,ni,flags,fan,delta", [
+    (300, 1, 1, 0, 6, 0),
+    (2000, 2, 3, sc.F_TRANSFORMS | sc.F_HOLES, 6, 0),
+    (5000, 3, 7, sc.F_TRANSFORMS, 4, 0x100000),
+    (12000, 1, 2, sc.F_TRANSFORMS | sc.F_HOLES, 6, 0),
+])
+def test_port_matches_reference_live(ntri, nb, ni, flags, fan, delta):
+    s = sc.Scene(ntri, seed=ntri + 1, n_blas=nb, n_instances=ni, flags=flags, max_fanout=fan)
+    rays = helpers.mixed_rays(600, ntri)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    for budget in (192, 512, 2048, 49152):
+        ref.register(s, delta); ref.form(budget); port.register(s, delta); port.form(budget)
+        tr, tp = ref.tables(), port.tables()
+        for k in tr:
+            assert np.array_equal(tr[k], tp[k]), k
+        for mode in (0, 1):
+            a, b = ref.trace(mode, rays), port.trace(mode, rays)
+            assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["txns"], b["txns"])
+            assert np.array_equal(a["treelet_ids"], b["treelet_ids"]) and same_hits(a["hits"], b["hits"])
+        assert ref.counters() == port.counters()
+
+
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_remap_matches_reference():
+    s = sc.Scene(2500, seed=4, n_blas=2, n_instances=3)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s, remap=True, stride=128); ref.form(1024)
+    port.register(s); port.form(1024)
+    base, o, m = ref.remap_table()
+    po, pm = port.remap_table(base, 128)
+    assert np.array_equal(o, po) and np.array_equal(m, pm)
+
+
+def test_port_parallel_equals_serial():
+    s = sc.Scene(8000, seed=6, n_blas=2, n_instances=2)
+    rays = helpers.mixed_rays(3000, 8)
+    p1, p4 = oracles.PortOracle(), oracles.PortOracle()
+    for p in (p1, p4):
+        p.register(s); p.form(512)
+    a, b = p1.trace(1, rays, nthreads=1), p4.trace(1, rays, nthreads=4)
+    assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["txns"], b["txns"]) and same_hits(a["hits"], b["hits"])
+    assert p1.counters() == p4.counters()
+
+
+def test_properties():
+    """Domain invariants of the reference semantics, checked on the port: TREELET and DFS agree on t for opaque
+    rays; DFS reports the LAST accepted leaf while TREELET reports the closest."""
+    s = sc.Scene(6000, seed=10)
+    rays = sc.rays_primary(64, 48, flags=_abi.FLAG_OPAQUE)
+    p = oracles.PortOracle(); p.register(s); p.form(512)
+    d, t = p.trace(0, rays), p.trace(1, rays)
+    assert np.array_equal(d["hits"]["hit"], t["hits"]["hit"])
+    assert np.array_equal(d["hits"]["t"].view(np.uint32), t["hits"]["t"].view(np.uint32))
+    assert d["hits"]["hit"].sum() > 100
+    # every DFS trace is a superset-length walk: it never culls by the closest hit at leaves
+    assert len(d["txns"]) >= len(t["txns"]) * 0.5

@@ -1,0 +1,178 @@
+// compact.cu -- exclusive scan of per-ray record counts and K3, the trace-compaction kernel that expands the
+// compact staging records into the reference's MemoryTransactionRecord {address,size,type}
+// (abstract_hardware_model.h:315-321) in the reference's per-ray transaction order, CSR over rays, plus the
+// treelet index of every record (addrToTreeletID, vulkan_ray_tracing.cc:468-472, as an index into the ascending
+// root table == treelet_addr_to_metadata_idx).  Also accumulates g_rt_mem_access_type[], accessedDataSize
+// (:2257-2261) and the per-treelet visit histogram the prefetcher's popularity vote is built from (shader.cc:3424-3433).
+#include "vsrt_device.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long block_scan_excl(unsigned long long v, unsigned long long* total, unsigned long long* sh /*[32]*/) {
+  // inclusive warp scan
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) sh[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long s = lane < (SCAN_THREADS / 32) ? sh[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    sh[lane] = s;   // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned long long warp_off = wid ? sh[wid - 1] : 0ull;
+  *total = sh[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ counts, uint64_t n, unsigned long long* __restrict__ tile_sums) {
+  __shared__ unsigned long long sh[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += counts[base + i];
+  unsigned long long tot;
+  block_scan_excl(s, &tot, sh);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(unsigned long long* __restrict__ tile_sums, uint64_t n_tiles) {
+  __shared__ unsigned long long sh[32];
+  unsigned long long carry = 0;
+  for (uint64_t b = 0; b < n_tiles; b += SCAN_THREADS) {
+    const uint64_t i = b + threadIdx.x;
+    const unsigned long long v = i < n_tiles ? tile_sums[i] : 0ull;
+    unsigned long long tot;
+    const unsigned long long ex = block_scan_excl(v, &tot, sh);
+    if (i < n_tiles) tile_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) tile_sums[n_tiles] = carry;   // grand total
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __restrict__ counts, uint64_t n, const unsigned long long* __restrict__ tile_sums,
+                                                            uint64_t n_tiles, unsigned long long* __restrict__ offsets) {
+  __shared__ unsigned long long sh[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t c[SCAN_ITEMS]; unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { c[i] = base + i < n ? counts[base + i] : 0u; s += c[i]; }
+  unsigned long long tot;
+  unsigned long long ex = block_scan_excl(s, &tot, sh) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) offsets[base + i] = ex; ex += c[i]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = tile_sums[n_tiles];
+}
+
+// ---------------------------------------------------------------- K3
+constexpr int K3_THREADS = 256;
+constexpr int K3_RAYS = 256;     // rays per CTA
+
+__device__ __forceinline__ uint32_t code_size(uint32_t code) { return code == C_INSTANCE ? 128u : (code == C_DESC ? 8u : 64u); }
+__device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_INTERNAL_TLAS ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code; }
+
+__global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
+  __shared__ unsigned long long s_off[K3_RAYS + 1];
+  __shared__ unsigned int s_hist[8];
+  const uint64_t r0 = (uint64_t)blockIdx.x * K3_RAYS;
+  const uint32_t nr = (uint32_t)min((uint64_t)K3_RAYS, p.n_rays - r0);
+  for (uint32_t i = threadIdx.x; i <= nr; i += K3_THREADS) s_off[i] = p.offsets[r0 + i];
+  if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned long long j0 = s_off[0], j1 = s_off[nr];
+  const ArenaView& av = p.av;
+  uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  for (unsigned long long jb = j0; jb < j1; jb += K3_THREADS) {
+    const unsigned long long j = jb + threadIdx.x;
+    const bool valid = j < j1;
+    uint32_t tid = VSRT_NO_TID;
+    if (valid) {
+      // ray of record j: last i with s_off[i] <= j
+      uint32_t lo = 0, hi = nr;
+      while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_off[m] <= j) lo = m; else hi = m; }
+      const uint32_t k = (uint32_t)(j - s_off[lo]);
+      const uint32_t* seg = p.stage + (r0 + lo) * (uint64_t)p.cap;
+      const uint32_t rec = __ldg(seg + k);
+      const uint32_t slot = rec >> 3, code = rec & 7u;
+      // host -> simulated-device offset the reference applies to this record
+      int64_t delta = av.tlas_delta;
+      if (!av.uniform_delta) {
+        if (code == C_STRUCT && k > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
+        else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k > 0) {
+          // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
+          for (uint32_t b = k; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
+        }
+      }
+      vsrt_txn t;
+      t.address = slot_to_host(av, slot) + (uint64_t)delta;
+      t.size = code_size(code); t.type = code_type(code);
+      tid = __ldg(p.tv.node_tid + slot);
+      if (j < p.out_capacity) {
+        *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)t.address, (uint32_t)(t.address >> 32), t.size, t.type);
+        p.tids[j] = tid;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) hc[c] += (t.type == (uint32_t)c) ? 1u : 0u;
+    }
+    if (p.treelet_hist) {
+      // warp-aggregated histogram: consecutive records of a ray mostly share a treelet
+      const unsigned act = __ballot_sync(0xffffffffu, valid && tid != VSRT_NO_TID);
+      if (valid && tid != VSRT_NO_TID) {
+        const unsigned peers = __match_any_sync(act, tid);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p.treelet_hist + tid, (unsigned long long)__popc(peers));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint32_t s = __reduce_add_sync(0xffffffffu, hc[c]);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_hist[c], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_hist[threadIdx.x]) {
+    const unsigned long long n = s_hist[threadIdx.x];
+    atomicAdd(p.counters->v + CI_TYPE0 + threadIdx.x, n);
+    const unsigned long long bytes = n * (threadIdx.x == VSRT_TXN_BVH_INSTANCE_LEAF ? 128ull : (threadIdx.x == VSRT_TXN_BVH_PRIMITIVE_LEAF_DESCRIPTOR ? 8ull : 64ull));
+    atomicAdd(p.counters->v + CI_ACCESSED, bytes);
+  }
+}
+
+__global__ void k_tid_to_addr(const ArenaView av, const TreeletView tv, const uint32_t* __restrict__ tids, uint64_t n, unsigned long long* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = tids[i];
+  out[i] = (t == VSRT_NO_TID || t >= tv.n_treelets) ? ~0ull : slot_to_host(av, __ldg(tv.tl_root + t)) + (uint64_t)av.tlas_delta;
+}
+
+}  // namespace
+
+size_t vsrt_scan_tmp_bytes(uint64_t n) { return ((n + SCAN_TILE - 1) / SCAN_TILE + 2) * sizeof(unsigned long long); }
+
+int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st) {
+  const uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  unsigned long long* sums = (unsigned long long*)tmp;
+  if (n_tiles == 0) { cudaMemsetAsync(offsets, 0, 8, st); return VSRT_OK; }
+  k_scan_tiles<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, sums);
+  k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(sums, n_tiles);
+  k_scan_write<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, sums, n_tiles, (unsigned long long*)offsets);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
+  const uint64_t grid = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
+  if (grid == 0) return VSRT_OK;
+  k_compact<<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out, cudaStream_t st) {
+  if (n == 0) return VSRT_OK;
+  k_tid_to_addr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(av, tv, tids, n, (unsigned long long*)out);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}

@@ -1,0 +1,267 @@
+// treelets.cu -- K0: treelet formation, the GPU restatement of VulkanRayTracing::createTreelets
+// (vulkan_ray_tracing.cc:823-1470) + buildNodeToRootMap (:475-489).
+//
+// The reference is a sequential top-down greedy BFS: a FIFO of candidate nodes is drained while the FRONT
+// candidate still fits the byte budget (:1117); when it does not, the treelet closes and EVERY queued candidate
+// becomes the root of a later treelet (:1167-1171).  A treelet's content is therefore a pure function of
+// (root, budget), and all roots discovered by one generation of treelets are independent: the kernel below forms
+// one generation ("wave") per launch, one thread per root, and the host loops over waves until no new root
+// appears.  Results are identical to the sequential algorithm because the final tables are keyed by address:
+//   * roots ascending by address  -> rank == treelet_addr_to_metadata_idx (:1311-1334)
+//   * node lists in BFS order, de-duplicated first-occurrence-wins (:1312-1330)
+//   * node -> root: "later (higher-address) roots overwrite" (:479-486)  == atomicMax over ranks.
+// The FIFO is never materialised: the processed-node list IS the queue prefix, so the queue front is "the next
+// unconsumed child of list[p]" and only a cursor (p, child index) is kept per thread.
+// The walk also validates what the reference asserts on (:926,:973,:2108 and every remaining_bytes >= 0).
+#include "vsrt_device.cuh"
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include <cstdio>
+
+namespace {
+
+struct FormState {
+  uint32_t* claimed;           // root bitmap
+  uint2* roots;                // worklist: (slot, kind)
+  unsigned int* n_roots;
+  unsigned long long* total_bvh;
+  uint32_t* err;
+};
+
+VS_DEV uint64_t mk_entry(uint32_t slot, uint32_t kind) { return (uint64_t)slot | ((uint64_t)kind << 32); }
+
+struct Walker {
+  const ArenaView& av; uint64_t* list; uint32_t n; int remaining; uint32_t err; uint32_t n_inst; unsigned long long bytes;
+  VS_DEV Walker(const ArenaView& a, uint64_t* l, int budget) : av(a), list(l), n(0), remaining(budget), err(0), n_inst(0), bytes(0) {}
+  VS_DEV void charge(int b) { remaining -= b; bytes += (unsigned)b; if (remaining < 0) err |= EF_BUDGET; }   // assert(remaining_bytes >= 0)
+  // "process" one popped candidate: append to the node list and charge its bytes (:886-1114)
+  VS_DEV void process(uint32_t slot, uint32_t kind) {
+    if (slot >= av.n_slots) { err |= EF_BAD_BVH; return; }
+    if (kind == K_TLAS_INTERNAL || kind == K_BLAS_INTERNAL) {
+      charge(64); list[n++] = mk_entry(slot, kind);
+      if (kind == K_TLAS_INTERNAL) {   // assert(node.ChildType[i] == NODE_TYPE_INSTANCE) for TLAS leaves, :926
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u) + 1);
+        const uint64_t info6 = ((uint64_t)b.z << 16) | (b.y >> 16);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { const uint32_t t = (uint32_t)(info6 >> (8 * i)) & 0x3fu; if ((t & 3u) && (t >> 2) > 1u) err |= EF_BAD_BVH; }
+      }
+    } else if (kind == K_INSTANCE) {
+      if (slot + 1 >= av.n_slots) { err |= EF_BAD_BVH; return; }
+      charge(128); list[n++] = mk_entry(slot, K_INSTANCE); n_inst++;
+      uint32_t hdr = 0; int64_t d;
+      if (!instance_blas_header(av, slot, hdr)) { err |= EF_BAD_BVH; return; }
+      if (!blas_delta_of(av, hdr, d)) { err |= EF_UNKNOWN_AS; return; }                                    // assert :973
+      charge(64); list[n++] = mk_entry(hdr, K_BLAS_HEADER);                                               // isBlasRoot entry, :975
+    } else {   // BLAS leaf: 64 bytes whether quad or procedural (:1100,:1109)
+      list[n++] = mk_entry(slot, K_BLAS_LEAF); charge(64);
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u));
+      if (((a.y >> 29) & 1u) == 0u && (a.w & 0x1ffffu) != 0u) err |= EF_BAD_BVH;                          // PrimitiveIndex1Delta, :2108
+    }
+  }
+};
+
+// One thread per root of the current wave.
+__global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const FormState fs, uint32_t begin, uint32_t count, int budget,
+                                                   uint32_t cap, uint64_t* __restrict__ pool, uint32_t* __restrict__ r_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const uint2 root = fs.roots[begin + t];
+  uint64_t* list = pool + (uint64_t)t * cap;
+  Walker w(av, list, budget);
+  uint32_t p = 0;
+  if (root.y == K_TLAS_HEADER) {                                   // :846-862
+    w.charge(64); list[w.n++] = mk_entry(root.x, K_TLAS_HEADER);
+    uint32_t rs = 0;
+    if (!header_root(av, root.x, rs)) w.err |= EF_BAD_BVH; else w.process(rs, K_TLAS_INTERNAL);
+    p = 1;
+  } else w.process(root.x, root.y);                                // a pending root is processed without a fit check (:1197)
+
+  // queue cursor: children of list[p] from child index ci on
+  uint32_t ci = 0, child = 0; uint64_t info6 = 0; bool loaded = false; bool closing = false;
+  while (p < w.n && !(w.err & (EF_BAD_BVH | EF_UNKNOWN_AS))) {
+    const uint64_t ent = list[p];
+    const uint32_t eslot = (uint32_t)ent, ekind = (uint32_t)(ent >> 32);
+    uint32_t cslot = 0, ckind = 0, csz = 0; bool found = false;
+    if (ekind == K_TLAS_INTERNAL || ekind == K_BLAS_INTERNAL) {
+      if (!loaded) {
+        const uint4* np = reinterpret_cast<const uint4*>(av.base + (uint64_t)eslot * 64u);
+        const uint4 a = __ldg(np), b = __ldg(np + 1);
+        child = eslot + a.w;                                        // ChildOffset in 64-byte units, relative to the node (:919)
+        info6 = ((uint64_t)b.z << 16) | (b.y >> 16);                // bytes 22..27
+        ci = 0; loaded = true;
+      }
+      while (ci < 6) {
+        const uint32_t t6 = (uint32_t)(info6 >> (8 * ci)) & 0x3fu;
+        if (t6 & 3u) { cslot = child; csz = t6 & 3u; const uint32_t ty = t6 >> 2;
+          ckind = (ekind == K_TLAS_INTERNAL) ? (ty == 0 ? K_TLAS_INTERNAL : K_INSTANCE) : (ty == 0 ? K_BLAS_INTERNAL : K_BLAS_LEAF);
+          found = true; break; }
+        ci++;
+      }
+    } else if (ekind == K_INSTANCE && ci == 0) {
+      // its single queued child is the BLAS root internal node (:987-990); the header entry sits at list[p+1]
+      const uint32_t hdr = (uint32_t)list[p + 1];
+      uint32_t rs = 0;
+      if (header_root(av, hdr, rs)) { cslot = rs; ckind = K_BLAS_INTERNAL; csz = 0; found = true; } else { w.err |= EF_BAD_BVH; break; }
+    }
+    if (!found) { p++; ci = 0; loaded = false; continue; }
+    if (!closing && w.remaining - (ckind == K_INSTANCE ? 192 : 64) >= 0) {      // front fits (:1117)
+      ci++; child += csz;
+      w.process(cslot, ckind);
+    } else {
+      // treelet closed: every queued candidate becomes a future root (:1167-1171)
+      closing = true;
+      ci++; child += csz;
+      if (cslot >= av.n_slots) { w.err |= EF_BAD_BVH; break; }
+      const uint32_t bit = 1u << (cslot & 31);
+      const uint32_t old = atomicOr(fs.claimed + (cslot >> 5), bit);
+      if (!(old & bit)) { const unsigned int idx = atomicAdd(fs.n_roots, 1u); fs.roots[idx] = make_uint2(cslot, ckind); }
+    }
+  }
+  // de-duplicate, first occurrence wins (:1312-1330).  A node can only repeat inside one treelet when two instance
+  // leaves of that treelet reference the same BLAS.
+  uint32_t n = w.n;
+  if (w.n_inst >= 2) {
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t s = (uint32_t)list[i]; bool dup = false;
+      for (uint32_t j = 0; j < o; j++) if ((uint32_t)list[j] == s) { dup = true; break; }
+      if (!dup) list[o++] = list[i];
+    }
+    n = o;
+  }
+  r_count[begin + t] = n;
+  atomicAdd(fs.total_bvh, w.bytes);
+  if (w.err) atomicOr(fs.err, w.err);
+}
+
+__global__ void k_popc(const uint32_t* __restrict__ bits, uint32_t nw, uint32_t* __restrict__ cnt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < nw) cnt[i] = __popc(bits[i]);
+}
+__global__ void k_narrow(const unsigned long long* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i];
+}
+// rank of every discovered root + scatter of (slot, count) into rank order
+__global__ void k_rank(const uint2* __restrict__ roots, const uint32_t* __restrict__ r_count, uint32_t n, const uint32_t* __restrict__ bits,
+                       const uint32_t* __restrict__ prefix, uint32_t* __restrict__ r_rank, uint32_t* __restrict__ tl_root, uint32_t* __restrict__ tl_count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const uint32_t s = roots[i].x, w = bits[s >> 5], b = 1u << (s & 31);
+  const uint32_t rk = prefix[s >> 5] + __popc(w & (b - 1));
+  r_rank[i] = rk; tl_root[rk] = s; tl_count[rk] = r_count[i];
+}
+// copy each root's list into the rank-ordered CSR and fold the node -> highest-root map (rank + 1, 0 = unmapped)
+__global__ void k_gather(const uint64_t* const* __restrict__ r_list, const uint32_t* __restrict__ r_count, const uint32_t* __restrict__ r_rank, uint32_t n,
+                         const unsigned long long* __restrict__ tl_off, uint64_t* __restrict__ tl_node, uint32_t* __restrict__ node_tid1,
+                         unsigned long long* __restrict__ n_mapped) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const uint64_t* src = r_list[i]; const uint32_t c = r_count[i], rk = r_rank[i];
+  uint64_t* dst = tl_node + tl_off[rk];
+  uint32_t fresh = 0;
+  for (uint32_t k = 0; k < c; k++) {
+    const uint64_t e = src[k]; dst[k] = e;
+    const uint32_t old = atomicMax(node_tid1 + (uint32_t)e, rk + 1u);
+    if (old == 0u) fresh++;
+  }
+  if (fresh) atomicAdd(n_mapped, (unsigned long long)fresh);
+}
+__global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) { const uint32_t v = node_tid[i]; node_tid[i] = v ? v - 1u : VSRT_NO_TID; }
+}
+__global__ void k_fill_ptrs(const uint64_t** r_list, uint32_t begin, uint32_t count, uint64_t* pool, uint32_t cap) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t < count) r_list[begin + t] = pool + (uint64_t)t * cap;
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errbuf, errcap, "%s: %s", #x, cudaGetErrorString(e_)); rc = VSRT_E_CUDA; goto done; } } while (0)
+
+}  // namespace
+
+int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,
+                              uint32_t* err_flags_dev, char* errbuf, size_t errcap) {
+  int rc = VSRT_OK;
+  const uint32_t ns = av.n_slots, nw = (ns + 31) / 32;
+  const uint32_t cap = budget / 64 + 2;
+  uint32_t* claimed = nullptr; uint2* roots = nullptr; unsigned int* n_roots_d = nullptr; unsigned long long* scal = nullptr;
+  uint32_t* r_count = nullptr; const uint64_t** r_list = nullptr; uint32_t* r_rank = nullptr;
+  uint32_t* popc = nullptr; unsigned long long* off64 = nullptr; void* scan_tmp = nullptr;
+  uint32_t* prefix = nullptr; uint32_t* tl_root = nullptr; uint32_t* tl_count = nullptr; unsigned long long* tl_off = nullptr;
+  uint64_t* tl_node = nullptr; uint32_t* node_tid = nullptr;
+  std::vector<uint64_t*> pools;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint32_t n_roots = 1, begin = 0, h_err = 0;
+  unsigned long long h_scal[2] = { 0, 0 }, n_entries = 0;
+  memset(out, 0, sizeof(*out)); memset(res, 0, sizeof(*res));
+  if (budget < 192) { snprintf(errbuf, errcap, "max_treelet_size %u < 192 (an instance-leaf root is charged 128+64 bytes, reference asserts)", budget); return VSRT_E_BUDGET; }
+
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(cudaMalloc(&claimed, (size_t)nw * 4)); CK(cudaMemsetAsync(claimed, 0, (size_t)nw * 4, st));
+  CK(cudaMalloc(&roots, (size_t)ns * sizeof(uint2)));
+  CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 16)); CK(cudaMemsetAsync(scal, 0, 16, st));
+  CK(cudaMalloc(&r_count, (size_t)ns * 4)); CK(cudaMalloc(&r_list, (size_t)ns * 8));
+  CK(cudaMemsetAsync(err_flags_dev, 0, 4, st));
+  CK(cudaEventRecord(ev0, st));
+  {
+    // seed: the first treelet is keyed by the TLAS header (:847)
+    const uint2 seed = make_uint2(av.tlas_slot, K_TLAS_HEADER); const unsigned int one = 1;
+    const uint32_t bit = 1u << (av.tlas_slot & 31);
+    CK(cudaMemcpyAsync(roots, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(n_roots_d, &one, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(claimed + (av.tlas_slot >> 5), &bit, 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  {
+    FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev };
+    while (begin < n_roots) {
+      const uint32_t count = n_roots - begin;
+      uint64_t* pool = nullptr;
+      CK(cudaMalloc(&pool, (size_t)count * cap * 8)); pools.push_back(pool);
+      k_form_wave<<<(count + 127) / 128, 128, 0, st>>>(av, fs, begin, count, (int)budget, cap, pool, r_count);
+      k_fill_ptrs<<<(count + 255) / 256, 256, 0, st>>>(r_list, begin, count, pool, cap);
+      CK(cudaGetLastError());
+      begin = n_roots;
+      CK(cudaMemcpyAsync(&n_roots, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(&h_err, err_flags_dev, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h_err) break;
+    }
+  }
+  if (h_err) {
+    rc = (h_err & EF_UNKNOWN_AS) ? VSRT_E_UNKNOWN_AS : (h_err & EF_BAD_BVH) ? VSRT_E_BAD_BVH : VSRT_E_BUDGET;
+    snprintf(errbuf, errcap, "treelet formation rejected the arena (flags 0x%x): %s", h_err,
+             rc == VSRT_E_UNKNOWN_AS ? "instance leaf references a BLAS that was never registered with vsrt_alloc_blas" :
+             rc == VSRT_E_BAD_BVH ? "malformed BVH (child out of bounds, non-instance TLAS leaf or PrimitiveIndex1Delta != 0)" :
+             "a node does not fit max_treelet_size (reference: assert(remaining_bytes >= 0))");
+    goto done;
+  }
+  // ---- rank roots by address: exclusive popcount prefix over the bitmap
+  CK(cudaMalloc(&popc, (size_t)nw * 4)); CK(cudaMalloc(&off64, ((size_t)std::max(nw, n_roots) + 1) * 8)); CK(cudaMalloc(&scan_tmp, vsrt_scan_tmp_bytes(std::max(nw, n_roots))));
+  CK(cudaMalloc(&prefix, (size_t)nw * 4));
+  k_popc<<<(nw + 255) / 256, 256, 0, st>>>(claimed, nw, popc);
+  if ((rc = vsrt_launch_scan(popc, nw, (uint64_t*)off64, scan_tmp, st)) != VSRT_OK) goto done;
+  k_narrow<<<(nw + 255) / 256, 256, 0, st>>>(off64, nw, prefix);
+  CK(cudaMalloc(&r_rank, (size_t)n_roots * 4)); CK(cudaMalloc(&tl_root, (size_t)n_roots * 4)); CK(cudaMalloc(&tl_count, (size_t)n_roots * 4));
+  CK(cudaMalloc(&tl_off, ((size_t)n_roots + 1) * 8));
+  k_rank<<<(n_roots + 255) / 256, 256, 0, st>>>(roots, r_count, n_roots, claimed, prefix, r_rank, tl_root, tl_count);
+  if ((rc = vsrt_launch_scan(tl_count, n_roots, (uint64_t*)tl_off, scan_tmp, st)) != VSRT_OK) goto done;
+  CK(cudaMemcpyAsync(&n_entries, tl_off + n_roots, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMalloc(&tl_node, (size_t)std::max<unsigned long long>(n_entries, 1) * 8));
+  CK(cudaMalloc(&node_tid, (size_t)ns * 4)); CK(cudaMemsetAsync(node_tid, 0, (size_t)ns * 4, st));
+  k_gather<<<(n_roots + 127) / 128, 128, 0, st>>>(r_list, r_count, r_rank, n_roots, tl_off, tl_node, node_tid, scal + 1);
+  k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ev1, st));
+  CK(cudaMemcpyAsync(h_scal, scal, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&res->ms, ev0, ev1));
+  res->n_treelets = n_roots; res->n_entries = n_entries; res->n_mapped = h_scal[1]; res->total_bvh = h_scal[0];
+  out->node_tid = node_tid; out->root_bits = claimed; out->root_prefix = prefix; out->tl_root = tl_root;
+  out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node;
+  node_tid = nullptr; claimed = nullptr; prefix = nullptr; tl_root = nullptr; tl_off = nullptr; tl_node = nullptr;
+done:
+  for (uint64_t* p : pools) cudaFree(p);
+  cudaFree(claimed); cudaFree(roots); cudaFree(n_roots_d); cudaFree(scal); cudaFree(r_count); cudaFree((void*)r_list); cudaFree(r_rank);
+  cudaFree(popc); cudaFree(off64); cudaFree(scan_tmp); cudaFree(prefix); cudaFree(tl_root); cudaFree(tl_count); cudaFree(tl_off);
+  cudaFree(tl_node); cudaFree(node_tid);
+  if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+  return rc;
+}

@@ -1,0 +1,510 @@
+// vsrt_capi.cu -- host side of the C-ABI in include/vsrt.h: the context (the reference keeps this state in
+// file-scope statics of vulkan_ray_tracing.cc: tlas_addr, blas_addr_map, treeletsFormed, rayCount, the treelet
+// maps), arena upload, and the K1 -> scan -> K3 pipeline.  No CPU implementation of the path exists here: every
+// entry point that computes launches the CUDA kernels of treelets.cu / traverse.cu / compact.cu.
+#include "vsrt_internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Reg { uint64_t host, size, dev; bool tlas; };
+
+thread_local char g_create_error[256] = "";
+
+template <typename T> struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = nullptr) {
+    if (n <= cap) return cudaSuccess;
+    size_t nc = std::max(n, cap + cap / 2);
+    T* q = nullptr; cudaError_t e = cudaMalloc(&q, nc * sizeof(T));
+    if (e != cudaSuccess) { nc = n; e = cudaMalloc(&q, nc * sizeof(T)); if (e != cudaSuccess) return e; }
+    if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+    p = q; cap = nc; return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct vsrt_context {
+  vsrt_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // registration (allocTLAS / allocBLAS)
+  std::vector<Reg> regs;
+  bool committed = false;
+  // arena
+  uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
+  std::vector<Span> spans; Span* d_spans = nullptr;
+  std::vector<BlasReg> blas; BlasReg* d_blas = nullptr;
+  // treelets (treeletsFormed + the static maps)
+  bool formed = false; uint64_t formed_tlas = 0; uint32_t formed_budget = 0;
+  FormOutputs fo{}; FormResult fr{};
+  std::vector<uint32_t> h_node_tid, h_tl_root; std::vector<uint64_t> h_tl_off, h_tl_node; bool mirrors = false;
+  // per-batch buffers
+  DevBuf<vsrt_ray> d_rays; DevBuf<vsrt_hit> d_hits; DevBuf<uint32_t> d_stage; DevBuf<uint32_t> d_counts;
+  DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint8_t> d_scan_tmp;
+  uint32_t stage_cap = 128;
+  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr;
+  DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
+  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+  vsrt_device_results last{};
+  uint64_t last_tlas = 0; int last_mode = 0;
+};
+
+namespace {
+
+int fail(vsrt_context* c, int code, const char* fmt, ...) {
+  char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf; else snprintf(g_create_error, sizeof(g_create_error), "%s", buf);
+  return code;
+}
+#define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, VSRT_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+void free_treelets(vsrt_context* c) {
+  cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node);
+  c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0;
+  c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
+}
+
+const Reg* find_tlas(const vsrt_context* c, uint64_t host) {
+  const Reg* r = nullptr;
+  for (const Reg& x : c->regs) if (x.tlas && x.host == host) r = &x;   // the last registration wins, like tlas_addr (:4896)
+  return r;
+}
+bool host_to_slot_h(const vsrt_context* c, uint64_t host, uint32_t* slot) {
+  for (const Span& s : c->spans) if (host >= s.host && host - s.host < s.size) { if ((host - s.host) & 63) return false; *slot = s.slot0 + (uint32_t)((host - s.host) >> 6); return true; }
+  return false;
+}
+uint64_t slot_to_host_h(const vsrt_context* c, uint32_t slot) {
+  for (size_t i = c->spans.size(); i-- > 0;) if (c->spans[i].slot0 <= slot) return c->spans[i].host + (uint64_t)(slot - c->spans[i].slot0) * 64;
+  return 0;
+}
+
+int make_view(vsrt_context* c, uint64_t tlas_host, ArenaView* av) {
+  const Reg* t = find_tlas(c, tlas_host);
+  if (!t) return fail(c, VSRT_E_UNKNOWN_AS, "TLAS %p was never registered with vsrt_alloc_tlas (reference: abort(), vulkan_ray_tracing.cc:1568)", (void*)tlas_host);
+  uint32_t slot = 0;
+  if (!host_to_slot_h(c, tlas_host, &slot)) return fail(c, VSRT_E_UNKNOWN_AS, "TLAS address not inside the committed arena");
+  av->base = c->d_arena; av->n_slots = (uint32_t)(c->arena_bytes / 64); av->n_spans = (uint32_t)c->spans.size(); av->n_blas = (uint32_t)c->blas.size();
+  av->tlas_slot = slot; av->spans = c->d_spans; av->blas = c->d_blas; av->tlas_delta = (int64_t)(t->dev - t->host);
+  av->uniform_delta = 1; av->pad = 0;
+  for (const BlasReg& b : c->blas) if (b.delta != av->tlas_delta) av->uniform_delta = 0;
+  return VSRT_OK;
+}
+TreeletView treelet_view(const vsrt_context* c) {
+  TreeletView tv; tv.node_tid = c->fo.node_tid; tv.root_bits = c->fo.root_bits; tv.root_prefix = c->fo.root_prefix; tv.tl_root = c->fo.tl_root;
+  tv.n_treelets = c->fr.n_treelets; tv.pad = 0; return tv;
+}
+
+int ensure_mirrors(vsrt_context* c) {
+  if (c->mirrors) return VSRT_OK;
+  const size_t ns = c->arena_bytes / 64, nt = c->fr.n_treelets, ne = c->fr.n_entries;
+  c->h_node_tid.resize(ns); c->h_tl_root.resize(nt); c->h_tl_off.resize(nt + 1); c->h_tl_node.resize(ne);
+  CUDA_OK(c, cudaMemcpy(c->h_node_tid.data(), c->fo.node_tid, ns * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(c, cudaMemcpy(c->h_tl_root.data(), c->fo.tl_root, nt * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(c, cudaMemcpy(c->h_tl_off.data(), c->fo.tl_off, (nt + 1) * 8, cudaMemcpyDeviceToHost));
+  if (ne) CUDA_OK(c, cudaMemcpy(c->h_tl_node.data(), c->fo.tl_node, ne * 8, cudaMemcpyDeviceToHost));
+  c->mirrors = true; return VSRT_OK;
+}
+// device address of a list entry: BLAS headers carry their own allocBLAS offset (:1149-1153), everything else the TLAS offset
+uint64_t entry_dev_addr(const vsrt_context* c, uint64_t entry, int64_t tlas_delta) {
+  const uint32_t slot = (uint32_t)entry, kind = (uint32_t)(entry >> 32);
+  const uint64_t host = slot_to_host_h(c, slot);
+  if (kind == K_BLAS_HEADER) for (const BlasReg& b : c->blas) if (b.hdr_slot == slot) return host + (uint64_t)b.delta;
+  return host + (uint64_t)tlas_delta;
+}
+int64_t formed_delta(const vsrt_context* c) { const Reg* t = find_tlas(c, c->formed_tlas); return t ? (int64_t)(t->dev - t->host) : 0; }
+
+// simulated-device address -> slot, honouring that BLAS headers are keyed by their allocBLAS address
+bool dev_addr_to_slot(const vsrt_context* c, uint64_t addr, uint32_t* slot) {
+  for (const BlasReg& b : c->blas) if (slot_to_host_h(c, b.hdr_slot) + (uint64_t)b.delta == addr) { *slot = b.hdr_slot; return true; }
+  return host_to_slot_h(c, addr - (uint64_t)formed_delta(c), slot);
+}
+
+int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
+  int rc = vsrt_commit(c); if (rc) return rc;
+  if (c->formed && c->formed_tlas == tlas && c->formed_budget == budget) return VSRT_OK;
+  free_treelets(c);
+  ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
+  char eb[400] = "";
+  rc = vsrt_launch_form_treelets(av, budget, c->stream, &c->fo, &c->fr, c->d_err, eb, sizeof(eb));
+  if (rc) return fail(c, rc, "%s", eb);
+  c->formed = true; c->formed_tlas = tlas; c->formed_budget = budget;
+  CUDA_OK(c, c->d_hist.ensure(std::max<size_t>(c->fr.n_treelets, 1)));
+  CUDA_OK(c, cudaMemsetAsync(c->d_hist.p, 0, (size_t)c->fr.n_treelets * 8, c->stream));
+  c->hist_n = c->fr.n_treelets;
+  return VSRT_OK;
+}
+
+// K1 -> scan -> K3 over rays already resident at d_rays
+int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st) {
+  if (mode != VSRT_MODE_DFS && mode != VSRT_MODE_TREELET) return fail(c, VSRT_E_INVALID, "mode must be VSRT_MODE_DFS or VSRT_MODE_TREELET");
+  int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;   // lazily, like :1593 / :2364
+  if (c->cfg.remap_to_treelet_layout) return fail(c, VSRT_E_UNSUPPORTED, "remap_to_treelet_layout in traces is not built yet (vsrt_treelet_remap gives the table)");
+  ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
+  const TreeletView tv = treelet_view(c);
+  c->last = vsrt_device_results{}; c->last_tlas = tlas; c->last_mode = mode;
+  CUDA_OK(c, c->d_hits.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_counts.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_offsets.ensure(n + 1));
+  CUDA_OK(c, c->d_scan_tmp.ensure(vsrt_scan_tmp_bytes(n)));
+  uint32_t launches = 0; uint64_t total = 0;
+  for (int attempt = 0;; attempt++) {
+    CUDA_OK(c, c->d_stage.ensure(std::max<uint64_t>(n, 1) * c->stage_cap));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_counters_bak, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
+    TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
+    tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err;
+    CUDA_OK(c, cudaEventRecord(c->ev[0], st));
+    rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, st); if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CUDA_OK(c, cudaEventRecord(c->ev[1], st));
+    rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
+    CUDA_OK(c, cudaEventRecord(c->ev[2], st));
+    launches += n ? 4 : 0;
+    uint32_t h_err = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&total, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(&h_err, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
+    if (h_err & EF_STACK) {
+      cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st);
+      return fail(c, VSRT_E_STACK_OVERFLOW, "a ray needed more than %u traversal-stack entries; raise vsrt_config.stack_entries", c->cfg.stack_entries ? c->cfg.stack_entries : 96);
+    }
+    if (h_err & EF_TRACE_CAP) {   // a ray produced more records than its staging segment holds: grow and redo the batch
+      if (attempt >= 8) return fail(c, VSRT_E_CAPACITY, "per-ray trace staging overflow");
+      CUDA_OK(c, cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
+      c->stage_cap *= 2;
+      continue;
+    }
+    break;
+  }
+  CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
+  CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
+  cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = c->d_txns.cap; cp.counters = c->d_counters; cp.treelet_hist = c->d_hist.p;
+  rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
+  CUDA_OK(c, cudaEventRecord(c->ev[3], st));
+  launches += n ? 1 : 0;
+  // rayCount (:1665): ids are global and 1-based; the counter advances by the batch size
+  {
+    unsigned long long before = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&before, c->d_counters->v + CI_RAY_COUNT, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    before += n;
+    CUDA_OK(c, cudaMemcpyAsync(c->d_counters->v + CI_RAY_COUNT, &before, 8, cudaMemcpyHostToDevice, st));
+    unsigned long long acc0 = 0, acc1 = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&acc0, c->d_counters_bak->v + CI_ACCESSED, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(&acc1, c->d_counters->v + CI_ACCESSED, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    c->last.algorithmic_bytes = acc1 - acc0;
+  }
+  c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p; c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p;
+  c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;
+  cudaEventElapsedTime(&c->last.traverse_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->last.scan_ms, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&c->last.compact_ms, c->ev[2], c->ev[3]);
+  return VSRT_OK;
+}
+
+}  // namespace
+
+// ================================================================= C-ABI
+extern "C" {
+
+void vsrt_default_config(vsrt_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->device = -1; cfg->max_treelet_size = 49152;   // gpu-sim.cc:910-912
+  cfg->stack_entries = 96;
+}
+
+int vsrt_config_parse(vsrt_config* cfg, const char* text) {
+  if (!cfg || !text) return VSRT_E_INVALID;
+  const char* p = text;
+  while (*p) {
+    const char* eol = strchr(p, '\n'); size_t len = eol ? (size_t)(eol - p) : strlen(p);
+    std::string line(p, len); p += len + (eol ? 1 : 0);
+    size_t h = line.find('#'); if (h != std::string::npos) line.resize(h);
+    char name[128]; long long val;
+    if (sscanf(line.c_str(), " -%127s %lld", name, &val) == 2) {
+      if (!strcmp(name, "max_treelet_size")) cfg->max_treelet_size = (uint32_t)val;
+      else if (!strcmp(name, "treelet_based_traversal")) cfg->treelet_based_traversal = (uint32_t)val;
+      else if (!strcmp(name, "remap_to_treelet_layout")) cfg->remap_to_treelet_layout = (uint32_t)val;
+      else if (!strcmp(name, "treelet_remap_stride")) cfg->treelet_remap_stride = (uint32_t)val;
+      else if (!strcmp(name, "load_treelet_metadata")) cfg->load_treelet_metadata = (uint32_t)val;
+    }
+  }
+  return VSRT_OK;
+}
+
+int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
+  if (!out) return VSRT_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, VSRT_E_NO_DEVICE, "no CUDA device (%s); libvsrt has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  vsrt_context* c = new vsrt_context();
+  if (cfg) c->cfg = *cfg; else vsrt_default_config(&c->cfg);
+  if (c->cfg.device >= 0) { if (c->cfg.device >= ndev || cudaSetDevice(c->cfg.device) != cudaSuccess) { delete c; return fail(nullptr, VSRT_E_NO_DEVICE, "cannot select CUDA device %d", cfg->device); } }
+  cudaGetDevice(&c->device);
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device);
+  if (prop.major < 10) { delete c; return fail(nullptr, VSRT_E_NO_DEVICE, "device %d is sm_%d%d; libvsrt is built for sm_100a only", c->device, prop.major, prop.minor); }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
+  ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
+  if (c->cfg.max_treelet_size == 0) c->cfg.max_treelet_size = 49152;
+  *out = c;
+  return VSRT_OK;
+}
+
+void vsrt_destroy(vsrt_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_treelets(c);
+  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err);
+  c->d_rays.release(); c->d_hits.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
+  c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release();
+  for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* vsrt_last_error(const vsrt_context* c) { return c ? c->err.c_str() : g_create_error; }
+
+static int add_reg(vsrt_context* c, const void* root, uint64_t size, uint64_t dev, bool tlas) {
+  if (!c || !root || size < 64) return c ? fail(c, VSRT_E_INVALID, "registration needs a non-null address and at least one 64-byte record") : VSRT_E_INVALID;
+  if (((uintptr_t)root & 63) != 0) return fail(c, VSRT_E_INVALID, "AS buffer %p is not 64-byte aligned", root);
+  for (Reg& r : c->regs) if (r.host == (uint64_t)(uintptr_t)root && r.tlas == tlas) { r.size = size; r.dev = dev; c->committed = false; return VSRT_OK; }   // std::map overwrite
+  c->regs.push_back(Reg{ (uint64_t)(uintptr_t)root, size, dev, tlas });
+  c->committed = false;
+  return VSRT_OK;
+}
+int vsrt_alloc_tlas(vsrt_context* c, const void* root, uint64_t size, uint64_t dev) { return add_reg(c, root, size, dev, true); }
+int vsrt_alloc_blas(vsrt_context* c, const void* root, uint64_t size, uint64_t dev) { return add_reg(c, root, size, dev, false); }
+
+int vsrt_commit(vsrt_context* c) {
+  if (!c) return VSRT_E_INVALID;
+  if (c->committed) return VSRT_OK;
+  if (c->regs.empty()) return fail(c, VSRT_E_UNKNOWN_AS, "no acceleration structure registered");
+  cudaSetDevice(c->device);
+  free_treelets(c);
+  // merge the registered ranges into disjoint spans, ascending by host address
+  std::vector<std::pair<uint64_t, uint64_t>> iv;
+  for (const Reg& r : c->regs) iv.push_back({ r.host, r.host + ((r.size + 63) & ~63ull) });
+  std::sort(iv.begin(), iv.end());
+  std::vector<std::pair<uint64_t, uint64_t>> mg;
+  for (auto& x : iv) { if (!mg.empty() && x.first <= mg.back().second) mg.back().second = std::max(mg.back().second, x.second); else mg.push_back(x); }
+  c->spans.clear(); uint64_t slots = 0;
+  for (auto& x : mg) { Span s; s.host = x.first; s.size = x.second - x.first; s.slot0 = (uint32_t)slots; s.n_slots = (uint32_t)(s.size / 64); c->spans.push_back(s); slots += s.size / 64; }
+  if (slots >= (1ull << 29)) return fail(c, VSRT_E_UNSUPPORTED, "arena of %llu bytes exceeds the 32 GiB the 29-bit trace record addresses", (unsigned long long)(slots * 64));
+  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); c->d_arena = nullptr; c->d_spans = nullptr; c->d_blas = nullptr;
+  c->arena_bytes = slots * 64;
+  CUDA_OK(c, cudaMalloc(&c->d_arena, c->arena_bytes));
+  for (const Span& s : c->spans) CUDA_OK(c, cudaMemcpyAsync(c->d_arena + (uint64_t)s.slot0 * 64, (const void*)(uintptr_t)s.host, s.size, cudaMemcpyHostToDevice, c->stream));
+  c->blas.clear();
+  for (const Reg& r : c->regs) if (!r.tlas) { BlasReg b; uint32_t slot = 0; host_to_slot_h(c, r.host, &slot); b.hdr_slot = slot; b.pad = 0; b.delta = (int64_t)(r.dev - r.host); c->blas.push_back(b); }
+  std::sort(c->blas.begin(), c->blas.end(), [](const BlasReg& a, const BlasReg& b) { return a.hdr_slot < b.hdr_slot; });
+  CUDA_OK(c, cudaMalloc(&c->d_spans, c->spans.size() * sizeof(Span)));
+  CUDA_OK(c, cudaMemcpyAsync(c->d_spans, c->spans.data(), c->spans.size() * sizeof(Span), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaMalloc(&c->d_blas, std::max<size_t>(c->blas.size(), 1) * sizeof(BlasReg)));
+  if (!c->blas.empty()) CUDA_OK(c, cudaMemcpyAsync(c->d_blas, c->blas.data(), c->blas.size() * sizeof(BlasReg), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->committed = true;
+  return VSRT_OK;
+}
+
+int vsrt_form_treelets(vsrt_context* c, const void* tlas, uint32_t max_bytes) {
+  if (!c || !tlas) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  if (max_bytes) c->cfg.max_treelet_size = max_bytes;
+  return do_form(c, (uint64_t)(uintptr_t)tlas, c->cfg.max_treelet_size);
+}
+
+int vsrt_treelet_info_get(vsrt_context* c, vsrt_treelet_info* out) {
+  if (!c || !out) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  out->n_treelets = c->fr.n_treelets; out->n_list_entries = c->fr.n_entries; out->n_mapped_nodes = c->fr.n_mapped; out->total_bvh_size = c->fr.total_bvh; out->form_ms = c->fr.ms;
+  return VSRT_OK;
+}
+
+int vsrt_treelet_table(vsrt_context* c, uint64_t* roots, uint64_t* list_offsets, uint64_t* node_addr, uint32_t* node_size) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  const int64_t d = formed_delta(c);
+  const size_t nt = c->fr.n_treelets;
+  if (roots) for (size_t t = 0; t < nt; t++) roots[t] = slot_to_host_h(c, c->h_tl_root[t]) + (uint64_t)d;
+  if (list_offsets) memcpy(list_offsets, c->h_tl_off.data(), (nt + 1) * 8);
+  for (size_t k = 0; k < c->h_tl_node.size(); k++) {
+    if (node_addr) node_addr[k] = entry_dev_addr(c, c->h_tl_node[k], d);
+    if (node_size) node_size[k] = ((uint32_t)(c->h_tl_node[k] >> 32) == K_INSTANCE) ? 128u : 64u;
+  }
+  return VSRT_OK;
+}
+
+int vsrt_node_map(vsrt_context* c, uint64_t* node_addr, uint64_t* root_addr) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  const int64_t d = formed_delta(c);
+  // keys: device address of every list entry; emitted in ascending key order
+  std::vector<std::pair<uint64_t, uint64_t>> kv; kv.reserve(c->fr.n_mapped);
+  std::vector<uint8_t> seen(c->h_node_tid.size(), 0);
+  for (uint64_t e : c->h_tl_node) {
+    const uint32_t slot = (uint32_t)e; if (seen[slot]) continue; seen[slot] = 1;
+    kv.push_back({ entry_dev_addr(c, e, d), slot_to_host_h(c, c->h_tl_root[c->h_node_tid[slot]]) + (uint64_t)d });
+  }
+  std::sort(kv.begin(), kv.end());
+  for (size_t i = 0; i < kv.size(); i++) { if (node_addr) node_addr[i] = kv[i].first; if (root_addr) root_addr[i] = kv[i].second; }
+  return VSRT_OK;
+}
+
+int vsrt_treelet_remap(vsrt_context* c, uint64_t base, uint64_t* n_out, uint64_t* orig, uint64_t* mapped) {
+  if (!c || !n_out) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  // remapBVHToTreeletLayout (:1473-1509): treelet i at base + i*(max + stride), root first, then the list in order;
+  // an entry that is already mapped keeps its first mapping but still advances the cursor (:1501-1503).
+  const int64_t d = formed_delta(c);
+  const uint64_t pitch = (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride;
+  std::vector<std::pair<uint64_t, uint64_t>> kv;
+  std::vector<uint8_t> seen(c->h_node_tid.size(), 0);
+  for (size_t t = 0; t < c->fr.n_treelets; t++) {
+    const uint32_t rslot = c->h_tl_root[t]; const uint64_t rnew = base + t * pitch;
+    uint32_t rsize = 64;
+    for (uint64_t k = c->h_tl_off[t]; k < c->h_tl_off[t + 1]; k++) if ((uint32_t)c->h_tl_node[k] == rslot && (uint32_t)(c->h_tl_node[k] >> 32) == K_INSTANCE) rsize = 128;
+    if (!seen[rslot]) { seen[rslot] = 1; kv.push_back({ slot_to_host_h(c, rslot) + (uint64_t)d, rnew }); }
+    uint64_t cur = rnew + rsize;
+    for (uint64_t k = c->h_tl_off[t]; k < c->h_tl_off[t + 1]; k++) {
+      const uint64_t e = c->h_tl_node[k]; const uint32_t slot = (uint32_t)e;
+      if (slot == rslot) continue;
+      if (!seen[slot]) { seen[slot] = 1; kv.push_back({ entry_dev_addr(c, e, d), cur }); }
+      cur += ((uint32_t)(e >> 32) == K_INSTANCE) ? 128u : 64u;
+    }
+  }
+  std::sort(kv.begin(), kv.end());
+  *n_out = kv.size();
+  for (size_t i = 0; i < kv.size(); i++) { if (orig) orig[i] = kv[i].first; if (mapped) mapped[i] = kv[i].second; }
+  return VSRT_OK;
+}
+
+int vsrt_addr_to_treelet(vsrt_context* c, uint64_t addr, uint64_t* root) {
+  if (!c || !root) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  uint32_t slot = 0;
+  if (!dev_addr_to_slot(c, addr, &slot) || c->h_node_tid[slot] == VSRT_NO_TID) return fail(c, VSRT_E_INVALID, "address 0x%llx is not a BVH node (reference: assert, vulkan_ray_tracing.cc:470)", (unsigned long long)addr);
+  *root = slot_to_host_h(c, c->h_tl_root[c->h_node_tid[slot]]) + (uint64_t)formed_delta(c);
+  return VSRT_OK;
+}
+
+int vsrt_is_treelet_root(vsrt_context* c, uint64_t addr) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  uint32_t slot = 0;
+  if (!host_to_slot_h(c, addr - (uint64_t)formed_delta(c), &slot)) return 0;
+  return std::binary_search(c->h_tl_root.begin(), c->h_tl_root.end(), slot) ? 1 : 0;
+}
+
+int vsrt_treelet_metadata_idx(vsrt_context* c, uint64_t root, uint32_t* idx) {
+  if (!c || !idx) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  uint32_t slot = 0;
+  if (!host_to_slot_h(c, root - (uint64_t)formed_delta(c), &slot)) return fail(c, VSRT_E_INVALID, "not a treelet root");
+  auto it = std::lower_bound(c->h_tl_root.begin(), c->h_tl_root.end(), slot);
+  if (it == c->h_tl_root.end() || *it != slot) return fail(c, VSRT_E_INVALID, "not a treelet root");
+  *idx = (uint32_t)(it - c->h_tl_root.begin());
+  return VSRT_OK;
+}
+
+int vsrt_trace_rays_device(vsrt_context* c, const void* tlas, int mode, uint64_t n, const void* rays_dev, void* stream, uint64_t* n_txn) {
+  if (!c || !tlas || (n && !rays_dev)) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, (const vsrt_ray*)rays_dev, n, stream ? (cudaStream_t)stream : c->stream);
+  if (n_txn) *n_txn = c->last.n_txn;
+  return rc;
+}
+
+int vsrt_trace_device_results(vsrt_context* c, vsrt_device_results* out) {
+  if (!c || !out) return VSRT_E_INVALID;
+  *out = c->last; return VSRT_OK;
+}
+
+int vsrt_trace_fetch(vsrt_context* c, vsrt_txn* txns, uint64_t cap, uint64_t* treelet_ids) {
+  if (!c) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  const uint64_t total = c->last.n_txn, m = std::min(total, cap);
+  if (txns && m) CUDA_OK(c, cudaMemcpyAsync(txns, c->d_txns.p, m * sizeof(vsrt_txn), cudaMemcpyDeviceToHost, c->stream));
+  if (treelet_ids && m) {
+    ArenaView av; int rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
+    CUDA_OK(c, c->d_tid_addr.ensure(m));
+    rc = vsrt_launch_tid_to_addr(av, treelet_view(c), c->d_tids.p, m, c->d_tid_addr.p, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
+    CUDA_OK(c, cudaMemcpyAsync(treelet_ids, c->d_tid_addr.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return total > cap ? VSRT_E_CAPACITY : VSRT_OK;
+}
+
+int vsrt_trace_rays(vsrt_context* c, const void* tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
+                    vsrt_txn* txns, uint64_t txn_capacity, uint64_t* treelet_ids, uint64_t* n_txn) {
+  if (!c || !tlas || (n && !rays)) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
+  if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));
+  int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, c->d_rays.p, n, c->stream);
+  if (n_txn) *n_txn = c->last.n_txn;
+  if (rc) return rc;
+  if (hits && n) CUDA_OK(c, cudaMemcpyAsync(hits, c->d_hits.p, n * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->stream));
+  if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets, c->d_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (txns || treelet_ids) return vsrt_trace_fetch(c, txns, txn_capacity, treelet_ids);
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VSRT_OK;
+}
+
+int vsrt_trace_ray_warp(vsrt_context* c, const void* tlas, uint32_t active_mask, const vsrt_ray rays[32], vsrt_hit hits[32],
+                        uint32_t txn_counts[32], vsrt_txn* txns, uint64_t txn_capacity, uint64_t* n_txn) {
+  if (!c || !tlas || !rays) return VSRT_E_INVALID;
+  // lanes are processed in lane order, active lanes only (core_t::execute_warp_inst_t, abstract_hardware_model.cc:3052-3063)
+  vsrt_ray packed[32]; int lane_of[32]; uint32_t n = 0;
+  for (int l = 0; l < 32; l++) if (active_mask & (1u << l)) { packed[n] = rays[l]; lane_of[n] = l; n++; }
+  vsrt_hit ph[32]; uint64_t off[33];
+  int rc = vsrt_trace_rays(c, tlas, c->cfg.treelet_based_traversal ? VSRT_MODE_TREELET : VSRT_MODE_DFS, n, packed, ph, off, txns, txn_capacity, nullptr, n_txn);
+  if (rc && rc != VSRT_E_CAPACITY) return rc;
+  if (txn_counts) memset(txn_counts, 0, 32 * sizeof(uint32_t));
+  for (uint32_t i = 0; i < n; i++) { if (hits) hits[lane_of[i]] = ph[i]; if (txn_counts) txn_counts[lane_of[i]] = (uint32_t)(off[i + 1] - off[i]); }
+  return rc;
+}
+
+int vsrt_get_counters(vsrt_context* c, vsrt_counters* out) {
+  if (!c || !out) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  static_assert(sizeof(vsrt_counters) == sizeof(DevCounters), "counter layouts must match");
+  CUDA_OK(c, cudaMemcpy(out, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost));
+  return VSRT_OK;
+}
+int vsrt_reset_counters(vsrt_context* c) {
+  if (!c) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  CUDA_OK(c, cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  if (c->hist_n) CUDA_OK(c, cudaMemset(c->d_hist.p, 0, (size_t)c->hist_n * 8));
+  return VSRT_OK;
+}
+int vsrt_counters_device(vsrt_context* c, void** counters_dev, void** hist_dev, uint64_t* n_treelets) {
+  if (!c) return VSRT_E_INVALID;
+  if (counters_dev) *counters_dev = c->d_counters;
+  if (hist_dev) *hist_dev = c->d_hist.p;
+  if (n_treelets) *n_treelets = c->hist_n;
+  return VSRT_OK;
+}
+
+}  // extern "C"

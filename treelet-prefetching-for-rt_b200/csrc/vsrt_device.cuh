@@ -1,0 +1,199 @@
+// vsrt_device.cuh -- device-side decode and ray math shared by the kernels.
+//
+// Bit-exactness contract: the reference is g++ -O3 on baseline x86-64 => scalar SSE2, no FMA, no
+// reassociation, denormals kept.  The library is compiled with -fmad=false -prec-div=true -prec-sqrt=true
+// -ftz=false; in addition every multiply that feeds an add is written with __fmul_rn/__fadd_rn so the operation
+// order is explicit and contraction is impossible even if a flag is lost.  MIN/MAX are the reference's ternary
+// macros (vulkan_ray_tracing.h:53-56): a NaN operand selects the SECOND argument, unlike fminf/fmaxf.
+#pragma once
+#include "vsrt_internal.h"
+
+#define VS_DEV __device__ __forceinline__
+
+VS_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
+VS_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
+VS_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
+VS_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+VS_DEV float rmin(float a, float b) { return (a < b) ? a : b; }
+VS_DEV float rmax(float a, float b) { return (a > b) ? a : b; }
+
+struct Node64 { uint32_t w[16]; };
+
+VS_DEV Node64 load_node(const uint8_t* base, uint32_t slot) {
+  const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)slot * 64u);
+  Node64 n;
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  n.w[0] = a.x; n.w[1] = a.y; n.w[2] = a.z; n.w[3] = a.w; n.w[4] = b.x; n.w[5] = b.y; n.w[6] = b.z; n.w[7] = b.w;
+  n.w[8] = c.x; n.w[9] = c.y; n.w[10] = c.z; n.w[11] = c.w; n.w[12] = d.x; n.w[13] = d.y; n.w[14] = d.z; n.w[15] = d.w;
+  return n;
+}
+// byte i (0..63) of a node held in registers; i must be a compile-time constant after unrolling
+VS_DEV uint32_t node_byte(const Node64& n, int i) { return (n.w[i >> 2] >> ((i & 3) * 8)) & 0xffu; }
+
+// GEN_RT_BVH_INTERNAL_NODE fields (reference util.h:134-207; wire offsets SURVEY A.1)
+VS_DEV int32_t node_child_offset(const Node64& n) { return (int32_t)n.w[3]; }
+VS_DEV uint32_t node_child_info(const Node64& n, int i) { return node_byte(n, 22 + i) & 0x3fu; }   // size = &3, type = >>2
+// 2^(e-8) as an exact float for the int8 exponent byte at `idx` (e-8 in [-136,119]); (float)q * 2^k is exact and
+// therefore equal to the reference's ldexpf((float)q, k)  (util.h:499-508).
+VS_DEV float node_scale(const Node64& n, int idx) {
+  int k = (int)(int8_t)node_byte(n, idx) - 8;
+  uint32_t bits = (k >= -126) ? ((uint32_t)(k + 127) << 23) : (1u << (k + 149));
+  return __uint_as_float(bits);
+}
+
+struct Ray8 { float ox, oy, oz, dx, dy, dz, tmin, tmax; };
+struct Idir { float x, y, z; };
+
+// calculate_idir, vulkan_ray_tracing.cc:220-235
+VS_DEV float idir1(float d) {
+  const float ooeps = 8.271806125530277e-25f;   // 2^-80
+  return fdiv(1.0f, (fabsf(d) > ooeps) ? d : copysignf(ooeps, d));
+}
+VS_DEV Idir calc_idir(const Ray8& r) { Idir i; i.x = idir1(r.dx); i.y = idir1(r.dy); i.z = idir1(r.dz); return i; }
+
+// ray_box_test + get_t_bound + magic_max7/magic_min7, vulkan_ray_tracing.cc:183-257
+VS_DEV bool ray_box(float lox, float loy, float loz, float hix, float hiy, float hiz, const Idir& id, const Ray8& r, float& thit) {
+  float lx = fmul(fsub(lox, r.ox), id.x), ly = fmul(fsub(loy, r.oy), id.y), lz = fmul(fsub(loz, r.oz), id.z);
+  float hx = fmul(fsub(hix, r.ox), id.x), hy = fmul(fsub(hiy, r.oy), id.y), hz = fmul(fsub(hiz, r.oz), id.z);
+  float t1 = rmax(rmin(lx, hx), r.tmin), t2 = rmax(rmin(ly, hy), t1), mn = rmax(rmin(lz, hz), t2);
+  float u1 = rmin(rmax(lx, hx), r.tmax), u2 = rmin(rmax(ly, hy), u1), mx = rmin(rmax(lz, hz), u2);
+  thit = mn;
+  return mn <= mx;
+}
+
+// Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
+// `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
+VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) {
+  const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
+  const float sx = node_scale(n, 18), sy = node_scale(n, 19), sz = node_scale(n, 20);
+  uint32_t mask = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    if ((node_child_info(n, i) & 3u) != 0u) {
+      float lox = fadd(ox, fmul((float)node_byte(n, 28 + i), sx)), hix = fadd(ox, fmul((float)node_byte(n, 34 + i), sx));
+      float loy = fadd(oy, fmul((float)node_byte(n, 40 + i), sy)), hiy = fadd(oy, fmul((float)node_byte(n, 46 + i), sy));
+      float loz = fadd(oz, fmul((float)node_byte(n, 52 + i), sz)), hiz = fadd(oz, fmul((float)node_byte(n, 58 + i), sz));
+      float th;
+      bool h = ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th);
+      if (h && th >= cull) h = false;
+      if (h) mask |= 1u << i;
+    }
+  }
+  return mask;
+}
+
+// Instance leaf -> object-space ray.  make_transformed_ray (:168-181) with float4x4::operator* (util.h:47-55):
+// res[i] = 0 + m[0][i]*v0 + m[1][i]*v1 + m[2][i]*v2 + m[3][i]*v3, W2O = wire A[0..8] rows + B[9..11] as row 3
+// (SURVEY A.1 matrix trap), column 3 = (0,0,0,1).
+struct InstCtx { Ray8 ray; Idir idir; float tmult; uint32_t inst_slot; };
+VS_DEV void make_object_ray(const uint8_t* base, uint32_t leaf_slot, const Ray8& w, InstCtx& c) {
+  const float* A = reinterpret_cast<const float*>(base + (uint64_t)leaf_slot * 64u + 16u);
+  const float* B = reinterpret_cast<const float*>(base + (uint64_t)leaf_slot * 64u + 80u);
+  float m[4][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) m[r][k] = __ldg(A + 3 * r + k);
+#pragma unroll
+  for (int k = 0; k < 3; k++) m[3][k] = __ldg(B + 9 + k);
+  float o[4], d[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    o[i] = fadd(fadd(fadd(fadd(0.0f, fmul(m[0][i], w.ox)), fmul(m[1][i], w.oy)), fmul(m[2][i], w.oz)), fmul(m[3][i], 1.0f));
+    d[i] = fadd(fadd(fadd(fadd(0.0f, fmul(m[0][i], w.dx)), fmul(m[1][i], w.dy)), fmul(m[2][i], w.dz)), fmul(m[3][i], 0.0f));
+  }
+  o[3] = fadd(fadd(fadd(fadd(0.0f, fmul(0.0f, w.ox)), fmul(0.0f, w.oy)), fmul(0.0f, w.oz)), fmul(1.0f, 1.0f));
+  c.ray.ox = fdiv(o[0], o[3]); c.ray.oy = fdiv(o[1], o[3]); c.ray.oz = fdiv(o[2], o[3]);
+  float norm = __fsqrt_rn(fadd(fadd(fmul(d[0], d[0]), fmul(d[1], d[1])), fmul(d[2], d[2])));
+  c.tmult = norm;
+  c.ray.dx = fdiv(d[0], norm); c.ray.dy = fdiv(d[1], norm); c.ray.dz = fdiv(d[2], norm);
+  c.ray.tmin = fmul(w.tmin, norm); c.ray.tmax = fmul(w.tmax, norm);
+  c.idir = calc_idir(c.ray);
+  c.inst_slot = leaf_slot;
+}
+
+VS_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) { return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz)); }
+
+// mt_ray_triangle_test, vulkan_ray_tracing.cc:3089-3111 (no epsilon, no culling); leaf = quad leaf in registers
+VS_DEV bool ray_tri(const Node64& q, const Ray8& r, float& thit) {
+  const float p0x = __uint_as_float(q.w[4]), p0y = __uint_as_float(q.w[5]), p0z = __uint_as_float(q.w[6]);
+  const float e1x = fsub(__uint_as_float(q.w[7]), p0x), e1y = fsub(__uint_as_float(q.w[8]), p0y), e1z = fsub(__uint_as_float(q.w[9]), p0z);
+  const float e2x = fsub(__uint_as_float(q.w[10]), p0x), e2y = fsub(__uint_as_float(q.w[11]), p0y), e2z = fsub(__uint_as_float(q.w[12]), p0z);
+  // pvec = cross(dir, v0v2)   (vector-math.cc:41-44)
+  const float px = fsub(fmul(r.dy, e2z), fmul(r.dz, e2y)), py = fsub(fmul(r.dz, e2x), fmul(r.dx, e2z)), pz = fsub(fmul(r.dx, e2y), fmul(r.dy, e2x));
+  const float det = dot3(e1x, e1y, e1z, px, py, pz);
+  const float idet = fdiv(1.0f, det);
+  const float tx = fsub(r.ox, p0x), ty = fsub(r.oy, p0y), tz = fsub(r.oz, p0z);
+  const float u = fmul(dot3(tx, ty, tz, px, py, pz), idet);
+  if (u < 0 || u > 1) return false;
+  // qvec = cross(tvec, v0v1)
+  const float qx = fsub(fmul(ty, e1z), fmul(tz, e1y)), qy = fsub(fmul(tz, e1x), fmul(tx, e1z)), qz = fsub(fmul(tx, e1y), fmul(ty, e1x));
+  const float v = fmul(dot3(r.dx, r.dy, r.dz, qx, qy, qz), idet);
+  if (v < 0 || fadd(u, v) > 1) return false;
+  thit = fmul(dot3(e2x, e2y, e2z, qx, qy, qz), idet);
+  return true;
+}
+
+// Barycentric, vulkan_ray_tracing.cc:3113-3130 -> {v, w, u}
+VS_DEV void barycentric(const Node64& q, float px, float py, float pz, float out[3]) {
+  const float ax = __uint_as_float(q.w[4]), ay = __uint_as_float(q.w[5]), az = __uint_as_float(q.w[6]);
+  const float v0x = fsub(__uint_as_float(q.w[7]), ax), v0y = fsub(__uint_as_float(q.w[8]), ay), v0z = fsub(__uint_as_float(q.w[9]), az);
+  const float v1x = fsub(__uint_as_float(q.w[10]), ax), v1y = fsub(__uint_as_float(q.w[11]), ay), v1z = fsub(__uint_as_float(q.w[12]), az);
+  const float v2x = fsub(px, ax), v2y = fsub(py, ay), v2z = fsub(pz, az);
+  const float d00 = dot3(v0x, v0y, v0z, v0x, v0y, v0z), d01 = dot3(v0x, v0y, v0z, v1x, v1y, v1z), d11 = dot3(v1x, v1y, v1z, v1x, v1y, v1z);
+  const float d20 = dot3(v2x, v2y, v2z, v0x, v0y, v0z), d21 = dot3(v2x, v2y, v2z, v1x, v1y, v1z);
+  const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+  const float v = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+  const float w = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+  out[0] = v; out[1] = w; out[2] = fsub(fsub(1.0f, v), w);
+}
+
+// ---- address translation between host addresses and packed-arena slots ----
+VS_DEV uint32_t span_of_slot(const ArenaView& av, uint32_t slot) {
+  uint32_t lo = 0, hi = av.n_spans;
+  while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (av.spans[m].slot0 <= slot) lo = m; else hi = m; }
+  return lo;
+}
+VS_DEV uint64_t slot_to_host(const ArenaView& av, uint32_t slot) {
+  const Span& s = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, slot)];
+  return s.host + (uint64_t)(slot - s.slot0) * 64u;
+}
+// returns false if the host address is outside every registered span or not 64-byte aligned
+VS_DEV bool host_to_slot(const ArenaView& av, uint64_t host, uint32_t& slot) {
+  uint32_t lo = 0, hi = av.n_spans;
+  while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (av.spans[m].host <= host) lo = m; else hi = m; }
+  const Span& s = av.spans[lo];
+  if (host < s.host || host - s.host >= s.size || ((host - s.host) & 63u)) return false;
+  slot = s.slot0 + (uint32_t)((host - s.host) >> 6);
+  return true;
+}
+// blas_addr_map lookup by header slot; false if the header was never registered with allocBLAS
+VS_DEV bool blas_delta_of(const ArenaView& av, uint32_t hdr_slot, int64_t& delta) {
+  uint32_t lo = 0, hi = av.n_blas;
+  while (lo < hi) { uint32_t m = (lo + hi) >> 1; uint32_t s = av.blas[m].hdr_slot; if (s == hdr_slot) { delta = av.blas[m].delta; return true; } if (s < hdr_slot) lo = m + 1; else hi = m; }
+  return false;
+}
+// instance leaf -> slot of the BLAS header it references (BVHAddress is relative to the leaf, :1902)
+VS_DEV bool instance_blas_header(const ArenaView& av, uint32_t leaf_slot, uint32_t& hdr_slot) {
+  const uint64_t rel = __ldg(reinterpret_cast<const unsigned long long*>(av.base + (uint64_t)leaf_slot * 64u + 64u));
+  if (rel == 0) return false;   // reference: assert(instanceLeaf.BVHAddress != NULL)
+  if (av.n_spans == 1 && (rel & 63u) == 0) {
+    int64_t s = (int64_t)leaf_slot + ((int64_t)rel >> 6);
+    if (s < 0 || s >= (int64_t)av.n_slots) return false;
+    hdr_slot = (uint32_t)s; return true;
+  }
+  return host_to_slot(av, slot_to_host(av, leaf_slot) + rel, hdr_slot);
+}
+// BLAS header -> slot of its root internal node (RootNodeOffset, bytes from the header)
+VS_DEV bool header_root(const ArenaView& av, uint32_t hdr_slot, uint32_t& root_slot) {
+  const uint64_t off = __ldg(reinterpret_cast<const unsigned long long*>(av.base + (uint64_t)hdr_slot * 64u));
+  if (off & 63u) return false;
+  uint64_t s = (uint64_t)hdr_slot + (off >> 6);
+  if (s >= av.n_slots) return false;
+  root_slot = (uint32_t)s; return true;
+}
+VS_DEV uint32_t root_rank(const TreeletView& tv, uint32_t slot) {   // treelet index of the treelet ROOTED at slot, or NO_TID
+  uint32_t w = __ldg(tv.root_bits + (slot >> 5)), b = 1u << (slot & 31);
+  if (!(w & b)) return VSRT_NO_TID;
+  return __ldg(tv.root_prefix + (slot >> 5)) + __popc(w & (b - 1));
+}

@@ -1,0 +1,108 @@
+// vsrt_internal.h -- shared declarations of the CUDA library behind include/vsrt.h.
+//
+// Data layout in HBM:
+//   arena        every registered AS buffer, merged into disjoint host spans, packed back to back in ascending
+//                host-address order.  A node is named by its 64-byte SLOT index in the packed arena (u32).
+//   node_tid     u32 per slot: index (ascending-root-address rank == the reference's treelet_addr_to_metadata_idx)
+//                of the treelet that owns the node, i.e. addrToTreeletID as an index.  NO_TID for non-nodes.
+//   root bitmap  1 bit per slot (is the slot a treelet root) + per-word exclusive popcount prefix -> rank(slot).
+//   treelet CSR  tl_root[t] (slot), tl_off[t], tl_node[k] (slot | kind in the top bits of a u64).
+//   staging      per ray `cap` compact trace records  (slot << 3) | code, written by the traversal kernel.
+//   outputs      vsrt_hit[n], u64 offsets[n+1], vsrt_txn[total], u32 treelet index[total].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vsrt.h"
+
+#define VSRT_NO_TID 0xFFFFFFFFu
+#define VSRT_NO_INST 0x7FFFFFFFu
+#define VSRT_MAX_SPANS_INLINE 8
+
+// compact trace-record codes: the TransactionType (0..6) except that a TLAS internal node is tagged 7 so the
+// expansion kernel can tell which host->device offset the reference would have applied in DFS mode.
+enum { C_STRUCT = 0, C_INTERNAL_BLAS = 1, C_INSTANCE = 2, C_DESC = 3, C_QUAD = 4, C_QUAD_HIT = 5, C_PROC = 6, C_INTERNAL_TLAS = 7 };
+
+// candidate / list-entry kinds of treelet formation
+enum { K_TLAS_HEADER = 0, K_TLAS_INTERNAL = 1, K_INSTANCE = 2, K_BLAS_HEADER = 3, K_BLAS_INTERNAL = 4, K_BLAS_LEAF = 5 };
+
+struct Span {             // one merged host range
+  uint64_t host;          // host address of the first byte
+  uint64_t size;          // bytes (multiple of 64)
+  uint32_t slot0;         // first slot in the packed arena
+  uint32_t n_slots;
+};
+struct BlasReg {          // blas_addr_map entry
+  uint32_t hdr_slot;      // slot of the GEN_RT_BVH header
+  uint32_t pad;
+  int64_t delta;          // simulated-device address - host address
+};
+
+// Everything a kernel needs to know about the arena; passed by value.
+struct ArenaView {
+  const uint8_t* base;    // device pointer, 64-byte aligned
+  uint32_t n_slots;
+  uint32_t n_spans;
+  uint32_t n_blas;
+  uint32_t tlas_slot;
+  const Span* spans;      // device, ascending
+  const BlasReg* blas;    // device, ascending hdr_slot
+  int64_t tlas_delta;     // tlas_addr - _topLevelAS
+  uint32_t uniform_delta; // 1 if every BLAS delta equals tlas_delta (then both reference conventions coincide)
+  uint32_t pad;
+};
+
+struct TreeletView {
+  const uint32_t* node_tid;     // [n_slots]
+  const uint32_t* root_bits;    // [ceil(n_slots/32)]
+  const uint32_t* root_prefix;  // [ceil(n_slots/32)]
+  const uint32_t* tl_root;      // [n_treelets] slot of each treelet root, ascending
+  uint32_t n_treelets;
+  uint32_t pad;
+};
+
+struct DevCounters {            // mirrors vsrt_counters (uint64 each)
+  unsigned long long v[VSRT_COUNTERS_N_SUM + VSRT_COUNTERS_N_MAX];
+};
+enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 11, CI_N_CLOSEST_RAYS = 12, CI_TOT_NODES = 13,
+       CI_ACCESSED = 14, CI_RAY_COUNT = 15, CI_MAX_NODES = 16, CI_MAX_DEPTH = 17 };
+
+// error flags raised by kernels (OR-ed into a device word)
+enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32 };
+
+// ---- launchers (each file implements its kernels) ----
+struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; };
+struct FormOutputs {      // device allocations owned by the context
+  uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
+};
+// Forms treelets for `budget`; allocates outputs with cudaMalloc (caller frees).  Returns VSRT_* code.
+int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,
+                              uint32_t* err_flags_dev, char* errbuf, size_t errcap);
+
+struct TraverseParams {
+  ArenaView av; TreeletView tv;
+  const vsrt_ray* rays; uint64_t n_rays;
+  vsrt_hit* hits;
+  uint32_t* stage;            // [n_rays * cap]
+  uint32_t* counts;           // [n_rays] records emitted per ray
+  uint32_t cap;               // staging records per ray
+  uint32_t mode;
+  DevCounters* counters;
+  uint32_t* err_flags;
+};
+int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, cudaStream_t st);
+
+// exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
+size_t vsrt_scan_tmp_bytes(uint64_t n);
+int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st);
+
+struct CompactParams {
+  ArenaView av; TreeletView tv;
+  const uint32_t* stage; uint32_t cap; uint32_t mode;
+  const uint64_t* offsets; uint64_t n_rays;
+  vsrt_txn* txns; uint32_t* tids; uint64_t out_capacity;
+  DevCounters* counters; unsigned long long* treelet_hist;   // may be NULL
+};
+int vsrt_launch_compact(const CompactParams& p, cudaStream_t st);
+
+// u32 treelet index -> u64 root device address (addrToTreeletID value)
+int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out, cudaStream_t st);

@@ -1,0 +1,239 @@
+"""ctypes binding of libvsrt.so (include/vsrt.h).  Mirrors the reference's call surface for this path:
+
+    reference (VulkanRayTracing statics)            here
+    ---------------------------------------------   -----------------------------------------
+    gpgpusim_allocTLAS / allocBLAS                  Context.alloc_tlas / alloc_blas / register(arena)
+    createTreelets (lazy, first ray)                Context.form_treelets
+    addrToTreeletID / isTreeletRoot                 Context.addr_to_treelet / is_treelet_root
+    traceRay / traceRayWithTreelets (per lane)      Context.trace(mode, rays)  (a batch of lanes)
+    g_rt_* counters                                 Context.counters()
+
+There is no Python/CPU implementation behind this module: if libvsrt.so is missing or no CUDA device is
+usable, load()/Context() raise."""
+import ctypes
+import os
+import numpy as np
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvsrt.so")
+_lib = None
+
+c_u64, c_u32, c_vp, c_int = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int
+
+# every symbol include/vsrt.h declares (tests check the library exports all of them)
+SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_error", "vsrt_config_parse",
+           "vsrt_alloc_tlas", "vsrt_alloc_blas", "vsrt_commit", "vsrt_form_treelets", "vsrt_treelet_info_get",
+           "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
+           "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
+           "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
+           "vsrt_counters_device"]
+
+
+class VsrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vsrt error %d (%s): %s" % (code, _abi.ERRORS.get(code, "?"), msg))
+        self.code = code
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libvsrt.so is not built (%s); run __graft_entry__.build() -- there is no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        getattr(L, s)
+    L.vsrt_default_config.argtypes = [ctypes.POINTER(_abi.Config)]
+    L.vsrt_create.argtypes = [ctypes.POINTER(_abi.Config), ctypes.POINTER(c_vp)]
+    L.vsrt_destroy.argtypes = [c_vp]
+    L.vsrt_last_error.restype = ctypes.c_char_p
+    L.vsrt_last_error.argtypes = [c_vp]
+    L.vsrt_config_parse.argtypes = [ctypes.POINTER(_abi.Config), ctypes.c_char_p]
+    L.vsrt_alloc_tlas.argtypes = [c_vp, c_vp, c_u64, c_u64]
+    L.vsrt_alloc_blas.argtypes = [c_vp, c_vp, c_u64, c_u64]
+    L.vsrt_commit.argtypes = [c_vp]
+    L.vsrt_form_treelets.argtypes = [c_vp, c_vp, c_u32]
+    L.vsrt_treelet_info_get.argtypes = [c_vp, ctypes.POINTER(_abi.TreeletInfo)]
+    L.vsrt_treelet_table.argtypes = [c_vp] * 5
+    L.vsrt_node_map.argtypes = [c_vp] * 3
+    L.vsrt_treelet_remap.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u64), c_vp, c_vp]
+    L.vsrt_addr_to_treelet.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u64)]
+    L.vsrt_is_treelet_root.argtypes = [c_vp, c_u64]
+    L.vsrt_treelet_metadata_idx.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u32)]
+    L.vsrt_trace_rays.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
+    L.vsrt_trace_fetch.argtypes = [c_vp, c_vp, c_u64, c_vp]
+    L.vsrt_trace_ray_warp.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
+    L.vsrt_trace_rays_device.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, ctypes.POINTER(c_u64)]
+    L.vsrt_trace_device_results.argtypes = [c_vp, ctypes.POINTER(_abi.DeviceResults)]
+    L.vsrt_get_counters.argtypes = [c_vp, c_vp]
+    L.vsrt_reset_counters.argtypes = [c_vp]
+    L.vsrt_counters_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
+    _lib = L
+    return L
+
+
+def parse_config(text):
+    L = load()
+    cfg = _abi.Config()
+    L.vsrt_default_config(ctypes.byref(cfg))
+    L.vsrt_config_parse(ctypes.byref(cfg), text.encode())
+    return cfg
+
+
+class Context:
+    def __init__(self, max_treelet_size=49152, device=-1, treelet_based_traversal=1, remap_to_treelet_layout=0,
+                 treelet_remap_stride=0, stack_entries=96, config=None):
+        L = load()
+        self.L = L
+        cfg = _abi.Config()
+        L.vsrt_default_config(ctypes.byref(cfg))
+        if config is not None:
+            cfg = config
+        else:
+            cfg.device = device
+            cfg.max_treelet_size = max_treelet_size
+            cfg.treelet_based_traversal = treelet_based_traversal
+            cfg.remap_to_treelet_layout = remap_to_treelet_layout
+            cfg.treelet_remap_stride = treelet_remap_stride
+            cfg.stack_entries = stack_entries
+        self.cfg = cfg
+        h = c_vp()
+        rc = L.vsrt_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            raise VsrtError(rc, L.vsrt_last_error(None).decode())
+        self.h = h
+        self.tlas = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vsrt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            raise VsrtError(rc, self.L.vsrt_last_error(self.h).decode())
+        return rc
+
+    # ---- registration -------------------------------------------------------------------------------------
+    def alloc_tlas(self, host_addr, size, dev_addr):
+        self._ck(self.L.vsrt_alloc_tlas(self.h, host_addr, size, dev_addr))
+        self.tlas = host_addr
+
+    def alloc_blas(self, host_addr, size, dev_addr):
+        self._ck(self.L.vsrt_alloc_blas(self.h, host_addr, size, dev_addr))
+
+    def register(self, arena, delta=0, blas_delta=None):
+        """Register a scene.Arena the way Mesa would: one allocTLAS + one allocBLAS per BLAS header."""
+        self._keep.append(arena)
+        self.alloc_tlas(arena.tlas, arena.size - arena.tlas_offset, arena.tlas + delta)
+        for i, (off, size) in enumerate(arena.blas):
+            d = delta if blas_delta is None else blas_delta[i]
+            self.alloc_blas(arena.base + off, size, arena.base + off + d)
+
+    def commit(self):
+        self._ck(self.L.vsrt_commit(self.h))
+
+    # ---- treelets -----------------------------------------------------------------------------------------
+    def form_treelets(self, budget=0):
+        self._ck(self.L.vsrt_form_treelets(self.h, self.tlas, budget))
+        return self.treelet_info()
+
+    def treelet_info(self):
+        ti = _abi.TreeletInfo()
+        self._ck(self.L.vsrt_treelet_info_get(self.h, ctypes.byref(ti)))
+        return ti
+
+    def tables(self):
+        ti = self.treelet_info()
+        roots = np.zeros(ti.n_treelets, np.uint64); offs = np.zeros(ti.n_treelets + 1, np.uint64)
+        na = np.zeros(ti.n_list_entries, np.uint64); ns = np.zeros(ti.n_list_entries, np.uint32)
+        self._ck(self.L.vsrt_treelet_table(self.h, _abi.ptr(roots), _abi.ptr(offs), _abi.ptr(na), _abi.ptr(ns)))
+        mk = np.zeros(ti.n_mapped_nodes, np.uint64); mv = np.zeros(ti.n_mapped_nodes, np.uint64)
+        self._ck(self.L.vsrt_node_map(self.h, _abi.ptr(mk), _abi.ptr(mv)))
+        return {"roots": roots, "counts": np.diff(offs).astype(np.uint32), "meta_idx": np.arange(ti.n_treelets, dtype=np.uint32),
+                "node_addr": na, "node_size": ns, "map_nodes": mk, "map_roots": mv, "offsets": offs}
+
+    def remap_table(self, base):
+        n = c_u64()
+        self._ck(self.L.vsrt_treelet_remap(self.h, base, ctypes.byref(n), None, None))
+        o = np.zeros(n.value, np.uint64); m = np.zeros(n.value, np.uint64)
+        self._ck(self.L.vsrt_treelet_remap(self.h, base, ctypes.byref(n), _abi.ptr(o), _abi.ptr(m)))
+        return o, m
+
+    def addr_to_treelet(self, addr):
+        r = c_u64()
+        self._ck(self.L.vsrt_addr_to_treelet(self.h, addr, ctypes.byref(r)))
+        return r.value
+
+    def is_treelet_root(self, addr):
+        rc = self.L.vsrt_is_treelet_root(self.h, addr)
+        if rc < 0:
+            self._ck(rc)
+        return bool(rc)
+
+    def metadata_idx(self, root):
+        i = c_u32()
+        self._ck(self.L.vsrt_treelet_metadata_idx(self.h, root, ctypes.byref(i)))
+        return i.value
+
+    # ---- traversal ----------------------------------------------------------------------------------------
+    def trace(self, mode, rays, want_trace=True, capacity=None):
+        """Host-buffer call (what a reference-side caller makes): rays in, hits + CSR trace + treelet ids out."""
+        rays = np.ascontiguousarray(rays, dtype=_abi.RAY)
+        n = len(rays)
+        hits = np.zeros(n, _abi.HIT); offs = np.zeros(n + 1, np.uint64)
+        total = c_u64()
+        if not want_trace:
+            self._ck(self.L.vsrt_trace_rays(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(offs), None, 0, None, ctypes.byref(total)))
+            return {"hits": hits, "offsets": offs, "total": total.value}
+        cap = capacity if capacity is not None else 0
+        txns = np.zeros(cap, _abi.TXN); tids = np.zeros(cap, np.uint64)
+        rc = self._ck(self.L.vsrt_trace_rays(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(offs),
+                                             _abi.ptr(txns) if cap else None, cap, _abi.ptr(tids) if cap else None, ctypes.byref(total)),
+                      allow=(-4,))
+        if total.value > cap or rc == -4 or cap == 0:
+            txns = np.zeros(total.value, _abi.TXN); tids = np.zeros(total.value, np.uint64)
+            if total.value:
+                self._ck(self.L.vsrt_trace_fetch(self.h, _abi.ptr(txns), total.value, _abi.ptr(tids)))
+        return {"hits": hits, "offsets": offs, "txns": txns[:total.value], "treelet_ids": tids[:total.value]}
+
+    def trace_warp(self, rays32, active_mask=0xffffffff, capacity=32 * 1024):
+        rays32 = np.ascontiguousarray(rays32, dtype=_abi.RAY)
+        assert len(rays32) == 32
+        hits = np.zeros(32, _abi.HIT); counts = np.zeros(32, np.uint32); txns = np.zeros(capacity, _abi.TXN); total = c_u64()
+        self._ck(self.L.vsrt_trace_ray_warp(self.h, self.tlas, active_mask, _abi.ptr(rays32), _abi.ptr(hits), _abi.ptr(counts), _abi.ptr(txns),
+                                            capacity, ctypes.byref(total)))
+        return {"hits": hits, "counts": counts, "txns": txns[:total.value]}
+
+    def trace_device(self, mode, rays_dev_ptr, n, stream=None):
+        total = c_u64()
+        self._ck(self.L.vsrt_trace_rays_device(self.h, self.tlas, mode, n, rays_dev_ptr, stream, ctypes.byref(total)))
+        return total.value
+
+    def device_results(self):
+        r = _abi.DeviceResults()
+        self._ck(self.L.vsrt_trace_device_results(self.h, ctypes.byref(r)))
+        return r
+
+    # ---- counters -----------------------------------------------------------------------------------------
+    def counters(self):
+        a = np.zeros(_abi.N_SUM + _abi.N_MAX, np.uint64)
+        self._ck(self.L.vsrt_get_counters(self.h, _abi.ptr(a)))
+        return dict(zip(_abi.COUNTER_FIELDS, (int(x) for x in a)))
+
+    def reset_counters(self):
+        self._ck(self.L.vsrt_reset_counters(self.h))
+
+    def counters_device(self):
+        cp, hp, n = c_vp(), c_vp(), c_u64()
+        self._ck(self.L.vsrt_counters_device(self.h, ctypes.byref(cp), ctypes.byref(hp), ctypes.byref(n)))
+        return cp.value, hp.value, n.value

@@ -206,6 +206,13 @@ class Context:
                 self._ck(self.L.vsrt_trace_fetch(self.h, _abi.ptr(txns), total.value, _abi.ptr(tids)))
         return {"hits": hits, "offsets": offs, "txns": txns[:total.value], "treelet_ids": tids[:total.value]}
 
+    def trace_into(self, mode, n, rays_ptr, hits_ptr, offsets_ptr, txns_ptr, txn_capacity, tids_ptr):
+        """vsrt_trace_rays on caller-owned (e.g. pinned) host buffers given as raw addresses; returns #records."""
+        total = c_u64()
+        self._ck(self.L.vsrt_trace_rays(self.h, self.tlas, mode, n, rays_ptr, hits_ptr, offsets_ptr, txns_ptr, txn_capacity, tids_ptr,
+                                        ctypes.byref(total)))
+        return total.value
+
     def trace_warp(self, rays32, active_mask=0xffffffff, capacity=32 * 1024):
         rays32 = np.ascontiguousarray(rays32, dtype=_abi.RAY)
         assert len(rays32) == 32

@@ -70,12 +70,18 @@ def mixed_rays(n_random, seed, w=48, h=32):
     return r
 
 
-def assert_trace_equal(o, g, what=""):
+def assert_trace_equal(o, g, what="", skip_unknown_tids=False):
     """o: oracle result (OHIT hits), g: CUDA result (vsrt_hit hits).  Bit-exact on everything."""
     assert np.array_equal(o["offsets"], g["offsets"]), what + ": per-ray record counts differ"
     assert np.array_equal(o["txns"]["address"], g["txns"]["address"]), what + ": node-visit addresses differ"
     assert np.array_equal(o["txns"]["size"], g["txns"]["size"]) and np.array_equal(o["txns"]["type"], g["txns"]["type"]), what + ": record size/type differ"
-    assert np.array_equal(o["treelet_ids"], g["treelet_ids"]), what + ": treelet ids differ"
+    if skip_unknown_tids:
+        # traceRay with per-BLAS device offsets emits BLAS-node addresses the reference's address-keyed treelet map
+        # does not contain (its addrToTreeletID would assert, :470); the oracle reports ~0 there
+        known = o["treelet_ids"] != np.uint64(0xFFFFFFFFFFFFFFFF)
+        assert np.array_equal(o["treelet_ids"][known], g["treelet_ids"][known]), what + ": treelet ids differ"
+    else:
+        assert np.array_equal(o["treelet_ids"], g["treelet_ids"]), what + ": treelet ids differ"
     oh, gh = o["hits"], g["hits"]
     assert np.array_equal(oh["hit"], gh["hit_geometry"]), what + ": hit flags differ"
     assert np.array_equal(oh["prim"], gh["primitive_index"]), what + ": primitive ids differ"

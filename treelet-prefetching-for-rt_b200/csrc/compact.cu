@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __r
 // ---------------------------------------------------------------- K3
 constexpr int K3_THREADS = 256;
 constexpr int K3_RAYS = 256;     // rays per CTA
+constexpr int K3_ILP = 4;        // independent records in flight per thread
 
 __device__ __forceinline__ uint32_t code_size(uint32_t code) { return code == C_INSTANCE ? 128u : (code == C_DESC ? 8u : 64u); }
 __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_INTERNAL_TLAS ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code; }
@@ -88,44 +89,56 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
   const unsigned long long j0 = s_off[0], j1 = s_off[nr];
   const ArenaView& av = p.av;
   uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-  for (unsigned long long jb = j0; jb < j1; jb += K3_THREADS) {
-    const unsigned long long j = jb + threadIdx.x;
-    const bool valid = j < j1;
-    uint32_t tid = VSRT_NO_TID;
-    if (valid) {
+  // K3_ILP records per thread per iteration, block-strided so every store instruction is fully coalesced; the
+  // independent chains (smem search -> staging load -> node_tid gather -> store) overlap each other's latency.
+  for (unsigned long long jb = j0; jb < j1; jb += (unsigned long long)K3_THREADS * K3_ILP) {
+    unsigned long long j[K3_ILP]; bool valid[K3_ILP]; uint32_t k[K3_ILP], ray[K3_ILP], rec[K3_ILP], tid[K3_ILP];
+#pragma unroll
+    for (int u = 0; u < K3_ILP; u++) {
+      j[u] = jb + (unsigned long long)u * K3_THREADS + threadIdx.x; valid[u] = j[u] < j1;
       // ray of record j: last i with s_off[i] <= j
       uint32_t lo = 0, hi = nr;
-      while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_off[m] <= j) lo = m; else hi = m; }
-      const uint32_t k = (uint32_t)(j - s_off[lo]);
-      const uint32_t* seg = p.stage + (r0 + lo) * (uint64_t)p.cap;
-      const uint32_t rec = __ldg(seg + k);
-      const uint32_t slot = rec >> 3, code = rec & 7u;
-      // host -> simulated-device offset the reference applies to this record
-      int64_t delta = av.tlas_delta;
-      if (!av.uniform_delta) {
-        if (code == C_STRUCT && k > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
-        else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k > 0) {
-          // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
-          for (uint32_t b = k; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
-        }
-      }
-      vsrt_txn t;
-      t.address = slot_to_host(av, slot) + (uint64_t)delta;
-      t.size = code_size(code); t.type = code_type(code);
-      tid = __ldg(p.tv.node_tid + slot);
-      if (j < p.out_capacity) {
-        *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)t.address, (uint32_t)(t.address >> 32), t.size, t.type);
-        p.tids[j] = tid;
-      }
+      if (valid[u]) { while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_off[m] <= j[u]) lo = m; else hi = m; } }
+      ray[u] = lo; k[u] = valid[u] ? (uint32_t)(j[u] - s_off[lo]) : 0u;
+    }
 #pragma unroll
-      for (int c = 0; c < 8; c++) hc[c] += (t.type == (uint32_t)c) ? 1u : 0u;
+    for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(p.stage + (r0 + ray[u]) * (uint64_t)p.cap + k[u]) : 0u;
+#pragma unroll
+    for (int u = 0; u < K3_ILP; u++) tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID;
+#pragma unroll
+    for (int u = 0; u < K3_ILP; u++) {
+      if (valid[u]) {
+        const uint32_t slot = rec[u] >> 3, code = rec[u] & 7u;
+        // host -> simulated-device offset the reference applies to this record
+        int64_t delta = av.tlas_delta;
+        if (!av.uniform_delta) {
+          const uint32_t* seg = p.stage + (r0 + ray[u]) * (uint64_t)p.cap;
+          if (code == C_STRUCT && k[u] > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
+          else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k[u] > 0) {
+            // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
+            for (uint32_t b = k[u]; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
+          }
+        }
+        const uint64_t address = slot_to_host(av, slot) + (uint64_t)delta;
+        const uint32_t type = code_type(code);
+        if (j[u] < p.out_capacity) {
+          *reinterpret_cast<uint4*>(p.txns + j[u]) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
+          p.tids[j[u]] = tid[u];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) hc[c] += (type == (uint32_t)c) ? 1u : 0u;
+      }
     }
     if (p.treelet_hist) {
       // warp-aggregated histogram: consecutive records of a ray mostly share a treelet
-      const unsigned act = __ballot_sync(0xffffffffu, valid && tid != VSRT_NO_TID);
-      if (valid && tid != VSRT_NO_TID) {
-        const unsigned peers = __match_any_sync(act, tid);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p.treelet_hist + tid, (unsigned long long)__popc(peers));
+#pragma unroll
+      for (int u = 0; u < K3_ILP; u++) {
+        const bool a = valid[u] && tid[u] != VSRT_NO_TID;
+        const unsigned act = __ballot_sync(0xffffffffu, a);
+        if (a) {
+          const unsigned peers = __match_any_sync(act, tid[u]);
+          if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p.treelet_hist + tid[u], (unsigned long long)__popc(peers));
+        }
       }
     }
   }

@@ -3,135 +3,242 @@
 //   MODE_DFS      VulkanRayTracing::traceRay            (vulkan_ray_tracing.cc:2309-3076)
 //   MODE_TREELET  VulkanRayTracing::traceRayWithTreelets (vulkan_ray_tracing.cc:1522-2307)
 //
-// One thread owns one ray from the first record to the hit record, so the visit order is the reference's by
+// One LANE owns one ray from its first record to its hit record, so the visit order is the reference's by
 // construction: DFS = LIFO stack where the first box-hit internal child is followed immediately (:2573,:2760);
 // TREELET = two LIFOs, children go to `current` when they live in the current treelet, else to `other`
-// (:1832-1856), `other` is drained only when `current` is empty (:1748-1754).  The kernel emits COMPACT trace
-// records (slot << 3 | code) into the ray's staging segment; scan + K3 (compact.cu) turn them into the reference's
-// 16-byte MemoryTransactionRecords in CSR order.
+// (:1832-1856), `other` is drained only when `current` is empty (:1748-1754).
+//
+// Scheduling (free to choose, because rays are independent): persistent warps.  A lane that finishes its ray is
+// refilled from a global ray counter once enough lanes of the warp are idle, and each warp iteration runs three
+// warp-uniform phases -- internal nodes, instance leaves, BLAS leaves -- so lanes execute the same code together.
+// A lane whose next entry is a BLAS leaf WAITS (it never skips ahead: the triangle test moves min_thit, which
+// culls later boxes) until LEAF_T lanes are waiting or no lane has other work; this batches the triangle tests,
+// which ran with ~3 of 32 lanes active in the one-thread-one-ray-one-pass formulation (profiles/README.md).
+//
+// The kernel emits COMPACT trace records (slot << 3 | code) into the ray's staging segment; scan + K3
+// (compact.cu) turn them into the reference's 16-byte MemoryTransactionRecords in CSR order.
 #include "vsrt_device.cuh"
+#include <algorithm>
 
 namespace {
 
-struct Entry { uint32_t slot; uint32_t meta; };   // meta = leaf << 31 | instance-leaf slot (VSRT_NO_INST = top level)
+// stack entry: slot + meta, meta = leaf << 31 | level << 23 | instance reference (23 bits).  The instance reference
+// is the instance leaf's slot relative to the first slot of the TLAS span (INST_NONE = the entry is a TLAS node).
+constexpr uint32_t INST_NONE = 0x7FFFFFu;
+struct Entry { uint32_t slot; uint32_t meta; };
 VS_DEV bool e_leaf(const Entry& e) { return (e.meta >> 31) != 0; }
-VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & 0x7FFFFFFFu; }
-VS_DEV bool e_top(const Entry& e) { return e_inst(e) == VSRT_NO_INST; }
+VS_DEV uint32_t e_level(const Entry& e) { return (e.meta >> 23) & 0xffu; }
+VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }
+VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
+VS_DEV uint32_t mk_meta(bool leaf, uint32_t level, uint32_t inst) { return (leaf ? 0x80000000u : 0u) | (level << 23) | inst; }
+
+constexpr int THREADS = 128;
+constexpr int REFILL_T = 8;    // refill a warp when at least this many lanes are idle (or all are)
+constexpr int LEAF_T = 6;      // run the leaf phase when at least this many lanes wait at a BLAS leaf
+
+enum { KIND_NONE = 0, KIND_INT = 1, KIND_INST = 2, KIND_LEAF = 3 };
 
 template <int MODE, int STACK_N>
-__global__ void __launch_bounds__(128) k_traverse(const TraverseParams p) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = r < p.n_rays;
-  uint32_t total_nodes = 0, max_level = 0, n_hit = 0, n_any = 0, n_term = 0, err = 0;
+__global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
+  const ArenaView& av = p.av;
+  const uint8_t* __restrict__ base = av.base;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
+  const bool force_exact = av.force_exact != 0;
 
-  if (active) {
-    const ArenaView& av = p.av;
-    const uint8_t* __restrict__ base = av.base;
-    const vsrt_ray* rp = p.rays + r;
-    Ray8 w;
-    w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
-    w.dx = __ldg(&rp->direction[0]); w.dy = __ldg(&rp->direction[1]); w.dz = __ldg(&rp->direction[2]); w.tmax = __ldg(&rp->tmax);
-    const uint32_t flags = __ldg(&rp->ray_flags);
-    const bool terminate = (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) != 0;   // :1650 / :2411
-    const bool opaque = (flags & VSRT_RAY_FLAG_OPAQUE) != 0;                      // skipAnyHitShader, :2413
-    n_term = terminate ? 1u : 0u;
-    const Idir widir = calc_idir(w);
+  // ---- per-lane accumulators of the functional counters (cuda-sim.h:155-166)
+  uint32_t sum_nodes = 0, max_nodes = 0, max_level = 0, n_hit = 0, n_any = 0, n_term = 0, n_rays_done = 0, err = 0;
 
-    uint32_t* __restrict__ out = p.stage + r * (uint64_t)p.cap;
-    const uint32_t cap = p.cap;
-    uint32_t cnt = 0;
+  // ---- per-lane ray state
+  Entry stk[STACK_N];
+  bool alive = false, fin = false, pend = false, exhausted = false;
+  Entry e; e.slot = 0; e.meta = 0;
+  uint64_t r = 0;
+  Ray8 w; Idir widir; bool w_exact = false;
+  uint32_t flags = 0, cnt = 0, ray_nodes = 0, cur_tid = VSRT_NO_TID;
+  int cur_n = 0, oth_n = 0;
+  bool have_next = false; Entry next; next.slot = 0; next.meta = 0;
+  float min_thit = 0.0f, min_thit_object = 0.0f;
+  uint32_t closest_leaf = 0, closest_inst = INST_NONE, n_all_hits = 0;
+  InstCtx ctx; ctx.inst_slot = VSRT_NO_INST; ctx.tmult = 1.0f; ctx.exact = false;
+  uint32_t* __restrict__ out = p.stage;
+  const uint32_t cap = p.cap;
+  w.ox = w.oy = w.oz = w.dx = w.dy = w.dz = w.tmin = w.tmax = 0.0f; widir.x = widir.y = widir.z = 0.0f; ctx.ray = w; ctx.idir = widir;
+
 #define EMIT(slot_, code_) do { if (cnt < cap) out[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
+#define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
+#define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
 
-    Entry stk[STACK_N];
-    uint8_t lvl[STACK_N];
-    int cur_n = 0, oth_n = 0;               // DFS uses cur only; TREELET: cur grows up from 0, other down from the top
-    uint32_t cur_tid = VSRT_NO_TID;
-
-    float min_thit = w.tmax, min_thit_object = 0.0f;                             // :1671
-    uint32_t closest_leaf = 0, closest_inst = VSRT_NO_INST, n_all_hits = 0;
-    InstCtx ctx; ctx.inst_slot = VSRT_NO_INST; ctx.tmult = 1.0f; ctx.ray = w; ctx.idir = widir;
-
-    EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
-    uint32_t top_root = 0;
-    bool have_next = false; Entry next; next.slot = 0; next.meta = 0; uint32_t next_lvl = 0;
-    if (!header_root(av, av.tlas_slot, top_root)) err |= EF_BAD_BVH;
-    else {
-      // scene box of the TLAS header (:1712-1741 / :2472-2484)
-      const float* hb = reinterpret_cast<const float*>(base + (uint64_t)av.tlas_slot * 64u + 8u);
-      float th;
-      if (ray_box(__ldg(hb), __ldg(hb + 1), __ldg(hb + 2), __ldg(hb + 3), __ldg(hb + 4), __ldg(hb + 5), widir, w, th)) {
-        Entry e; e.slot = top_root; e.meta = VSRT_NO_INST;
-        if (MODE == VSRT_MODE_TREELET) {
-          cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
-          if (__ldg(p.tv.node_tid + top_root) == cur_tid) { stk[cur_n] = e; lvl[cur_n] = 1; cur_n++; }
-          else { stk[STACK_N - 1] = e; lvl[STACK_N - 1] = 1; oth_n = 1; }
-        } else { stk[0] = e; lvl[0] = 1; cur_n = 1; }
-        max_level = 1;
+  while (true) {
+    // ================= refill: finalize finished rays, fetch new ones
+    const unsigned idle = __ballot_sync(full, !alive);
+    if (idle == full || (!exhausted && __popc(idle) >= REFILL_T)) {
+      if (fin) {
+        // ---- hit record (:2211-2245 / :2990-3033) and per-ray counters
+        fin = false;
+        if (cnt > cap) err |= EF_TRACE_CAP;
+        p.counts[r] = cnt;
+        vsrt_hit h;
+        h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
+        h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
+        h.intersection_point[0] = h.intersection_point[1] = h.intersection_point[2] = 0.0f;
+        h.n_all_hits = n_all_hits; h.instance_leaf_address = 0;
+        if (min_thit < w.tmax) {
+          n_hit++;
+          const Node64 q = load_node(base, closest_leaf);
+          const uint32_t ci = inst_base + closest_inst;
+          if (ctx.inst_slot != ci) make_object_ray(base, ci, w, ctx);
+          h.hit_geometry = 1; h.world_min_thit = min_thit;
+          h.geometry_index = q.w[1] & 0x0fffffffu; h.primitive_index = q.w[2];
+          h.instance_index = __ldg(reinterpret_cast<const uint32_t*>(base + (uint64_t)ci * 64u + 72u));
+          h.intersection_point[0] = fadd(w.ox, fmul(w.dx, min_thit));
+          h.intersection_point[1] = fadd(w.oy, fmul(w.dy, min_thit));
+          h.intersection_point[2] = fadd(w.oz, fmul(w.dz, min_thit));
+          barycentric(q, fadd(ctx.ray.ox, fmul(ctx.ray.dx, min_thit_object)), fadd(ctx.ray.oy, fmul(ctx.ray.dy, min_thit_object)),
+                      fadd(ctx.ray.oz, fmul(ctx.ray.dz, min_thit_object)), h.barycentric);
+          h.instance_leaf_address = slot_to_host(av, ci);
+        }
+        p.hits[r] = h;
+        sum_nodes += ray_nodes; if (ray_nodes > max_nodes) max_nodes = ray_nodes;
+        n_rays_done++;
       }
+      if (!exhausted) {
+        const int n_idle = __popc(idle);
+        unsigned long long b0 = 0;
+        if (lane == 0) b0 = atomicAdd(p.next_ray, (unsigned long long)n_idle);
+        b0 = __shfl_sync(full, b0, 0);
+        if (b0 + (unsigned long long)n_idle >= p.n_rays) exhausted = true;
+        if (!alive) {
+          const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
+          if (nr < p.n_rays) {
+            // ---- start ray nr (:1650-1741 / :2411-2484)
+            r = nr; alive = true; pend = false; have_next = false;
+            const vsrt_ray* rp = p.rays + r;
+            w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
+            w.dx = __ldg(&rp->direction[0]); w.dy = __ldg(&rp->direction[1]); w.dz = __ldg(&rp->direction[2]); w.tmax = __ldg(&rp->tmax);
+            flags = __ldg(&rp->ray_flags);
+            if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) n_term++;
+            widir = calc_idir(w);
+            w_exact = force_exact || ray_needs_exact(w);
+            out = p.stage + r * (uint64_t)cap; cnt = 0; ray_nodes = 0;
+            cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID;
+            min_thit = w.tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE; n_all_hits = 0;   // :1671
+            ctx.inst_slot = VSRT_NO_INST;
+            EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
+            uint32_t top_root = 0;
+            if (!header_root(av, av.tlas_slot, top_root)) err |= EF_BAD_BVH;
+            else {
+              // scene box of the TLAS header (:1712-1741 / :2472-2484)
+              const float* hb = reinterpret_cast<const float*>(base + (uint64_t)av.tlas_slot * 64u + 8u);
+              float th;
+              if (ray_box(__ldg(hb), __ldg(hb + 1), __ldg(hb + 2), __ldg(hb + 3), __ldg(hb + 4), __ldg(hb + 5), widir, w, th)) {
+                Entry c; c.slot = top_root; c.meta = mk_meta(false, 1, INST_NONE);
+                if (MODE == VSRT_MODE_TREELET) {
+                  cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
+                  if (__ldg(p.tv.node_tid + top_root) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
+                } else PUSH_CUR(c);
+                if (max_level < 1) max_level = 1;
+              }
+            }
+          }
+        }
+      }
+      if (__ballot_sync(full, alive) == 0u) { if (exhausted) break; else continue; }
     }
 
-    while (true) {
-      Entry e; uint32_t level;
-      if (MODE == VSRT_MODE_DFS && have_next) { e = next; level = next_lvl; have_next = false; }
+    // ================= pop the next entry of every lane that holds none
+    if (alive && !pend) {
+      if (MODE == VSRT_MODE_DFS && have_next) { e = next; have_next = false; pend = true; }
       else {
-        if (cur_n == 0) {
-          if (MODE == VSRT_MODE_DFS || oth_n == 0) break;
-          // :1748-1754 -- move the front of `other` into `current`; current_treelet_root becomes that node's HOST
+        if (cur_n == 0 && MODE == VSRT_MODE_TREELET && oth_n != 0) {
+          // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
           // address, which equals a treelet's device address only for the root at (host - tlas_delta).
-          Entry m = stk[STACK_N - oth_n]; uint8_t ml = lvl[STACK_N - oth_n]; oth_n--;
-          stk[0] = m; lvl[0] = ml; cur_n = 1;
+          const Entry m = stk[STACK_N - oth_n]; oth_n--;
+          stk[0] = m; cur_n = 1;
           if (av.tlas_delta == 0) cur_tid = root_rank(p.tv, m.slot);
           else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, m.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
         }
-        cur_n--; e = stk[cur_n]; level = lvl[cur_n];
+        if (cur_n == 0) { alive = false; fin = true; }
+        else { cur_n--; e = stk[cur_n]; pend = true; }
       }
-      const bool top = e_top(e);
-      if (!e_leaf(e)) {
-        // ---- internal node (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
+    }
+    const int kind = !pend ? KIND_NONE : (!e_leaf(e) ? KIND_INT : (e_top(e) ? KIND_INST : KIND_LEAF));
+
+    // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
+    const unsigned m_int = __ballot_sync(full, kind == KIND_INT);
+    if (m_int) {
+      if (kind == KIND_INT) {
+        pend = false;
+        const bool top = e_top(e);
         const Node64 n = load_node(base, e.slot);
-        EMIT(e.slot, top ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); total_nodes++;
-        if (!top && ctx.inst_slot != e_inst(e)) make_object_ray(base, e_inst(e), w, ctx);
-        const uint32_t mask = top ? test_children(n, w, widir, min_thit) : test_children(n, ctx.ray, ctx.idir, fmul(min_thit, ctx.tmult));
+        EMIT(e.slot, top ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
+        if (!top && ctx.inst_slot != inst_base + e_inst(e)) make_object_ray(base, inst_base + e_inst(e), w, ctx);
+        // one call site for TLAS (world ray) and BLAS (object ray of the entry's instance)
+        Ray8 rr; Idir ri;
+        rr.ox = top ? w.ox : ctx.ray.ox; rr.oy = top ? w.oy : ctx.ray.oy; rr.oz = top ? w.oz : ctx.ray.oz;
+        rr.dx = top ? w.dx : ctx.ray.dx; rr.dy = top ? w.dy : ctx.ray.dy; rr.dz = top ? w.dz : ctx.ray.dz;
+        rr.tmin = top ? w.tmin : ctx.ray.tmin; rr.tmax = top ? w.tmax : ctx.ray.tmax;
+        ri.x = top ? widir.x : ctx.idir.x; ri.y = top ? widir.y : ctx.idir.y; ri.z = top ? widir.z : ctx.idir.z;
+        const float cull = top ? min_thit : fmul(min_thit, ctx.tmult);            // :1791 / :1989
+        const uint32_t mask = (w_exact || (!top && ctx.exact)) ? test_children_exact(n, rr, ri, cull) : test_children(n, rr, ri, cull);
         uint32_t child = e.slot + (uint32_t)node_child_offset(n);
-        const uint32_t clevel = level < 255u ? level + 1u : 255u;
-        if (mask) { if (clevel > max_level) max_level = clevel; }
+        const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
+        if (mask && clevel > max_level) max_level = clevel;
+        const uint32_t inst = e_inst(e);
 #pragma unroll
         for (int i = 0; i < 6; i++) {
           const uint32_t info = node_child_info(n, i);
           if ((mask >> i) & 1u) {
-            Entry c; c.slot = child; c.meta = (e.meta & 0x7FFFFFFFu) | (((info >> 2) != 0u) ? 0x80000000u : 0u);
+            Entry c; c.slot = child; c.meta = mk_meta((info >> 2) != 0u, clevel, inst);
             if (MODE == VSRT_MODE_DFS) {
-              if ((info >> 2) == 0u && !have_next) { next = c; next_lvl = clevel; have_next = true; }   // first hit internal child
-              else if (cur_n < STACK_N) { stk[cur_n] = c; lvl[cur_n] = (uint8_t)clevel; cur_n++; }
+              if ((info >> 2) == 0u && !have_next) { next = c; have_next = true; }   // first hit internal child is followed
+              else if (cur_n < STACK_N) PUSH_CUR(c);
               else err |= EF_STACK;
             } else {
               if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-              else if (__ldg(p.tv.node_tid + child) == cur_tid) { stk[cur_n] = c; lvl[cur_n] = (uint8_t)clevel; cur_n++; }
-              else { oth_n++; stk[STACK_N - oth_n] = c; lvl[STACK_N - oth_n] = (uint8_t)clevel; }
+              else if (__ldg(p.tv.node_tid + child) == cur_tid) PUSH_CUR(c);
+              else PUSH_OTH(c);
             }
           }
           child += info & 3u;
         }
-      } else if (top) {
-        // ---- instance leaf (:1876-1953 / :2602-2677)
-        EMIT(e.slot, C_INSTANCE); total_nodes++;
+      }
+    }
+
+    // ================= phase 2: instance leaves (:1876-1953 / :2602-2677)
+    const unsigned m_inst = __ballot_sync(full, kind == KIND_INST);
+    if (m_inst) {
+      if (kind == KIND_INST) {
+        pend = false;
+        EMIT(e.slot, C_INSTANCE); ray_nodes++;
         uint32_t hdr = 0, broot = 0;
-        if (!instance_blas_header(av, e.slot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; break; }
-        EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
-        make_object_ray(base, e.slot, w, ctx);
-        Entry c; c.slot = broot; c.meta = e.slot;                                // BLAS root inherits the leaf's level (:1944)
-        if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) { stk[cur_n] = c; lvl[cur_n] = (uint8_t)level; cur_n++; } else err |= EF_STACK; }
+        const uint32_t iref = e.slot - inst_base;
+        if (!instance_blas_header(av, e.slot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; alive = false; fin = true; }
+        else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; alive = false; fin = true; }
         else {
-          if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-          else if (__ldg(p.tv.node_tid + broot) == cur_tid) { stk[cur_n] = c; lvl[cur_n] = (uint8_t)level; cur_n++; }
-          else { oth_n++; stk[STACK_N - oth_n] = c; lvl[STACK_N - oth_n] = (uint8_t)level; }
+          EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
+          make_object_ray(base, e.slot, w, ctx);
+          Entry c; c.slot = broot; c.meta = mk_meta(false, e_level(e), iref);      // BLAS root inherits the leaf's level (:1944)
+          if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
+          else {
+            if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
+            else if (__ldg(p.tv.node_tid + broot) == cur_tid) PUSH_CUR(c);
+            else PUSH_OTH(c);
+          }
         }
-      } else {
-        // ---- BLAS leaf (:2073-2204 / :2789-2985)
+      }
+    }
+
+    // ================= phase 3: BLAS leaves (:2073-2204 / :2789-2985), batched
+    const unsigned m_leaf = __ballot_sync(full, kind == KIND_LEAF);
+    if (m_leaf && (__popc(m_leaf) >= LEAF_T || (m_int | m_inst) == 0u)) {
+      if (kind == KIND_LEAF) {
+        pend = false;
         EMIT(e.slot, C_DESC);
         const Node64 q = load_node(base, e.slot);
         if (((q.w[1] >> 29) & 1u) == 0u) {
-          if (ctx.inst_slot != e_inst(e)) make_object_ray(base, e_inst(e), w, ctx);
+          if (ctx.inst_slot != inst_base + e_inst(e)) make_object_ray(base, inst_base + e_inst(e), w, ctx);
           float thit = 0.0f;
           const bool hit = ray_tri(q, ctx.ray, thit);
           const float tw = fdiv(thit, ctx.tmult);
@@ -139,68 +246,61 @@ __global__ void __launch_bounds__(128) k_traverse(const TraverseParams p) {
           if (MODE == VSRT_MODE_TREELET) acc = acc && tw < min_thit;              // :2127
           if (acc) {
             if (MODE == VSRT_MODE_TREELET) min_thit = tw;
-            else { if (opaque && tw < min_thit) min_thit = tw; if (!opaque) { n_all_hits++; n_any++; } }   // :2850, :2869-2929
+            else {
+              const bool opaque = (flags & VSRT_RAY_FLAG_OPAQUE) != 0;            // skipAnyHitShader, :2413
+              if (opaque && tw < min_thit) min_thit = tw;                         // :2850
+              if (!opaque) { n_all_hits++; n_any++; }                             // :2869-2929
+            }
             min_thit_object = thit; closest_leaf = e.slot; closest_inst = e_inst(e);
-            EMIT(e.slot, C_QUAD_HIT); total_nodes++;
-            if (terminate) { cur_n = 0; oth_n = 0; have_next = false; }           // :2151-2155 / :2932-2935
-          } else { EMIT(e.slot, C_QUAD); total_nodes++; }
-        } else { EMIT(e.slot, C_PROC); total_nodes++; }                           // intersection-table transactions: not built yet
+            EMIT(e.slot, C_QUAD_HIT); ray_nodes++;
+            if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) { cur_n = 0; oth_n = 0; have_next = false; }   // :2151-2155 / :2932-2935
+          } else { EMIT(e.slot, C_QUAD); ray_nodes++; }
+        } else { EMIT(e.slot, C_PROC); ray_nodes++; }                             // intersection-table transactions: not built yet
       }
     }
-#undef EMIT
-    if (cnt > cap) err |= EF_TRACE_CAP;
-    p.counts[r] = cnt;
-
-    // ---- hit record (:2211-2245 / :2990-3033)
-    vsrt_hit h;
-    h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
-    h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
-    h.intersection_point[0] = h.intersection_point[1] = h.intersection_point[2] = 0.0f;
-    h.n_all_hits = n_all_hits; h.instance_leaf_address = 0;
-    if (min_thit < w.tmax) {
-      n_hit = 1;
-      const Node64 q = load_node(base, closest_leaf);
-      if (ctx.inst_slot != closest_inst) make_object_ray(base, closest_inst, w, ctx);
-      h.hit_geometry = 1; h.world_min_thit = min_thit;
-      h.geometry_index = q.w[1] & 0x0fffffffu; h.primitive_index = q.w[2];
-      h.instance_index = __ldg(reinterpret_cast<const uint32_t*>(base + (uint64_t)closest_inst * 64u + 72u));
-      h.intersection_point[0] = fadd(w.ox, fmul(w.dx, min_thit));
-      h.intersection_point[1] = fadd(w.oy, fmul(w.dy, min_thit));
-      h.intersection_point[2] = fadd(w.oz, fmul(w.dz, min_thit));
-      barycentric(q, fadd(ctx.ray.ox, fmul(ctx.ray.dx, min_thit_object)), fadd(ctx.ray.oy, fmul(ctx.ray.dy, min_thit_object)),
-                  fadd(ctx.ray.oz, fmul(ctx.ray.dz, min_thit_object)), h.barycentric);
-      h.instance_leaf_address = slot_to_host(av, closest_inst);
-    }
-    p.hits[r] = h;
   }
+#undef EMIT
+#undef PUSH_CUR
+#undef PUSH_OTH
 
-  // ---- functional counters (cuda-sim.h:155-166): warp-reduce, one atomic per warp
-  const unsigned full = 0xffffffffu;
-  const uint32_t s_nodes = __reduce_add_sync(full, total_nodes), s_hit = __reduce_add_sync(full, n_hit);
-  const uint32_t s_any = __reduce_add_sync(full, n_any), s_term = __reduce_add_sync(full, n_term), s_act = __reduce_add_sync(full, active ? 1u : 0u);
-  const uint32_t m_nodes = __reduce_max_sync(full, total_nodes), m_lvl = __reduce_max_sync(full, max_level), e_all = __reduce_or_sync(full, err);
-  if ((threadIdx.x & 31) == 0) {
+  // ---- functional counters: warp-reduce, one atomic per warp
+  const uint32_t s_nodes = __reduce_add_sync(full, sum_nodes), s_hit = __reduce_add_sync(full, n_hit);
+  const uint32_t s_any = __reduce_add_sync(full, n_any), s_term = __reduce_add_sync(full, n_term), s_act = __reduce_add_sync(full, n_rays_done);
+  const uint32_t m_nodes = __reduce_max_sync(full, max_nodes), m_lvl = __reduce_max_sync(full, max_level), e_all = __reduce_or_sync(full, err);
+  if (lane == 0) {
     unsigned long long* c = p.counters->v;
-    atomicAdd(c + CI_TOT_NODES, (unsigned long long)s_nodes);
+    if (s_nodes) atomicAdd(c + CI_TOT_NODES, (unsigned long long)s_nodes);
     if (s_hit) atomicAdd(c + CI_NUM_HITS, (unsigned long long)s_hit);
     if (s_any) atomicAdd(c + CI_NUM_ANY_HITS, (unsigned long long)s_any);
     if (s_term) atomicAdd(c + CI_N_ANYHIT_RAYS, (unsigned long long)s_term);
     if (s_act - s_term) atomicAdd(c + CI_N_CLOSEST_RAYS, (unsigned long long)(s_act - s_term));
+    if (s_act) atomicAdd(c + CI_RAY_COUNT, (unsigned long long)s_act);
     atomicMax(c + CI_MAX_NODES, (unsigned long long)m_nodes);
     atomicMax(c + CI_MAX_DEPTH, (unsigned long long)m_lvl);
     if (e_all) atomicOr(p.err_flags, e_all);
   }
 }
 
+template <int MODE, int STACK_N>
+int launch_mode(const TraverseParams& p, cudaStream_t st) {
+  static int blocks_per_sm = 0, n_sm = 0;
+  if (blocks_per_sm == 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_traverse<MODE, STACK_N>, THREADS, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 4;
+  }
+  // persistent grid: every resident warp keeps pulling rays until the counter runs out
+  const uint64_t want = (p.n_rays + THREADS - 1) / THREADS;
+  const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);
+  if (grid == 0) return VSRT_OK;
+  k_traverse<MODE, STACK_N><<<grid, THREADS, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
 template <int STACK_N>
 int launch_n(const TraverseParams& p, cudaStream_t st) {
-  const unsigned block = 128;
-  const uint64_t grid = (p.n_rays + block - 1) / block;
-  if (grid == 0) return VSRT_OK;
-  if (grid > 0x7fffffffull) return VSRT_E_INVALID;
-  if (p.mode == VSRT_MODE_TREELET) k_traverse<VSRT_MODE_TREELET, STACK_N><<<(unsigned)grid, block, 0, st>>>(p);
-  else k_traverse<VSRT_MODE_DFS, STACK_N><<<(unsigned)grid, block, 0, st>>>(p);
-  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+  if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
+  return p.mode == VSRT_MODE_TREELET ? launch_mode<VSRT_MODE_TREELET, STACK_N>(p, st) : launch_mode<VSRT_MODE_DFS, STACK_N>(p, st);
 }
 
 }  // namespace

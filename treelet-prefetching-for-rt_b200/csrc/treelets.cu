@@ -40,6 +40,10 @@ struct Walker {
     if (slot >= av.n_slots) { err |= EF_BAD_BVH; return; }
     if (kind == K_TLAS_INTERNAL || kind == K_BLAS_INTERNAL) {
       charge(64); list[n++] = mk_entry(slot, kind);
+      {   // a non-finite node origin lets a NaN reach the slab test: traversal must then keep the ternary MIN/MAX
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u));
+        if (!finite3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z))) err |= EF_NONFINITE;
+      }
       if (kind == K_TLAS_INTERNAL) {   // assert(node.ChildType[i] == NODE_TYPE_INSTANCE) for TLAS leaves, :926
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u) + 1);
         const uint64_t info6 = ((uint64_t)b.z << 16) | (b.y >> 16);
@@ -221,9 +225,11 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
       CK(cudaMemcpyAsync(&n_roots, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(&h_err, err_flags_dev, 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      if (h_err) break;
+      if (h_err & ~EF_NONFINITE) break;
     }
   }
+  res->nonfinite = (h_err & EF_NONFINITE) ? 1u : 0u;
+  h_err &= ~(uint32_t)EF_NONFINITE;
   if (h_err) {
     rc = (h_err & EF_UNKNOWN_AS) ? VSRT_E_UNKNOWN_AS : (h_err & EF_BAD_BVH) ? VSRT_E_BAD_BVH : VSRT_E_BUDGET;
     snprintf(errbuf, errcap, "treelet formation rejected the arena (flags 0x%x): %s", h_err,

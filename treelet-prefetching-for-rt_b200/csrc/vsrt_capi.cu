@@ -53,7 +53,8 @@ struct vsrt_context {
   DevBuf<vsrt_ray> d_rays; DevBuf<vsrt_hit> d_hits; DevBuf<uint32_t> d_stage; DevBuf<uint32_t> d_counts;
   DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint8_t> d_scan_tmp;
   uint32_t stage_cap = 128;
-  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr;
+  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
+  DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
@@ -96,7 +97,7 @@ int make_view(vsrt_context* c, uint64_t tlas_host, ArenaView* av) {
   if (!host_to_slot_h(c, tlas_host, &slot)) return fail(c, VSRT_E_UNKNOWN_AS, "TLAS address not inside the committed arena");
   av->base = c->d_arena; av->n_slots = (uint32_t)(c->arena_bytes / 64); av->n_spans = (uint32_t)c->spans.size(); av->n_blas = (uint32_t)c->blas.size();
   av->tlas_slot = slot; av->spans = c->d_spans; av->blas = c->d_blas; av->tlas_delta = (int64_t)(t->dev - t->host);
-  av->uniform_delta = 1; av->pad = 0;
+  av->uniform_delta = 1; av->force_exact = (c->formed && c->fr.nonfinite) ? 1u : 0u;
   for (const BlasReg& b : c->blas) if (b.delta != av->tlas_delta) av->uniform_delta = 0;
   return VSRT_OK;
 }
@@ -161,13 +162,13 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaMemcpyAsync(c->d_counters_bak, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
-    tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err;
+    tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
     rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, st); if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
     rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
-    launches += n ? 4 : 0;
+    launches += n ? 4 : 0;   // k_traverse + 3 scan kernels
     uint32_t h_err = 0;
     CUDA_OK(c, cudaMemcpyAsync(&total, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(&h_err, c->d_err, 4, cudaMemcpyDeviceToHost, st));
@@ -191,18 +192,13 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
   CUDA_OK(c, cudaEventRecord(c->ev[3], st));
   launches += n ? 1 : 0;
-  // rayCount (:1665): ids are global and 1-based; the counter advances by the batch size
   {
-    unsigned long long before = 0;
-    CUDA_OK(c, cudaMemcpyAsync(&before, c->d_counters->v + CI_RAY_COUNT, 8, cudaMemcpyDeviceToHost, st));
+    // rayCount (:1665) advanced by the traversal kernel; accessedDataSize delta of this batch = its algorithmic bytes
+    DevCounters now;
+    CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
-    before += n;
-    CUDA_OK(c, cudaMemcpyAsync(c->d_counters->v + CI_RAY_COUNT, &before, 8, cudaMemcpyHostToDevice, st));
-    unsigned long long acc0 = 0, acc1 = 0;
-    CUDA_OK(c, cudaMemcpyAsync(&acc0, c->d_counters_bak->v + CI_ACCESSED, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaMemcpyAsync(&acc1, c->d_counters->v + CI_ACCESSED, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaStreamSynchronize(st));
-    c->last.algorithmic_bytes = acc1 - acc0;
+    c->last.algorithmic_bytes = now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
+    c->h_prev = now;
   }
   c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p; c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p;
   c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;
@@ -255,7 +251,7 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device);
   if (prop.major < 10) { delete c; return fail(nullptr, VSRT_E_NO_DEVICE, "device %d is sm_%d%d; libvsrt is built for sm_100a only", c->device, prop.major, prop.minor); }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
   ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
   for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
@@ -269,7 +265,7 @@ void vsrt_destroy(vsrt_context* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_treelets(c);
-  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err);
+  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -496,6 +492,7 @@ int vsrt_reset_counters(vsrt_context* c) {
   if (!c) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
   CUDA_OK(c, cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  c->h_prev = DevCounters{};
   if (c->hist_n) CUDA_OK(c, cudaMemset(c->d_hist.p, 0, (size_t)c->hist_n * 8));
   return VSRT_OK;
 }

@@ -61,31 +61,60 @@ VS_DEV bool ray_box(float lox, float loy, float loz, float hix, float hiy, float
   return mn <= mx;
 }
 
+// Exact (float)byte without the quarter-rate I2F pipe: PRMT builds 0x4B0000qq == 2^23 + q, the subtraction is exact.
+VS_DEV float byte_to_float(const Node64& n, int i) {
+  return fsub(__uint_as_float(__byte_perm(n.w[i >> 2], 0x4B000000u, 0x7540u | (uint32_t)(i & 3))), 8388608.0f);
+}
+// lo = Origin + ldexpf((float)q, exp-8) (util.h:499-508).  q * 2^k is exact, so the single rounding of the
+// reference's add is exactly the single rounding of one FMA.
+VS_DEV float dequant(const Node64& n, int i, float scale, float org) { return __fmaf_rn(byte_to_float(n, i), scale, org); }
+
+// ray_box_test with IEEE min/max (one FMNMX each) instead of the ternary macros.  Identical results whenever no
+// operand is NaN: the only other difference is the sign of a zero result, which no later comparison can observe.
+// Callers use it only for rays and nodes whose coordinates were checked to be NaN-free (see `exact` below).
+VS_DEV bool ray_box_fast(float lox, float loy, float loz, float hix, float hiy, float hiz, const Idir& id, const Ray8& r, float& thit) {
+  float lx = fmul(fsub(lox, r.ox), id.x), ly = fmul(fsub(loy, r.oy), id.y), lz = fmul(fsub(loz, r.oz), id.z);
+  float hx = fmul(fsub(hix, r.ox), id.x), hy = fmul(fsub(hiy, r.oy), id.y), hz = fmul(fsub(hiz, r.oz), id.z);
+  float mn = fmaxf(fminf(lz, hz), fmaxf(fminf(ly, hy), fmaxf(fminf(lx, hx), r.tmin)));
+  float mx = fminf(fmaxf(lz, hz), fminf(fmaxf(ly, hy), fminf(fmaxf(lx, hx), r.tmax)));
+  thit = mn;
+  return mn <= mx;
+}
+
 // Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
 // `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
-VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) {
+// EXACT = true keeps the reference's ternary MIN/MAX (NaN picks the second operand); it is taken for rays or
+// arenas with non-finite coordinates, where a NaN can reach the slab test.
+template <bool EXACT>
+__device__ __forceinline__ uint32_t test_children_impl(const Node64& n, const Ray8& r, const Idir& id, float cull) {
   const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
   const float sx = node_scale(n, 18), sy = node_scale(n, 19), sz = node_scale(n, 20);
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     if ((node_child_info(n, i) & 3u) != 0u) {
-      float lox = fadd(ox, fmul((float)node_byte(n, 28 + i), sx)), hix = fadd(ox, fmul((float)node_byte(n, 34 + i), sx));
-      float loy = fadd(oy, fmul((float)node_byte(n, 40 + i), sy)), hiy = fadd(oy, fmul((float)node_byte(n, 46 + i), sy));
-      float loz = fadd(oz, fmul((float)node_byte(n, 52 + i), sz)), hiz = fadd(oz, fmul((float)node_byte(n, 58 + i), sz));
+      const float lox = dequant(n, 28 + i, sx, ox), hix = dequant(n, 34 + i, sx, ox);
+      const float loy = dequant(n, 40 + i, sy, oy), hiy = dequant(n, 46 + i, sy, oy);
+      const float loz = dequant(n, 52 + i, sz, oz), hiz = dequant(n, 58 + i, sz, oz);
       float th;
-      bool h = ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th);
+      bool h = EXACT ? ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th) : ray_box_fast(lox, loy, loz, hix, hiy, hiz, id, r, th);
       if (h && th >= cull) h = false;
       if (h) mask |= 1u << i;
     }
   }
   return mask;
 }
+VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<false>(n, r, id, cull); }
+// rare path (non-finite ray or arena): kept out of line so it does not bloat the hot loop's instruction footprint
+__device__ __noinline__ uint32_t test_children_exact(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<true>(n, r, id, cull); }
+VS_DEV bool finite3(float a, float b, float c) { return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f); }
+// true if a NaN could reach the slab test for this ray: any non-finite origin/direction, NaN tmin/tmax
+VS_DEV bool ray_needs_exact(const Ray8& r) { return !(finite3(r.ox, r.oy, r.oz) && finite3(r.dx, r.dy, r.dz) && r.tmin == r.tmin && r.tmax == r.tmax); }
 
 // Instance leaf -> object-space ray.  make_transformed_ray (:168-181) with float4x4::operator* (util.h:47-55):
 // res[i] = 0 + m[0][i]*v0 + m[1][i]*v1 + m[2][i]*v2 + m[3][i]*v3, W2O = wire A[0..8] rows + B[9..11] as row 3
 // (SURVEY A.1 matrix trap), column 3 = (0,0,0,1).
-struct InstCtx { Ray8 ray; Idir idir; float tmult; uint32_t inst_slot; };
+struct InstCtx { Ray8 ray; Idir idir; float tmult; uint32_t inst_slot; bool exact; };
 VS_DEV void make_object_ray(const uint8_t* base, uint32_t leaf_slot, const Ray8& w, InstCtx& c) {
   const float* A = reinterpret_cast<const float*>(base + (uint64_t)leaf_slot * 64u + 16u);
   const float* B = reinterpret_cast<const float*>(base + (uint64_t)leaf_slot * 64u + 80u);
@@ -110,6 +139,7 @@ VS_DEV void make_object_ray(const uint8_t* base, uint32_t leaf_slot, const Ray8&
   c.ray.tmin = fmul(w.tmin, norm); c.ray.tmax = fmul(w.tmax, norm);
   c.idir = calc_idir(c.ray);
   c.inst_slot = leaf_slot;
+  c.exact = ray_needs_exact(c.ray);
 }
 
 VS_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) { return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz)); }

@@ -48,7 +48,7 @@ struct ArenaView {
   const BlasReg* blas;    // device, ascending hdr_slot
   int64_t tlas_delta;     // tlas_addr - _topLevelAS
   uint32_t uniform_delta; // 1 if every BLAS delta equals tlas_delta (then both reference conventions coincide)
-  uint32_t pad;
+  uint32_t force_exact;   // 1 if some node origin is not finite: a NaN can reach the slab test, keep the ternary MIN/MAX
 };
 
 struct TreeletView {
@@ -67,10 +67,10 @@ enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 1
        CI_ACCESSED = 14, CI_RAY_COUNT = 15, CI_MAX_NODES = 16, CI_MAX_DEPTH = 17 };
 
 // error flags raised by kernels (OR-ed into a device word)
-enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32 };
+enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */ };
 
 // ---- launchers (each file implements its kernels) ----
-struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; };
+struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; };
 struct FormOutputs {      // device allocations owned by the context
   uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
 };
@@ -88,6 +88,7 @@ struct TraverseParams {
   uint32_t mode;
   DevCounters* counters;
   uint32_t* err_flags;
+  unsigned long long* next_ray;   // global ray counter the persistent warps pull from (zeroed by the launcher)
 };
 int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, cudaStream_t st);
 

@@ -15,7 +15,7 @@ namespace {
 
 struct Reg { uint64_t host, size, dev; bool tlas; };
 
-thread_local char g_create_error[256] = "";
+thread_local char g_create_error[512] = "";
 
 template <typename T> struct DevBuf {
   T* p = nullptr; size_t cap = 0;

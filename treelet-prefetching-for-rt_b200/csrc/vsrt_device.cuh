@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t test_children_impl(const Node64& n, const Ra
 }
 VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<false>(n, r, id, cull); }
 // rare path (non-finite ray or arena): kept out of line so it does not bloat the hot loop's instruction footprint
-__device__ __noinline__ uint32_t test_children_exact(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<true>(n, r, id, cull); }
+static __device__ __noinline__ uint32_t test_children_exact(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<true>(n, r, id, cull); }
 VS_DEV bool finite3(float a, float b, float c) { return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f); }
 // true if a NaN could reach the slab test for this ray: any non-finite origin/direction, NaN tmin/tmax
 VS_DEV bool ray_needs_exact(const Ray8& r) { return !(finite3(r.ox, r.oy, r.oz) && finite3(r.dx, r.dy, r.dz) && r.tmin == r.tmin && r.tmax == r.tmax); }

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __r
 constexpr int K3_THREADS = 256;
 constexpr int K3_RAYS = 256;     // rays per CTA
 constexpr int K3_ILP = 4;        // independent records in flight per thread
+constexpr int K3_HASH_BITS = 10; // CTA-private treelet histogram: 1024 (key,count) slots in shared memory
 
 __device__ __forceinline__ uint32_t code_size(uint32_t code) { return code == C_INSTANCE ? 128u : (code == C_DESC ? 8u : 64u); }
 __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_INTERNAL_TLAS ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code; }
@@ -81,6 +82,8 @@ __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_
 __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
   __shared__ unsigned long long s_off[K3_RAYS + 1];
   __shared__ unsigned int s_hist[8];
+  __shared__ unsigned int s_hkey[1 << K3_HASH_BITS], s_hcnt[1 << K3_HASH_BITS];
+  for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS) { s_hkey[i] = VSRT_NO_TID; s_hcnt[i] = 0; }
   const uint64_t r0 = (uint64_t)blockIdx.x * K3_RAYS;
   const uint32_t nr = (uint32_t)min((uint64_t)K3_RAYS, p.n_rays - r0);
   for (uint32_t i = threadIdx.x; i <= nr; i += K3_THREADS) s_off[i] = p.offsets[r0 + i];
@@ -130,17 +133,34 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
       }
     }
     if (p.treelet_hist) {
-      // warp-aggregated histogram: consecutive records of a ray mostly share a treelet
+      // Treelet visit histogram.  The hot bins (the treelets at the top of the tree) receive a record from every
+      // ray, and same-address atomics serialise in L2, so: (1) lanes hold consecutive records, runs of one treelet
+      // are folded with a shuffle + ballot and only the run head adds; (2) the CTA accumulates into a small
+      // shared-memory hash table and flushes it once at the end; only table collisions go straight to L2.
 #pragma unroll
       for (int u = 0; u < K3_ILP; u++) {
+        const int lane = threadIdx.x & 31;
         const bool a = valid[u] && tid[u] != VSRT_NO_TID;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, tid[u], 1);
         const unsigned act = __ballot_sync(0xffffffffu, a);
-        if (a) {
-          const unsigned peers = __match_any_sync(act, tid[u]);
-          if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p.treelet_hist + tid[u], (unsigned long long)__popc(peers));
+        const bool head = a && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != tid[u]);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (head) {
+          // run = lanes up to the next head or the first inactive lane
+          const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
+          const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
+          const uint32_t h = (tid[u] * 2654435761u) >> (32 - K3_HASH_BITS);
+          const uint32_t old = atomicCAS(&s_hkey[h], VSRT_NO_TID, tid[u]);
+          if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&s_hcnt[h], run);
+          else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
         }
       }
     }
+  }
+  if (p.treelet_hist) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS)
+      if (s_hkey[i] != VSRT_NO_TID && s_hcnt[i]) atomicAdd(p.treelet_hist + s_hkey[i], (unsigned long long)s_hcnt[i]);
   }
 #pragma unroll
   for (int c = 0; c < 8; c++) {

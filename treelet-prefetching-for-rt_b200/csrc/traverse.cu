@@ -12,8 +12,13 @@
 // refilled from a global ray counter once enough lanes of the warp are idle, and each warp iteration runs three
 // warp-uniform phases -- internal nodes, instance leaves, BLAS leaves -- so lanes execute the same code together.
 // A lane whose next entry is a BLAS leaf WAITS (it never skips ahead: the triangle test moves min_thit, which
-// culls later boxes) until LEAF_T lanes are waiting or no lane has other work; this batches the triangle tests,
+// culls later boxes) until leaf_t lanes are waiting or no lane has other work; this batches the triangle tests,
 // which ran with ~3 of 32 lanes active in the one-thread-one-ray-one-pass formulation (profiles/README.md).
+//
+// EXACT = false is the hot kernel: IEEE min/max (FMNMX) in the slab test, valid only while no NaN can reach it.
+// Rays (or instances) with non-finite coordinates are not traced by it: it marks them (counts[r] = RAY_DEFERRED,
+// EF_NEED_EXACT) and the launcher runs the EXACT = true instantiation, which keeps the reference's ternary
+// MIN/MAX, over just those rays.  An arena with a non-finite node origin runs EXACT for every ray.
 //
 // The kernel emits COMPACT trace records (slot << 3 | code) into the ray's staging segment; scan + K3
 // (compact.cu) turn them into the reference's 16-byte MemoryTransactionRecords in CSR order.
@@ -25,27 +30,33 @@ namespace {
 // stack entry: slot + meta, meta = leaf << 31 | level << 23 | instance reference (23 bits).  The instance reference
 // is the instance leaf's slot relative to the first slot of the TLAS span (INST_NONE = the entry is a TLAS node).
 constexpr uint32_t INST_NONE = 0x7FFFFFu;
+constexpr uint32_t RAY_DEFERRED = 0xFFFFFFFFu;
 struct Entry { uint32_t slot; uint32_t meta; };
 VS_DEV bool e_leaf(const Entry& e) { return (e.meta >> 31) != 0; }
 VS_DEV uint32_t e_level(const Entry& e) { return (e.meta >> 23) & 0xffu; }
 VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }
 VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
-VS_DEV uint32_t mk_meta(bool leaf, uint32_t level, uint32_t inst) { return (leaf ? 0x80000000u : 0u) | (level << 23) | inst; }
 
 constexpr int THREADS = 128;
-constexpr int REFILL_T = 8;    // refill a warp when at least this many lanes are idle (or all are)
-constexpr int LEAF_T = 6;      // run the leaf phase when at least this many lanes wait at a BLAS leaf
-
+#ifndef VSRT_K1_MIN_BLOCKS
+#define VSRT_K1_MIN_BLOCKS 6
+#endif
 enum { KIND_NONE = 0, KIND_INT = 1, KIND_INST = 2, KIND_LEAF = 3 };
 
-template <int MODE, int STACK_N>
-__global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
+// The ray the lane is currently testing against: the world ray inside the TLAS, the object-space ray of instance
+// `inst` inside a BLAS (make_transformed_ray, :168-181).  Rebuilt only when a popped entry belongs to another
+// context, so the hot loop never selects between two register sets.
+struct ActiveRay { Ray8 ray; Idir idir; float tmult; uint32_t inst; bool nonfinite; };
+
+template <int MODE, int STACK_N, bool EXACT>
+__global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const TraverseParams p) {
   const ArenaView& av = p.av;
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
-  const bool force_exact = av.force_exact != 0;
+  const int REFILL_T = (int)p.refill_t, LEAF_T = (int)p.leaf_t;
+  const bool only_deferred = EXACT && p.only_deferred != 0;
 
   // ---- per-lane accumulators of the functional counters (cuda-sim.h:155-166)
   uint32_t sum_nodes = 0, max_nodes = 0, max_level = 0, n_hit = 0, n_any = 0, n_term = 0, n_rays_done = 0, err = 0;
@@ -55,20 +66,23 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
   bool alive = false, fin = false, pend = false, exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
   uint64_t r = 0;
-  Ray8 w; Idir widir; bool w_exact = false;
-  uint32_t flags = 0, cnt = 0, ray_nodes = 0, cur_tid = VSRT_NO_TID;
+  Ray8 w; w.ox = w.oy = w.oz = w.dx = w.dy = w.dz = w.tmin = w.tmax = 0.0f;
+  ActiveRay a; a.ray = w; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
+  uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0, cur_tid = VSRT_NO_TID;
   int cur_n = 0, oth_n = 0;
   bool have_next = false; Entry next; next.slot = 0; next.meta = 0;
   float min_thit = 0.0f, min_thit_object = 0.0f;
-  uint32_t closest_leaf = 0, closest_inst = INST_NONE, n_all_hits = 0;
-  InstCtx ctx; ctx.inst_slot = VSRT_NO_INST; ctx.tmult = 1.0f; ctx.exact = false;
+  uint32_t closest_leaf = 0, closest_inst = INST_NONE;
   uint32_t* __restrict__ out = p.stage;
   const uint32_t cap = p.cap;
-  w.ox = w.oy = w.oz = w.dx = w.dy = w.dz = w.tmin = w.tmax = 0.0f; widir.x = widir.y = widir.z = 0.0f; ctx.ray = w; ctx.idir = widir;
 
 #define EMIT(slot_, code_) do { if (cnt < cap) out[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
 #define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
 #define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
+  // switch the active ray to context `inst_` (INST_NONE = world)
+#define ACTIVATE(inst_) do { const uint32_t i_ = (inst_); if (a.inst != i_) { a.inst = i_; \
+      if (i_ == INST_NONE) { a.ray = w; a.idir = calc_idir(w); a.tmult = 1.0f; a.nonfinite = false; } \
+      else { InstCtx c_; make_object_ray(base, inst_base + i_, w, c_); a.ray = c_.ray; a.idir = c_.idir; a.tmult = c_.tmult; a.nonfinite = c_.exact; } } } while (0)
 
   while (true) {
     // ================= refill: finalize finished rays, fetch new ones
@@ -83,24 +97,26 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
         h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
         h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
         h.intersection_point[0] = h.intersection_point[1] = h.intersection_point[2] = 0.0f;
-        h.n_all_hits = n_all_hits; h.instance_leaf_address = 0;
+        h.n_all_hits = ray_any; h.instance_leaf_address = 0;
         if (min_thit < w.tmax) {
           n_hit++;
           const Node64 q = load_node(base, closest_leaf);
+          ACTIVATE(closest_inst);
           const uint32_t ci = inst_base + closest_inst;
-          if (ctx.inst_slot != ci) make_object_ray(base, ci, w, ctx);
           h.hit_geometry = 1; h.world_min_thit = min_thit;
           h.geometry_index = q.w[1] & 0x0fffffffu; h.primitive_index = q.w[2];
           h.instance_index = __ldg(reinterpret_cast<const uint32_t*>(base + (uint64_t)ci * 64u + 72u));
           h.intersection_point[0] = fadd(w.ox, fmul(w.dx, min_thit));
           h.intersection_point[1] = fadd(w.oy, fmul(w.dy, min_thit));
           h.intersection_point[2] = fadd(w.oz, fmul(w.dz, min_thit));
-          barycentric(q, fadd(ctx.ray.ox, fmul(ctx.ray.dx, min_thit_object)), fadd(ctx.ray.oy, fmul(ctx.ray.dy, min_thit_object)),
-                      fadd(ctx.ray.oz, fmul(ctx.ray.dz, min_thit_object)), h.barycentric);
+          barycentric(q, fadd(a.ray.ox, fmul(a.ray.dx, min_thit_object)), fadd(a.ray.oy, fmul(a.ray.dy, min_thit_object)),
+                      fadd(a.ray.oz, fmul(a.ray.dz, min_thit_object)), h.barycentric);
           h.instance_leaf_address = slot_to_host(av, ci);
         }
         p.hits[r] = h;
         sum_nodes += ray_nodes; if (ray_nodes > max_nodes) max_nodes = ray_nodes;
+        n_any += ray_any;
+        if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) n_term++;
         n_rays_done++;
       }
       if (!exhausted) {
@@ -111,34 +127,35 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
         if (b0 + (unsigned long long)n_idle >= p.n_rays) exhausted = true;
         if (!alive) {
           const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
-          if (nr < p.n_rays) {
+          if (nr < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
             // ---- start ray nr (:1650-1741 / :2411-2484)
-            r = nr; alive = true; pend = false; have_next = false;
+            r = nr; pend = false; have_next = false;
             const vsrt_ray* rp = p.rays + r;
             w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
             w.dx = __ldg(&rp->direction[0]); w.dy = __ldg(&rp->direction[1]); w.dz = __ldg(&rp->direction[2]); w.tmax = __ldg(&rp->tmax);
             flags = __ldg(&rp->ray_flags);
-            if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) n_term++;
-            widir = calc_idir(w);
-            w_exact = force_exact || ray_needs_exact(w);
-            out = p.stage + r * (uint64_t)cap; cnt = 0; ray_nodes = 0;
-            cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID;
-            min_thit = w.tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE; n_all_hits = 0;   // :1671
-            ctx.inst_slot = VSRT_NO_INST;
-            EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
-            uint32_t top_root = 0;
-            if (!header_root(av, av.tlas_slot, top_root)) err |= EF_BAD_BVH;
+            if (!EXACT && ray_needs_exact(w)) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; }   // left to the EXACT pass
             else {
-              // scene box of the TLAS header (:1712-1741 / :2472-2484)
-              const float* hb = reinterpret_cast<const float*>(base + (uint64_t)av.tlas_slot * 64u + 8u);
-              float th;
-              if (ray_box(__ldg(hb), __ldg(hb + 1), __ldg(hb + 2), __ldg(hb + 3), __ldg(hb + 4), __ldg(hb + 5), widir, w, th)) {
-                Entry c; c.slot = top_root; c.meta = mk_meta(false, 1, INST_NONE);
-                if (MODE == VSRT_MODE_TREELET) {
-                  cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
-                  if (__ldg(p.tv.node_tid + top_root) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
-                } else PUSH_CUR(c);
-                if (max_level < 1) max_level = 1;
+              alive = true;
+              a.inst = INST_NONE; a.ray = w; a.idir = calc_idir(w); a.tmult = 1.0f; a.nonfinite = false;
+              out = p.stage + r * (uint64_t)cap; cnt = 0; ray_nodes = 0; ray_any = 0;
+              cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID;
+              min_thit = w.tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE;   // :1671
+              EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
+              uint32_t top_root = 0;
+              if (!header_root(av, av.tlas_slot, top_root)) err |= EF_BAD_BVH;
+              else {
+                // scene box of the TLAS header (:1712-1741 / :2472-2484)
+                const float* hb = reinterpret_cast<const float*>(base + (uint64_t)av.tlas_slot * 64u + 8u);
+                float th;
+                if (ray_box(__ldg(hb), __ldg(hb + 1), __ldg(hb + 2), __ldg(hb + 3), __ldg(hb + 4), __ldg(hb + 5), a.idir, w, th)) {
+                  Entry c; c.slot = top_root; c.meta = (1u << 23) | INST_NONE;
+                  if (MODE == VSRT_MODE_TREELET) {
+                    cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
+                    if (__ldg(p.tv.node_tid + top_root) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
+                  } else PUSH_CUR(c);
+                  if (max_level < 1) max_level = 1;
+                }
               }
             }
           }
@@ -151,15 +168,13 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
     if (alive && !pend) {
       if (MODE == VSRT_MODE_DFS && have_next) { e = next; have_next = false; pend = true; }
       else {
-        if (cur_n == 0 && MODE == VSRT_MODE_TREELET && oth_n != 0) {
+        if (MODE == VSRT_MODE_TREELET && cur_n == 0 && oth_n != 0) {
           // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
           // address, which equals a treelet's device address only for the root at (host - tlas_delta).
-          const Entry m = stk[STACK_N - oth_n]; oth_n--;
-          stk[0] = m; cur_n = 1;
-          if (av.tlas_delta == 0) cur_tid = root_rank(p.tv, m.slot);
-          else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, m.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
-        }
-        if (cur_n == 0) { alive = false; fin = true; }
+          e = stk[STACK_N - oth_n]; oth_n--; pend = true;
+          if (av.tlas_delta == 0) cur_tid = root_rank(p.tv, e.slot);
+          else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
+        } else if (cur_n == 0) { alive = false; fin = true; }
         else { cur_n--; e = stk[cur_n]; pend = true; }
       }
     }
@@ -170,38 +185,37 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
     if (m_int) {
       if (kind == KIND_INT) {
         pend = false;
-        const bool top = e_top(e);
         const Node64 n = load_node(base, e.slot);
-        EMIT(e.slot, top ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
-        if (!top && ctx.inst_slot != inst_base + e_inst(e)) make_object_ray(base, inst_base + e_inst(e), w, ctx);
-        // one call site for TLAS (world ray) and BLAS (object ray of the entry's instance)
-        Ray8 rr; Idir ri;
-        rr.ox = top ? w.ox : ctx.ray.ox; rr.oy = top ? w.oy : ctx.ray.oy; rr.oz = top ? w.oz : ctx.ray.oz;
-        rr.dx = top ? w.dx : ctx.ray.dx; rr.dy = top ? w.dy : ctx.ray.dy; rr.dz = top ? w.dz : ctx.ray.dz;
-        rr.tmin = top ? w.tmin : ctx.ray.tmin; rr.tmax = top ? w.tmax : ctx.ray.tmax;
-        ri.x = top ? widir.x : ctx.idir.x; ri.y = top ? widir.y : ctx.idir.y; ri.z = top ? widir.z : ctx.idir.z;
-        const float cull = top ? min_thit : fmul(min_thit, ctx.tmult);            // :1791 / :1989
-        const uint32_t mask = (w_exact || (!top && ctx.exact)) ? test_children_exact(n, rr, ri, cull) : test_children(n, rr, ri, cull);
-        uint32_t child = e.slot + (uint32_t)node_child_offset(n);
-        const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
-        if (mask && clevel > max_level) max_level = clevel;
         const uint32_t inst = e_inst(e);
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-          const uint32_t info = node_child_info(n, i);
-          if ((mask >> i) & 1u) {
-            Entry c; c.slot = child; c.meta = mk_meta((info >> 2) != 0u, clevel, inst);
+        EMIT(e.slot, inst == INST_NONE ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
+        ACTIVATE(inst);
+        if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; alive = false; }   // degenerate instance transform
+        else {
+          uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult));   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
+          // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868); sizes are 0..3 -> 4-bit prefix fields
+          const uint32_t i0 = node_child_info(n, 0), i1 = node_child_info(n, 1), i2 = node_child_info(n, 2), i3 = node_child_info(n, 3), i4 = node_child_info(n, 4), i5 = node_child_info(n, 5);
+          const uint32_t p1 = i0 & 3u, p2 = p1 + (i1 & 3u), p3 = p2 + (i2 & 3u), p4 = p3 + (i3 & 3u), p5 = p4 + (i4 & 3u);
+          const uint32_t offs = (p1 << 4) | (p2 << 8) | (p3 << 12) | (p4 << 16) | (p5 << 20);
+          const uint32_t leafbits = ((i0 >> 2) ? 1u : 0u) | ((i1 >> 2) ? 2u : 0u) | ((i2 >> 2) ? 4u : 0u) | ((i3 >> 2) ? 8u : 0u) | ((i4 >> 2) ? 16u : 0u) | ((i5 >> 2) ? 32u : 0u);
+          const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
+          const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
+          if (mask && clevel > max_level) max_level = clevel;
+          const uint32_t cmeta = (clevel << 23) | inst;
+          while (mask) {                                   // hit children in slot order (:1810-1869)
+            const int i = __ffs(mask) - 1; mask &= mask - 1u;
+            Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u);
+            const bool leaf = (leafbits >> i) & 1u;
+            c.meta = cmeta | (leaf ? 0x80000000u : 0u);
             if (MODE == VSRT_MODE_DFS) {
-              if ((info >> 2) == 0u && !have_next) { next = c; have_next = true; }   // first hit internal child is followed
+              if (!leaf && !have_next) { next = c; have_next = true; }   // first hit internal child is followed (:2573)
               else if (cur_n < STACK_N) PUSH_CUR(c);
               else err |= EF_STACK;
             } else {
               if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-              else if (__ldg(p.tv.node_tid + child) == cur_tid) PUSH_CUR(c);
+              else if (__ldg(p.tv.node_tid + c.slot) == cur_tid) PUSH_CUR(c);
               else PUSH_OTH(c);
             }
           }
-          child += info & 3u;
         }
       }
     }
@@ -218,8 +232,7 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
         else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; alive = false; fin = true; }
         else {
           EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
-          make_object_ray(base, e.slot, w, ctx);
-          Entry c; c.slot = broot; c.meta = mk_meta(false, e_level(e), iref);      // BLAS root inherits the leaf's level (:1944)
+          Entry c; c.slot = broot; c.meta = (e_level(e) << 23) | iref;             // BLAS root inherits the leaf's level (:1944)
           if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
           else {
             if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
@@ -238,10 +251,10 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
         EMIT(e.slot, C_DESC);
         const Node64 q = load_node(base, e.slot);
         if (((q.w[1] >> 29) & 1u) == 0u) {
-          if (ctx.inst_slot != inst_base + e_inst(e)) make_object_ray(base, inst_base + e_inst(e), w, ctx);
+          ACTIVATE(e_inst(e));
           float thit = 0.0f;
-          const bool hit = ray_tri(q, ctx.ray, thit);
-          const float tw = fdiv(thit, ctx.tmult);
+          const bool hit = ray_tri(q, a.ray, thit);
+          const float tw = fdiv(thit, a.tmult);
           bool acc = hit && w.tmin <= tw && tw <= w.tmax;                         // :2843
           if (MODE == VSRT_MODE_TREELET) acc = acc && tw < min_thit;              // :2127
           if (acc) {
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
             else {
               const bool opaque = (flags & VSRT_RAY_FLAG_OPAQUE) != 0;            // skipAnyHitShader, :2413
               if (opaque && tw < min_thit) min_thit = tw;                         // :2850
-              if (!opaque) { n_all_hits++; n_any++; }                             // :2869-2929
+              if (!opaque) ray_any++;                                             // :2869-2929
             }
             min_thit_object = thit; closest_leaf = e.slot; closest_inst = e_inst(e);
             EMIT(e.slot, C_QUAD_HIT); ray_nodes++;
@@ -262,6 +275,7 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
 #undef EMIT
 #undef PUSH_CUR
 #undef PUSH_OTH
+#undef ACTIVATE
 
   // ---- functional counters: warp-reduce, one atomic per warp
   const uint32_t s_nodes = __reduce_add_sync(full, sum_nodes), s_hit = __reduce_add_sync(full, n_hit);
@@ -281,32 +295,33 @@ __global__ void __launch_bounds__(THREADS) k_traverse(const TraverseParams p) {
   }
 }
 
-template <int MODE, int STACK_N>
+template <int MODE, int STACK_N, bool EXACT>
 int launch_mode(const TraverseParams& p, cudaStream_t st) {
   static int blocks_per_sm = 0, n_sm = 0;
   if (blocks_per_sm == 0) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_traverse<MODE, STACK_N>, THREADS, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_traverse<MODE, STACK_N, EXACT>, THREADS, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 4;
   }
-  // persistent grid: every resident warp keeps pulling rays until the counter runs out
+  // persistent grid (a multiple of the SM count): every resident warp keeps pulling rays until the counter runs out
   const uint64_t want = (p.n_rays + THREADS - 1) / THREADS;
   const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);
   if (grid == 0) return VSRT_OK;
-  k_traverse<MODE, STACK_N><<<grid, THREADS, 0, st>>>(p);
+  if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
+  k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
 template <int STACK_N>
-int launch_n(const TraverseParams& p, cudaStream_t st) {
-  if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
-  return p.mode == VSRT_MODE_TREELET ? launch_mode<VSRT_MODE_TREELET, STACK_N>(p, st) : launch_mode<VSRT_MODE_DFS, STACK_N>(p, st);
+int launch_n(const TraverseParams& p, bool exact, cudaStream_t st) {
+  if (p.mode == VSRT_MODE_TREELET) return exact ? launch_mode<VSRT_MODE_TREELET, STACK_N, true>(p, st) : launch_mode<VSRT_MODE_TREELET, STACK_N, false>(p, st);
+  return exact ? launch_mode<VSRT_MODE_DFS, STACK_N, true>(p, st) : launch_mode<VSRT_MODE_DFS, STACK_N, false>(p, st);
 }
 
 }  // namespace
 
-int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, cudaStream_t st) {
-  if (stack_entries <= 96) return launch_n<96>(p, st);
-  if (stack_entries <= 192) return launch_n<192>(p, st);
-  return launch_n<384>(p, st);
+int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st) {
+  if (stack_entries <= 96) return launch_n<96>(p, exact, st);
+  if (stack_entries <= 192) return launch_n<192>(p, exact, st);
+  return launch_n<384>(p, exact, st);
 }

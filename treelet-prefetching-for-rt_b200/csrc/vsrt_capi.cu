@@ -163,12 +163,28 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
+    { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
+    tp.only_deferred = 0; tp.pad = 0;
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
-    rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, st); if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, av.force_exact != 0, st);
+    if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    launches += n ? 1 : 0;
+    if (!av.force_exact && n) {
+      // rays (or instances) with non-finite coordinates were deferred by the fast kernel: run the EXACT kernel on them
+      uint32_t e1 = 0;
+      CUDA_OK(c, cudaMemcpyAsync(&e1, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(c, cudaStreamSynchronize(st));
+      if (e1 & EF_NEED_EXACT) {
+        tp.only_deferred = 1;
+        rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, true, st);
+        if (rc) return fail(c, rc, "exact traversal kernel launch failed");
+        launches++;
+      }
+    }
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
     rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
-    launches += n ? 4 : 0;   // k_traverse + 3 scan kernels
+    launches += n ? 3 : 0;   // 3 scan kernels
     uint32_t h_err = 0;
     CUDA_OK(c, cudaMemcpyAsync(&total, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(&h_err, c->d_err, 4, cudaMemcpyDeviceToHost, st));
@@ -188,7 +204,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   }
   CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
   CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
-  cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = c->d_txns.cap; cp.counters = c->d_counters; cp.treelet_hist = c->d_hist.p;
+  cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = c->d_txns.cap; cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
   rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
   CUDA_OK(c, cudaEventRecord(c->ev[3], st));
   launches += n ? 1 : 0;

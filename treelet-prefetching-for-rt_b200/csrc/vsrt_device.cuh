@@ -36,8 +36,9 @@ VS_DEV uint32_t node_child_info(const Node64& n, int i) { return node_byte(n, 22
 // 2^(e-8) as an exact float for the int8 exponent byte at `idx` (e-8 in [-136,119]); (float)q * 2^k is exact and
 // therefore equal to the reference's ldexpf((float)q, k)  (util.h:499-508).
 VS_DEV float node_scale(const Node64& n, int idx) {
-  int k = (int)(int8_t)node_byte(n, idx) - 8;
-  uint32_t bits = (k >= -126) ? ((uint32_t)(k + 127) << 23) : (1u << (k + 149));
+  const int k = (int)(int8_t)node_byte(n, idx) - 8;
+  // normal floats for k >= -126 (every sane BVH); denormal powers of two below that
+  const uint32_t bits = (k >= -126) ? ((uint32_t)(k + 127) << 23) : (1u << ((k + 149) & 31));
   return __uint_as_float(bits);
 }
 
@@ -84,29 +85,24 @@ VS_DEV bool ray_box_fast(float lox, float loy, float loz, float hix, float hiy, 
 // Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
 // `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
 // EXACT = true keeps the reference's ternary MIN/MAX (NaN picks the second operand); it is taken for rays or
-// arenas with non-finite coordinates, where a NaN can reach the slab test.
+// arenas with non-finite coordinates, where a NaN can reach the slab test.  Straight-line code: all six slots are
+// evaluated and empty slots (ChildSize == 0) are masked out at the end.
 template <bool EXACT>
-__device__ __forceinline__ uint32_t test_children_impl(const Node64& n, const Ray8& r, const Idir& id, float cull) {
+VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) {
   const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
   const float sx = node_scale(n, 18), sy = node_scale(n, 19), sz = node_scale(n, 20);
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    if ((node_child_info(n, i) & 3u) != 0u) {
-      const float lox = dequant(n, 28 + i, sx, ox), hix = dequant(n, 34 + i, sx, ox);
-      const float loy = dequant(n, 40 + i, sy, oy), hiy = dequant(n, 46 + i, sy, oy);
-      const float loz = dequant(n, 52 + i, sz, oz), hiz = dequant(n, 58 + i, sz, oz);
-      float th;
-      bool h = EXACT ? ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th) : ray_box_fast(lox, loy, loz, hix, hiy, hiz, id, r, th);
-      if (h && th >= cull) h = false;
-      if (h) mask |= 1u << i;
-    }
+    const float lox = dequant(n, 28 + i, sx, ox), hix = dequant(n, 34 + i, sx, ox);
+    const float loy = dequant(n, 40 + i, sy, oy), hiy = dequant(n, 46 + i, sy, oy);
+    const float loz = dequant(n, 52 + i, sz, oz), hiz = dequant(n, 58 + i, sz, oz);
+    float th;
+    const bool h = EXACT ? ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th) : ray_box_fast(lox, loy, loz, hix, hiy, hiz, id, r, th);
+    mask |= (h && !(th >= cull) && (node_byte(n, 22 + i) & 3u) != 0u) ? (1u << i) : 0u;
   }
   return mask;
 }
-VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<false>(n, r, id, cull); }
-// rare path (non-finite ray or arena): kept out of line so it does not bloat the hot loop's instruction footprint
-static __device__ __noinline__ uint32_t test_children_exact(const Node64& n, const Ray8& r, const Idir& id, float cull) { return test_children_impl<true>(n, r, id, cull); }
 VS_DEV bool finite3(float a, float b, float c) { return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f); }
 // true if a NaN could reach the slab test for this ray: any non-finite origin/direction, NaN tmin/tmax
 VS_DEV bool ray_needs_exact(const Ray8& r) { return !(finite3(r.ox, r.oy, r.oz) && finite3(r.dx, r.dy, r.dz) && r.tmin == r.tmin && r.tmax == r.tmax); }

@@ -67,7 +67,7 @@ enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 1
        CI_ACCESSED = 14, CI_RAY_COUNT = 15, CI_MAX_NODES = 16, CI_MAX_DEPTH = 17 };
 
 // error flags raised by kernels (OR-ed into a device word)
-enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */ };
+enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */, EF_NEED_EXACT = 128 /* not an error */ };
 
 // ---- launchers (each file implements its kernels) ----
 struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; };
@@ -89,8 +89,12 @@ struct TraverseParams {
   DevCounters* counters;
   uint32_t* err_flags;
   unsigned long long* next_ray;   // global ray counter the persistent warps pull from (zeroed by the launcher)
+  uint32_t refill_t;              // refill a warp when at least this many lanes are idle
+  uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
+  uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
+  uint32_t pad;
 };
-int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, cudaStream_t st);
+int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
 
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);

@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 WIDTH, HEIGHT = 1920, 1080
 N_TRI = 1_000_000
 SCENE_SEED = 0x5EED0001 + 1
-BUDGET = 512          # configs/tested-cfgs/treelet_prefetching/gpgpusim.config:219
-MODE = 1              # -treelet_based_traversal 1 (gpgpusim.config:225)
+BUDGET = int(os.environ.get("VSRT_BENCH_BUDGET", "512"))   # configs/tested-cfgs/treelet_prefetching/gpgpusim.config:219
+MODE = int(os.environ.get("VSRT_BENCH_MODE", "1"))          # -treelet_based_traversal 1 (gpgpusim.config:225)
 METRIC = "rays/s (traversal + access trace + treelet ids)"
 
 

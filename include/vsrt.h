@@ -221,6 +221,10 @@ int vsrt_reset_counters(vsrt_context* ctx);
  * all-reduces (SUM over the first part and the histogram, MAX over the 2 max fields).
  * vsrt_set_counters_device writes reduced values back. */
 int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_hist_dev, uint64_t* n_treelets);
+/* Host copy of the per-treelet visit histogram (records whose node belongs to treelet i, metadata-index order):
+ * the popularity data the RT unit's treelet prefetcher votes on (shader.cc:3424-3433), accumulated over every
+ * batch since the last vsrt_reset_counters / vsrt_form_treelets. */
+int vsrt_get_treelet_histogram(vsrt_context* ctx, uint64_t* hist, uint64_t capacity);
 
 #ifdef __cplusplus
 }

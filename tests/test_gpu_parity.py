@@ -117,6 +117,41 @@ def test_clustered_scene_and_bounces(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("budget", [512, 49152])
+def test_treelet_histogram(api, budget):
+    """The per-treelet visit histogram equals a bincount of the trace's treelet ids (metadata-index order), summed
+    over batches and both variants; vsrt_reset_counters clears it."""
+    s = sc.Scene(8000, seed=31, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    ctx = api.Context(max_treelet_size=budget, device=0)
+    ctx.register(s); ctx.form_treelets()
+    roots = ctx.tables()["roots"]
+    expect = np.zeros(len(roots), np.uint64)
+    for mode, rays in ((1, helpers.mixed_rays(3000, 1)), (0, sc.rays_primary(80, 60, flags=_abi.FLAG_OPAQUE)), (1, sc.rays_random(5000, seed=2))):
+        g = ctx.trace(mode, rays)
+        idx = np.searchsorted(roots, g["treelet_ids"])
+        assert np.array_equal(roots[idx], g["treelet_ids"])
+        expect += np.bincount(idx, minlength=len(roots)).astype(np.uint64)
+    assert np.array_equal(ctx.treelet_histogram(), expect)
+    ctx.reset_counters()
+    assert ctx.treelet_histogram().sum() == 0
+    ctx.close()
+
+
+def test_nonfinite_rays_take_the_exact_path(api):
+    """Rays with NaN/inf coordinates are deferred by the fast kernel (FMNMX slab test) to the EXACT kernel, which keeps
+    the reference's ternary MIN/MAX; results must still match the oracle bit for bit."""
+    s = sc.Scene(3000, seed=17, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    rays = helpers.mixed_rays(600, 4)
+    rays["origin"][5::17, 0] = np.inf
+    rays["direction"][3::19, 1] = np.nan
+    rays["tmin"][7::23] = np.nan
+    rays["tmax"][11::29] = np.inf
+    rays["origin"][13::31, 2] = -np.inf
+    with np.errstate(all="ignore"):
+        run_case(api, s, rays, 512)
+        run_case(api, s, rays, 4096, modes=(1,))
+
+
 def test_empty_and_ragged_batches(api):
     s = sc.Scene(1000, seed=3)
     ctx = api.Context(max_treelet_size=512, device=0)

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
 #pragma unroll
     for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(p.stage + (r0 + ray[u]) * (uint64_t)p.cap + k[u]) : 0u;
 #pragma unroll
-    for (int u = 0; u < K3_ILP; u++) tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID;
+    for (int u = 0; u < K3_ILP; u++) { tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID; if (tid[u] != VSRT_NO_TID) tid[u] &= VSRT_TID_MASK; }
 #pragma unroll
     for (int u = 0; u < K3_ILP; u++) {
       if (valid[u]) {

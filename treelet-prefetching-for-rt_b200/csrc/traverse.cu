@@ -38,6 +38,7 @@ VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }
 VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 
 constexpr int THREADS = 128;
+VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 6
 #endif
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
                   Entry c; c.slot = top_root; c.meta = (1u << 23) | INST_NONE;
                   if (MODE == VSRT_MODE_TREELET) {
                     cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
-                    if (__ldg(p.tv.node_tid + top_root) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
+                    if ((__ldg(p.tv.node_tid + top_root) & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
                   } else PUSH_CUR(c);
                   if (max_level < 1) max_level = 1;
                 }
@@ -172,8 +173,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
           // address, which equals a treelet's device address only for the root at (host - tlas_delta).
           e = stk[STACK_N - oth_n]; oth_n--; pend = true;
-          if (av.tlas_delta == 0) cur_tid = root_rank(p.tv, e.slot);
-          else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
+          if (av.tlas_delta == 0) {
+            const uint32_t tc = __ldg(p.tv.node_tid + e.slot);
+            cur_tid = (tc & VSRT_TID_SELF_ROOTED) ? (tc & VSRT_TID_MASK) : root_rank(p.tv, e.slot);
+          } else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
         } else if (cur_n == 0) { alive = false; fin = true; }
         else { cur_n--; e = stk[cur_n]; pend = true; }
       }
@@ -201,20 +204,37 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
           if (mask && clevel > max_level) max_level = clevel;
           const uint32_t cmeta = (clevel << 23) | inst;
-          while (mask) {                                   // hit children in slot order (:1810-1869)
-            const int i = __ffs(mask) - 1; mask &= mask - 1u;
-            Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u);
-            const bool leaf = (leafbits >> i) & 1u;
-            c.meta = cmeta | (leaf ? 0x80000000u : 0u);
-            if (MODE == VSRT_MODE_DFS) {
-              if (!leaf && !have_next) { next = c; have_next = true; }   // first hit internal child is followed (:2573)
-              else if (cur_n < STACK_N) PUSH_CUR(c);
-              else err |= EF_STACK;
-            } else {
-              if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-              else if (__ldg(p.tv.node_tid + c.slot) == cur_tid) PUSH_CUR(c);
-              else PUSH_OTH(c);
+          // hit children in slot order (:1810-1869); the node_tid gathers are issued together, ahead of the pushes
+          uint32_t ctid[6];
+          if (MODE == VSRT_MODE_TREELET) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) ctid[i] = ((mask >> i) & 1u) ? __ldg(p.tv.node_tid + child0 + ((offs >> (4 * i)) & 15u)) : 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) {
+            if ((mask >> i) & 1u) {
+              Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u);
+              const bool leaf = (leafbits >> i) & 1u;
+              c.meta = cmeta | (leaf ? 0x80000000u : 0u);
+              if (MODE == VSRT_MODE_DFS) {
+                if (!leaf && !have_next) { next = c; have_next = true; }   // first hit internal child is followed (:2573)
+                else if (cur_n < STACK_N) PUSH_CUR(c);
+                else err |= EF_STACK;
+              } else {
+                if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
+                else if ((ctid[i] & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c);
+                else PUSH_OTH(c);
+              }
             }
+          }
+          // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the
+          // iteration (other phases, refill vote) runs
+          if (p.prefetch) {
+            uint32_t ns = 0xFFFFFFFFu;
+            if (MODE == VSRT_MODE_DFS && have_next) ns = next.slot;
+            else if (cur_n) ns = stk[cur_n - 1].slot;
+            else if (MODE == VSRT_MODE_TREELET && oth_n) ns = stk[STACK_N - oth_n].slot;
+            if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)ns * 64u);
           }
         }
       }
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
           else {
             if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-            else if (__ldg(p.tv.node_tid + broot) == cur_tid) PUSH_CUR(c);
+            else if ((__ldg(p.tv.node_tid + broot) & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c);
             else PUSH_OTH(c);
           }
         }

@@ -168,8 +168,17 @@ __global__ void k_gather(const uint64_t* const* __restrict__ r_list, const uint3
   }
   if (fresh) atomicAdd(n_mapped, (unsigned long long)fresh);
 }
-__global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) { const uint32_t v = node_tid[i]; node_tid[i] = v ? v - 1u : VSRT_NO_TID; }
+// node_tid[slot] = treelet index | VSRT_TID_SELF_ROOTED when the slot is itself the root of that treelet (the common
+// case for a treelet root; it differs only when a shared BLAS puts a root inside a higher-addressed treelet too)
+__global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ prefix) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = node_tid[i];
+  if (!v) { node_tid[i] = VSRT_NO_TID; return; }
+  uint32_t t = v - 1u;
+  const uint32_t w = bits[i >> 5], b = 1u << (i & 31);
+  if ((w & b) && prefix[i >> 5] + __popc(w & (b - 1)) == t) t |= VSRT_TID_SELF_ROOTED;
+  node_tid[i] = t;
 }
 __global__ void k_fill_ptrs(const uint64_t** r_list, uint32_t begin, uint32_t count, uint64_t* pool, uint32_t cap) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t < count) r_list[begin + t] = pool + (uint64_t)t * cap;
@@ -253,7 +262,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   CK(cudaMalloc(&tl_node, (size_t)std::max<unsigned long long>(n_entries, 1) * 8));
   CK(cudaMalloc(&node_tid, (size_t)ns * 4)); CK(cudaMemsetAsync(node_tid, 0, (size_t)ns * 4, st));
   k_gather<<<(n_roots + 127) / 128, 128, 0, st>>>(r_list, r_count, r_rank, n_roots, tl_off, tl_node, node_tid, scal + 1);
-  k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns);
+  k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns, claimed, prefix);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev1, st));
   CK(cudaMemcpyAsync(h_scal, scal, 16, cudaMemcpyDeviceToHost, st));

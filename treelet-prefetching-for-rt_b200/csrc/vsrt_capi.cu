@@ -111,6 +111,7 @@ int ensure_mirrors(vsrt_context* c) {
   const size_t ns = c->arena_bytes / 64, nt = c->fr.n_treelets, ne = c->fr.n_entries;
   c->h_node_tid.resize(ns); c->h_tl_root.resize(nt); c->h_tl_off.resize(nt + 1); c->h_tl_node.resize(ne);
   CUDA_OK(c, cudaMemcpy(c->h_node_tid.data(), c->fo.node_tid, ns * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t& t : c->h_node_tid) if (t != VSRT_NO_TID) t &= VSRT_TID_MASK;
   CUDA_OK(c, cudaMemcpy(c->h_tl_root.data(), c->fo.tl_root, nt * 4, cudaMemcpyDeviceToHost));
   CUDA_OK(c, cudaMemcpy(c->h_tl_off.data(), c->fo.tl_off, (nt + 1) * 8, cudaMemcpyDeviceToHost));
   if (ne) CUDA_OK(c, cudaMemcpy(c->h_tl_node.data(), c->fo.tl_node, ne * 8, cudaMemcpyDeviceToHost));
@@ -164,7 +165,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
-    tp.only_deferred = 0; tp.pad = 0;
+    tp.only_deferred = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
     rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, av.force_exact != 0, st);
     if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -510,6 +511,15 @@ int vsrt_reset_counters(vsrt_context* c) {
   CUDA_OK(c, cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
   c->h_prev = DevCounters{};
   if (c->hist_n) CUDA_OK(c, cudaMemset(c->d_hist.p, 0, (size_t)c->hist_n * 8));
+  return VSRT_OK;
+}
+int vsrt_get_treelet_histogram(vsrt_context* c, uint64_t* hist, uint64_t capacity) {
+  if (!c || !hist) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  if (capacity < c->hist_n) return fail(c, VSRT_E_CAPACITY, "histogram needs %u entries", c->hist_n);
+  cudaSetDevice(c->device);
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  CUDA_OK(c, cudaMemcpy(hist, c->d_hist.p, (size_t)c->hist_n * 8, cudaMemcpyDeviceToHost));
   return VSRT_OK;
 }
 int vsrt_counters_device(vsrt_context* c, void** counters_dev, void** hist_dev, uint64_t* n_treelets) {

@@ -4,7 +4,8 @@
 //   arena        every registered AS buffer, merged into disjoint host spans, packed back to back in ascending
 //                host-address order.  A node is named by its 64-byte SLOT index in the packed arena (u32).
 //   node_tid     u32 per slot: index (ascending-root-address rank == the reference's treelet_addr_to_metadata_idx)
-//                of the treelet that owns the node, i.e. addrToTreeletID as an index.  NO_TID for non-nodes.
+//                of the treelet that owns the node, i.e. addrToTreeletID as an index, | bit 31 when the slot is that
+//                treelet's own root.  NO_TID for non-nodes.
 //   root bitmap  1 bit per slot (is the slot a treelet root) + per-word exclusive popcount prefix -> rank(slot).
 //   treelet CSR  tl_root[t] (slot), tl_off[t], tl_node[k] (slot | kind in the top bits of a u64).
 //   staging      per ray `cap` compact trace records  (slot << 3) | code, written by the traversal kernel.
@@ -15,6 +16,8 @@
 #include "vsrt.h"
 
 #define VSRT_NO_TID 0xFFFFFFFFu
+#define VSRT_TID_SELF_ROOTED 0x80000000u   // flag in node_tid[]: the slot is the root of the treelet it is mapped to
+#define VSRT_TID_MASK 0x7FFFFFFFu
 #define VSRT_NO_INST 0x7FFFFFFFu
 #define VSRT_MAX_SPANS_INLINE 8
 
@@ -92,7 +95,7 @@ struct TraverseParams {
   uint32_t refill_t;              // refill a warp when at least this many lanes are idle
   uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
   uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
-  uint32_t pad;
+  uint32_t prefetch;              // issue an L1 prefetch for the node a lane will pop next
 };
 int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
 

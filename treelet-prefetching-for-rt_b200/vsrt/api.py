@@ -27,7 +27,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
-           "vsrt_counters_device"]
+           "vsrt_counters_device", "vsrt_get_treelet_histogram"]
 
 
 class VsrtError(RuntimeError):
@@ -70,6 +70,7 @@ def load():
     L.vsrt_get_counters.argtypes = [c_vp, c_vp]
     L.vsrt_reset_counters.argtypes = [c_vp]
     L.vsrt_counters_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
+    L.vsrt_get_treelet_histogram.argtypes = [c_vp, c_vp, c_u64]
     _lib = L
     return L
 
@@ -239,6 +240,12 @@ class Context:
 
     def reset_counters(self):
         self._ck(self.L.vsrt_reset_counters(self.h))
+
+    def treelet_histogram(self):
+        n = self.treelet_info().n_treelets
+        h = np.zeros(n, np.uint64)
+        self._ck(self.L.vsrt_get_treelet_histogram(self.h, _abi.ptr(h), n))
+        return h
 
     def counters_device(self):
         cp, hp, n = c_vp(), c_vp(), c_u64()

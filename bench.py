@@ -104,8 +104,9 @@ def build_scene_and_rays(n_gpus, rank, flags=0):
     from vsrt import scene as sc
     t0 = time.time()
     s = sc.Scene(N_TRI, seed=SCENE_SEED)
-    per = WIDTH * HEIGHT
-    rays = sc.rays_primary(WIDTH, HEIGHT, spp=n_gpus, seed=SCENE_SEED, flags=flags, first=rank * per, count=per)
+    from vsrt import shard
+    first, count = shard.shard_range(WIDTH * HEIGHT * n_gpus, n_gpus, rank)     # contiguous ray-id block of this rank
+    rays = sc.rays_primary(WIDTH, HEIGHT, spp=n_gpus, seed=SCENE_SEED, flags=flags, first=first, count=count)
     return s, rays, time.time() - t0
 
 
@@ -205,7 +206,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
-    from vsrt import _abi
+    from vsrt import _abi, shard
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,8 +245,7 @@ def run_cuda(args):
                 # the path's only exchange: per-frame reduce of counters + treelet visit histogram.
                 # Reduced into scratch copies so the per-rank counters keep their own totals.
                 s2, m2, h2 = reduce_bufs[0].clone(), reduce_bufs[1].clone(), reduce_bufs[2].clone()
-                dist.all_reduce(s2, op=dist.ReduceOp.SUM); dist.all_reduce(m2, op=dist.ReduceOp.MAX); dist.all_reduce(h2, op=dist.ReduceOp.SUM)
-                return s2, m2, h2
+                return shard.reduce_counters(dist, s2, m2, h2)
         return None
 
     for _ in range(args.warmup):

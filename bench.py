@@ -63,10 +63,18 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        """Start of the timed region: only samples written after this point are used (if there are any)."""
+        try:
+            self.f.flush()
+            self.skip = len(open(self.f.name).read().splitlines())
+        except Exception:
+            self.skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -79,7 +87,11 @@ class ClockSampler:
             self.p.kill()
         self.f.flush(); self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        lines = self.f.read().splitlines()
+        skip = getattr(self, "skip", 0)
+        if len(lines) - skip >= 2:
+            lines = lines[skip:]
+        for line in lines:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
@@ -238,23 +250,34 @@ def run_cuda(args):
         hist = torch.as_tensor(_DevArray(hptr, 8 * nt), device=dev).view(torch.int64)
         reduce_bufs = (csum, cmax, hist)
 
+    red_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    red_state = {"done": None, "out": None}
+
     def step():
         with torch.cuda.stream(stream):
             ctx.trace_device(MODE, rays_dev.data_ptr(), n, stream.cuda_stream)
             if reduce_bufs is not None:
-                # the path's only exchange: per-frame reduce of counters + treelet visit histogram.
-                # Reduced into scratch copies so the per-rank counters keep their own totals.
+                # the path's only exchange: per-frame reduce of counters + treelet visit histogram, into
+                # scratch copies (the per-rank counters keep their own totals).  It runs on a side stream so that the
+                # reduce of frame i overlaps the traversal of frame i+1; frame i+1's reduce waits for it.
                 s2, m2, h2 = reduce_bufs[0].clone(), reduce_bufs[1].clone(), reduce_bufs[2].clone()
-                return shard.reduce_counters(dist, s2, m2, h2)
-        return None
+                ready = torch.cuda.Event(); ready.record(stream)
+                with torch.cuda.stream(red_stream):
+                    red_stream.wait_event(ready)
+                    shard.reduce_counters(dist, s2, m2, h2)
+                    red_state["done"] = torch.cuda.Event(); red_state["done"].record(red_stream)
+                red_state["out"] = (s2, m2, h2)
+        return red_state["out"]
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~100 ms to come up
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     trav_ms = scan_ms = comp_ms = 0.0
     launches = 0
@@ -265,6 +288,8 @@ def run_cuda(args):
             ev[i][0].record(stream)
         reduced = step()
         with torch.cuda.stream(stream):
+            if i == args.steps - 1 and red_state["done"] is not None:
+                stream.wait_event(red_state["done"])   # the last frame's reduce is inside the timed region
             ev[i][1].record(stream)
         r = ctx.device_results()
         trav_ms += r.traverse_ms; scan_ms += r.scan_ms; comp_ms += r.compact_ms; launches += r.kernel_launches
@@ -365,7 +390,7 @@ def res_stage_bytes(ctx):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)

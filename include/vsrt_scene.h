@@ -48,8 +48,8 @@ const float* vsrt_scene_triangles(const vsrt_scene* s, uint64_t* n);
  * VSRT_E_BAD_BVH and writes a message. */
 int vsrt_arena_validate(const uint8_t* arena, uint64_t size, uint64_t tlas_offset, char* msg, uint32_t msg_cap);
 
-/* Pinhole camera at (0,0,3.5) looking down -z, vfov 45 deg, pixel centres (+ hashed stratified jitter when
- * spp > 1).  Rays [first, first+count) of the frame in x-fastest, then sample, then y order. */
+/* Pinhole camera at (0,0,3.5) looking down -z, vfov 45 deg.  Ray id = sample*(W*H) + y*W + x; sample 0 goes through
+ * the pixel centres, the others are jittered (hash of the ray id).  Writes rays [first, first+count). */
 void vsrt_rays_primary(uint32_t width, uint32_t height, uint32_t spp, uint64_t seed, uint32_t ray_flags,
                        uint64_t first, uint64_t count, vsrt_ray* out);
 /* Diffuse bounce: for every ray i that hit, a cosine-weighted direction about the geometric normal of the hit

@@ -442,9 +442,11 @@ extern "C" void vsrt_rays_primary(uint32_t W, uint32_t H, uint32_t spp, uint64_t
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < (int64_t)count; k++) {
     uint64_t id = first + (uint64_t)k;
-    uint32_t x = (uint32_t)(id % W); uint64_t r = id / W; uint32_t sm = (uint32_t)(r % spp); uint32_t y = (uint32_t)(r / spp);
+    // ray id = sample * (W*H) + y * W + x: a contiguous block of W*H ids is one full frame of one sample, so ranks
+    // that take consecutive blocks get statistically identical work
+    uint32_t x = (uint32_t)(id % W); uint64_t r = id / W; uint32_t y = (uint32_t)(r % H); uint32_t sm = (uint32_t)(r / H);
     float jx = 0.5f, jy = 0.5f;
-    if (spp > 1) { jx = u01(seed, id, 0); jy = u01(seed, id, 1); }
+    if (sm > 0) { jx = u01(seed, id, 0); jy = u01(seed, id, 1); }   // sample 0 = pixel centres, the others jittered
     float px = (((float)x + jx) / (float)W * 2.0f - 1.0f) * tan_half * aspect;
     float py = (1.0f - ((float)y + jy) / (float)H * 2.0f) * tan_half;
     float d[3] = { px, py, -1.0f }; float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);

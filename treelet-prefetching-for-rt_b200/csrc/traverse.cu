@@ -40,7 +40,7 @@ VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 constexpr int THREADS = 128;
 VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_MIN_BLOCKS
-#define VSRT_K1_MIN_BLOCKS 6
+#define VSRT_K1_MIN_BLOCKS 7
 #endif
 enum { KIND_NONE = 0, KIND_INT = 1, KIND_INST = 2, KIND_LEAF = 3 };
 
@@ -59,31 +59,37 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   const int REFILL_T = (int)p.refill_t, LEAF_T = (int)p.leaf_t;
   const bool only_deferred = EXACT && p.only_deferred != 0;
 
-  // ---- per-lane accumulators of the functional counters (cuda-sim.h:155-166)
-  uint32_t sum_nodes = 0, max_nodes = 0, max_level = 0, n_hit = 0, n_any = 0, n_term = 0, n_rays_done = 0, err = 0;
+  // ---- functional counters (cuda-sim.h:155-166): per-CTA accumulators in shared memory, touched only when a ray is
+  // finalised (keeps them out of the register file of the hot loop)
+  __shared__ unsigned int s_cnt[8];   // 0 sum_nodes 1 max_nodes 2 max_level 3 n_hit 4 n_any 5 n_term 6 n_rays_done 7 err
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t max_level = 0, err = 0;
 
   // ---- per-lane ray state
   Entry stk[STACK_N];
   bool alive = false, fin = false, pend = false, exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
-  uint64_t r = 0;
-  Ray8 w; w.ox = w.oy = w.oz = w.dx = w.dy = w.dz = w.tmin = w.tmax = 0.0f;
-  ActiveRay a; a.ray = w; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
+  uint32_t r = 0;
+  float w_tmin = 0.0f, w_tmax = 0.0f;   // the world ray's origin/direction are re-read from p.rays[r] when needed
+  ActiveRay a; a.ray.ox = a.ray.oy = a.ray.oz = a.ray.dx = a.ray.dy = a.ray.dz = a.ray.tmin = a.ray.tmax = 0.0f; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
   uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0, cur_tid = VSRT_NO_TID;
   int cur_n = 0, oth_n = 0;
   bool have_next = false; Entry next; next.slot = 0; next.meta = 0;
   float min_thit = 0.0f, min_thit_object = 0.0f;
   uint32_t closest_leaf = 0, closest_inst = INST_NONE;
-  uint32_t* __restrict__ out = p.stage;
   const uint32_t cap = p.cap;
 
-#define EMIT(slot_, code_) do { if (cnt < cap) out[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
+#define EMIT(slot_, code_) do { if (cnt < cap) p.stage[(uint64_t)r * cap + cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
 #define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
 #define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
   // switch the active ray to context `inst_` (INST_NONE = world)
-#define ACTIVATE(inst_) do { const uint32_t i_ = (inst_); if (a.inst != i_) { a.inst = i_; \
-      if (i_ == INST_NONE) { a.ray = w; a.idir = calc_idir(w); a.tmult = 1.0f; a.nonfinite = false; } \
-      else { InstCtx c_; make_object_ray(base, inst_base + i_, w, c_); a.ray = c_.ray; a.idir = c_.idir; a.tmult = c_.tmult; a.nonfinite = c_.exact; } } } while (0)
+#define LOAD_WORLD(w_) do { const vsrt_ray* rp_ = p.rays + r; \
+      (w_).ox = __ldg(&rp_->origin[0]); (w_).oy = __ldg(&rp_->origin[1]); (w_).oz = __ldg(&rp_->origin[2]); (w_).tmin = w_tmin; \
+      (w_).dx = __ldg(&rp_->direction[0]); (w_).dy = __ldg(&rp_->direction[1]); (w_).dz = __ldg(&rp_->direction[2]); (w_).tmax = w_tmax; } while (0)
+#define ACTIVATE(inst_) do { const uint32_t i_ = (inst_); if (a.inst != i_) { a.inst = i_; Ray8 w_; LOAD_WORLD(w_); \
+      if (i_ == INST_NONE) { a.ray = w_; a.idir = calc_idir(w_); a.tmult = 1.0f; a.nonfinite = false; } \
+      else { InstCtx c_; make_object_ray(base, inst_base + i_, w_, c_); a.ray = c_.ray; a.idir = c_.idir; a.tmult = c_.tmult; a.nonfinite = c_.exact; } } } while (0)
 
   while (true) {
     // ================= refill: finalize finished rays, fetch new ones
@@ -99,8 +105,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
         h.intersection_point[0] = h.intersection_point[1] = h.intersection_point[2] = 0.0f;
         h.n_all_hits = ray_any; h.instance_leaf_address = 0;
-        if (min_thit < w.tmax) {
-          n_hit++;
+        if (min_thit < w_tmax) {
+          atomicAdd(&s_cnt[3], 1u);
+          Ray8 w; LOAD_WORLD(w);
           const Node64 q = load_node(base, closest_leaf);
           ACTIVATE(closest_inst);
           const uint32_t ci = inst_base + closest_inst;
@@ -115,10 +122,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           h.instance_leaf_address = slot_to_host(av, ci);
         }
         p.hits[r] = h;
-        sum_nodes += ray_nodes; if (ray_nodes > max_nodes) max_nodes = ray_nodes;
-        n_any += ray_any;
-        if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) n_term++;
-        n_rays_done++;
+        atomicAdd(&s_cnt[0], ray_nodes); atomicMax(&s_cnt[1], ray_nodes);
+        if (ray_any) atomicAdd(&s_cnt[4], ray_any);
+        if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) atomicAdd(&s_cnt[5], 1u);
+        atomicAdd(&s_cnt[6], 1u);
       }
       if (!exhausted) {
         const int n_idle = __popc(idle);
@@ -130,18 +137,20 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
           if (nr < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
             // ---- start ray nr (:1650-1741 / :2411-2484)
-            r = nr; pend = false; have_next = false;
+            r = (uint32_t)nr; pend = false; have_next = false;
             const vsrt_ray* rp = p.rays + r;
+            Ray8 w;
             w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
             w.dx = __ldg(&rp->direction[0]); w.dy = __ldg(&rp->direction[1]); w.dz = __ldg(&rp->direction[2]); w.tmax = __ldg(&rp->tmax);
             flags = __ldg(&rp->ray_flags);
             if (!EXACT && ray_needs_exact(w)) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; }   // left to the EXACT pass
             else {
               alive = true;
+              w_tmin = w.tmin; w_tmax = w.tmax;
               a.inst = INST_NONE; a.ray = w; a.idir = calc_idir(w); a.tmult = 1.0f; a.nonfinite = false;
-              out = p.stage + r * (uint64_t)cap; cnt = 0; ray_nodes = 0; ray_any = 0;
+              cnt = 0; ray_nodes = 0; ray_any = 0;
               cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID;
-              min_thit = w.tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE;   // :1671
+              min_thit = w_tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE;   // :1671
               EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
               uint32_t top_root = 0;
               if (!header_root(av, av.tlas_slot, top_root)) err |= EF_BAD_BVH;
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           float thit = 0.0f;
           const bool hit = ray_tri(q, a.ray, thit);
           const float tw = fdiv(thit, a.tmult);
-          bool acc = hit && w.tmin <= tw && tw <= w.tmax;                         // :2843
+          bool acc = hit && w_tmin <= tw && tw <= w_tmax;                         // :2843
           if (MODE == VSRT_MODE_TREELET) acc = acc && tw < min_thit;              // :2127
           if (acc) {
             if (MODE == VSRT_MODE_TREELET) min_thit = tw;
@@ -296,13 +305,15 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #undef PUSH_CUR
 #undef PUSH_OTH
 #undef ACTIVATE
+#undef LOAD_WORLD
 
-  // ---- functional counters: warp-reduce, one atomic per warp
-  const uint32_t s_nodes = __reduce_add_sync(full, sum_nodes), s_hit = __reduce_add_sync(full, n_hit);
-  const uint32_t s_any = __reduce_add_sync(full, n_any), s_term = __reduce_add_sync(full, n_term), s_act = __reduce_add_sync(full, n_rays_done);
-  const uint32_t m_nodes = __reduce_max_sync(full, max_nodes), m_lvl = __reduce_max_sync(full, max_level), e_all = __reduce_or_sync(full, err);
-  if (lane == 0) {
+  // ---- functional counters: one set of atomics per CTA
+  atomicMax(&s_cnt[2], max_level);
+  if (err) atomicOr(&s_cnt[7], err);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     unsigned long long* c = p.counters->v;
+    const unsigned int s_nodes = s_cnt[0], m_nodes = s_cnt[1], m_lvl = s_cnt[2], s_hit = s_cnt[3], s_any = s_cnt[4], s_term = s_cnt[5], s_act = s_cnt[6], e_all = s_cnt[7];
     if (s_nodes) atomicAdd(c + CI_TOT_NODES, (unsigned long long)s_nodes);
     if (s_hit) atomicAdd(c + CI_NUM_HITS, (unsigned long long)s_hit);
     if (s_any) atomicAdd(c + CI_NUM_ANY_HITS, (unsigned long long)s_any);

@@ -150,6 +150,7 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
 // K1 -> scan -> K3 over rays already resident at d_rays
 int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st) {
   if (mode != VSRT_MODE_DFS && mode != VSRT_MODE_TREELET) return fail(c, VSRT_E_INVALID, "mode must be VSRT_MODE_DFS or VSRT_MODE_TREELET");
+  if (n >= (1ull << 32) - 1) return fail(c, VSRT_E_INVALID, "a batch holds at most 2^32-2 rays; split the frame");
   int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;   // lazily, like :1593 / :2364
   if (c->cfg.remap_to_treelet_layout) return fail(c, VSRT_E_UNSUPPORTED, "remap_to_treelet_layout in traces is not built yet (vsrt_treelet_remap gives the table)");
   ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;

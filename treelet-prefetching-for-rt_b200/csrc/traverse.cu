@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   ActiveRay a; a.ray.ox = a.ray.oy = a.ray.oz = a.ray.dx = a.ray.dy = a.ray.dz = a.ray.tmin = a.ray.tmax = 0.0f; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
   uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0, cur_tid = VSRT_NO_TID;
   int cur_n = 0, oth_n = 0;
+  bool in_cur = false;   // TREELET: the popped node is known to belong to the current treelet (node_tid == cur_tid)
   bool have_next = false; Entry next; next.slot = 0; next.meta = 0;
   float min_thit = 0.0f, min_thit_object = 0.0f;
   uint32_t closest_leaf = 0, closest_inst = INST_NONE;
@@ -184,10 +185,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           e = stk[STACK_N - oth_n]; oth_n--; pend = true;
           if (av.tlas_delta == 0) {
             const uint32_t tc = __ldg(p.tv.node_tid + e.slot);
-            cur_tid = (tc & VSRT_TID_SELF_ROOTED) ? (tc & VSRT_TID_MASK) : root_rank(p.tv, e.slot);
-          } else { uint32_t s2; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
+            in_cur = (tc & VSRT_TID_SELF_ROOTED) != 0u;
+            cur_tid = in_cur ? (tc & VSRT_TID_MASK) : root_rank(p.tv, e.slot);
+          } else { uint32_t s2; in_cur = false; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
         } else if (cur_n == 0) { alive = false; fin = true; }
-        else { cur_n--; e = stk[cur_n]; pend = true; }
+        else { cur_n--; e = stk[cur_n]; pend = true; in_cur = true; }   // entries of `current` were pushed because node_tid == cur_tid
       }
     }
     const int kind = !pend ? KIND_NONE : (!e_leaf(e) ? KIND_INT : (e_top(e) ? KIND_INST : KIND_LEAF));
@@ -213,27 +215,49 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
           if (mask && clevel > max_level) max_level = clevel;
           const uint32_t cmeta = (clevel << 23) | inst;
-          // hit children in slot order (:1810-1869); the node_tid gathers are issued together, ahead of the pushes
-          uint32_t ctid[6];
+          // hit children in slot order (:1810-1869), pushed without branches: every child computes its stack position and
+          // stores under a predicate
           if (MODE == VSRT_MODE_TREELET) {
+            // which children belong to the CURRENT treelet (:1832): K0 left "child i is in this node's treelet" in the
+            // node's pad byte (+17), valid whenever the node itself is in the current treelet; otherwise (a node taken from
+            // `other` that is not the root of its treelet, or the host/device offset quirk) look the children up
+            uint32_t mc = node_byte(n, 17);
+            if (!in_cur) {
+              mc = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) ctid[i] = ((mask >> i) & 1u) ? __ldg(p.tv.node_tid + child0 + ((offs >> (4 * i)) & 15u)) : 0u;
-          }
+              for (int i = 0; i < 6; i++)
+                if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + ((offs >> (4 * i)) & 15u)) & VSRT_TID_MASK) == cur_tid) mc |= 1u << i; }
+            }
+            const uint32_t mcur = mask & mc, moth = mask & ~mc;
+            if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
+            else {
+              int pc = cur_n, po = STACK_N - 1 - oth_n;
 #pragma unroll
-          for (int i = 0; i < 6; i++) {
-            if ((mask >> i) & 1u) {
-              Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u);
-              const bool leaf = (leafbits >> i) & 1u;
-              c.meta = cmeta | (leaf ? 0x80000000u : 0u);
-              if (MODE == VSRT_MODE_DFS) {
-                if (!leaf && !have_next) { next = c; have_next = true; }   // first hit internal child is followed (:2573)
-                else if (cur_n < STACK_N) PUSH_CUR(c);
-                else err |= EF_STACK;
-              } else {
-                if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-                else if ((ctid[i] & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c);
-                else PUSH_OTH(c);
+              for (int i = 0; i < 6; i++) {
+                Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u); c.meta = cmeta | (((leafbits >> i) & 1u) << 31);
+                const int bc = (int)((mcur >> i) & 1u), bo = (int)((moth >> i) & 1u);
+                if (bc | bo) stk[bc ? pc : po] = c;
+                pc += bc; po -= bo;
               }
+              cur_n = pc; oth_n = STACK_N - 1 - po;
+            }
+          } else {
+            // the first hit internal child is followed (:2573); every other hit child is pushed in slot order
+            const uint32_t mint = mask & ~leafbits;
+            const uint32_t nx = mint & (0u - mint);          // lowest set bit, 0 if none
+            const uint32_t mpush = mask & ~nx;
+            if (cur_n + __popc(mpush) > STACK_N) err |= EF_STACK;
+            else {
+              int pc = cur_n;
+#pragma unroll
+              for (int i = 0; i < 6; i++) {
+                Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u); c.meta = cmeta | (((leafbits >> i) & 1u) << 31);
+                if ((nx >> i) & 1u) { next = c; have_next = true; }
+                const int b = (int)((mpush >> i) & 1u);
+                if (b) stk[pc] = c;
+                pc += b;
+              }
+              cur_n = pc;
             }
           }
           // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the

@@ -82,6 +82,16 @@ VS_DEV bool ray_box_fast(float lox, float loy, float loz, float hix, float hiy, 
   return mn <= mx;
 }
 
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per issued instruction,
+// each half bit-identical to the scalar __fadd_rn / __fmul_rn / __fmaf_rn (no FTZ, no contraction).
+VS_DEV uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+VS_DEV void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+VS_DEV uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+VS_DEV uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+VS_DEV uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// 2^23 + byte i of the node as a float (the PRMT half of byte_to_float)
+VS_DEV float byte_magic(const Node64& n, int i) { return __uint_as_float(__byte_perm(n.w[i >> 2], 0x4B000000u, 0x7540u | (uint32_t)(i & 3))); }
+
 // Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
 // `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
 // EXACT = true keeps the reference's ternary MIN/MAX (NaN picks the second operand); it is taken for rays or
@@ -92,14 +102,38 @@ VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, fl
   const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
   const float sx = node_scale(n, 18), sy = node_scale(n, 19), sz = node_scale(n, 20);
   uint32_t mask = 0;
+  if (EXACT) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const float lox = dequant(n, 28 + i, sx, ox), hix = dequant(n, 34 + i, sx, ox);
-    const float loy = dequant(n, 40 + i, sy, oy), hiy = dequant(n, 46 + i, sy, oy);
-    const float loz = dequant(n, 52 + i, sz, oz), hiz = dequant(n, 58 + i, sz, oz);
-    float th;
-    const bool h = EXACT ? ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th) : ray_box_fast(lox, loy, loz, hix, hiy, hiz, id, r, th);
-    mask |= (h && !(th >= cull) && (node_byte(n, 22 + i) & 3u) != 0u) ? (1u << i) : 0u;
+    for (int i = 0; i < 6; i++) {
+      const float lox = dequant(n, 28 + i, sx, ox), hix = dequant(n, 34 + i, sx, ox);
+      const float loy = dequant(n, 40 + i, sy, oy), hiy = dequant(n, 46 + i, sy, oy);
+      const float loz = dequant(n, 52 + i, sz, oz), hiz = dequant(n, 58 + i, sz, oz);
+      float th;
+      const bool h = ray_box(lox, loy, loz, hix, hiy, hiz, id, r, th);
+      mask |= (h && !(th >= cull) && (node_byte(n, 22 + i) & 3u) != 0u) ? (1u << i) : 0u;
+    }
+  } else {
+    // Same operations in the same order as ray_box_fast(dequant(..)), issued as packed pairs: (lo.x, lo.y), (hi.x, hi.y),
+    // (lo.z, hi.z).  a - b is written a + (-b), which is the same IEEE operation.
+    const uint64_t magic = pk2(-8388608.0f, -8388608.0f);
+    const uint64_t s_xy = pk2(sx, sy), s_zz = pk2(sz, sz), o_xy = pk2(ox, oy), o_zz = pk2(oz, oz);
+    const uint64_t nr_xy = pk2(-r.ox, -r.oy), nr_zz = pk2(-r.oz, -r.oz), id_xy = pk2(id.x, id.y), id_zz = pk2(id.z, id.z);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const uint64_t a = mul2(add2(fma2(add2(pk2(byte_magic(n, 28 + i), byte_magic(n, 40 + i)), magic), s_xy, o_xy), nr_xy), id_xy);
+      const uint64_t b = mul2(add2(fma2(add2(pk2(byte_magic(n, 34 + i), byte_magic(n, 46 + i)), magic), s_xy, o_xy), nr_xy), id_xy);
+      const uint64_t c = mul2(add2(fma2(add2(pk2(byte_magic(n, 52 + i), byte_magic(n, 58 + i)), magic), s_zz, o_zz), nr_zz), id_zz);
+      float lx, ly, hx, hy, lz, hz;
+      upk2(a, lx, ly); upk2(b, hx, hy); upk2(c, lz, hz);
+      const float mn = fmaxf(fminf(lz, hz), fmaxf(fminf(ly, hy), fmaxf(fminf(lx, hx), r.tmin)));
+      const float mx = fminf(fmaxf(lz, hz), fminf(fmaxf(ly, hy), fminf(fmaxf(lx, hx), r.tmax)));
+      mask |= (mn <= mx && !(mn >= cull)) ? (1u << i) : 0u;
+    }
+    // empty slots (ChildSize == 0) never hit
+    const uint32_t i0 = n.w[5] >> 16, i1 = n.w[6];   // bytes 22,23 | 24..27
+    const uint32_t present = ((i0 & 0x3u) ? 1u : 0u) | ((i0 & 0x300u) ? 2u : 0u) | ((i1 & 0x3u) ? 4u : 0u) | ((i1 & 0x300u) ? 8u : 0u) |
+                             ((i1 & 0x30000u) ? 16u : 0u) | ((i1 & 0x3000000u) ? 32u : 0u);
+    mask &= present;
   }
   return mask;
 }

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   bool alive = false, fin = false, pend = false, exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
   uint32_t r = 0;
+  uint32_t* rstage = p.stage;            // staging segment of ray r
   float w_tmin = 0.0f, w_tmax = 0.0f;   // the world ray's origin/direction are re-read from p.rays[r] when needed
   ActiveRay a; a.ray.ox = a.ray.oy = a.ray.oz = a.ray.dx = a.ray.dy = a.ray.dz = a.ray.tmin = a.ray.tmax = 0.0f; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
   uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0, cur_tid = VSRT_NO_TID;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   uint32_t closest_leaf = 0, closest_inst = INST_NONE;
   const uint32_t cap = p.cap;
 
-#define EMIT(slot_, code_) do { if (cnt < cap) p.stage[(uint64_t)r * cap + cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
+#define EMIT(slot_, code_) do { if (cnt < cap) rstage[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
 #define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
 #define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
   // switch the active ray to context `inst_` (INST_NONE = world)
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
           if (nr < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
             // ---- start ray nr (:1650-1741 / :2411-2484)
-            r = (uint32_t)nr; pend = false; have_next = false;
+            r = (uint32_t)nr; rstage = p.stage + nr * cap; pend = false; have_next = false;
             const vsrt_ray* rp = p.rays + r;
             Ray8 w;
             w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
@@ -205,12 +206,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         ACTIVATE(inst);
         if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; alive = false; }   // degenerate instance transform
         else {
-          uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult));   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
+          uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic23);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
           // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868); sizes are 0..3 -> 4-bit prefix fields
-          const uint32_t i0 = node_child_info(n, 0), i1 = node_child_info(n, 1), i2 = node_child_info(n, 2), i3 = node_child_info(n, 3), i4 = node_child_info(n, 4), i5 = node_child_info(n, 5);
-          const uint32_t p1 = i0 & 3u, p2 = p1 + (i1 & 3u), p3 = p2 + (i2 & 3u), p4 = p3 + (i3 & 3u), p5 = p4 + (i4 & 3u);
-          const uint32_t offs = (p1 << 4) | (p2 << 8) | (p3 << 12) | (p4 << 16) | (p5 << 20);
-          const uint32_t leafbits = ((i0 >> 2) ? 1u : 0u) | ((i1 >> 2) ? 2u : 0u) | ((i2 >> 2) ? 4u : 0u) | ((i3 >> 2) ? 8u : 0u) | ((i4 >> 2) ? 16u : 0u) | ((i5 >> 2) ? 32u : 0u);
+          // the six info bytes (22..27) handled as packed bytes: inclusive prefix sums of the sizes by one multiply, "type != 0"
+          // (leaf) as bit 7 of each byte
+          const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;
+          const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;
+          const uint32_t lf4 = ((lo4 & 0x3c3c3c3cu) + 0x7f7f7f7fu) & 0x80808080u, lf2 = ((hi2 & 0x3c3cu) + 0x7f7fu) & 0x8080u;
+          uint32_t coff[6], clf[6];
+          coff[0] = 0u; coff[1] = pre4 & 0xffu; coff[2] = (pre4 >> 8) & 0xffu; coff[3] = (pre4 >> 16) & 0xffu; coff[4] = pre4 >> 24; coff[5] = coff[4] + (hi2 & 3u);
+          clf[0] = (lf4 << 24) & 0x80000000u; clf[1] = (lf4 << 16) & 0x80000000u; clf[2] = (lf4 << 8) & 0x80000000u; clf[3] = lf4 & 0x80000000u;
+          clf[4] = (lf2 << 24) & 0x80000000u; clf[5] = (lf2 << 16) & 0x80000000u;
           const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
           const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
           if (mask && clevel > max_level) max_level = clevel;
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               mc = 0;
 #pragma unroll
               for (int i = 0; i < 6; i++)
-                if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + ((offs >> (4 * i)) & 15u)) & VSRT_TID_MASK) == cur_tid) mc |= 1u << i; }
+                if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + coff[i]) & VSRT_TID_MASK) == cur_tid) mc |= 1u << i; }
             }
             const uint32_t mcur = mask & mc, moth = mask & ~mc;
             if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               int pc = cur_n, po = STACK_N - 1 - oth_n;
 #pragma unroll
               for (int i = 0; i < 6; i++) {
-                Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u); c.meta = cmeta | (((leafbits >> i) & 1u) << 31);
+                Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
                 const int bc = (int)((mcur >> i) & 1u), bo = (int)((moth >> i) & 1u);
                 if (bc | bo) stk[bc ? pc : po] = c;
                 pc += bc; po -= bo;
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             }
           } else {
             // the first hit internal child is followed (:2573); every other hit child is pushed in slot order
+            const uint32_t leafbits = ((((lf4 >> 7) * 0x00204081u) >> 21) & 15u) | ((((lf2 >> 7) * 0x00204081u) >> 17) & 0x30u);
             const uint32_t mint = mask & ~leafbits;
             const uint32_t nx = mint & (0u - mint);          // lowest set bit, 0 if none
             const uint32_t mpush = mask & ~nx;
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               int pc = cur_n;
 #pragma unroll
               for (int i = 0; i < 6; i++) {
-                Entry c; c.slot = child0 + ((offs >> (4 * i)) & 15u); c.meta = cmeta | (((leafbits >> i) & 1u) << 31);
+                Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
                 if ((nx >> i) & 1u) { next = c; have_next = true; }
                 const int b = (int)((mpush >> i) & 1u);
                 if (b) stk[pc] = c;

@@ -89,8 +89,18 @@ VS_DEV void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;"
 VS_DEV uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 VS_DEV uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 VS_DEV uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// 2^23 + byte i of the node as a float (the PRMT half of byte_to_float)
-VS_DEV float byte_magic(const Node64& n, int i) { return __uint_as_float(__byte_perm(n.w[i >> 2], 0x4B000000u, 0x7540u | (uint32_t)(i & 3))); }
+// 2^23 + byte i of the node as a float (the PRMT half of byte_to_float).  `magic` = 0x4B000000 held in a register so the
+// byte selector can be the instruction's immediate (one PRMT, no selector MOV).
+VS_DEV float byte_magic(const Node64& n, int i, uint32_t magic) {
+  uint32_t d;
+  switch (i & 3) {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7540;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7541;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7542;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7543;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
+  }
+  return __uint_as_float(d);
+}
 
 // Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
 // `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
@@ -98,9 +108,12 @@ VS_DEV float byte_magic(const Node64& n, int i) { return __uint_as_float(__byte_
 // arenas with non-finite coordinates, where a NaN can reach the slab test.  Straight-line code: all six slots are
 // evaluated and empty slots (ChildSize == 0) are masked out at the end.
 template <bool EXACT>
-VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull) {
+VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull, uint32_t magic23) {
   const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
-  const float sx = node_scale(n, 18), sy = node_scale(n, 19), sz = node_scale(n, 20);
+  // 2^(e-8) per axis; exponents below -126 (denormal scales, no sane BVH) take the general path
+  const int kx = (int)(int8_t)node_byte(n, 18) - 8, ky = (int)(int8_t)node_byte(n, 19) - 8, kz = (int)(int8_t)node_byte(n, 20) - 8;
+  float sx = __uint_as_float((uint32_t)(kx + 127) << 23), sy = __uint_as_float((uint32_t)(ky + 127) << 23), sz = __uint_as_float((uint32_t)(kz + 127) << 23);
+  if (min(kx, min(ky, kz)) < -126) { sx = node_scale(n, 18); sy = node_scale(n, 19); sz = node_scale(n, 20); }
   uint32_t mask = 0;
   if (EXACT) {
 #pragma unroll
@@ -120,19 +133,19 @@ VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, fl
     const uint64_t nr_xy = pk2(-r.ox, -r.oy), nr_zz = pk2(-r.oz, -r.oz), id_xy = pk2(id.x, id.y), id_zz = pk2(id.z, id.z);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      const uint64_t a = mul2(add2(fma2(add2(pk2(byte_magic(n, 28 + i), byte_magic(n, 40 + i)), magic), s_xy, o_xy), nr_xy), id_xy);
-      const uint64_t b = mul2(add2(fma2(add2(pk2(byte_magic(n, 34 + i), byte_magic(n, 46 + i)), magic), s_xy, o_xy), nr_xy), id_xy);
-      const uint64_t c = mul2(add2(fma2(add2(pk2(byte_magic(n, 52 + i), byte_magic(n, 58 + i)), magic), s_zz, o_zz), nr_zz), id_zz);
+      const uint64_t a = mul2(add2(fma2(add2(pk2(byte_magic(n, 28 + i, magic23), byte_magic(n, 40 + i, magic23)), magic), s_xy, o_xy), nr_xy), id_xy);
+      const uint64_t b = mul2(add2(fma2(add2(pk2(byte_magic(n, 34 + i, magic23), byte_magic(n, 46 + i, magic23)), magic), s_xy, o_xy), nr_xy), id_xy);
+      const uint64_t c = mul2(add2(fma2(add2(pk2(byte_magic(n, 52 + i, magic23), byte_magic(n, 58 + i, magic23)), magic), s_zz, o_zz), nr_zz), id_zz);
       float lx, ly, hx, hy, lz, hz;
       upk2(a, lx, ly); upk2(b, hx, hy); upk2(c, lz, hz);
       const float mn = fmaxf(fminf(lz, hz), fmaxf(fminf(ly, hy), fmaxf(fminf(lx, hx), r.tmin)));
       const float mx = fminf(fmaxf(lz, hz), fminf(fmaxf(ly, hy), fminf(fmaxf(lx, hx), r.tmax)));
       mask |= (mn <= mx && !(mn >= cull)) ? (1u << i) : 0u;
     }
-    // empty slots (ChildSize == 0) never hit
-    const uint32_t i0 = n.w[5] >> 16, i1 = n.w[6];   // bytes 22,23 | 24..27
-    const uint32_t present = ((i0 & 0x3u) ? 1u : 0u) | ((i0 & 0x300u) ? 2u : 0u) | ((i1 & 0x3u) ? 4u : 0u) | ((i1 & 0x300u) ? 8u : 0u) |
-                             ((i1 & 0x30000u) ? 16u : 0u) | ((i1 & 0x3000000u) ? 32u : 0u);
+    // empty slots (ChildSize == 0) never hit: bit 0 of each info byte = size != 0, gathered into six bits by a multiply
+    const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;                  // bytes 22..25 | 26,27
+    const uint32_t nz4 = (lo4 | (lo4 >> 1)) & 0x01010101u, nz2 = (hi2 | (hi2 >> 1)) & 0x0101u;
+    const uint32_t present = (((nz4 * 0x00204081u) >> 21) & 15u) | (((nz2 * 0x00204081u) >> 17) & 0x30u);
     mask &= present;
   }
   return mask;

@@ -42,7 +42,7 @@ VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
-enum { KIND_NONE = 0, KIND_INT = 1, KIND_INST = 2, KIND_LEAF = 3 };
+enum { ST_IDLE = 0, ST_FIN = 1, ST_POP = 2, ST_INT = 3, ST_INST = 4, ST_LEAF = 5 };   // lane state
 
 // The ray the lane is currently testing against: the world ray inside the TLAS, the object-space ray of instance
 // `inst` inside a BLAS (make_transformed_ray, :168-181).  Rebuilt only when a popped entry belongs to another
@@ -66,18 +66,22 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   __syncthreads();
   uint32_t max_level = 0, err = 0;
 
-  // ---- per-lane ray state
+  // ---- per-lane ray state.  `st` is the lane's whole control state: no ray / ray finished (hit record pending) / entry
+  // wanted / an entry of one of the three kinds in `e` waiting for its phase.
   Entry stk[STACK_N];
-  bool alive = false, fin = false, pend = false, exhausted = false;
+  uint32_t st = ST_IDLE; bool exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
   uint32_t r = 0;
   uint32_t* rstage = p.stage;            // staging segment of ray r
   float w_tmin = 0.0f, w_tmax = 0.0f;   // the world ray's origin/direction are re-read from p.rays[r] when needed
   ActiveRay a; a.ray.ox = a.ray.oy = a.ray.oz = a.ray.dx = a.ray.dy = a.ray.dz = a.ray.tmin = a.ray.tmax = 0.0f; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
-  uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0, cur_tid = VSRT_NO_TID;
+  uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0;
+  // TREELET: the current treelet (current_treelet_root, :1707/:1752) is kept lazily.  tid_known: cur_tid is its index;
+  // otherwise cur_tid holds the SLOT of the self-rooted node that was moved over from `other`, and the index is looked up
+  // only when something has to be compared with it (BLAS roots, the rare generic path).
+  uint32_t cur_tid = VSRT_NO_TID; bool tid_known = true;
   int cur_n = 0, oth_n = 0;
-  bool in_cur = false;   // TREELET: the popped node is known to belong to the current treelet (node_tid == cur_tid)
-  bool have_next = false; Entry next; next.slot = 0; next.meta = 0;
+  bool in_cur = false;   // TREELET: the node in `e` is known to belong to the current treelet (node_tid == current index)
   float min_thit = 0.0f, min_thit_object = 0.0f;
   uint32_t closest_leaf = 0, closest_inst = INST_NONE;
   const uint32_t cap = p.cap;
@@ -85,6 +89,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #define EMIT(slot_, code_) do { if (cnt < cap) rstage[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
 #define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
 #define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
+#define CUR_TID() (tid_known ? cur_tid : (tid_known = true, cur_tid = __ldg(p.tv.node_tid + cur_tid) & VSRT_TID_MASK))
   // switch the active ray to context `inst_` (INST_NONE = world)
 #define LOAD_WORLD(w_) do { const vsrt_ray* rp_ = p.rays + r; \
       (w_).ox = __ldg(&rp_->origin[0]); (w_).oy = __ldg(&rp_->origin[1]); (w_).oz = __ldg(&rp_->origin[2]); (w_).tmin = w_tmin; \
@@ -95,11 +100,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
   while (true) {
     // ================= refill: finalize finished rays, fetch new ones
-    const unsigned idle = __ballot_sync(full, !alive);
+    const unsigned idle = __ballot_sync(full, st <= ST_FIN);
     if (idle == full || (!exhausted && __popc(idle) >= REFILL_T)) {
-      if (fin) {
+      if (st == ST_FIN) {
         // ---- hit record (:2211-2245 / :2990-3033) and per-ray counters
-        fin = false;
+        st = ST_IDLE;
         if (cnt > cap) err |= EF_TRACE_CAP;
         p.counts[r] = cnt;
         vsrt_hit h;
@@ -135,11 +140,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         if (lane == 0) b0 = atomicAdd(p.next_ray, (unsigned long long)n_idle);
         b0 = __shfl_sync(full, b0, 0);
         if (b0 + (unsigned long long)n_idle >= p.n_rays) exhausted = true;
-        if (!alive) {
+        if (st == ST_IDLE) {
           const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
           if (nr < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
             // ---- start ray nr (:1650-1741 / :2411-2484)
-            r = (uint32_t)nr; rstage = p.stage + nr * cap; pend = false; have_next = false;
+            r = (uint32_t)nr; rstage = p.stage + nr * cap;
             const vsrt_ray* rp = p.rays + r;
             Ray8 w;
             w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
@@ -147,11 +152,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             flags = __ldg(&rp->ray_flags);
             if (!EXACT && ray_needs_exact(w)) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; }   // left to the EXACT pass
             else {
-              alive = true;
+              st = ST_POP;
               w_tmin = w.tmin; w_tmax = w.tmax;
               a.inst = INST_NONE; a.ray = w; a.idir = calc_idir(w); a.tmult = 1.0f; a.nonfinite = false;
               cnt = 0; ray_nodes = 0; ray_any = 0;
-              cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID;
+              cur_n = 0; oth_n = 0; cur_tid = VSRT_NO_TID; tid_known = true;
               min_thit = w_tmax; min_thit_object = 0.0f; closest_leaf = 0; closest_inst = INST_NONE;   // :1671
               EMIT(av.tlas_slot, C_STRUCT);                                                // :1685 / :2447
               uint32_t top_root = 0;
@@ -164,7 +169,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
                   Entry c; c.slot = top_root; c.meta = (1u << 23) | INST_NONE;
                   if (MODE == VSRT_MODE_TREELET) {
                     cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
-                    if ((__ldg(p.tv.node_tid + top_root) & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else PUSH_OTH(c);
+                    const uint32_t tr = __ldg(p.tv.node_tid + top_root);
+                    if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { c.slot |= (tr & VSRT_TID_SELF_ROOTED); PUSH_OTH(c); }
                   } else PUSH_CUR(c);
                   if (max_level < 1) max_level = 1;
                 }
@@ -173,141 +179,143 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           }
         }
       }
-      if (__ballot_sync(full, alive) == 0u) { if (exhausted) break; else continue; }
+      if (__ballot_sync(full, st > ST_FIN) == 0u) { if (exhausted) break; else continue; }
     }
 
-    // ================= pop the next entry of every lane that holds none
-    if (alive && !pend) {
-      if (MODE == VSRT_MODE_DFS && have_next) { e = next; have_next = false; pend = true; }
-      else {
-        if (MODE == VSRT_MODE_TREELET && cur_n == 0 && oth_n != 0) {
-          // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
-          // address, which equals a treelet's device address only for the root at (host - tlas_delta).
-          e = stk[STACK_N - oth_n]; oth_n--; pend = true;
-          if (av.tlas_delta == 0) {
-            const uint32_t tc = __ldg(p.tv.node_tid + e.slot);
-            in_cur = (tc & VSRT_TID_SELF_ROOTED) != 0u;
-            cur_tid = in_cur ? (tc & VSRT_TID_MASK) : root_rank(p.tv, e.slot);
-          } else { uint32_t s2; in_cur = false; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
-        } else if (cur_n == 0) { alive = false; fin = true; }
-        else { cur_n--; e = stk[cur_n]; pend = true; in_cur = true; }   // entries of `current` were pushed because node_tid == cur_tid
-      }
+    // ================= pop the next entry of every lane that wants one
+    if (st == ST_POP) {
+      const bool fc = cur_n != 0;
+      if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
+        e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
+        if (MODE == VSRT_MODE_TREELET) {
+          const bool selfroot = (e.slot >> 31) != 0u;
+          e.slot &= 0x7FFFFFFFu;
+          if (fc) { cur_n--; in_cur = true; }       // entries of `current` were pushed because node_tid == current treelet
+          else {
+            // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
+            // address, which equals a treelet's device address only for the root at (host - tlas_delta).
+            oth_n--;
+            if (av.tlas_delta == 0) {
+              in_cur = selfroot; cur_tid = e.slot; tid_known = false;
+              if (!selfroot) { cur_tid = root_rank(p.tv, e.slot); tid_known = true; }
+            } else { uint32_t s2; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
+          }
+        } else cur_n--;
+        st = !e_leaf(e) ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF);
+      } else st = ST_FIN;
     }
-    const int kind = !pend ? KIND_NONE : (!e_leaf(e) ? KIND_INT : (e_top(e) ? KIND_INST : KIND_LEAF));
 
     // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
-    const unsigned m_int = __ballot_sync(full, kind == KIND_INT);
-    if (m_int) {
-      if (kind == KIND_INT) {
-        pend = false;
-        const Node64 n = load_node(base, e.slot);
-        const uint32_t inst = e_inst(e);
-        EMIT(e.slot, inst == INST_NONE ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
-        ACTIVATE(inst);
-        if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; alive = false; }   // degenerate instance transform
-        else {
-          uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic23);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
-          // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868); sizes are 0..3 -> 4-bit prefix fields
-          // the six info bytes (22..27) handled as packed bytes: inclusive prefix sums of the sizes by one multiply, "type != 0"
-          // (leaf) as bit 7 of each byte
-          const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;
-          const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;
-          const uint32_t lf4 = ((lo4 & 0x3c3c3c3cu) + 0x7f7f7f7fu) & 0x80808080u, lf2 = ((hi2 & 0x3c3cu) + 0x7f7fu) & 0x8080u;
-          uint32_t coff[6], clf[6];
-          coff[0] = 0u; coff[1] = pre4 & 0xffu; coff[2] = (pre4 >> 8) & 0xffu; coff[3] = (pre4 >> 16) & 0xffu; coff[4] = pre4 >> 24; coff[5] = coff[4] + (hi2 & 3u);
-          clf[0] = (lf4 << 24) & 0x80000000u; clf[1] = (lf4 << 16) & 0x80000000u; clf[2] = (lf4 << 8) & 0x80000000u; clf[3] = lf4 & 0x80000000u;
-          clf[4] = (lf2 << 24) & 0x80000000u; clf[5] = (lf2 << 16) & 0x80000000u;
-          const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
-          const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
-          if (mask && clevel > max_level) max_level = clevel;
-          const uint32_t cmeta = (clevel << 23) | inst;
-          // hit children in slot order (:1810-1869), pushed without branches: every child computes its stack position and
-          // stores under a predicate
-          if (MODE == VSRT_MODE_TREELET) {
-            // which children belong to the CURRENT treelet (:1832): K0 left "child i is in this node's treelet" in the
-            // node's pad byte (+17), valid whenever the node itself is in the current treelet; otherwise (a node taken from
-            // `other` that is not the root of its treelet, or the host/device offset quirk) look the children up
-            uint32_t mc = node_byte(n, 17);
-            if (!in_cur) {
-              mc = 0;
+    if (st == ST_INT) {
+      st = ST_POP;
+      const Node64 n = load_node(base, e.slot);
+      const uint32_t inst = e_inst(e);
+      EMIT(e.slot, inst == INST_NONE ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
+      ACTIVATE(inst);
+      if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; st = ST_IDLE; }   // degenerate instance transform
+      else {
+        uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic23);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
+        // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
+        // bytes: inclusive prefix sums of the sizes by one multiply, "type != 0" (leaf) as bit 7 of each byte; bit 7 of the
+        // stored byte itself (ignored by the reference's & 0x3f) is K0's "this child is the root of its own treelet"
+        const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;
+        const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;
+        const uint32_t lf4 = ((lo4 & 0x3c3c3c3cu) + 0x7f7f7f7fu) & 0x80808080u, lf2 = ((hi2 & 0x3c3cu) + 0x7f7fu) & 0x8080u;
+        uint32_t coff[6], clf[6];
+        coff[0] = 0u; coff[1] = pre4 & 0xffu; coff[2] = (pre4 >> 8) & 0xffu; coff[3] = (pre4 >> 16) & 0xffu; coff[4] = pre4 >> 24; coff[5] = coff[4] + (hi2 & 3u);
+        clf[0] = (lf4 << 24) & 0x80000000u; clf[1] = (lf4 << 16) & 0x80000000u; clf[2] = (lf4 << 8) & 0x80000000u; clf[3] = lf4 & 0x80000000u;
+        clf[4] = (lf2 << 24) & 0x80000000u; clf[5] = (lf2 << 16) & 0x80000000u;
+        const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
+        const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
+        if (mask && clevel > max_level) max_level = clevel;
+        const uint32_t cmeta = (clevel << 23) | inst;
+        // hit children in slot order (:1810-1869), pushed without branches: every child computes its stack position and
+        // stores under a predicate
+        if (MODE == VSRT_MODE_TREELET) {
+          // which children belong to the CURRENT treelet (:1832): K0 left "child i is in this node's treelet" in the
+          // node's pad byte (+17), valid whenever the node itself is in the current treelet; otherwise (a node taken from
+          // `other` that is not the root of its treelet, or the host/device offset quirk) look the children up
+          uint32_t mc = node_byte(n, 17);
+          if (!in_cur) {
+            mc = 0;
+            const uint32_t ct = CUR_TID();
 #pragma unroll
-              for (int i = 0; i < 6; i++)
-                if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + coff[i]) & VSRT_TID_MASK) == cur_tid) mc |= 1u << i; }
-            }
-            const uint32_t mcur = mask & mc, moth = mask & ~mc;
-            if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
-            else {
-              int pc = cur_n, po = STACK_N - 1 - oth_n;
-#pragma unroll
-              for (int i = 0; i < 6; i++) {
-                Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
-                const int bc = (int)((mcur >> i) & 1u), bo = (int)((moth >> i) & 1u);
-                if (bc | bo) stk[bc ? pc : po] = c;
-                pc += bc; po -= bo;
-              }
-              cur_n = pc; oth_n = STACK_N - 1 - po;
-            }
-          } else {
-            // the first hit internal child is followed (:2573); every other hit child is pushed in slot order
-            const uint32_t leafbits = ((((lf4 >> 7) * 0x00204081u) >> 21) & 15u) | ((((lf2 >> 7) * 0x00204081u) >> 17) & 0x30u);
-            const uint32_t mint = mask & ~leafbits;
-            const uint32_t nx = mint & (0u - mint);          // lowest set bit, 0 if none
-            const uint32_t mpush = mask & ~nx;
-            if (cur_n + __popc(mpush) > STACK_N) err |= EF_STACK;
-            else {
-              int pc = cur_n;
-#pragma unroll
-              for (int i = 0; i < 6; i++) {
-                Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
-                if ((nx >> i) & 1u) { next = c; have_next = true; }
-                const int b = (int)((mpush >> i) & 1u);
-                if (b) stk[pc] = c;
-                pc += b;
-              }
-              cur_n = pc;
-            }
+            for (int i = 0; i < 6; i++)
+              if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + coff[i]) & VSRT_TID_MASK) == ct) mc |= 1u << i; }
           }
-          // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the
-          // iteration (other phases, refill vote) runs
-          if (p.prefetch) {
-            uint32_t ns = 0xFFFFFFFFu;
-            if (MODE == VSRT_MODE_DFS && have_next) ns = next.slot;
-            else if (cur_n) ns = stk[cur_n - 1].slot;
-            else if (MODE == VSRT_MODE_TREELET && oth_n) ns = stk[STACK_N - oth_n].slot;
-            if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)ns * 64u);
+          uint32_t csr[6];   // "root of its own treelet" flag of each child, moved to bit 31 of the entry's slot word
+          csr[0] = (lo4 << 24) & 0x80000000u; csr[1] = (lo4 << 16) & 0x80000000u; csr[2] = (lo4 << 8) & 0x80000000u; csr[3] = lo4 & 0x80000000u;
+          csr[4] = (hi2 << 24) & 0x80000000u; csr[5] = (hi2 << 16) & 0x80000000u;
+          const uint32_t mcur = mask & mc, moth = mask & ~mc;
+          if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
+          else {
+            int pc = cur_n, po = STACK_N - 1 - oth_n;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+              Entry c; c.slot = (child0 + coff[i]) | csr[i]; c.meta = cmeta | clf[i];
+              const int bc = (int)((mcur >> i) & 1u), bo = (int)((moth >> i) & 1u);
+              if (bc | bo) stk[bc ? pc : po] = c;
+              pc += bc; po -= bo;
+            }
+            cur_n = pc; oth_n = STACK_N - 1 - po;
           }
+        } else {
+          // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
+          const uint32_t leafbits = ((((lf4 >> 7) * 0x00204081u) >> 21) & 15u) | ((((lf2 >> 7) * 0x00204081u) >> 17) & 0x30u);
+          const uint32_t mint = mask & ~leafbits;
+          const uint32_t nx = mint & (0u - mint);          // lowest set bit, 0 if none
+          const uint32_t mpush = mask & ~nx;
+          if (cur_n + __popc(mpush) > STACK_N) err |= EF_STACK;
+          else {
+            int pc = cur_n;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+              Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
+              if ((nx >> i) & 1u) { e = c; st = ST_INT; }
+              const int b = (int)((mpush >> i) & 1u);
+              if (b) stk[pc] = c;
+              pc += b;
+            }
+            cur_n = pc;
+          }
+        }
+        // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the
+        // iteration (other phases, refill vote) runs
+        if (p.prefetch) {
+          uint32_t ns = 0xFFFFFFFFu;
+          if (MODE == VSRT_MODE_DFS && st == ST_INT) ns = e.slot;
+          else if (cur_n) ns = stk[cur_n - 1].slot;
+          else if (MODE == VSRT_MODE_TREELET && oth_n) ns = stk[STACK_N - oth_n].slot;
+          if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)(ns & 0x7FFFFFFFu) * 64u);
         }
       }
     }
-
     // ================= phase 2: instance leaves (:1876-1953 / :2602-2677)
-    const unsigned m_inst = __ballot_sync(full, kind == KIND_INST);
-    if (m_inst) {
-      if (kind == KIND_INST) {
-        pend = false;
-        EMIT(e.slot, C_INSTANCE); ray_nodes++;
-        uint32_t hdr = 0, broot = 0;
-        const uint32_t iref = e.slot - inst_base;
-        if (!instance_blas_header(av, e.slot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; alive = false; fin = true; }
-        else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; alive = false; fin = true; }
+    else if (st == ST_INST) {
+      st = ST_POP;
+      EMIT(e.slot, C_INSTANCE); ray_nodes++;
+      uint32_t hdr = 0, broot = 0;
+      const uint32_t iref = e.slot - inst_base;
+      if (!instance_blas_header(av, e.slot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; st = ST_FIN; }
+      else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; st = ST_FIN; }
+      else {
+        EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
+        Entry c; c.slot = broot; c.meta = (e_level(e) << 23) | iref;             // BLAS root inherits the leaf's level (:1944)
+        if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
         else {
-          EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
-          Entry c; c.slot = broot; c.meta = (e_level(e) << 23) | iref;             // BLAS root inherits the leaf's level (:1944)
-          if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
-          else {
-            if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
-            else if ((__ldg(p.tv.node_tid + broot) & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c);
-            else PUSH_OTH(c);
-          }
+          const uint32_t tb = __ldg(p.tv.node_tid + broot);
+          if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
+          else if ((tb & VSRT_TID_MASK) == CUR_TID()) PUSH_CUR(c);
+          else { c.slot |= (tb & VSRT_TID_SELF_ROOTED); PUSH_OTH(c); }
         }
       }
     }
 
     // ================= phase 3: BLAS leaves (:2073-2204 / :2789-2985), batched
-    const unsigned m_leaf = __ballot_sync(full, kind == KIND_LEAF);
-    if (m_leaf && (__popc(m_leaf) >= LEAF_T || (m_int | m_inst) == 0u)) {
-      if (kind == KIND_LEAF) {
-        pend = false;
+    const unsigned m_leaf = __ballot_sync(full, st == ST_LEAF);
+    if (m_leaf && (__popc(m_leaf) >= LEAF_T || __ballot_sync(full, st == ST_INT || st == ST_INST || st == ST_POP) == 0u)) {
+      if (st == ST_LEAF) {
+        st = ST_POP;
         EMIT(e.slot, C_DESC);
         const Node64 q = load_node(base, e.slot);
         if (((q.w[1] >> 29) & 1u) == 0u) {
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             }
             min_thit_object = thit; closest_leaf = e.slot; closest_inst = e_inst(e);
             EMIT(e.slot, C_QUAD_HIT); ray_nodes++;
-            if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) { cur_n = 0; oth_n = 0; have_next = false; }   // :2151-2155 / :2932-2935
+            if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) { cur_n = 0; oth_n = 0; }   // :2151-2155 / :2932-2935
           } else { EMIT(e.slot, C_QUAD); ray_nodes++; }
         } else { EMIT(e.slot, C_PROC); ray_nodes++; }                             // intersection-table transactions: not built yet
       }
@@ -335,6 +343,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #undef EMIT
 #undef PUSH_CUR
 #undef PUSH_OTH
+#undef CUR_TID
 #undef ACTIVATE
 #undef LOAD_WORLD
 

@@ -180,10 +180,13 @@ __global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n, const uin
   if ((w & b) && prefix[i >> 5] + __popc(w & (b - 1)) == t) t |= VSRT_TID_SELF_ROOTED;
   node_tid[i] = t;
 }
-// Per internal node: bit i of the arena copy's pad byte (+17, "one unused byte" of GEN_RT_BVH_INTERNAL_NODE_unpack,
-// util.h:146) = child slot i exists and is mapped to the SAME treelet as the node.  K1 reads it with the node's 64 bytes
-// and so needs no node_tid gather per child while the node is in the ray's current treelet.  One thread per list entry;
-// a node listed by several treelets (shared BLAS) gets the same value from each.
+// Per internal node, written into spare bits of the context's private arena copy so that K1 gets them with the node's own
+// 64 bytes instead of gathering node_tid per child:
+//   pad byte +17 ("one unused byte" of GEN_RT_BVH_INTERNAL_NODE_unpack, util.h:146), bit i: child slot i exists and is
+//     mapped to the SAME treelet as the node;
+//   bit 7 of child-info byte 22+i (the reference reads these bytes & 0x3f, util.h:160): child i is the root of the treelet
+//     it is mapped to (VSRT_TID_SELF_ROOTED of node_tid[child]; also set for an unmapped child, like the flag itself).
+// One thread per list entry; a node listed by several treelets (shared BLAS) gets the same value from each.
 __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, const uint64_t* __restrict__ tl_node, unsigned long long n_entries,
                              const uint32_t* __restrict__ node_tid) {
   const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,21 +194,25 @@ __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, cons
   const uint64_t e = tl_node[k];
   const uint32_t slot = (uint32_t)e, kind = (uint32_t)(e >> 32);
   if (kind != K_TLAS_INTERNAL && kind != K_BLAS_INTERNAL) return;
-  const uint4* np = reinterpret_cast<const uint4*>(arena + (uint64_t)slot * 64u);
+  uint8_t* node = arena + (uint64_t)slot * 64u;
+  const uint4* np = reinterpret_cast<const uint4*>(node);
   const uint4 a = np[0], b = np[1];
   const uint32_t own = node_tid[slot];
   uint32_t child = slot + a.w, m = 0;
   const uint64_t info6 = ((uint64_t)b.z << 16) | (b.y >> 16);
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    const uint32_t sz = (uint32_t)(info6 >> (8 * i)) & 3u;
-    if (sz && child < n_slots && own != VSRT_NO_TID) {
+    const uint32_t info = (uint32_t)(info6 >> (8 * i)) & 0xffu, sz = info & 3u;
+    uint32_t self = 0;
+    if (sz && child < n_slots) {
       const uint32_t t = node_tid[child];
-      if (t != VSRT_NO_TID && ((t ^ own) & VSRT_TID_MASK) == 0u) m |= 1u << i;
+      if (own != VSRT_NO_TID && t != VSRT_NO_TID && ((t ^ own) & VSRT_TID_MASK) == 0u) m |= 1u << i;
+      self = (t & VSRT_TID_SELF_ROOTED) ? 0x80u : 0u;
     }
+    node[22 + i] = (uint8_t)((info & 0x7fu) | self);
     child += sz;
   }
-  arena[(uint64_t)slot * 64u + 17u] = (uint8_t)m;
+  node[17] = (uint8_t)m;
 }
 __global__ void k_fill_ptrs(const uint64_t** r_list, uint32_t begin, uint32_t count, uint64_t* pool, uint32_t cap) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t < count) r_list[begin + t] = pool + (uint64_t)t * cap;

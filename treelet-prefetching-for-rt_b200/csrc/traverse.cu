@@ -27,12 +27,15 @@
 
 namespace {
 
-// stack entry: slot + meta, meta = leaf << 31 | level << 23 | instance reference (23 bits).  The instance reference
-// is the instance leaf's slot relative to the first slot of the TLAS span (INST_NONE = the entry is a TLAS node).
+// stack entry, two words:
+//   slot  bit 31 "root of its own treelet" (TREELET mode, consumed when the entry is taken from `other`), bit 30 leaf,
+//         bits 0..28 the arena slot
+//   meta  level << 23 | instance reference (23 bits).  The instance reference is the instance leaf's slot relative to the
+//         first slot of the TLAS span (INST_NONE = the entry is a TLAS node).
 constexpr uint32_t INST_NONE = 0x7FFFFFu;
 constexpr uint32_t RAY_DEFERRED = 0xFFFFFFFFu;
+constexpr uint32_t SLOT_MASK = 0x1FFFFFFFu, SLOT_LEAF = 0x40000000u, SLOT_SELFROOT = 0x80000000u;
 struct Entry { uint32_t slot; uint32_t meta; };
-VS_DEV bool e_leaf(const Entry& e) { return (e.meta >> 31) != 0; }
 VS_DEV uint32_t e_level(const Entry& e) { return (e.meta >> 23) & 0xffu; }
 VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }
 VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
                   if (MODE == VSRT_MODE_TREELET) {
                     cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
                     const uint32_t tr = __ldg(p.tv.node_tid + top_root);
-                    if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { c.slot |= (tr & VSRT_TID_SELF_ROOTED); PUSH_OTH(c); }
+                    if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { c.slot |= (tr & VSRT_TID_SELF_ROOTED) ? SLOT_SELFROOT : 0u; PUSH_OTH(c); }
                   } else PUSH_CUR(c);
                   if (max_level < 1) max_level = 1;
                 }
@@ -187,9 +190,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
         e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
+        const bool selfroot = (e.slot & SLOT_SELFROOT) != 0u, leaf = (e.slot & SLOT_LEAF) != 0u;
+        e.slot &= SLOT_MASK;
         if (MODE == VSRT_MODE_TREELET) {
-          const bool selfroot = (e.slot >> 31) != 0u;
-          e.slot &= 0x7FFFFFFFu;
           if (fc) { cur_n--; in_cur = true; }       // entries of `current` were pushed because node_tid == current treelet
           else {
             // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             } else { uint32_t s2; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
           }
         } else cur_n--;
-        st = !e_leaf(e) ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF);
+        st = !leaf ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF);
       } else st = ST_FIN;
     }
 
@@ -216,21 +219,16 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       else {
         uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic23);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
         // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
-        // bytes: inclusive prefix sums of the sizes by one multiply, "type != 0" (leaf) as bit 7 of each byte; bit 7 of the
-        // stored byte itself (ignored by the reference's & 0x3f) is K0's "this child is the root of its own treelet"
+        // bytes: prefix sums of the sizes by one multiply; K0 left two flags in the bits the reference ignores (& 0x3f):
+        // bit 7 "this child is the root of its own treelet", bit 6 "leaf" (type != 0) -- exactly bits 31/30 of an entry's slot
         const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;
-        const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;
-        const uint32_t lf4 = ((lo4 & 0x3c3c3c3cu) + 0x7f7f7f7fu) & 0x80808080u, lf2 = ((hi2 & 0x3c3cu) + 0x7f7fu) & 0x8080u;
-        uint32_t coff[6], clf[6];
-        coff[0] = 0u; coff[1] = pre4 & 0xffu; coff[2] = (pre4 >> 8) & 0xffu; coff[3] = (pre4 >> 16) & 0xffu; coff[4] = pre4 >> 24; coff[5] = coff[4] + (hi2 & 3u);
-        clf[0] = (lf4 << 24) & 0x80000000u; clf[1] = (lf4 << 16) & 0x80000000u; clf[2] = (lf4 << 8) & 0x80000000u; clf[3] = lf4 & 0x80000000u;
-        clf[4] = (lf2 << 24) & 0x80000000u; clf[5] = (lf2 << 16) & 0x80000000u;
+        const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;                       // byte j = size_0 + .. + size_j
+        const uint32_t t4 = pre4 >> 24, xlo = pre4 << 8, xhi = t4 | ((t4 + (hi2 & 3u)) << 8);   // byte i of {xlo, xhi} = offset of child i
         const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
         const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
         if (mask && clevel > max_level) max_level = clevel;
         const uint32_t cmeta = (clevel << 23) | inst;
-        // hit children in slot order (:1810-1869), pushed without branches: every child computes its stack position and
-        // stores under a predicate
+        // hit children in slot order (:1810-1869): one loop turn per hit child (a node rarely has more than two)
         if (MODE == VSRT_MODE_TREELET) {
           // which children belong to the CURRENT treelet (:1832): K0 left "child i is in this node's treelet" in the
           // node's pad byte (+17), valid whenever the node itself is in the current treelet; otherwise (a node taken from
@@ -239,44 +237,37 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (!in_cur) {
             mc = 0;
             const uint32_t ct = CUR_TID();
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-              if ((mask >> i) & 1u) { if ((__ldg(p.tv.node_tid + child0 + coff[i]) & VSRT_TID_MASK) == ct) mc |= 1u << i; }
+            for (uint32_t m = mask; m; m &= m - 1u) {
+              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(m & (0u - m)));
+              if ((__ldg(p.tv.node_tid + child0 + __byte_perm(xlo, xhi, sel)) & VSRT_TID_MASK) == ct) mc |= m & (0u - m);
+            }
           }
-          uint32_t csr[6];   // "root of its own treelet" flag of each child, moved to bit 31 of the entry's slot word
-          csr[0] = (lo4 << 24) & 0x80000000u; csr[1] = (lo4 << 16) & 0x80000000u; csr[2] = (lo4 << 8) & 0x80000000u; csr[3] = lo4 & 0x80000000u;
-          csr[4] = (hi2 << 24) & 0x80000000u; csr[5] = (hi2 << 16) & 0x80000000u;
-          const uint32_t mcur = mask & mc, moth = mask & ~mc;
+          const uint32_t mcur = mask & mc;
           if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
           else {
-            int pc = cur_n, po = STACK_N - 1 - oth_n;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-              Entry c; c.slot = (child0 + coff[i]) | csr[i]; c.meta = cmeta | clf[i];
-              const int bc = (int)((mcur >> i) & 1u), bo = (int)((moth >> i) & 1u);
-              if (bc | bo) stk[bc ? pc : po] = c;
-              pc += bc; po -= bo;
+            int po = STACK_N - 1 - oth_n;
+            for (uint32_t m = mask; m; ) {
+              const uint32_t bit = m & (0u - m); m ^= bit;
+              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(bit));
+              Entry c; c.slot = (child0 + __byte_perm(xlo, xhi, sel)) | ((__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u); c.meta = cmeta;
+              const bool ic = (mcur & bit) != 0u;
+              stk[ic ? cur_n : po] = c;
+              cur_n += ic ? 1 : 0; po -= ic ? 0 : 1;
             }
-            cur_n = pc; oth_n = STACK_N - 1 - po;
+            oth_n = STACK_N - 1 - po;
           }
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
-          const uint32_t leafbits = ((((lf4 >> 7) * 0x00204081u) >> 21) & 15u) | ((((lf2 >> 7) * 0x00204081u) >> 17) & 0x30u);
-          const uint32_t mint = mask & ~leafbits;
-          const uint32_t nx = mint & (0u - mint);          // lowest set bit, 0 if none
-          const uint32_t mpush = mask & ~nx;
-          if (cur_n + __popc(mpush) > STACK_N) err |= EF_STACK;
+          if (cur_n + __popc(mask) > STACK_N) err |= EF_STACK;
           else {
-            int pc = cur_n;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-              Entry c; c.slot = child0 + coff[i]; c.meta = cmeta | clf[i];
-              if ((nx >> i) & 1u) { e = c; st = ST_INT; }
-              const int b = (int)((mpush >> i) & 1u);
-              if (b) stk[pc] = c;
-              pc += b;
+            for (uint32_t m = mask; m; ) {
+              const uint32_t bit = m & (0u - m); m ^= bit;
+              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(bit));
+              const uint32_t fl = (__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u;
+              Entry c; c.slot = child0 + __byte_perm(xlo, xhi, sel); c.meta = cmeta;
+              if (!(fl & SLOT_LEAF) && st != ST_INT) { e = c; st = ST_INT; }
+              else { c.slot |= fl; stk[cur_n] = c; cur_n++; }
             }
-            cur_n = pc;
           }
         }
         // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the
@@ -286,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (MODE == VSRT_MODE_DFS && st == ST_INT) ns = e.slot;
           else if (cur_n) ns = stk[cur_n - 1].slot;
           else if (MODE == VSRT_MODE_TREELET && oth_n) ns = stk[STACK_N - oth_n].slot;
-          if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)(ns & 0x7FFFFFFFu) * 64u);
+          if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)(ns & SLOT_MASK) * 64u);
         }
       }
     }
@@ -306,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           const uint32_t tb = __ldg(p.tv.node_tid + broot);
           if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
           else if ((tb & VSRT_TID_MASK) == CUR_TID()) PUSH_CUR(c);
-          else { c.slot |= (tb & VSRT_TID_SELF_ROOTED); PUSH_OTH(c); }
+          else { c.slot |= (tb & VSRT_TID_SELF_ROOTED) ? SLOT_SELFROOT : 0u; PUSH_OTH(c); }
         }
       }
     }

@@ -185,7 +185,8 @@ __global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n, const uin
 //   pad byte +17 ("one unused byte" of GEN_RT_BVH_INTERNAL_NODE_unpack, util.h:146), bit i: child slot i exists and is
 //     mapped to the SAME treelet as the node;
 //   bit 7 of child-info byte 22+i (the reference reads these bytes & 0x3f, util.h:160): child i is the root of the treelet
-//     it is mapped to (VSRT_TID_SELF_ROOTED of node_tid[child]; also set for an unmapped child, like the flag itself).
+//     it is mapped to (VSRT_TID_SELF_ROOTED of node_tid[child]; also set for an unmapped child, like the flag itself);
+//   bit 6 of the same byte: child i is a leaf (ChildType != 0).  Bits 7/6 are bits 31/30 of a traversal-stack entry.
 // One thread per list entry; a node listed by several treelets (shared BLAS) gets the same value from each.
 __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, const uint64_t* __restrict__ tl_node, unsigned long long n_entries,
                              const uint32_t* __restrict__ node_tid) {
@@ -209,7 +210,7 @@ __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, cons
       if (own != VSRT_NO_TID && t != VSRT_NO_TID && ((t ^ own) & VSRT_TID_MASK) == 0u) m |= 1u << i;
       self = (t & VSRT_TID_SELF_ROOTED) ? 0x80u : 0u;
     }
-    node[22 + i] = (uint8_t)((info & 0x7fu) | self);
+    node[22 + i] = (uint8_t)((info & 0x3fu) | ((info & 0x3cu) ? 0x40u : 0u) | self);
     child += sz;
   }
   node[17] = (uint8_t)m;

@@ -40,6 +40,8 @@ VS_DEV uint32_t e_level(const Entry& e) { return (e.meta >> 23) & 0xffu; }
 VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }
 VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 
+VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(one_bit)); return i; }   // FLO
+
 constexpr int THREADS = 128;
 VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_MIN_BLOCKS
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       ACTIVATE(inst);
       if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; st = ST_IDLE; }   // degenerate instance transform
       else {
-        uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic23);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
+        uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic16);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
         // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
         // bytes: prefix sums of the sizes by one multiply; K0 left two flags in the bits the reference ignores (& 0x3f):
         // bit 7 "this child is the root of its own treelet", bit 6 "leaf" (type != 0) -- exactly bits 31/30 of an entry's slot
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             mc = 0;
             const uint32_t ct = CUR_TID();
             for (uint32_t m = mask; m; m &= m - 1u) {
-              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(m & (0u - m)));
+              const uint32_t sel = 0x7770u + bit_index(m & (0u - m));
               if ((__ldg(p.tv.node_tid + child0 + __byte_perm(xlo, xhi, sel)) & VSRT_TID_MASK) == ct) mc |= m & (0u - m);
             }
           }
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             int po = STACK_N - 1 - oth_n;
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
-              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(bit));
+              const uint32_t sel = 0x7770u + bit_index(bit);
               Entry c; c.slot = (child0 + __byte_perm(xlo, xhi, sel)) | ((__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u); c.meta = cmeta;
               const bool ic = (mcur & bit) != 0u;
               stk[ic ? cur_n : po] = c;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           else {
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
-              const uint32_t sel = 0x7770u + (31u - (uint32_t)__clz(bit));
+              const uint32_t sel = 0x7770u + bit_index(bit);
               const uint32_t fl = (__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u;
               Entry c; c.slot = child0 + __byte_perm(xlo, xhi, sel); c.meta = cmeta;
               if (!(fl & SLOT_LEAF) && st != ST_INT) { e = c; st = ST_INT; }

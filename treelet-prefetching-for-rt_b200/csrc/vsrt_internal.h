@@ -96,7 +96,7 @@ struct TraverseParams {
   uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
   uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
   uint32_t prefetch;              // issue an L1 prefetch for the node a lane will pop next
-  uint32_t magic23;               // 0x4B000000 (2^23 as float bits), passed as data so it lives in a register (see byte_magic)
+  uint32_t magic16;               // 0x64646464 (fp16 1024 in each half), passed as data so it lives in a register (byte_pair_f16)
 };
 int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
 

@@ -72,90 +72,122 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __r
 
 // ---------------------------------------------------------------- K3
 constexpr int K3_THREADS = 256;
-constexpr int K3_RAYS = 256;     // rays per CTA
-constexpr int K3_ILP = 4;        // independent records in flight per thread
+constexpr int K3_WARPS = K3_THREADS / 32;
+constexpr int K3_RAYS = K3_WARPS * 32;   // rays per CTA: every warp owns 32 consecutive rays and their contiguous output range
+constexpr int K3_ILP = 4;        // independent 32-record windows in flight per warp
 constexpr int K3_HASH_BITS = 10; // CTA-private treelet histogram: 1024 (key,count) slots in shared memory
 
 __device__ __forceinline__ uint32_t code_size(uint32_t code) { return code == C_INSTANCE ? 128u : (code == C_DESC ? 8u : 64u); }
 __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_INTERNAL_TLAS ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code; }
 
+// One warp expands the records of 32 consecutive rays.  The warp's output range [offsets[r], offsets[r + 32]) is
+// contiguous; it is walked in windows of 32 records, one record per lane, so the 16-byte and 4-byte stores of a window are
+// single coalesced transactions.  Which ray a record belongs to is found without a search: the lanes hold the 32 start
+// offsets, one REDUX.OR builds the bitmap of ray starts inside the window and a popcount of the bits at or below the lane
+// gives the ray (every ray has at least its TLAS-header record; a warp that sees an empty ray counts with shuffles instead).
 __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
-  __shared__ unsigned long long s_off[K3_RAYS + 1];
   __shared__ unsigned int s_hist[8];
   __shared__ unsigned int s_hkey[1 << K3_HASH_BITS], s_hcnt[1 << K3_HASH_BITS];
   for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS) { s_hkey[i] = VSRT_NO_TID; s_hcnt[i] = 0; }
-  const uint64_t r0 = (uint64_t)blockIdx.x * K3_RAYS;
-  const uint32_t nr = (uint32_t)min((uint64_t)K3_RAYS, p.n_rays - r0);
-  for (uint32_t i = threadIdx.x; i <= nr; i += K3_THREADS) s_off[i] = p.offsets[r0 + i];
   if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
   __syncthreads();
-  const unsigned long long j0 = s_off[0], j1 = s_off[nr];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const ArenaView& av = p.av;
+  const bool one_span = av.n_spans == 1;
+  const uint64_t span_host = one_span ? av.spans[0].host : 0ull;
+  const uint64_t rw0 = (uint64_t)blockIdx.x * K3_RAYS + (uint64_t)(threadIdx.x >> 5) * 32u;
   uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-  // K3_ILP records per thread per iteration, block-strided so every store instruction is fully coalesced; the
-  // independent chains (smem search -> staging load -> node_tid gather -> store) overlap each other's latency.
-  for (unsigned long long jb = j0; jb < j1; jb += (unsigned long long)K3_THREADS * K3_ILP) {
-    unsigned long long j[K3_ILP]; bool valid[K3_ILP]; uint32_t k[K3_ILP], ray[K3_ILP], rec[K3_ILP], tid[K3_ILP];
-#pragma unroll
-    for (int u = 0; u < K3_ILP; u++) {
-      j[u] = jb + (unsigned long long)u * K3_THREADS + threadIdx.x; valid[u] = j[u] < j1;
-      // ray of record j: last i with s_off[i] <= j
-      uint32_t lo = 0, hi = nr;
-      if (valid[u]) { while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (s_off[m] <= j[u]) lo = m; else hi = m; } }
-      ray[u] = lo; k[u] = valid[u] ? (uint32_t)(j[u] - s_off[lo]) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(p.stage + (r0 + ray[u]) * (uint64_t)p.cap + k[u]) : 0u;
-#pragma unroll
-    for (int u = 0; u < K3_ILP; u++) { tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID; if (tid[u] != VSRT_NO_TID) tid[u] &= VSRT_TID_MASK; }
-#pragma unroll
-    for (int u = 0; u < K3_ILP; u++) {
-      if (valid[u]) {
-        const uint32_t slot = rec[u] >> 3, code = rec[u] & 7u;
-        // host -> simulated-device offset the reference applies to this record
-        int64_t delta = av.tlas_delta;
-        if (!av.uniform_delta) {
-          const uint32_t* seg = p.stage + (r0 + ray[u]) * (uint64_t)p.cap;
-          if (code == C_STRUCT && k[u] > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
-          else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k[u] > 0) {
-            // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
-            for (uint32_t b = k[u]; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
-          }
-        }
-        const uint64_t address = slot_to_host(av, slot) + (uint64_t)delta;
-        const uint32_t type = code_type(code);
-        if (j[u] < p.out_capacity) {
-          *reinterpret_cast<uint4*>(p.txns + j[u]) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
-          p.tids[j[u]] = tid[u];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; c++) hc[c] += (type == (uint32_t)c) ? 1u : 0u;
-      }
-    }
-    if (p.treelet_hist) {
-      // Treelet visit histogram.  The hot bins (the treelets at the top of the tree) receive a record from every
-      // ray, and same-address atomics serialise in L2, so: (1) lanes hold consecutive records, runs of one treelet
-      // are folded with a shuffle + ballot and only the run head adds; (2) the CTA accumulates into a small
-      // shared-memory hash table and flushes it once at the end; only table collisions go straight to L2.
+  if (rw0 < p.n_rays) {
+    const uint32_t nr = (uint32_t)min((uint64_t)32, p.n_rays - rw0);
+    const unsigned long long my_off = p.offsets[rw0 + min((uint32_t)lane, nr)];
+    const unsigned long long j0 = __shfl_sync(full, my_off, 0), j1 = p.offsets[rw0 + nr];
+    const uint32_t total = (uint32_t)(j1 - j0);
+    const bool rvalid = (uint32_t)lane < nr;
+    const uint32_t rel = rvalid ? (uint32_t)(my_off - j0) : 0xFFFFFFFFu;
+    const uint32_t nxt = __shfl_down_sync(full, rel, 1);
+    const bool any_empty = __ballot_sync(full, rvalid && (((uint32_t)lane + 1u < nr ? nxt : total) == rel)) != 0u;
+    const uint32_t* stage_w = p.stage + rw0 * (uint64_t)p.cap;
+    unsigned long long packed = 0; uint32_t since_flush = 0;
+    for (uint32_t wb = 0; wb < total; wb += 32u * K3_ILP) {
+      uint32_t pos[K3_ILP], k[K3_ILP], ray[K3_ILP], rec[K3_ILP], tid[K3_ILP]; bool valid[K3_ILP];
 #pragma unroll
       for (int u = 0; u < K3_ILP; u++) {
-        const int lane = threadIdx.x & 31;
-        const bool a = valid[u] && tid[u] != VSRT_NO_TID;
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, tid[u], 1);
-        const unsigned act = __ballot_sync(0xffffffffu, a);
-        const bool head = a && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != tid[u]);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (head) {
-          // run = lanes up to the next head or the first inactive lane
-          const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
-          const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
-          const uint32_t h = (tid[u] * 2654435761u) >> (32 - K3_HASH_BITS);
-          const uint32_t old = atomicCAS(&s_hkey[h], VSRT_NO_TID, tid[u]);
-          if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&s_hcnt[h], run);
-          else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
+        const uint32_t wbase = wb + 32u * u;
+        pos[u] = wbase + (uint32_t)lane; valid[u] = pos[u] < total;
+        if (!any_empty) {
+          const uint32_t nle = __popc(__ballot_sync(full, rel <= wbase));                     // rays that start at or before the window
+          const uint32_t bit = (rel > wbase && rel - wbase < 32u) ? (1u << (rel - wbase)) : 0u;
+          const uint32_t starts = __reduce_or_sync(full, bit);                                  // ray starts inside the window
+          ray[u] = nle - 1u + __popc(starts & ((2u << lane) - 1u));
+        } else {
+          uint32_t c = 0;
+          for (int m = 0; m < 32; m++) { const uint32_t rm = __shfl_sync(full, rel, m); c += (rm <= pos[u]) ? 1u : 0u; }
+          ray[u] = c - 1u;
+        }
+        if (!valid[u]) ray[u] = 0;
+        k[u] = pos[u] - __shfl_sync(full, rel, (int)ray[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(stage_w + (uint64_t)ray[u] * p.cap + k[u]) : 0u;
+#pragma unroll
+      for (int u = 0; u < K3_ILP; u++) { tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID; if (tid[u] != VSRT_NO_TID) tid[u] &= VSRT_TID_MASK; }
+#pragma unroll
+      for (int u = 0; u < K3_ILP; u++) {
+        if (valid[u]) {
+          const uint32_t slot = rec[u] >> 3, code = rec[u] & 7u;
+          // host -> simulated-device offset the reference applies to this record
+          int64_t delta = av.tlas_delta;
+          if (!av.uniform_delta) {
+            const uint32_t* seg = stage_w + (uint64_t)ray[u] * p.cap;
+            if (code == C_STRUCT && k[u] > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
+            else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k[u] > 0) {
+              // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
+              for (uint32_t b = k[u]; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
+            }
+          }
+          const uint64_t address = (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta;
+          const uint32_t type = code_type(code);
+          const unsigned long long j = j0 + pos[u];
+          if (j < p.out_capacity) {
+            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
+            p.tids[j] = tid[u];
+          }
+          packed += 1ull << (8u * type);        // g_rt_mem_access_type[type]++, eight 8-bit lanes
+        }
+      }
+      since_flush += K3_ILP;
+      if (since_flush > 255u - K3_ILP) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(packed >> (8 * c)) & 0xffu;
+        packed = 0; since_flush = 0;
+      }
+      if (p.treelet_hist) {
+        // Treelet visit histogram.  The hot bins (the treelets at the top of the tree) receive a record from every
+        // ray, and same-address atomics serialise in L2, so: (1) lanes hold consecutive records, runs of one treelet
+        // are folded with a shuffle + ballot and only the run head adds; (2) the CTA accumulates into a small
+        // shared-memory hash table and flushes it once at the end; only table collisions go straight to L2.
+#pragma unroll
+        for (int u = 0; u < K3_ILP; u++) {
+          const bool a = valid[u] && tid[u] != VSRT_NO_TID;
+          const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
+          const unsigned act = __ballot_sync(full, a);
+          const bool head = a && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != tid[u]);
+          const unsigned heads = __ballot_sync(full, head);
+          if (head) {
+            // run = lanes up to the next head or the first inactive lane
+            const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
+            const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
+            const uint32_t h = (tid[u] * 2654435761u) >> (32 - K3_HASH_BITS);
+            const uint32_t old = atomicCAS(&s_hkey[h], VSRT_NO_TID, tid[u]);
+            if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&s_hcnt[h], run);
+            else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
+          }
         }
       }
     }
+#pragma unroll
+    for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(packed >> (8 * c)) & 0xffu;
   }
   if (p.treelet_hist) {
     __syncthreads();

@@ -5,6 +5,7 @@
 // root table == treelet_addr_to_metadata_idx).  Also accumulates g_rt_mem_access_type[], accessedDataSize
 // (:2257-2261) and the per-treelet visit histogram the prefetcher's popularity vote is built from (shader.cc:3424-3433).
 #include "vsrt_device.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -75,7 +76,14 @@ constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_RAYS = K3_WARPS * 32;   // rays per CTA: every warp owns 32 consecutive rays and their contiguous output range
 constexpr int K3_ILP = 4;        // independent 32-record windows in flight per warp
-constexpr int K3_HASH_BITS = 10; // CTA-private treelet histogram: 1024 (key,count) slots in shared memory
+#ifndef VSRT_K3_HASH_BITS
+#define VSRT_K3_HASH_BITS 10
+#endif
+#ifndef VSRT_K3_PERSIST
+#define VSRT_K3_PERSIST 0   // measured: a persistent grid saturates the CTA-private table and is slower (1.10 vs 0.72 ms)
+#endif
+constexpr int K3_HASH_BITS = VSRT_K3_HASH_BITS; // CTA-private treelet histogram: 2^bits (key,count) slots in shared memory, flushed once per CTA
+constexpr int K3_CTAS_PER_SM = 4; // only for the persistent-grid A/B variant (VSRT_K3_PERSIST=1)
 
 __device__ __forceinline__ uint32_t code_size(uint32_t code) { return code == C_INSTANCE ? 128u : (code == C_DESC ? 8u : 64u); }
 __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_INTERNAL_TLAS ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code; }
@@ -96,9 +104,11 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
   const ArenaView& av = p.av;
   const bool one_span = av.n_spans == 1;
   const uint64_t span_host = one_span ? av.spans[0].host : 0ull;
-  const uint64_t rw0 = (uint64_t)blockIdx.x * K3_RAYS + (uint64_t)(threadIdx.x >> 5) * 32u;
   uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-  if (rw0 < p.n_rays) {
+  const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const uint64_t rw0 = blk * K3_RAYS + (uint64_t)(threadIdx.x >> 5) * 32u;
+    if (rw0 >= p.n_rays) continue;
     const uint32_t nr = (uint32_t)min((uint64_t)32, p.n_rays - rw0);
     const unsigned long long my_off = p.offsets[rw0 + min((uint32_t)lane, nr)];
     const unsigned long long j0 = __shfl_sync(full, my_off, 0), j1 = p.offsets[rw0 + nr];
@@ -230,8 +240,13 @@ int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void
 }
 
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
-  const uint64_t grid = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
-  if (grid == 0) return VSRT_OK;
+  const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
+  if (n_blocks == 0) return VSRT_OK;
+  static int n_sm = 0;
+  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  int per_sm = K3_CTAS_PER_SM;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact, K3_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const uint64_t grid = VSRT_K3_PERSIST ? std::min<uint64_t>(n_blocks, (uint64_t)n_sm * (uint64_t)per_sm) : n_blocks;
   k_compact<<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

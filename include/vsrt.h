@@ -167,6 +167,10 @@ int vsrt_node_map(vsrt_context* ctx, uint64_t* node_addr, uint64_t* root_addr);
 /* remapBVHToTreeletLayout (:1473-1509): original device address -> address in the treelet layout, ascending
  * original order; base = where the reference's gpgpusim_malloc would have put treelet_layout_bvh. */
 int vsrt_treelet_remap(vsrt_context* ctx, uint64_t base, uint64_t* n_out, uint64_t* orig_addr, uint64_t* new_addr);
+/* -remap_to_treelet_layout 1: every trace record carries original_bvh_to_treelet_bvh_mapping[address] and every treelet
+ * id the remapped root (:1369-1412, :1682, :1763, ...).  The mapping depends on where the reference's gpgpusim_malloc
+ * placed treelet_layout_bvh (:1477); pass that address here before tracing (the remap table is rebuilt when it changes). */
+int vsrt_set_treelet_layout_base(vsrt_context* ctx, uint64_t base);
 /* addrToTreeletID (:468): device address of the treelet root owning `addr`; VSRT_E_INVALID if unknown
  * (the reference asserts). */
 int vsrt_addr_to_treelet(vsrt_context* ctx, uint64_t addr, uint64_t* root);

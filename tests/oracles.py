@@ -182,6 +182,21 @@ class PortOracle(_Base):
             return self.trace(mode, rays, cap_per_ray * 4, nthreads)
         return self._finish_trace(n, total, hits, counts, txns, tids)
 
+    def trace_remapped(self, mode, rays, base, stride, budget):
+        """-remap_to_treelet_layout 1 (vulkan_ray_tracing.cc:1682,:1763,...): the same visit sequence with every record
+        address sent through original_bvh_to_treelet_bvh_mapping and every treelet id replaced by the remapped root
+        (treelet i of the ascending root order sits at base + i * (max_treelet_size + stride))."""
+        t = self.trace(mode, rays)
+        o, m = self.remap_table(base, stride)
+        idx = np.searchsorted(o, t["txns"]["address"])
+        assert np.array_equal(o[idx], t["txns"]["address"]), "a traced address is missing from the remap table"
+        txns = t["txns"].copy(); txns["address"] = m[idx]
+        roots = self.tables()["roots"]
+        ridx = np.searchsorted(roots, t["treelet_ids"])
+        assert np.array_equal(roots[ridx], t["treelet_ids"])
+        tids = (np.uint64(base) + ridx.astype(np.uint64) * np.uint64(budget + stride)).astype(np.uint64)
+        return {"hits": t["hits"], "offsets": t["offsets"], "txns": txns, "treelet_ids": tids}
+
     def counters(self):
         a = np.zeros(len(OCNT_FIELDS), np.uint64)
         self.L.vo_get_counters(self.h, _abi.ptr(a))

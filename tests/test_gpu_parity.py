@@ -240,6 +240,31 @@ def test_remap_table(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_remapped_traces(api, mode):
+    """-remap_to_treelet_layout 1: records and treelet ids in treelet-layout addresses, against the reference run with the
+    option on (or the pinned port when oracle/_ref is absent)."""
+    s = sc.Scene(3000, seed=13, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(2000, 21)
+    if oracles.have_ref():
+        ref = oracles.RefOracle(); ref.register(s, remap=True, stride=256); ref.form(1024)
+        base = ref.remap_table()[0]
+        o = ref.trace(mode, rays)
+    else:
+        base = 0x7f0000000000
+        port = oracles.PortOracle(); port.register(s); port.form(1024)
+        o = port.trace_remapped(mode, rays, base, 256, 1024)
+    ctx = api.Context(max_treelet_size=1024, device=0, treelet_remap_stride=256, remap_to_treelet_layout=1)
+    ctx.register(s); ctx.form_treelets()
+    with pytest.raises(api.VsrtError):
+        ctx.trace(mode, rays[:4])              # the layout base is an input (gpgpusim_malloc's answer in the reference)
+    ctx.set_treelet_layout_base(base)
+    g = ctx.trace(mode, rays)
+    assert np.array_equal(o["offsets"], g["offsets"]) and np.array_equal(o["txns"], g["txns"])
+    assert np.array_equal(o["treelet_ids"], g["treelet_ids"])
+    ctx.close()
+
+
 def test_large_scene_properties(api):
     """Full-size style check through size-independent properties (no oracle): both variants agree on hit t
     for opaque closest-hit rays; per-ray records start with the TLAS header; counters equal the trace."""

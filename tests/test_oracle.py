@@ -84,6 +84,22 @@ def test_remap_matches_reference():
     assert np.array_equal(o, po) and np.array_equal(m, pm)
 
 
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_remapped_traces_match_reference():
+    """-remap_to_treelet_layout 1: the port's remapped trace (visit order unchanged, addresses and treelet ids through the
+    remap table) equals what the reference itself emits with the option on, in both variants."""
+    s = sc.Scene(2500, seed=4, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(1500, 5)
+    for mode in (0, 1):
+        ref, port = oracles.RefOracle(), oracles.PortOracle()
+        ref.register(s, remap=True, stride=128); ref.form(1024)
+        port.register(s); port.form(1024)
+        base = ref.remap_table()[0]
+        a, b = ref.trace(mode, rays), port.trace_remapped(mode, rays, base, 128, 1024)
+        assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["txns"], b["txns"])
+        assert np.array_equal(a["treelet_ids"], b["treelet_ids"]) and same_hits(a["hits"], b["hits"])
+
+
 def test_port_parallel_equals_serial():
     s = sc.Scene(8000, seed=6, n_blas=2, n_instances=2)
     rays = helpers.mixed_rays(3000, 8)

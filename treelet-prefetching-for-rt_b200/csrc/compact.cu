@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
               for (uint32_t b = k[u]; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
             }
           }
-          const uint64_t address = (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta;
+          // original_bvh_to_treelet_bvh_mapping[addr + offset] in every record when the layout is remapped (:1682,:1763,...)
+          const uint64_t address = p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta;
           const uint32_t type = code_type(code);
           const unsigned long long j = j0 + pos[u];
           if (j < p.out_capacity) {
@@ -218,11 +219,13 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
   }
 }
 
-__global__ void k_tid_to_addr(const ArenaView av, const TreeletView tv, const uint32_t* __restrict__ tids, uint64_t n, unsigned long long* __restrict__ out) {
+__global__ void k_tid_to_addr(const ArenaView av, const TreeletView tv, const uint32_t* __restrict__ tids, uint64_t n, unsigned long long* __restrict__ out,
+                              unsigned long long remap_base, unsigned long long remap_pitch) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t t = tids[i];
-  out[i] = (t == VSRT_NO_TID || t >= tv.n_treelets) ? ~0ull : slot_to_host(av, __ldg(tv.tl_root + t)) + (uint64_t)av.tlas_delta;
+  if (t == VSRT_NO_TID || t >= tv.n_treelets) out[i] = ~0ull;
+  else out[i] = remap_pitch ? remap_base + (unsigned long long)t * remap_pitch : slot_to_host(av, __ldg(tv.tl_root + t)) + (uint64_t)av.tlas_delta;
 }
 
 }  // namespace
@@ -251,8 +254,9 @@ int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
-int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out, cudaStream_t st) {
+int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out,
+                            uint64_t remap_base, uint64_t remap_pitch, cudaStream_t st) {
   if (n == 0) return VSRT_OK;
-  k_tid_to_addr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(av, tv, tids, n, (unsigned long long*)out);
+  k_tid_to_addr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(av, tv, tids, n, (unsigned long long*)out, remap_base, remap_pitch);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

@@ -219,6 +219,36 @@ __global__ void k_fill_ptrs(const uint64_t** r_list, uint32_t begin, uint32_t co
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t < count) r_list[begin + t] = pool + (uint64_t)t * cap;
 }
 
+// ---- remapBVHToTreeletLayout (:1473-1509) as a per-slot table: treelet t (ascending root order) starts at base + t * pitch,
+// its root first, then its list entries in order; an entry keeps the mapping of the FIRST treelet (lowest index) that lists
+// it but still advances the cursor of every later treelet (:1501-1503).  "First treelet that lists it" is an atomicMin over
+// treelet indices, after which every treelet can lay out its own entries independently.
+__global__ void k_remap_owner(const uint32_t* __restrict__ tl_root, const unsigned long long* __restrict__ tl_off, const uint64_t* __restrict__ tl_node,
+                              uint32_t n_treelets, uint32_t* __restrict__ owner) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_treelets) return;
+  atomicMin(owner + tl_root[t], t);
+  for (unsigned long long k = tl_off[t]; k < tl_off[t + 1]; k++) atomicMin(owner + (uint32_t)tl_node[k], t);
+}
+__global__ void k_remap_assign(const uint32_t* __restrict__ tl_root, const unsigned long long* __restrict__ tl_off, const uint64_t* __restrict__ tl_node,
+                               uint32_t n_treelets, const uint32_t* __restrict__ owner, unsigned long long base, unsigned long long pitch,
+                               unsigned long long* __restrict__ remap) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_treelets) return;
+  const uint32_t rslot = tl_root[t];
+  const unsigned long long rnew = base + (unsigned long long)t * pitch;
+  if (owner[rslot] == t) remap[rslot] = rnew;
+  // root.first.size: 128 when the root is an instance leaf (:927), 64 otherwise
+  unsigned long long cur = rnew + 64ull;
+  for (unsigned long long k = tl_off[t]; k < tl_off[t + 1]; k++) if ((uint32_t)tl_node[k] == rslot && (uint32_t)(tl_node[k] >> 32) == K_INSTANCE) cur = rnew + 128ull;
+  for (unsigned long long k = tl_off[t]; k < tl_off[t + 1]; k++) {
+    const uint64_t e = tl_node[k]; const uint32_t slot = (uint32_t)e;
+    if (slot == rslot) continue;
+    if (owner[slot] == t) remap[slot] = cur;
+    cur += ((uint32_t)(e >> 32) == K_INSTANCE) ? 128ull : 64ull;
+  }
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(errbuf, errcap, "%s: %s", #x, cudaGetErrorString(e_)); rc = VSRT_E_CUDA; goto done; } } while (0)
 
 }  // namespace
@@ -316,4 +346,20 @@ done:
   cudaFree(tl_node); cudaFree(node_tid);
   if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
   return rc;
+}
+
+int vsrt_launch_remap(const FormOutputs& fo, uint32_t n_treelets, uint32_t n_slots, uint64_t base, uint64_t pitch, uint64_t* remap_dev, cudaStream_t st) {
+  uint32_t* owner = nullptr;
+  if (cudaMalloc(&owner, (size_t)std::max(n_slots, 1u) * 4) != cudaSuccess) return VSRT_E_CUDA;
+  cudaMemsetAsync(owner, 0xff, (size_t)n_slots * 4, st);
+  cudaMemsetAsync(remap_dev, 0, (size_t)n_slots * 8, st);     // unmapped -> 0, like std::map::operator[] on a missing key
+  if (n_treelets) {
+    k_remap_owner<<<(n_treelets + 127) / 128, 128, 0, st>>>(fo.tl_root, (const unsigned long long*)fo.tl_off, fo.tl_node, n_treelets, owner);
+    k_remap_assign<<<(n_treelets + 127) / 128, 128, 0, st>>>(fo.tl_root, (const unsigned long long*)fo.tl_off, fo.tl_node, n_treelets, owner, base, pitch,
+                                                            (unsigned long long*)remap_dev);
+  }
+  const cudaError_t e = cudaGetLastError();
+  cudaStreamSynchronize(st);
+  cudaFree(owner);
+  return e == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

@@ -56,6 +56,8 @@ struct vsrt_context {
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
   DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
+  // -remap_to_treelet_layout: where gpgpusim_malloc put treelet_layout_bvh (:1477), and the per-slot table
+  uint64_t layout_base = 0; bool layout_base_set = false; DevBuf<uint64_t> d_remap; bool remap_valid = false;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
   uint64_t last_tlas = 0; int last_mode = 0;
@@ -72,7 +74,7 @@ int fail(vsrt_context* c, int code, const char* fmt, ...) {
 
 void free_treelets(vsrt_context* c) {
   cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node);
-  c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0;
+  c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
 }
 
@@ -152,7 +154,17 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   if (mode != VSRT_MODE_DFS && mode != VSRT_MODE_TREELET) return fail(c, VSRT_E_INVALID, "mode must be VSRT_MODE_DFS or VSRT_MODE_TREELET");
   if (n >= (1ull << 32) - 1) return fail(c, VSRT_E_INVALID, "a batch holds at most 2^32-2 rays; split the frame");
   int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;   // lazily, like :1593 / :2364
-  if (c->cfg.remap_to_treelet_layout) return fail(c, VSRT_E_UNSUPPORTED, "remap_to_treelet_layout in traces is not built yet (vsrt_treelet_remap gives the table)");
+  const uint64_t remap_pitch = c->cfg.remap_to_treelet_layout ? (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride : 0;
+  if (c->cfg.remap_to_treelet_layout) {
+    if (!c->layout_base_set) return fail(c, VSRT_E_INVALID, "remap_to_treelet_layout needs vsrt_set_treelet_layout_base (the address gpgpusim_malloc gave treelet_layout_bvh, vulkan_ray_tracing.cc:1477)");
+    if (!c->remap_valid) {
+      const uint32_t ns = (uint32_t)(c->arena_bytes / 64);
+      CUDA_OK(c, c->d_remap.ensure(std::max<uint32_t>(ns, 1)));
+      rc = vsrt_launch_remap(c->fo, c->fr.n_treelets, ns, c->layout_base, remap_pitch, c->d_remap.p, c->stream);
+      if (rc) return fail(c, rc, "treelet-layout remap kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+      c->remap_valid = true;
+    }
+  }
   ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
   const TreeletView tv = treelet_view(c);
   c->last = vsrt_device_results{}; c->last_tlas = tlas; c->last_mode = mode;
@@ -207,6 +219,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
   CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
   cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = c->d_txns.cap; cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
+  cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
   rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
   CUDA_OK(c, cudaEventRecord(c->ev[3], st));
   launches += n ? 1 : 0;
@@ -285,7 +298,7 @@ void vsrt_destroy(vsrt_context* c) {
   free_treelets(c);
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
-  c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release();
+  c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -340,6 +353,13 @@ int vsrt_form_treelets(vsrt_context* c, const void* tlas, uint32_t max_bytes) {
   cudaSetDevice(c->device);
   if (max_bytes) c->cfg.max_treelet_size = max_bytes;
   return do_form(c, (uint64_t)(uintptr_t)tlas, c->cfg.max_treelet_size);
+}
+
+int vsrt_set_treelet_layout_base(vsrt_context* c, uint64_t base) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->layout_base_set || c->layout_base != base) c->remap_valid = false;
+  c->layout_base = base; c->layout_base_set = true;
+  return VSRT_OK;
 }
 
 int vsrt_treelet_info_get(vsrt_context* c, vsrt_treelet_info* out) {
@@ -462,7 +482,8 @@ int vsrt_trace_fetch(vsrt_context* c, vsrt_txn* txns, uint64_t cap, uint64_t* tr
   if (treelet_ids && m) {
     ArenaView av; int rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
     CUDA_OK(c, c->d_tid_addr.ensure(m));
-    rc = vsrt_launch_tid_to_addr(av, treelet_view(c), c->d_tids.p, m, c->d_tid_addr.p, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
+    const uint64_t pitch = c->cfg.remap_to_treelet_layout ? (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride : 0;
+    rc = vsrt_launch_tid_to_addr(av, treelet_view(c), c->d_tids.p, m, c->d_tid_addr.p, c->layout_base, pitch, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
     CUDA_OK(c, cudaMemcpyAsync(treelet_ids, c->d_tid_addr.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));

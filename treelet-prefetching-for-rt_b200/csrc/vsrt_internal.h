@@ -81,6 +81,9 @@ struct FormOutputs {      // device allocations owned by the context
 int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,
                               uint32_t* err_flags_dev, char* errbuf, size_t errcap);
 
+// remapBVHToTreeletLayout as a device table: remap_dev[slot] = address of the node in the treelet layout (0 = unmapped)
+int vsrt_launch_remap(const FormOutputs& fo, uint32_t n_treelets, uint32_t n_slots, uint64_t base, uint64_t pitch, uint64_t* remap_dev, cudaStream_t st);
+
 struct TraverseParams {
   ArenaView av; TreeletView tv;
   const vsrt_ray* rays; uint64_t n_rays;
@@ -110,8 +113,11 @@ struct CompactParams {
   const uint64_t* offsets; uint64_t n_rays;
   vsrt_txn* txns; uint32_t* tids; uint64_t out_capacity;
   DevCounters* counters; unsigned long long* treelet_hist;   // may be NULL
+  const uint64_t* remap;      // -remap_to_treelet_layout: record address = remap[slot] (NULL = original addresses)
 };
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st);
 
 // u32 treelet index -> u64 root device address (addrToTreeletID value)
-int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out, cudaStream_t st);
+// remap_pitch != 0: roots are reported in the treelet layout, remap_base + index * remap_pitch
+int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out,
+                            uint64_t remap_base, uint64_t remap_pitch, cudaStream_t st);

@@ -24,7 +24,7 @@ c_u64, c_u32, c_vp, c_int = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, c
 # every symbol include/vsrt.h declares (tests check the library exports all of them)
 SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_error", "vsrt_config_parse",
            "vsrt_alloc_tlas", "vsrt_alloc_blas", "vsrt_commit", "vsrt_form_treelets", "vsrt_treelet_info_get",
-           "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
+           "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_set_treelet_layout_base", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
            "vsrt_counters_device", "vsrt_get_treelet_histogram"]
@@ -59,6 +59,7 @@ def load():
     L.vsrt_treelet_table.argtypes = [c_vp] * 5
     L.vsrt_node_map.argtypes = [c_vp] * 3
     L.vsrt_treelet_remap.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u64), c_vp, c_vp]
+    L.vsrt_set_treelet_layout_base.argtypes = [c_vp, c_u64]
     L.vsrt_addr_to_treelet.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_is_treelet_root.argtypes = [c_vp, c_u64]
     L.vsrt_treelet_metadata_idx.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u32)]
@@ -169,6 +170,10 @@ class Context:
         o = np.zeros(n.value, np.uint64); m = np.zeros(n.value, np.uint64)
         self._ck(self.L.vsrt_treelet_remap(self.h, base, ctypes.byref(n), _abi.ptr(o), _abi.ptr(m)))
         return o, m
+
+    def set_treelet_layout_base(self, base):
+        """-remap_to_treelet_layout: where the reference's gpgpusim_malloc placed treelet_layout_bvh."""
+        self._ck(self.L.vsrt_set_treelet_layout_base(self.h, int(base)))
 
     def addr_to_treelet(self, addr):
         r = c_u64()

@@ -27,6 +27,15 @@ mkdir -p "$OUT"
   sed -n '123,129p;136,140p' "$R/cuda-sim/vulkan_ray_tracing.cc"
   sed -n '148,257p;456,510p;823,1520p;1522,2307p;2309,3076p;3089,3130p' "$R/cuda-sim/vulkan_ray_tracing.cc"
   cat "$HERE/ref_shim/ref_api.cc"
+  # ---- RT-unit replay helpers: RTMemoryTransactionRecord, rt_unit::sort_mem_accesses and the
+  # treelet-prefetch vote block of rt_unit::cycle, the latter spliced in as the body of a member function
+  sed -n '1372,1401p' "$R/abstract_hardware_model.h"
+  cat "$HERE/ref_shim/shim_rtunit.h"
+  sed -n '3012,3164p' "$R/gpgpu-sim/shader.cc"
+  echo 'void rt_unit::prefetch_vote_block() {'
+  sed -n '3419,3684p' "$R/gpgpu-sim/shader.cc"
+  echo '  out_root = prefetched_treelet_root; out_num_nodes = num_nodes_to_prefetch; out_seen = true; } }'
+  cat "$HERE/ref_shim/ref_api_rtunit.cc"
 } | sed 's/next_node_addr > 0/next_node_addr != 0/g' > "$OUT/ref_tu.cc"
 g++ -O3 -fpermissive -w -std=c++14 -fPIC -shared -I/usr/local/cuda/include \
     "$OUT/ref_tu.cc" -o "$OUT/libvsrt_ref.so"

@@ -15,6 +15,8 @@
 #include <map>
 #include <deque>
 #include <list>
+#include <bitset>
+#include <set>
 #include <string>
 #include <fstream>
 #include <iostream>

@@ -724,3 +724,105 @@ int64_t vo_trace(vo_ctx* c, const void* tlas_v, int mode, uint32_t n, const vo_r
   free(ws); free(blk_first); if (!counts) free(cnt);
   return ret;
 }
+
+/* ================================================================ RT-unit replay helpers
+ * Restatement of the two pure pieces of rt_unit (gpgpu-sim/shader.cc) that consume the trace; pinned against the
+ * reference bodies in oracle/_ref (tests/test_oracle.py). */
+
+/* rt_unit::sort_mem_accesses, shader.cc:3012-3089, on one ray's list t[0..n), in place.
+ * method 1 ("loose", :3057-3086): treelets in order of first appearance; inside a treelet the accesses in their original
+ *   order -- but every access is replaced by the FIRST record of the list that has the same address (:3069-3076), so the
+ *   8-byte descriptor record of a leaf appears twice and its 64-byte record never.
+ * method 0 ("strict", :3027-3056): treelets in order of first appearance; for each, walk the treelet's node list in
+ *   formation order and emit all records of that address, original order (:3046-3054).  A node listed by several treelets
+ *   is emitted with the first visited treelet that lists it. */
+static void sort_one(vo_ctx* c, int method, vo_txn* t, uint32_t n, vo_txn* tmp, uint64_t* tag, uint64_t* order, uint8_t* done) {
+  uint32_t n_order = 0, o = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!map_get(&c->node_root, t[i].address, &tag[i])) tag[i] = 0;   /* addrToTreeletID; the reference asserts on unknown addresses */
+    uint32_t j = 0; while (j < n_order && order[j] != tag[i]) j++;
+    if (j == n_order) order[n_order++] = tag[i];
+  }
+  if (method == 1) {
+    for (uint32_t q = 0; q < n_order; q++)
+      for (uint32_t i = 0; i < n; i++) if (tag[i] == order[q]) {
+        uint32_t f = 0; while (t[f].address != t[i].address) f++;
+        tmp[o++] = t[f];
+      }
+  } else {
+    memset(done, 0, n);
+    for (uint32_t q = 0; q < n_order; q++) {
+      uint64_t idx;
+      if (!map_get(&c->root_idx, order[q], &idx)) continue;
+      const vo_treelet* tl = &c->treelets[idx];
+      for (uint32_t k = 0; k < tl->count; k++) {
+        const uint64_t a = c->lnodes[tl->first + k].addr;
+        for (uint32_t i = 0; i < n; i++) if (!done[i] && t[i].address == a) { tmp[o++] = t[i]; done[i] = 1; }
+      }
+    }
+  }
+  /* the reference asserts mem_accesses.size() == sorted.size() (:3087); keep whatever was not placed at the end */
+  if (method == 0) for (uint32_t i = 0; i < n && o < n; i++) if (!done[i]) tmp[o++] = t[i];
+  memcpy(t, tmp, (size_t)n * sizeof(vo_txn));
+}
+void vo_sort_trace(vo_ctx* c, int method, uint64_t n_rays, const uint64_t* offsets, vo_txn* txns) {
+  uint32_t cap = 0;
+  for (uint64_t r = 0; r < n_rays; r++) { const uint64_t n = offsets[r + 1] - offsets[r]; if (n > cap) cap = (uint32_t)n; }
+  vo_txn* tmp = (vo_txn*)malloc((size_t)(cap + 1) * sizeof(vo_txn));
+  uint64_t* tag = (uint64_t*)malloc((size_t)(cap + 1) * 8); uint64_t* order = (uint64_t*)malloc((size_t)(cap + 1) * 8);
+  uint8_t* done = (uint8_t*)malloc(cap + 1);
+  for (uint64_t r = 0; r < n_rays; r++) sort_one(c, method, txns + offsets[r], (uint32_t)(offsets[r + 1] - offsets[r]), tmp, tag, order, done);
+  free(tmp); free(tag); free(order); free(done);
+}
+
+/* The treelet-prefetch vote of rt_unit::cycle, shader.cc:3419-3640, for one group of rays with a fresh unit (no
+ * last_prefetched_treelet history).  Ray r votes with addrToTreeletID of its pending access txns[offsets[r] + front[r]]
+ * (:3424-3433); the winner is the first maximum in ascending root-address order (std::map iteration, strict '>').
+ *   heuristic 0: always submit the whole treelet (:3438-3446)
+ *   heuristic 1: submit iff votes/total >= threshold (:3487-3514)
+ *   heuristic 2: submit the first (int)(n_nodes * votes/total + 0.5) nodes (:3515-3534)
+ *   heuristic 3: submit the last that many nodes (:3535-3552, :3566)
+ * Chunks (:3566-3620): per node, when load_metadata, per_meta/32 chunks of the metadata row
+ * treelet_addr_to_metadata_idx[NODE address] (0 unless the node is itself a root -- std::map::operator[], :3571) first,
+ * then ceil(size/32) chunks of the node; each chunk is (address, owner address). */
+typedef struct { uint64_t root; uint32_t votes, total, submit, n_nodes, first_node, num_nodes; } vo_prefetch_decision;
+int64_t vo_prefetch_vote(vo_ctx* c, int heuristic, double threshold, int load_metadata, uint64_t metadata_base, uint32_t per_meta,
+                         uint64_t n_rays, const uint64_t* ray_ids, const uint64_t* offsets, const uint32_t* front, const vo_txn* txns,
+                         vo_prefetch_decision* dec, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t cap) {
+  uint32_t* tally = (uint32_t*)calloc(c->n_treelets ? c->n_treelets : 1, 4);
+  uint32_t total = 0;
+  for (uint64_t i = 0; i < n_rays; i++) {
+    const uint64_t r = ray_ids ? ray_ids[i] : i, k = offsets[r] + (front ? front[r] : 0);
+    uint64_t root, idx;
+    if (k >= offsets[r + 1]) continue;
+    if (!map_get(&c->node_root, txns[k].address, &root) || !map_get(&c->root_idx, root, &idx)) continue;
+    tally[idx]++; total++;
+  }
+  int64_t best = -1; uint32_t bestv = 0;
+  for (uint64_t t = 0; t < c->n_treelets; t++) if (tally[t] > bestv) { bestv = tally[t]; best = (int64_t)t; }   /* 0-vote treelets are not in the map */
+  memset(dec, 0, sizeof(*dec));
+  dec->total = total;
+  uint64_t n = 0;
+  if (best >= 0) {
+    const vo_treelet* tl = &c->treelets[best];
+    const double pct = (double)bestv / (double)total;
+    dec->root = tl->root; dec->votes = bestv; dec->n_nodes = tl->count;
+    const uint32_t part = (uint32_t)(int)((double)tl->count * pct + 0.5);
+    dec->submit = (heuristic == 1) ? (pct >= threshold) : 1u;
+    dec->num_nodes = (heuristic == 2 || heuristic == 3) ? part : tl->count;
+    dec->first_node = (heuristic == 3) ? tl->count - part : 0u;
+    if (dec->submit) {
+      for (uint32_t j = dec->first_node; j < dec->first_node + dec->num_nodes; j++) {
+        const vo_lnode* e = &c->lnodes[tl->first + j];
+        if (load_metadata) {
+          uint64_t idx = 0; if (!map_get(&c->root_idx, e->addr, &idx)) idx = 0;
+          const uint64_t ma = metadata_base + idx * (uint64_t)per_meta;
+          for (uint32_t q = 0; q < per_meta / 32; q++) { if (n < cap && chunk_addr) { chunk_addr[n] = ma + q * 32ull; chunk_owner[n] = ma; } n++; }
+        }
+        for (uint32_t q = 0; q < (e->size + 31) / 32; q++) { if (n < cap && chunk_addr) { chunk_addr[n] = e->addr + q * 32ull; chunk_owner[n] = e->addr; } n++; }
+      }
+    }
+  }
+  free(tally);
+  return (int64_t)n;
+}

@@ -29,6 +29,11 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+# vsrt_prefetch_decision / ref_prefetch_decision / vo_prefetch_decision
+PDEC = np.dtype([("root", np.uint64), ("votes", np.uint32), ("total", np.uint32), ("submit", np.uint32), ("n_nodes", np.uint32),
+                 ("first_node", np.uint32), ("num_nodes", np.uint32)])
+
+
 class _Base:
     def _finish_trace(self, n, total, hits, counts, txns, tids):
         offsets = np.zeros(n + 1, dtype=np.uint64)
@@ -53,6 +58,10 @@ class RefOracle(_Base):
         L.ref_trace.argtypes = [c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.c_int]
         L.ref_get_counters.argtypes = [c_vp]
         L.ref_config.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int]
+        L.ref_sort_trace.argtypes = [ctypes.c_int, c_u64, c_vp, c_vp]
+        L.ref_prefetch_vote.restype = ctypes.c_int64
+        L.ref_prefetch_vote.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64]
+        L.ref_set_treelet_metadata.argtypes = [c_u64, ctypes.c_uint]
         self.L = L
         self.tlas = None
 
@@ -99,6 +108,26 @@ class RefOracle(_Base):
             return self.trace(mode, rays, cap_per_ray * 4)   # NB: re-runs the rays (counters double count)
         return self._finish_trace(n, total, hits, counts, txns, tids)
 
+    def sort_trace(self, method, trace):
+        """rt_unit::sort_mem_accesses (shader.cc:3012) on every ray of a trace dict; returns the sorted record array."""
+        t = trace["txns"].copy()
+        self.L.ref_sort_trace(method, len(trace["offsets"]) - 1, _abi.ptr(trace["offsets"]), _abi.ptr(t))
+        return t
+
+    def prefetch_vote(self, trace, ray_ids, heuristic, threshold=0.0, front=None, metadata=None):
+        """The treelet-prefetch vote block of rt_unit::cycle (shader.cc:3419-3685) for one group of rays."""
+        ids = np.ascontiguousarray(ray_ids, np.uint64)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        if metadata:
+            self.L.ref_set_treelet_metadata(metadata[0], metadata[1])
+        dec = np.zeros(1, PDEC)
+        args = (heuristic, threshold, 1 if metadata else 0, len(ids), _abi.ptr(ids), _abi.ptr(trace["offsets"]),
+                _abi.ptr(fr) if fr is not None else None, _abi.ptr(trace["txns"]), _abi.ptr(dec))
+        n = self.L.ref_prefetch_vote(*args, None, None, 0)
+        ca = np.zeros(n, np.uint64); co = np.zeros(n, np.uint64)
+        self.L.ref_prefetch_vote(*args, _abi.ptr(ca), _abi.ptr(co), n)
+        return dec[0], ca, co
+
     def counters(self):
         a = np.zeros(len(OCNT_FIELDS), np.uint64)
         self.L.ref_get_counters(_abi.ptr(a))
@@ -125,6 +154,10 @@ class PortOracle(_Base):
         L.vo_trace.argtypes = [c_vp, c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.c_int]
         L.vo_get_counters.argtypes = [c_vp, c_vp]
         L.vo_reset_counters.argtypes = [c_vp]
+        L.vo_sort_trace.argtypes = [c_vp, ctypes.c_int, c_u64, c_vp, c_vp]
+        L.vo_prefetch_vote.restype = ctypes.c_int64
+        L.vo_prefetch_vote.argtypes = [c_vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_u64, ctypes.c_uint32, c_u64, c_vp, c_vp, c_vp, c_vp,
+                                       c_vp, c_vp, c_vp, c_u64]
         self.L = L
         self.h = None
 
@@ -181,6 +214,23 @@ class PortOracle(_Base):
         if total < 0:
             return self.trace(mode, rays, cap_per_ray * 4, nthreads)
         return self._finish_trace(n, total, hits, counts, txns, tids)
+
+    def sort_trace(self, method, trace):
+        t = trace["txns"].copy()
+        self.L.vo_sort_trace(self.h, method, len(trace["offsets"]) - 1, _abi.ptr(trace["offsets"]), _abi.ptr(t))
+        return t
+
+    def prefetch_vote(self, trace, ray_ids, heuristic, threshold=0.0, front=None, metadata=None):
+        ids = np.ascontiguousarray(ray_ids, np.uint64)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        mb, mp = metadata if metadata else (0, 0)
+        dec = np.zeros(1, PDEC)
+        args = (self.h, heuristic, threshold, 1 if metadata else 0, mb, mp, len(ids), _abi.ptr(ids), _abi.ptr(trace["offsets"]),
+                _abi.ptr(fr) if fr is not None else None, _abi.ptr(trace["txns"]), _abi.ptr(dec))
+        n = self.L.vo_prefetch_vote(*args, None, None, 0)
+        ca = np.zeros(n, np.uint64); co = np.zeros(n, np.uint64)
+        self.L.vo_prefetch_vote(*args, _abi.ptr(ca), _abi.ptr(co), n)
+        return dec[0], ca, co
 
     def trace_remapped(self, mode, rays, base, stride, budget):
         """-remap_to_treelet_layout 1 (vulkan_ray_tracing.cc:1682,:1763,...): the same visit sequence with every record

@@ -100,6 +100,48 @@ def test_remapped_traces_match_reference():
         assert np.array_equal(a["treelet_ids"], b["treelet_ids"]) and same_hits(a["hits"], b["hits"])
 
 
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+@pytest.mark.parametrize("budget", [512, 4096])
+def test_rt_unit_sort_matches_reference(budget):
+    """rt_unit::sort_mem_accesses (shader.cc:3012-3089), both -sort_method values, on a scene whose shared BLAS puts
+    nodes into several treelet lists."""
+    s = sc.Scene(2500, seed=4, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(400, 5)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s); ref.form(budget); port.register(s); port.form(budget)
+    for mode in (0, 1):
+        t = port.trace(mode, rays)
+        for method in (0, 1):
+            a, b = ref.sort_trace(method, t), port.sort_trace(method, t)
+            assert np.array_equal(a, b), (mode, method)
+            assert not np.array_equal(a, t["txns"])      # the sort does something on these traces
+
+
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_rt_unit_prefetch_vote_matches_reference():
+    """The treelet-prefetch vote block of rt_unit::cycle (shader.cc:3419-3685): decision and queued 32-byte chunks for
+    groups of rays at different points of their lists, all four heuristics, with and without metadata loads."""
+    s = sc.Scene(2500, seed=4, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(512, 9)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s); ref.form(1024); port.register(s); port.form(1024)
+    t = port.trace(1, rays)
+    counts = np.diff(t["offsets"]).astype(np.int64)
+    rng = np.random.default_rng(3)
+    checked = 0
+    for g0, g1 in ((0, 32), (32, 160), (100, 512), (7, 9)):
+        ids = np.arange(g0, g1)
+        for step in (0, 1, 3, 8, 10 ** 6):
+            front = np.minimum(rng.integers(0, step + 1, len(rays)), 10 ** 6).astype(np.uint32)
+            for h, thr in ((0, 0.0), (1, 0.3), (1, 0.9), (2, 0.0), (3, 0.0)):
+                for meta in (None, (0x5000000000, (1024 // 64) * 4)):
+                    (da, ca, oa), (db, cb, ob) = ref.prefetch_vote(t, ids, h, thr, front, meta), port.prefetch_vote(t, ids, h, thr, front, meta)
+                    assert da == db, (g0, g1, step, h, thr, da, db)
+                    assert np.array_equal(ca, cb) and np.array_equal(oa, ob)
+                    checked += int(da["submit"])
+    assert checked > 20
+
+
 def test_port_parallel_equals_serial():
     s = sc.Scene(8000, seed=6, n_blas=2, n_instances=2)
     rays = helpers.mixed_rays(3000, 8)

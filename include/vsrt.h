@@ -208,7 +208,8 @@ typedef struct vsrt_device_results {
   const void* hits;          /* vsrt_hit[n_rays] */
   const void* trace_offsets; /* uint64_t[n_rays+1] */
   const void* txns;          /* vsrt_txn[n_txn] */
-  const void* treelet_ids;   /* uint64_t[n_txn] */
+  const void* treelet_ids;   /* uint32_t[n_txn]: treelet INDEX of every record (ascending-root order == treelet_addr_to_metadata_idx,
+                                0xFFFFFFFF = not a BVH node); vsrt_trace_fetch expands it to the 64-bit root addresses */
   uint64_t n_rays, n_txn;
   uint64_t algorithmic_bytes; /* sum of txn.size over the batch == accessedDataSize delta */
   float traverse_ms, scan_ms, compact_ms; /* device time of the three stages of the last batch */
@@ -229,6 +230,43 @@ int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_
  * the popularity data the RT unit's treelet prefetcher votes on (shader.cc:3424-3433), accumulated over every
  * batch since the last vsrt_reset_counters / vsrt_form_treelets. */
 int vsrt_get_treelet_histogram(vsrt_context* ctx, uint64_t* hist, uint64_t capacity);
+
+/* ---- RT-unit replay helpers: what rt_unit (gpgpu-sim/shader.cc) does with the trace, batched over the last batch ----
+ * rt_unit::sort_mem_accesses (shader.cc:3012-3089) applied to every ray's list: method = -sort_method (0 strict treelet
+ * order, 1 loose).  The device trace of the last batch is replaced by the sorted one (CSR offsets unchanged):
+ * vsrt_trace_fetch / vsrt_trace_device_results return the sorted lists afterwards.  Sorting always starts from the
+ * original order, so the call may be repeated with the other method. */
+int vsrt_sort_trace(vsrt_context* ctx, int method);
+
+/* The treelet prefetcher of rt_unit::cycle (shader.cc:3419-3640).  -treelet_prefetch_heuristic / -treelet_prefetch_threshold /
+ * -load_treelet_metadata of gpgpusim.config; treelet_metadata_base = what gpgpusim_malloc returned for treelet_metadata
+ * (vulkan_ray_tracing.cc:1603; the row size is (max_treelet_size / 64) * 4, :1601-1602). */
+typedef struct vsrt_prefetch_config {
+  uint32_t heuristic;              /* 0 always, 1 popularity threshold, 2 partial (first nodes), 3 partial (last nodes) */
+  uint32_t load_treelet_metadata;
+  double threshold;
+  uint64_t treelet_metadata_base;
+} vsrt_prefetch_config;
+typedef struct vsrt_prefetch_decision {
+  uint64_t treelet_root;   /* prefetched_treelet_root (device address); 0 = no thread had a pending access */
+  uint32_t votes, total;   /* treelet_prefetch_priority[root], total_threads */
+  uint32_t submit;         /* submit_prefetch && root != nullptr */
+  uint32_t n_nodes;        /* nodes_in_treelet.size() */
+  uint32_t first_node;     /* nodes [first_node, first_node + num_nodes) of the treelet's list are queued */
+  uint32_t num_nodes;
+} vsrt_prefetch_decision;     /* 32 bytes */
+/* One vote per group of rays of the last batch (the threads of the warps resident in one RT unit).  Group g holds
+ * ray_ids[group_offsets[g] .. group_offsets[g+1]) (ray_ids NULL: the ray ids themselves); ray r votes with the treelet of
+ * record front[r] of its list (front NULL: the first record; a ray whose list is exhausted does not vote, :3426).  The
+ * winner is the most voted treelet, lowest root address among equals (:3441).  A fresh unit per group: the caller keeps
+ * last_prefetched_treelet and the queue-occupancy test (:3537,:3556). */
+int vsrt_prefetch_vote(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uint64_t n_groups, const uint64_t* group_offsets,
+                       const uint64_t* ray_ids, const uint32_t* front, vsrt_prefetch_decision* decisions);
+/* prefetch_mem_access_q entries of every decision (:3566-3620): chunk_offsets[n_groups+1] is a CSR over
+ * (chunk_addr, chunk_owner) = (32-byte chunk address, address of the node or metadata row it belongs to).  Returns
+ * VSRT_E_CAPACITY if capacity < *n_chunks (offsets are still complete). */
+int vsrt_prefetch_chunks(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uint64_t n_groups, const vsrt_prefetch_decision* decisions,
+                         uint64_t* chunk_offsets, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t capacity, uint64_t* n_chunks);
 
 #ifdef __cplusplus
 }

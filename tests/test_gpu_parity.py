@@ -265,6 +265,62 @@ def test_remapped_traces(api, mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("budget", [512, 4096])
+def test_sort_trace(api, budget):
+    """rt_unit::sort_mem_accesses (shader.cc:3012-3089), both -sort_method values and both traversal variants, on a scene
+    whose shared BLAS lists nodes in several treelets."""
+    s = sc.Scene(3000, seed=13, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(1500, 23)
+    orc = oracles.RefOracle() if oracles.have_ref() else oracles.PortOracle()
+    orc.register(s); orc.form(budget)
+    ctx = api.Context(max_treelet_size=budget, device=0); ctx.register(s); ctx.form_treelets()
+    for mode in (0, 1):
+        o = orc.trace(mode, rays)
+        ctx.trace(mode, rays)
+        for method in (1, 0, 1):                   # repeated calls always sort the ORIGINAL order
+            want = orc.sort_trace(method, o)
+            got, tids = ctx.sort_trace(method)
+            assert np.array_equal(want, got), (mode, method)
+            roots = orc.tables()
+            idx = np.searchsorted(roots["map_nodes"], got["address"])
+            assert np.array_equal(roots["map_roots"][idx], tids)        # the ids travel with their records
+    ctx.close()
+
+
+def test_prefetch_vote_and_chunks(api):
+    """Treelet-prefetch vote of rt_unit::cycle (shader.cc:3419-3640) and the chunks it queues, per group of rays."""
+    s = sc.Scene(3000, seed=13, n_blas=2, n_instances=3)
+    rays = helpers.mixed_rays(6000, 29)
+    orc = oracles.RefOracle() if oracles.have_ref() else oracles.PortOracle()
+    orc.register(s); orc.form(1024)
+    ctx = api.Context(max_treelet_size=1024, device=0); ctx.register(s); ctx.form_treelets()
+    o = orc.trace(1, rays); ctx.trace(1, rays)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(rays)).astype(np.uint64)
+    meta = (0x5000000000, (1024 // 64) * 4)
+    for go, ids in ((np.arange(0, len(rays) + 1, 32), None), (np.array([0, 5, 5, 900, 6000]), None), (np.array([0, 64, 300, 5000]), perm)):
+        for step in (0, 2, 7, 10 ** 6):
+            front = rng.integers(0, step + 1, len(rays)).astype(np.uint32)
+            for h, thr in ((0, 0.0), (1, 0.5), (2, 0.0), (3, 0.0)):
+                for use_meta in (False, True):
+                    dec = ctx.prefetch_vote(go, h, thr, ids, front, use_meta, meta[0])
+                    offs, ca, co = ctx.prefetch_chunks(dec, h, use_meta, meta[0])
+                    picks = range(len(go) - 1) if len(go) < 10 else rng.choice(len(go) - 1, 12, replace=False)
+                    for g in picks:
+                        gi = np.arange(go[g], go[g + 1]) if ids is None else ids[go[g]:go[g + 1]]
+                        d, a, b = orc.prefetch_vote(o, gi, h, thr, front, meta if use_meta else None)
+                        got = dec[g]
+                        assert (int(got["treelet_root"]), int(got["votes"]), int(got["total"]), int(got["submit"]), int(got["n_nodes"]), int(got["first_node"]), int(got["num_nodes"])) == \
+                               (int(d["root"]), int(d["votes"]), int(d["total"]), int(d["submit"]), int(d["n_nodes"]), int(d["first_node"]), int(d["num_nodes"])), (g, h, step)
+                        assert np.array_equal(ca[offs[g]:offs[g + 1]], a) and np.array_equal(co[offs[g]:offs[g + 1]], b), (g, h, step)
+    # one group larger than the shared-memory path
+    big = rng.integers(0, len(rays), 9000).astype(np.uint64)
+    dec = ctx.prefetch_vote(np.array([0, 9000]), 2, 0.0, big, None)
+    d, a, b = orc.prefetch_vote(o, big, 2, 0.0, None, None)
+    assert (int(dec[0]["treelet_root"]), int(dec[0]["votes"]), int(dec[0]["total"]), int(dec[0]["num_nodes"])) == (int(d["root"]), int(d["votes"]), int(d["total"]), int(d["num_nodes"]))
+    ctx.close()
+
+
 def test_large_scene_properties(api):
     """Full-size style check through size-independent properties (no oracle): both variants agree on hit t
     for opaque closest-hit rays; per-ray records start with the TLAS header; counters equal the trace."""

@@ -58,6 +58,9 @@ struct vsrt_context {
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
   // -remap_to_treelet_layout: where gpgpusim_malloc put treelet_layout_bvh (:1477), and the per-slot table
   uint64_t layout_base = 0; bool layout_base_set = false; DevBuf<uint64_t> d_remap; bool remap_valid = false;
+  // replay helpers: sorted copy of the last trace, inverted treelet lists (slot -> (treelet, position))
+  DevBuf<vsrt_txn> d_txns_sorted; DevBuf<uint32_t> d_tids_sorted; DevBuf<uint64_t> d_sort_keys;
+  uint64_t* d_inv_off = nullptr; uint2* d_inv = nullptr;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
   uint64_t last_tlas = 0; int last_mode = 0;
@@ -75,6 +78,7 @@ int fail(vsrt_context* c, int code, const char* fmt, ...) {
 void free_treelets(vsrt_context* c) {
   cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node);
   c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
+  cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
 }
 
@@ -299,6 +303,7 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -478,12 +483,12 @@ int vsrt_trace_fetch(vsrt_context* c, vsrt_txn* txns, uint64_t cap, uint64_t* tr
   if (!c) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
   const uint64_t total = c->last.n_txn, m = std::min(total, cap);
-  if (txns && m) CUDA_OK(c, cudaMemcpyAsync(txns, c->d_txns.p, m * sizeof(vsrt_txn), cudaMemcpyDeviceToHost, c->stream));
+  if (txns && m) CUDA_OK(c, cudaMemcpyAsync(txns, c->last.txns, m * sizeof(vsrt_txn), cudaMemcpyDeviceToHost, c->stream));
   if (treelet_ids && m) {
     ArenaView av; int rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
     CUDA_OK(c, c->d_tid_addr.ensure(m));
     const uint64_t pitch = c->cfg.remap_to_treelet_layout ? (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride : 0;
-    rc = vsrt_launch_tid_to_addr(av, treelet_view(c), c->d_tids.p, m, c->d_tid_addr.p, c->layout_base, pitch, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
+    rc = vsrt_launch_tid_to_addr(av, treelet_view(c), (const uint32_t*)c->last.treelet_ids, m, c->d_tid_addr.p, c->layout_base, pitch, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
     CUDA_OK(c, cudaMemcpyAsync(treelet_ids, c->d_tid_addr.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -550,6 +555,122 @@ int vsrt_counters_device(vsrt_context* c, void** counters_dev, void** hist_dev, 
   if (hist_dev) *hist_dev = c->d_hist.p;
   if (n_treelets) *n_treelets = c->hist_n;
   return VSRT_OK;
+}
+
+// ---------------------------------------------------------------- RT-unit replay helpers
+int vsrt_sort_trace(vsrt_context* c, int method) {
+  if (!c) return VSRT_E_INVALID;
+  if (method != 0 && method != 1) return fail(c, VSRT_E_INVALID, "sort method must be 0 (strict) or 1 (loose), -sort_method of gpgpusim.config");
+  if (!c->formed || !c->last.trace_offsets) return fail(c, VSRT_E_INVALID, "no trace to sort: call vsrt_trace_rays / vsrt_trace_rays_device first");
+  cudaSetDevice(c->device);
+  const uint64_t n = c->last.n_rays, total = c->last.n_txn;
+  CUDA_OK(c, c->d_txns_sorted.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids_sorted.ensure(std::max<uint64_t>(total, 1)));
+  CUDA_OK(c, c->d_sort_keys.ensure(std::max<uint64_t>(total, 1)));
+  if (method == 0 && !c->d_inv_off) {
+    int rc = vsrt_launch_build_inverse(c->fo, c->fr.n_treelets, c->fr.n_entries, (uint32_t)(c->arena_bytes / 64), &c->d_inv_off, &c->d_inv, c->stream);
+    if (rc) return fail(c, rc, "building the inverted treelet lists failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  int rc = vsrt_launch_sort_trace(method, c->d_offsets.p, n, c->d_txns.p, c->d_tids.p, c->d_stage.p, c->stage_cap, c->d_inv_off, c->d_inv,
+                                  c->d_txns_sorted.p, c->d_tids_sorted.p, c->d_sort_keys.p, c->stream);
+  if (rc) return fail(c, rc, "sort kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->last.txns = c->d_txns_sorted.p; c->last.treelet_ids = c->d_tids_sorted.p;
+  return VSRT_OK;
+}
+
+}  // extern "C"
+
+namespace {
+uint64_t treelet_root_address(vsrt_context* c, uint32_t t) {
+  if (c->cfg.remap_to_treelet_layout) return c->layout_base + (uint64_t)t * ((uint64_t)c->formed_budget + c->cfg.treelet_remap_stride);
+  return slot_to_host_h(c, c->h_tl_root[t]) + (uint64_t)formed_delta(c);
+}
+bool treelet_index_of(vsrt_context* c, uint64_t root, uint32_t* idx) {
+  if (c->cfg.remap_to_treelet_layout) {
+    const uint64_t pitch = (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride;
+    if (root < c->layout_base || (root - c->layout_base) % pitch) return false;
+    const uint64_t t = (root - c->layout_base) / pitch; if (t >= c->fr.n_treelets) return false;
+    *idx = (uint32_t)t; return true;
+  }
+  uint32_t slot = 0;
+  if (!host_to_slot_h(c, root - (uint64_t)formed_delta(c), &slot)) return false;
+  auto it = std::lower_bound(c->h_tl_root.begin(), c->h_tl_root.end(), slot);
+  if (it == c->h_tl_root.end() || *it != slot) return false;
+  *idx = (uint32_t)(it - c->h_tl_root.begin()); return true;
+}
+template <typename T> cudaError_t upload(T** dev, const T* host, size_t n, cudaStream_t st) {
+  *dev = nullptr; if (!host || !n) return cudaSuccess;
+  cudaError_t e = cudaMalloc(dev, n * sizeof(T)); if (e != cudaSuccess) return e;
+  return cudaMemcpyAsync(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+}  // namespace
+
+extern "C" {
+
+int vsrt_prefetch_vote(vsrt_context* c, const vsrt_prefetch_config* cfg, uint64_t n_groups, const uint64_t* group_offsets,
+                       const uint64_t* ray_ids, const uint32_t* front, vsrt_prefetch_decision* decisions) {
+  if (!c || !cfg || (n_groups && (!group_offsets || !decisions))) return VSRT_E_INVALID;
+  if (cfg->heuristic > 3) return fail(c, VSRT_E_INVALID, "treelet_prefetch_heuristic must be 0..3");
+  if (!c->formed || !c->last.trace_offsets) return fail(c, VSRT_E_INVALID, "no trace to vote on: call vsrt_trace_rays / vsrt_trace_rays_device first");
+  if (n_groups == 0) return VSRT_OK;
+  cudaSetDevice(c->device);
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  const uint64_t n_ids = group_offsets[n_groups];
+  if (!ray_ids && n_ids > c->last.n_rays) return fail(c, VSRT_E_INVALID, "groups cover %llu rays, the last batch has %llu", (unsigned long long)n_ids, (unsigned long long)c->last.n_rays);
+  uint64_t* d_go = nullptr; uint64_t* d_ids = nullptr; uint32_t* d_front = nullptr; vsrt_prefetch_decision* d_out = nullptr;
+  bool ok = upload(&d_go, group_offsets, n_groups + 1, c->stream) == cudaSuccess && upload(&d_ids, ray_ids, n_ids, c->stream) == cudaSuccess &&
+            upload(&d_front, front, c->last.n_rays, c->stream) == cudaSuccess && cudaMalloc(&d_out, n_groups * sizeof(vsrt_prefetch_decision)) == cudaSuccess;
+  rc = ok ? vsrt_launch_prefetch_vote((const uint64_t*)c->last.trace_offsets, (const uint32_t*)c->last.treelet_ids, c->last.n_rays, d_go, group_offsets, d_ids, d_front,
+                                      n_groups, c->fo, c->fr.n_treelets, cfg->heuristic, cfg->threshold, d_out, c->stream) : VSRT_E_CUDA;
+  if (rc == VSRT_OK && (cudaMemcpyAsync(decisions, d_out, n_groups * sizeof(vsrt_prefetch_decision), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                        cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = VSRT_E_CUDA;
+  cudaFree(d_go); cudaFree(d_ids); cudaFree(d_front); cudaFree(d_out);
+  if (rc) return fail(c, rc, "prefetch vote failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (uint64_t g = 0; g < n_groups; g++) decisions[g].treelet_root = decisions[g].treelet_root == ~0ull ? 0ull : treelet_root_address(c, (uint32_t)decisions[g].treelet_root);
+  return VSRT_OK;
+}
+
+int vsrt_prefetch_chunks(vsrt_context* c, const vsrt_prefetch_config* cfg, uint64_t n_groups, const vsrt_prefetch_decision* decisions,
+                         uint64_t* chunk_offsets, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t capacity, uint64_t* n_chunks) {
+  if (!c || !cfg || (n_groups && !decisions)) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  if (n_chunks) *n_chunks = 0;
+  if (n_groups == 0) { if (chunk_offsets) chunk_offsets[0] = 0; return VSRT_OK; }
+  cudaSetDevice(c->device);
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  if (c->cfg.remap_to_treelet_layout && !c->remap_valid) return fail(c, VSRT_E_INVALID, "remapped layout: trace once (or set the layout base) before asking for prefetch chunks");
+  std::vector<vsrt_prefetch_decision> dec(decisions, decisions + n_groups);
+  for (auto& d : dec) {
+    uint32_t idx = 0;
+    if (d.treelet_root == 0 || !d.submit) { d.treelet_root = ~0ull; d.submit = 0; continue; }
+    if (!treelet_index_of(c, d.treelet_root, &idx)) return fail(c, VSRT_E_INVALID, "decision names 0x%llx, which is not a treelet root", (unsigned long long)d.treelet_root);
+    d.treelet_root = idx;
+  }
+  ArenaView av; rc = make_view(c, c->formed_tlas, &av); if (rc) return rc;
+  const uint32_t per_meta = (c->formed_budget / 64u) * 4u;       // per_treelet_metadata_size, vulkan_ray_tracing.cc:1601-1602
+  vsrt_prefetch_decision* d_dec = nullptr; uint32_t* d_cnt = nullptr; uint64_t* d_off = nullptr; void* d_tmp = nullptr; uint64_t* d_ca = nullptr; uint64_t* d_co = nullptr;
+  uint64_t total = 0;
+  bool ok = upload(&d_dec, dec.data(), n_groups, c->stream) == cudaSuccess && cudaMalloc(&d_cnt, n_groups * 4) == cudaSuccess &&
+            cudaMalloc(&d_off, (n_groups + 1) * 8) == cudaSuccess && cudaMalloc(&d_tmp, vsrt_scan_tmp_bytes(n_groups)) == cudaSuccess;
+  rc = ok ? VSRT_OK : VSRT_E_CUDA;
+  const uint64_t* remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
+  if (rc == VSRT_OK) rc = vsrt_launch_prefetch_chunks(false, av, treelet_view(c), c->fo, remap, d_dec, n_groups, cfg->load_treelet_metadata, per_meta, cfg->treelet_metadata_base,
+                                                      d_cnt, nullptr, nullptr, nullptr, 0, c->stream);
+  if (rc == VSRT_OK) rc = vsrt_launch_scan(d_cnt, n_groups, d_off, d_tmp, c->stream);
+  if (rc == VSRT_OK && (cudaMemcpyAsync(&total, d_off + n_groups, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = VSRT_E_CUDA;
+  if (rc == VSRT_OK && chunk_offsets && cudaMemcpy(chunk_offsets, d_off, (n_groups + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = VSRT_E_CUDA;
+  if (n_chunks) *n_chunks = total;
+  const uint64_t m = std::min(total, capacity);
+  if (rc == VSRT_OK && m && chunk_addr && chunk_owner) {
+    ok = cudaMalloc(&d_ca, total * 8) == cudaSuccess && cudaMalloc(&d_co, total * 8) == cudaSuccess;
+    rc = ok ? vsrt_launch_prefetch_chunks(true, av, treelet_view(c), c->fo, remap, d_dec, n_groups, cfg->load_treelet_metadata, per_meta, cfg->treelet_metadata_base,
+                                          d_cnt, d_off, d_ca, d_co, total, c->stream) : VSRT_E_CUDA;
+    if (rc == VSRT_OK && (cudaMemcpyAsync(chunk_addr, d_ca, m * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                          cudaMemcpyAsync(chunk_owner, d_co, m * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = VSRT_E_CUDA;
+  }
+  cudaFree(d_dec); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_ca); cudaFree(d_co);
+  if (rc) return fail(c, rc, "prefetch chunk generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return total > capacity ? VSRT_E_CAPACITY : VSRT_OK;
 }
 
 }  // extern "C"

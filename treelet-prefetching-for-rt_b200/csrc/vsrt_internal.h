@@ -121,3 +121,18 @@ int vsrt_launch_compact(const CompactParams& p, cudaStream_t st);
 // remap_pitch != 0: roots are reported in the treelet layout, remap_base + index * remap_pitch
 int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const uint32_t* tids, uint64_t n, uint64_t* out,
                             uint64_t remap_base, uint64_t remap_pitch, cudaStream_t st);
+
+// ---- RT-unit replay helpers (replay.cu) ----
+int vsrt_launch_build_inverse(const FormOutputs& fo, uint32_t n_treelets, uint64_t n_entries, uint32_t n_slots,
+                              uint64_t** inv_off_out, uint2** inv_out, cudaStream_t st);
+int vsrt_launch_sort_trace(int method, const uint64_t* offsets, uint64_t n_rays, const vsrt_txn* txns, const uint32_t* tids,
+                           const uint32_t* stage, uint32_t cap, const uint64_t* inv_off, const uint2* inv,
+                           vsrt_txn* out_txns, uint32_t* out_tids, uint64_t* key_scratch, cudaStream_t st);
+// out_dev[g].treelet_root receives the treelet INDEX (~0 = nobody voted); the caller converts to a root address
+int vsrt_launch_prefetch_vote(const uint64_t* offsets, const uint32_t* tids, uint64_t n_rays_batch, const uint64_t* group_offsets_dev,
+                              const uint64_t* group_offsets_host, const uint64_t* ray_ids_dev, const uint32_t* front_dev, uint64_t n_groups,
+                              const FormOutputs& fo, uint32_t n_treelets, uint32_t heuristic, double threshold,
+                              vsrt_prefetch_decision* out_dev, cudaStream_t st);
+int vsrt_launch_prefetch_chunks(bool fill, const ArenaView& av, const TreeletView& tv, const FormOutputs& fo, const uint64_t* remap,
+                                const vsrt_prefetch_decision* dec_dev, uint64_t n_groups, uint32_t load_metadata, uint32_t per_meta, uint64_t metadata_base,
+                                uint32_t* counts, const uint64_t* chunk_off, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t capacity, cudaStream_t st);

@@ -46,6 +46,16 @@ class DeviceResults(ctypes.Structure):
                 ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class PrefetchConfig(ctypes.Structure):
+    _fields_ = [("heuristic", ctypes.c_uint32), ("load_treelet_metadata", ctypes.c_uint32), ("threshold", ctypes.c_double),
+                ("treelet_metadata_base", ctypes.c_uint64)]
+
+
+# vsrt_prefetch_decision
+PDEC = np.dtype([("treelet_root", np.uint64), ("votes", np.uint32), ("total", np.uint32), ("submit", np.uint32), ("n_nodes", np.uint32),
+                 ("first_node", np.uint32), ("num_nodes", np.uint32)])
+
+
 def ptr(a):
     """ctypes void* of a numpy array (or None)."""
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)

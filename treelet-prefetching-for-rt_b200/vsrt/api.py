@@ -27,7 +27,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_set_treelet_layout_base", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
-           "vsrt_counters_device", "vsrt_get_treelet_histogram"]
+           "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks"]
 
 
 class VsrtError(RuntimeError):
@@ -65,6 +65,9 @@ def load():
     L.vsrt_treelet_metadata_idx.argtypes = [c_vp, c_u64, ctypes.POINTER(c_u32)]
     L.vsrt_trace_rays.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
     L.vsrt_trace_fetch.argtypes = [c_vp, c_vp, c_u64, c_vp]
+    L.vsrt_sort_trace.argtypes = [c_vp, c_int]
+    L.vsrt_prefetch_vote.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp]
+    L.vsrt_prefetch_chunks.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_trace_ray_warp.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_trace_rays_device.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, ctypes.POINTER(c_u64)]
     L.vsrt_trace_device_results.argtypes = [c_vp, ctypes.POINTER(_abi.DeviceResults)]
@@ -236,6 +239,39 @@ class Context:
         r = _abi.DeviceResults()
         self._ck(self.L.vsrt_trace_device_results(self.h, ctypes.byref(r)))
         return r
+
+    # ---- RT-unit replay helpers ---------------------------------------------------------------------------
+    def fetch_trace(self):
+        """Records and 64-bit treelet ids of the last batch as they are on the device now (sorted if sort_trace ran)."""
+        n = self.device_results().n_txn
+        txns = np.zeros(n, _abi.TXN); tids = np.zeros(n, np.uint64)
+        if n:
+            self._ck(self.L.vsrt_trace_fetch(self.h, _abi.ptr(txns), n, _abi.ptr(tids)))
+        return txns, tids
+
+    def sort_trace(self, method):
+        """rt_unit::sort_mem_accesses over every ray of the last batch; returns the sorted (records, treelet ids)."""
+        self._ck(self.L.vsrt_sort_trace(self.h, method))
+        return self.fetch_trace()
+
+    def prefetch_vote(self, group_offsets, heuristic=0, threshold=0.0, ray_ids=None, front=None, load_metadata=False, metadata_base=0):
+        cfg = _abi.PrefetchConfig(heuristic, 1 if load_metadata else 0, threshold, metadata_base)
+        go = np.ascontiguousarray(group_offsets, np.uint64)
+        ids = None if ray_ids is None else np.ascontiguousarray(ray_ids, np.uint64)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        dec = np.zeros(len(go) - 1, _abi.PDEC)
+        self._ck(self.L.vsrt_prefetch_vote(self.h, ctypes.byref(cfg), len(go) - 1, _abi.ptr(go), _abi.ptr(ids), _abi.ptr(fr), _abi.ptr(dec)))
+        return dec
+
+    def prefetch_chunks(self, decisions, heuristic=0, load_metadata=False, metadata_base=0):
+        cfg = _abi.PrefetchConfig(heuristic, 1 if load_metadata else 0, 0.0, metadata_base)
+        dec = np.ascontiguousarray(decisions, _abi.PDEC)
+        offs = np.zeros(len(dec) + 1, np.uint64); n = c_u64()
+        self._ck(self.L.vsrt_prefetch_chunks(self.h, ctypes.byref(cfg), len(dec), _abi.ptr(dec), _abi.ptr(offs), None, None, 0, ctypes.byref(n)), allow=(-4,))
+        ca = np.zeros(n.value, np.uint64); co = np.zeros(n.value, np.uint64)
+        if n.value:
+            self._ck(self.L.vsrt_prefetch_chunks(self.h, ctypes.byref(cfg), len(dec), _abi.ptr(dec), _abi.ptr(offs), _abi.ptr(ca), _abi.ptr(co), n.value, ctypes.byref(n)))
+        return offs, ca, co
 
     # ---- counters -----------------------------------------------------------------------------------------
     def counters(self):

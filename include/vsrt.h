@@ -268,6 +268,16 @@ int vsrt_prefetch_vote(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uint6
 int vsrt_prefetch_chunks(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uint64_t n_groups, const vsrt_prefetch_decision* decisions,
                          uint64_t* chunk_offsets, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t capacity, uint64_t* n_chunks);
 
+/* rt_unit::schedule_next_warp (shader.cc:4307-4392): which resident warp of each RT unit issues next.  Unit u holds the
+ * warps [unit_warp_offsets[u], unit_warp_offsets[u+1]) in m_current_warps order; warp w is the 32 ray ids
+ * warp_ray_ids[32*w .. 32*w+31] of the last batch (~0 = no thread in that lane); stalled[w] != 0 takes a warp out
+ * (NULL: none is stalled); last_prefetched[u] = the unit's last_prefetched_treelet (0 = none); front as in
+ * vsrt_prefetch_vote.  scheduler = -treelet_scheduler: 0 first non-stalled warp, 1 first warp with a thread whose pending
+ * access is in that treelet, 2 the warp with the most such threads; 1 and 2 fall back to 0.  pick[u] = warp index, -1 if
+ * every warp is stalled. */
+int vsrt_schedule_pick(vsrt_context* ctx, int scheduler, uint64_t n_units, const uint64_t* unit_warp_offsets, const uint64_t* warp_ray_ids,
+                       const uint8_t* stalled, const uint64_t* last_prefetched, const uint32_t* front, int64_t* pick);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ mkdir -p "$OUT"
   # treelet-prefetch vote block of rt_unit::cycle, the latter spliced in as the body of a member function
   sed -n '1372,1401p' "$R/abstract_hardware_model.h"
   cat "$HERE/ref_shim/shim_rtunit.h"
-  sed -n '3012,3164p' "$R/gpgpu-sim/shader.cc"
+  sed -n '3012,3164p;4307,4392p' "$R/gpgpu-sim/shader.cc"
   echo 'void rt_unit::prefetch_vote_block() {'
   sed -n '3419,3684p' "$R/gpgpu-sim/shader.cc"
   echo '  out_root = prefetched_treelet_root; out_num_nodes = num_nodes_to_prefetch; out_seen = true; } }'

@@ -52,6 +52,29 @@ int64_t ref_prefetch_vote(int heuristic, double threshold, int load_metadata, ui
   return (int64_t)n;
 }
 
+// rt_unit::schedule_next_warp (:4307-4392) for one RT unit: warps in m_current_warps order, lane l of warp w is ray
+// ray_ids[32 * w + l] (~0 = no thread), pending access = txns[offsets[ray] + front[ray]].  Returns the index of the
+// picked warp or -1.
+int64_t ref_schedule_pick(int scheduler, uint64_t last_prefetched, uint64_t n_warps, const uint64_t* ray_ids, const uint8_t* stalled,
+                          const uint64_t* offsets, const uint32_t* front, const ref_txn* txns) {
+  rt_unit u;
+  u.cfg.m_treelet_scheduler = (unsigned)scheduler; u.cfg.m_treelet_prefetch = true;
+  u.last_prefetched_treelet = (uint8_t*)last_prefetched;
+  for (uint64_t w = 0; w < n_warps; w++) {
+    ref_warp_inst& wi = u.m_current_warps[(unsigned)w];
+    wi.uid = (unsigned)w; wi.m_empty = false; wi.stalled = stalled && stalled[w];
+    for (int l = 0; l < 32; l++) {
+      const uint64_t r = ray_ids[32 * w + l];
+      if (r == ~0ull) continue;
+      for (uint64_t k = offsets[r] + (front ? front[r] : 0); k < offsets[r + 1]; k++)
+        wi.th[l].RT_mem_accesses.push_back(RTMemoryTransactionRecord(txns[k].address, txns[k].size, (TransactionType)txns[k].type));
+    }
+  }
+  warp_inst_t picked;
+  u.schedule_next_warp(picked);
+  return picked.empty() ? -1 : (int64_t)picked.get_uid();
+}
+
 void ref_set_treelet_metadata(uint64_t base, unsigned per_treelet_size) {
   VulkanRayTracing::treelet_metadata = (void*)base; VulkanRayTracing::per_treelet_metadata_size = per_treelet_size;
 }

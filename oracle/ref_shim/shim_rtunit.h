@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- stand-in for the parts of rt_unit (gpgpu-sim/shader.h) that the two extracted bodies of
-// shader.cc touch: rt_unit::sort_mem_accesses (:3012-3164) and the treelet-prefetch vote block of rt_unit::cycle
-// (:3419-3685), which build_ref.sh splices in as the body of rt_unit::prefetch_vote_block().  Own code: only names and
+// shader.cc touch: rt_unit::sort_mem_accesses (:3012-3164), rt_unit::schedule_next_warp (:4307-4392) and the
+// treelet-prefetch vote block of rt_unit::cycle (:3419-3685), which build_ref.sh splices in as the body of
+// rt_unit::prefetch_vote_block().  Own code: only names and
 // types the extracted lines need, no reference text.
 #pragma once
 #include <bitset>
@@ -8,15 +9,22 @@
 #define THREAD_SORT_DPRINTF(...)
 #define TOMMY_DPRINTF(...)
 #define SECOND_PREFETCH_DPRINTF(...)
+#define RT_SCHEDULER_DPRINTF(...)
 
 struct ref_rt_thread_info { std::deque<RTMemoryTransactionRecord> RT_mem_accesses; };
 struct ref_warp_inst {
   ref_rt_thread_info th[32];
+  unsigned uid; bool stalled, m_empty;
+  ref_warp_inst() : uid(0), stalled(false), m_empty(true) {}
   ref_rt_thread_info& get_thread_info(unsigned i) { return th[i]; }
+  bool is_stalled() const { return stalled; }
+  bool empty() const { return m_empty; }
+  unsigned get_uid() const { return uid; }
 };
+typedef ref_warp_inst warp_inst_t;
 struct ref_rt_config {
   bool m_treelet_prefetch; unsigned prefetch_delay; unsigned m_treelet_prefetch_heuristic; double m_treelet_prefetch_threshold;
-  unsigned m_max_prefetch_queue_size; bool m_flush_prefetch_queue_on_new_treelet; bool load_treelet_metadata;
+  unsigned m_max_prefetch_queue_size; bool m_flush_prefetch_queue_on_new_treelet; bool load_treelet_metadata; unsigned m_treelet_scheduler;
   bool prefetch_next_treelet_when_queue_empty; unsigned m_sort_method;
 };
 struct ref_rt_gpu { unsigned long long gpu_sim_cycle, gpu_tot_sim_cycle; };
@@ -45,4 +53,5 @@ class rt_unit {
   }
   void sort_mem_accesses(std::deque<RTMemoryTransactionRecord>& mem_accesses, std::map<uint8_t*, int> node_access_counts_per_treelet = std::map<uint8_t*, int>());
   void prefetch_vote_block();
+  void schedule_next_warp(warp_inst_t& inst);
 };

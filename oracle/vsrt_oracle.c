@@ -826,3 +826,29 @@ int64_t vo_prefetch_vote(vo_ctx* c, int heuristic, double threshold, int load_me
   free(tally);
   return (int64_t)n;
 }
+
+/* rt_unit::schedule_next_warp, shader.cc:4307-4392, for one RT unit.  Warps in m_current_warps order; lane l of warp w is
+ * ray ray_ids[32 * w + l] (~0 = no thread); a thread "matches" when addrToTreeletID of its pending access equals
+ * last_prefetched_treelet.  scheduler 1: first non-stalled warp with a matching thread (:4313-4343); scheduler 2: the
+ * non-stalled warp with the most matching threads, first among equals, at least one (:4345-4378); both fall back to --
+ * and scheduler 0 is -- the first non-stalled warp (:4381-4390).  Returns the warp index or -1. */
+int64_t vo_schedule_pick(vo_ctx* c, int scheduler, uint64_t last_prefetched, uint64_t n_warps, const uint64_t* ray_ids, const uint8_t* stalled,
+                         const uint64_t* offsets, const uint32_t* front, const vo_txn* txns) {
+  int64_t first_free = -1, best = -1; uint32_t best_n = 0;
+  for (uint64_t w = 0; w < n_warps; w++) {
+    if (stalled && stalled[w]) continue;
+    if (first_free < 0) first_free = (int64_t)w;
+    if (scheduler != 1 && scheduler != 2) break;
+    uint32_t m = 0;
+    for (int l = 0; l < 32; l++) {
+      const uint64_t r = ray_ids[32 * w + l]; uint64_t root;
+      if (r == ~0ull) continue;
+      const uint64_t k = offsets[r] + (front ? front[r] : 0);
+      if (k >= offsets[r + 1]) continue;
+      if (map_get(&c->node_root, txns[k].address, &root) && root == last_prefetched) m++;
+    }
+    if (scheduler == 1 && m) return (int64_t)w;
+    if (scheduler == 2 && m > best_n) { best_n = m; best = (int64_t)w; }
+  }
+  return best >= 0 ? best : first_free;
+}

@@ -62,6 +62,8 @@ class RefOracle(_Base):
         L.ref_prefetch_vote.restype = ctypes.c_int64
         L.ref_prefetch_vote.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64]
         L.ref_set_treelet_metadata.argtypes = [c_u64, ctypes.c_uint]
+        L.ref_schedule_pick.restype = ctypes.c_int64
+        L.ref_schedule_pick.argtypes = [ctypes.c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp]
         self.L = L
         self.tlas = None
 
@@ -114,6 +116,14 @@ class RefOracle(_Base):
         self.L.ref_sort_trace(method, len(trace["offsets"]) - 1, _abi.ptr(trace["offsets"]), _abi.ptr(t))
         return t
 
+    def schedule_pick(self, trace, scheduler, last_prefetched, warp_ray_ids, stalled=None, front=None):
+        """rt_unit::schedule_next_warp (shader.cc:4307-4392) for one unit."""
+        ids = np.ascontiguousarray(warp_ray_ids, np.uint64)
+        st = None if stalled is None else np.ascontiguousarray(stalled, np.uint8)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        return self.L.ref_schedule_pick(scheduler, int(last_prefetched), len(ids) // 32, _abi.ptr(ids), _abi.ptr(st), _abi.ptr(trace["offsets"]),
+                                        _abi.ptr(fr), _abi.ptr(trace["txns"]))
+
     def prefetch_vote(self, trace, ray_ids, heuristic, threshold=0.0, front=None, metadata=None):
         """The treelet-prefetch vote block of rt_unit::cycle (shader.cc:3419-3685) for one group of rays."""
         ids = np.ascontiguousarray(ray_ids, np.uint64)
@@ -155,6 +165,8 @@ class PortOracle(_Base):
         L.vo_get_counters.argtypes = [c_vp, c_vp]
         L.vo_reset_counters.argtypes = [c_vp]
         L.vo_sort_trace.argtypes = [c_vp, ctypes.c_int, c_u64, c_vp, c_vp]
+        L.vo_schedule_pick.restype = ctypes.c_int64
+        L.vo_schedule_pick.argtypes = [c_vp, ctypes.c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.vo_prefetch_vote.restype = ctypes.c_int64
         L.vo_prefetch_vote.argtypes = [c_vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_u64, ctypes.c_uint32, c_u64, c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_vp, c_vp, c_u64]
@@ -231,6 +243,13 @@ class PortOracle(_Base):
         ca = np.zeros(n, np.uint64); co = np.zeros(n, np.uint64)
         self.L.vo_prefetch_vote(*args, _abi.ptr(ca), _abi.ptr(co), n)
         return dec[0], ca, co
+
+    def schedule_pick(self, trace, scheduler, last_prefetched, warp_ray_ids, stalled=None, front=None):
+        ids = np.ascontiguousarray(warp_ray_ids, np.uint64)
+        st = None if stalled is None else np.ascontiguousarray(stalled, np.uint8)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        return self.L.vo_schedule_pick(self.h, scheduler, int(last_prefetched), len(ids) // 32, _abi.ptr(ids), _abi.ptr(st), _abi.ptr(trace["offsets"]),
+                                       _abi.ptr(fr), _abi.ptr(trace["txns"]))
 
     def trace_remapped(self, mode, rays, base, stride, budget):
         """-remap_to_treelet_layout 1 (vulkan_ray_tracing.cc:1682,:1763,...): the same visit sequence with every record

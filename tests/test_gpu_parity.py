@@ -321,6 +321,30 @@ def test_prefetch_vote_and_chunks(api):
     ctx.close()
 
 
+def test_schedule_pick(api):
+    """rt_unit::schedule_next_warp (shader.cc:4307-4392) for many units at once."""
+    from test_oracle import _units
+    s = sc.Scene(3000, seed=13, n_blas=2, n_instances=3)
+    rays = sc.rays_primary(64, 32)
+    orc = oracles.RefOracle() if oracles.have_ref() else oracles.PortOracle()
+    orc.register(s); orc.form(512)
+    ctx = api.Context(max_treelet_size=512, device=0); ctx.register(s); ctx.form_treelets()
+    o = orc.trace(1, rays); ctx.trace(1, rays)
+    rng = np.random.default_rng(17)
+    offs, ids, st = _units(rng, len(rays), 200)
+    roots = np.unique(o["treelet_ids"])
+    front = rng.integers(0, 12, len(rays)).astype(np.uint32)
+    lp = roots[rng.integers(0, min(len(roots), 6), len(offs) - 1)]          # popular treelets near the top of the tree
+    lp[::7] = 0
+    for sched in (0, 1, 2):
+        got = ctx.schedule_pick(sched, offs, ids, st, lp, front)
+        for u in range(len(offs) - 1):
+            w0, w1 = int(offs[u]), int(offs[u + 1])
+            want = orc.schedule_pick(o, sched, int(lp[u]), ids[32 * w0:32 * w1], st[w0:w1], front)
+            assert (int(got[u]) - w0 if got[u] >= 0 else -1) == want, (sched, u)
+    ctx.close()
+
+
 def test_large_scene_properties(api):
     """Full-size style check through size-independent properties (no oracle): both variants agree on hit t
     for opaque closest-hit rays; per-ray records start with the TLAS header; counters equal the trace."""

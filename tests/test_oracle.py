@@ -142,6 +142,43 @@ def test_rt_unit_prefetch_vote_matches_reference():
     assert checked > 20
 
 
+def _units(rng, n_rays, n_units):
+    """Random RT units: 1-6 warps each, random (possibly repeated, possibly absent) rays per lane, some stalled."""
+    offs = [0]; ids = []; st = []
+    for _ in range(n_units):
+        nw = int(rng.integers(1, 7))
+        for _w in range(nw):
+            lanes = rng.integers(0, n_rays, 32).astype(np.uint64)
+            lanes[rng.random(32) < 0.2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+            ids.append(lanes); st.append(1 if rng.random() < 0.3 else 0)
+        offs.append(offs[-1] + nw)
+    return np.array(offs, np.uint64), np.concatenate(ids), np.array(st, np.uint8)
+
+
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_rt_unit_schedule_pick_matches_reference():
+    """rt_unit::schedule_next_warp (shader.cc:4307-4392), -treelet_scheduler 0 / 1 (OMR) / 2 (PMR)."""
+    s = sc.Scene(2500, seed=4, n_blas=2, n_instances=3)
+    rays = sc.rays_primary(32, 16)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s); ref.form(512); port.register(s); port.form(512)
+    t = port.trace(1, rays)
+    rng = np.random.default_rng(11)
+    offs, ids, st = _units(rng, len(rays), 60)
+    roots = np.unique(t["treelet_ids"])
+    picked = set()
+    for u in range(len(offs) - 1):
+        w0, w1 = int(offs[u]), int(offs[u + 1])
+        front = rng.integers(0, 12, len(rays)).astype(np.uint32)
+        for sched in (0, 1, 2):
+            for lp in (0, int(roots[rng.integers(0, len(roots))]), int(t["treelet_ids"][int(t["offsets"][int(ids[32 * w0 + 3]) % len(rays)])])):
+                a = ref.schedule_pick(t, sched, lp, ids[32 * w0:32 * w1], st[w0:w1], front)
+                b = port.schedule_pick(t, sched, lp, ids[32 * w0:32 * w1], st[w0:w1], front)
+                assert a == b, (u, sched, lp)
+                picked.add((sched, a))
+    assert len(picked) > 8
+
+
 def test_port_parallel_equals_serial():
     s = sc.Scene(8000, seed=6, n_blas=2, n_instances=2)
     rays = helpers.mixed_rays(3000, 8)

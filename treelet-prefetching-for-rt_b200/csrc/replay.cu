@@ -192,6 +192,34 @@ __global__ void k_vote_large_finish(const VoteParams p, uint64_t g, unsigned lon
   if (t != VSRT_NO_TID) p.hist_scratch[t] = 0;       // leave the scratch zeroed for the next large group
 }
 
+// ------------------------------------------------------------------ schedule_next_warp (:4307-4392)
+// One warp of threads per RT unit; it walks the unit's resident warps in m_current_warps order, lane l looking at thread l.
+__global__ void k_schedule_pick(const unsigned long long* __restrict__ offsets, const uint32_t* __restrict__ tids, uint64_t n_rays_batch,
+                                const unsigned long long* __restrict__ unit_offsets, const unsigned long long* __restrict__ warp_ray_ids,
+                                const uint8_t* __restrict__ stalled, const uint32_t* __restrict__ target_tid, const uint32_t* __restrict__ front,
+                                uint64_t n_units, int scheduler, long long* __restrict__ pick) {
+  const uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n_units) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t target = target_tid[u];
+  long long first_free = -1, best = -1; uint32_t best_n = 0;
+  for (unsigned long long w = unit_offsets[u]; w < unit_offsets[u + 1]; w++) {
+    if (stalled && stalled[w]) continue;
+    if (first_free < 0) first_free = (long long)w;
+    if ((scheduler != 1 && scheduler != 2) || target == VSRT_NO_TID) break;
+    const unsigned long long r = warp_ray_ids[32ull * w + lane];
+    bool match = false;
+    if (r < n_rays_batch) {
+      const unsigned long long k = offsets[r] + (front ? front[r] : 0u);
+      match = k < offsets[r + 1] && tids[k] == target;
+    }
+    const uint32_t m = __popc(__ballot_sync(0xffffffffu, match));
+    if (scheduler == 1 && m) { best = (long long)w; break; }
+    if (scheduler == 2 && m > best_n) { best_n = m; best = (long long)w; }
+  }
+  if (lane == 0) pick[u] = best >= 0 ? best : first_free;
+}
+
 // ------------------------------------------------------------------ prefetch chunks
 struct ChunkParams {
   ArenaView av; TreeletView tv;
@@ -312,5 +340,15 @@ int vsrt_launch_prefetch_chunks(bool fill, const ArenaView& av, const TreeletVie
   p.counts = counts;
   const unsigned grid = (unsigned)((n_groups + 127) / 128);
   if (fill) k_prefetch_chunks<true><<<grid, 128, 0, st>>>(p); else k_prefetch_chunks<false><<<grid, 128, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+int vsrt_launch_schedule_pick(const uint64_t* offsets, const uint32_t* tids, uint64_t n_rays_batch, const uint64_t* unit_offsets_dev,
+                              const uint64_t* warp_ray_ids_dev, const uint8_t* stalled_dev, const uint32_t* target_tid_dev, const uint32_t* front_dev,
+                              uint64_t n_units, int scheduler, int64_t* pick_dev, cudaStream_t st) {
+  if (n_units == 0) return VSRT_OK;
+  k_schedule_pick<<<(unsigned)((n_units + 3) / 4), 128, 0, st>>>((const unsigned long long*)offsets, tids, n_rays_batch, (const unsigned long long*)unit_offsets_dev,
+                                                                 (const unsigned long long*)warp_ray_ids_dev, stalled_dev, target_tid_dev, front_dev, n_units, scheduler,
+                                                                 (long long*)pick_dev);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

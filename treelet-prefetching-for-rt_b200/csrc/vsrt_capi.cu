@@ -673,4 +673,27 @@ int vsrt_prefetch_chunks(vsrt_context* c, const vsrt_prefetch_config* cfg, uint6
   return total > capacity ? VSRT_E_CAPACITY : VSRT_OK;
 }
 
+int vsrt_schedule_pick(vsrt_context* c, int scheduler, uint64_t n_units, const uint64_t* unit_warp_offsets, const uint64_t* warp_ray_ids,
+                       const uint8_t* stalled, const uint64_t* last_prefetched, const uint32_t* front, int64_t* pick) {
+  if (!c || (n_units && (!unit_warp_offsets || !warp_ray_ids || !pick))) return VSRT_E_INVALID;
+  if (scheduler < 0 || scheduler > 2) return fail(c, VSRT_E_INVALID, "treelet_scheduler must be 0, 1 or 2");
+  if (!c->formed || !c->last.trace_offsets) return fail(c, VSRT_E_INVALID, "no trace: call vsrt_trace_rays / vsrt_trace_rays_device first");
+  if (n_units == 0) return VSRT_OK;
+  cudaSetDevice(c->device);
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  const uint64_t n_warps = unit_warp_offsets[n_units];
+  std::vector<uint32_t> target(n_units, VSRT_NO_TID);
+  if (last_prefetched) for (uint64_t u = 0; u < n_units; u++) { uint32_t t; if (last_prefetched[u] && treelet_index_of(c, last_prefetched[u], &t)) target[u] = t; }
+  uint64_t* d_uo = nullptr; uint64_t* d_ids = nullptr; uint8_t* d_st = nullptr; uint32_t* d_tg = nullptr; uint32_t* d_front = nullptr; int64_t* d_pick = nullptr;
+  bool ok = upload(&d_uo, unit_warp_offsets, n_units + 1, c->stream) == cudaSuccess && upload(&d_ids, warp_ray_ids, n_warps * 32, c->stream) == cudaSuccess &&
+            upload(&d_st, stalled, n_warps, c->stream) == cudaSuccess && upload(&d_tg, target.data(), n_units, c->stream) == cudaSuccess &&
+            upload(&d_front, front, c->last.n_rays, c->stream) == cudaSuccess && cudaMalloc(&d_pick, n_units * 8) == cudaSuccess;
+  rc = ok ? vsrt_launch_schedule_pick((const uint64_t*)c->last.trace_offsets, (const uint32_t*)c->last.treelet_ids, c->last.n_rays, d_uo, d_ids, d_st, d_tg, d_front,
+                                      n_units, scheduler, d_pick, c->stream) : VSRT_E_CUDA;
+  if (rc == VSRT_OK && (cudaMemcpyAsync(pick, d_pick, n_units * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = VSRT_E_CUDA;
+  cudaFree(d_uo); cudaFree(d_ids); cudaFree(d_st); cudaFree(d_tg); cudaFree(d_front); cudaFree(d_pick);
+  if (rc) return fail(c, rc, "schedule pick failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return VSRT_OK;
+}
+
 }  // extern "C"

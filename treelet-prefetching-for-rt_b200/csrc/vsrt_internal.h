@@ -136,3 +136,6 @@ int vsrt_launch_prefetch_vote(const uint64_t* offsets, const uint32_t* tids, uin
 int vsrt_launch_prefetch_chunks(bool fill, const ArenaView& av, const TreeletView& tv, const FormOutputs& fo, const uint64_t* remap,
                                 const vsrt_prefetch_decision* dec_dev, uint64_t n_groups, uint32_t load_metadata, uint32_t per_meta, uint64_t metadata_base,
                                 uint32_t* counts, const uint64_t* chunk_off, uint64_t* chunk_addr, uint64_t* chunk_owner, uint64_t capacity, cudaStream_t st);
+int vsrt_launch_schedule_pick(const uint64_t* offsets, const uint32_t* tids, uint64_t n_rays_batch, const uint64_t* unit_offsets_dev,
+                              const uint64_t* warp_ray_ids_dev, const uint8_t* stalled_dev, const uint32_t* target_tid_dev, const uint32_t* front_dev,
+                              uint64_t n_units, int scheduler, int64_t* pick_dev, cudaStream_t st);

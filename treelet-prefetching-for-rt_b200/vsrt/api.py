@@ -27,7 +27,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_set_treelet_layout_base", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
-           "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks"]
+           "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick"]
 
 
 class VsrtError(RuntimeError):
@@ -66,6 +66,7 @@ def load():
     L.vsrt_trace_rays.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
     L.vsrt_trace_fetch.argtypes = [c_vp, c_vp, c_u64, c_vp]
     L.vsrt_sort_trace.argtypes = [c_vp, c_int]
+    L.vsrt_schedule_pick.argtypes = [c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.vsrt_prefetch_vote.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp]
     L.vsrt_prefetch_chunks.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_trace_ray_warp.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
@@ -272,6 +273,15 @@ class Context:
         if n.value:
             self._ck(self.L.vsrt_prefetch_chunks(self.h, ctypes.byref(cfg), len(dec), _abi.ptr(dec), _abi.ptr(offs), _abi.ptr(ca), _abi.ptr(co), n.value, ctypes.byref(n)))
         return offs, ca, co
+
+    def schedule_pick(self, scheduler, unit_warp_offsets, warp_ray_ids, stalled=None, last_prefetched=None, front=None):
+        uo = np.ascontiguousarray(unit_warp_offsets, np.uint64); ids = np.ascontiguousarray(warp_ray_ids, np.uint64)
+        st = None if stalled is None else np.ascontiguousarray(stalled, np.uint8)
+        lp = None if last_prefetched is None else np.ascontiguousarray(last_prefetched, np.uint64)
+        fr = None if front is None else np.ascontiguousarray(front, np.uint32)
+        pick = np.zeros(len(uo) - 1, np.int64)
+        self._ck(self.L.vsrt_schedule_pick(self.h, scheduler, len(uo) - 1, _abi.ptr(uo), _abi.ptr(ids), _abi.ptr(st), _abi.ptr(lp), _abi.ptr(fr), _abi.ptr(pick)))
+        return pick
 
     # ---- counters -----------------------------------------------------------------------------------------
     def counters(self):

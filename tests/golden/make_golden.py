@@ -60,5 +60,78 @@ def main():
         print("%s: %d bytes (arena %d B, %d rays)" % (path, os.path.getsize(path), arena.size, len(rays)))
 
 
+def replay_groups(n_rays):
+    """The groups / units every replay fixture test uses (deterministic)."""
+    rng = np.random.default_rng(77)
+    go = np.array([0, 32, 64, 200, n_rays], np.uint64)
+    front = rng.integers(0, 9, n_rays).astype(np.uint32)
+    unit_offs = np.array([0, 3, 4, 9], np.uint64)
+    lanes = rng.integers(0, n_rays, 9 * 32).astype(np.uint64)
+    lanes[rng.random(len(lanes)) < 0.15] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    stalled = np.array([0, 1, 0, 0, 1, 0, 0, 0, 1], np.uint8)
+    return go, front, unit_offs, lanes, stalled
+
+
+def main_replay():
+    """golden_replay.npz: what the reference's rt_unit bodies (sort_mem_accesses, the prefetch vote block, schedule_next_warp)
+    and its -remap_to_treelet_layout traversal return on one instanced scene (shared BLAS)."""
+    ref = oracles.RefOracle()
+    arena = sc.Scene(1500, seed=1500, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    rays = helpers.mixed_rays(320, 4, 16, 12)
+    budget, stride = 1024, 128
+    out = {"arena": np.array(arena.bytes), "tlas_offset": np.uint64(arena.tlas_offset), "blas": np.array(arena.blas, np.uint64).reshape(-1, 2),
+           "rays": rays, "budget": np.uint32(budget), "stride": np.uint32(stride)}
+    ref.register(arena); ref.form(budget)
+    go, front, unit_offs, lanes, stalled = replay_groups(len(rays))
+    for mode in (0, 1):
+        t = ref.trace(mode, rays)
+        for method in (0, 1):
+            st = ref.sort_trace(method, t)
+            p = "m%d_s%d_" % (mode, method)
+            out[p + "addr"] = rel(st["address"], arena.base); out[p + "size"] = st["size"].astype(np.uint8); out[p + "type"] = st["type"].astype(np.uint8)
+    t = ref.trace(1, rays)
+    meta = (0x5000000000, (budget // 64) * 4)
+    for h, thr in ((0, 0.0), (1, 0.4), (2, 0.0), (3, 0.0)):
+        for use_meta in (0, 1):
+            decs = []; chunks = []; owners = []; offs = [0]
+            for g in range(len(go) - 1):
+                d, ca, co = ref.prefetch_vote(t, np.arange(go[g], go[g + 1]), h, thr, front, meta if use_meta else None)
+                d = d.copy()
+                if d["root"]:
+                    d["root"] = d["root"] - np.uint64(arena.base) + np.uint64(1)       # 0 stays "no root"; the first treelet sits at offset 0
+                decs.append(d)
+                node = co < np.uint64(meta[0])          # metadata rows live at meta[0]; node chunks are arena addresses
+                chunks.append(np.where(node, ca - np.uint64(arena.base), ca)); owners.append(np.where(node, co - np.uint64(arena.base), co))
+                offs.append(offs[-1] + len(ca))
+            p = "h%d_meta%d_" % (h, use_meta)
+            out[p + "dec"] = np.array(decs, oracles.PDEC); out[p + "chunk_off"] = np.array(offs, np.uint64)
+            out[p + "chunk_addr"] = np.concatenate(chunks).astype(np.uint64); out[p + "chunk_owner"] = np.concatenate(owners).astype(np.uint64)
+    roots = np.unique(t["treelet_ids"])
+    lp = np.array([roots[0], 0, roots[min(2, len(roots) - 1)]], np.uint64)
+    out["sched_lp"] = np.where(lp != 0, lp - np.uint64(arena.base) + np.uint64(1), 0).astype(np.uint64)   # offset + 1, 0 = none
+    for sched in (0, 1, 2):
+        picks = []
+        for u in range(len(unit_offs) - 1):
+            w0, w1 = int(unit_offs[u]), int(unit_offs[u + 1])
+            picks.append(ref.schedule_pick(t, sched, int(lp[u]), lanes[32 * w0:32 * w1], stalled[w0:w1], front))
+        out["sched%d_pick" % sched] = np.array(picks, np.int64)
+    # -remap_to_treelet_layout 1 (addresses relative to treelet_layout_bvh).  Its own scene, one instance per BLAS: on a
+    # shared BLAS the reference aborts in remapBVHToTreeletLayout (assert at vulkan_ray_tracing.cc:1487).
+    arena2 = sc.Scene(1500, seed=1501, n_blas=2, n_instances=2, flags=sc.F_TRANSFORMS)
+    out["remap_arena"] = np.array(arena2.bytes); out["remap_tlas_offset"] = np.uint64(arena2.tlas_offset)
+    out["remap_blas"] = np.array(arena2.blas, np.uint64).reshape(-1, 2)
+    ref.register(arena2, remap=True, stride=stride); ref.form(budget)
+    base = ref.remap_table()[0]
+    for mode in (0, 1):
+        r = ref.trace(mode, rays)
+        p = "remap_m%d_" % mode
+        out[p + "offsets"] = r["offsets"]; out[p + "addr"] = rel(r["txns"]["address"], base)
+        out[p + "size"] = r["txns"]["size"].astype(np.uint8); out[p + "type"] = r["txns"]["type"].astype(np.uint8); out[p + "tid"] = rel(r["treelet_ids"], base)
+    path = os.path.join(HERE, "replay_inst1500.npz")
+    np.savez_compressed(path, **out)
+    print("%s: %d bytes" % (path, os.path.getsize(path)))
+
+
 if __name__ == "__main__":
     main()
+    main_replay()

@@ -385,3 +385,44 @@ def test_cuda_matches_golden(api, path):
         for mode in (0, 1):
             helpers.assert_trace_equal(golden_util.expected_trace(z, b, mode, arena.base), ctx.trace(mode, rays), "golden b%d m%d" % (b, mode))
         ctx.close()
+
+
+def test_cuda_matches_replay_fixture(api):
+    """rt_unit helpers and remapped traces of the CUDA path against tests/golden/replay_inst1500.npz (recorded from the
+    reference's own rt_unit bodies and its -remap_to_treelet_layout traversal)."""
+    z, arena, arena2, rays = golden_util.load_replay()
+    budget, stride = int(z["budget"]), int(z["stride"])
+    go, front, unit_offs, lanes, stalled = golden_util.replay_groups(len(rays))
+    ctx = api.Context(max_treelet_size=budget, device=0); ctx.register(arena); ctx.form_treelets()
+    for mode in (0, 1):
+        ctx.trace(mode, rays)
+        for method in (0, 1):
+            got, _ = ctx.sort_trace(method)
+            assert np.array_equal(got, golden_util.replay_txns(z, "m%d_s%d_" % (mode, method), arena.base)), (mode, method)
+    ctx.trace(1, rays)
+    for h, thr in ((0, 0.0), (1, 0.4), (2, 0.0), (3, 0.0)):
+        for use_meta in (0, 1):
+            p = "h%d_meta%d_" % (h, use_meta)
+            dec = ctx.prefetch_vote(go, h, thr, None, front, bool(use_meta), golden_util.META_BASE)
+            offs, ca, co = ctx.prefetch_chunks(dec, h, bool(use_meta), golden_util.META_BASE)
+            want = z[p + "dec"]
+            assert np.array_equal(dec["treelet_root"], np.where(want["root"] != 0, want["root"] - np.uint64(1) + np.uint64(arena.base), 0).astype(np.uint64))
+            for k in ("votes", "total", "submit", "n_nodes", "first_node", "num_nodes"):
+                assert np.array_equal(dec[k], want[k]), (h, use_meta, k)
+            woffs, wca, wco = golden_util.replay_chunks(z, p, arena.base)
+            assert np.array_equal(offs, woffs) and np.array_equal(ca, wca) and np.array_equal(co, wco)
+    lp = np.where(z["sched_lp"] != 0, z["sched_lp"] - np.uint64(1) + np.uint64(arena.base), 0).astype(np.uint64)
+    for sched in (0, 1, 2):
+        got = ctx.schedule_pick(sched, unit_offs, lanes, stalled, lp, front)
+        want = z["sched%d_pick" % sched]
+        assert np.array_equal(np.where(got >= 0, got - unit_offs[:-1].astype(np.int64), -1), want), sched
+    ctx.close()
+    base = 0x7e0000000000
+    ctx = api.Context(max_treelet_size=budget, device=0, treelet_remap_stride=stride, remap_to_treelet_layout=1)
+    ctx.register(arena2); ctx.form_treelets(); ctx.set_treelet_layout_base(base)
+    for mode in (0, 1):
+        g = ctx.trace(mode, rays)
+        p = "remap_m%d_" % mode
+        assert np.array_equal(g["offsets"], z[p + "offsets"]) and np.array_equal(g["txns"], golden_util.replay_txns(z, p, base))
+        assert np.array_equal(g["treelet_ids"], z[p + "tid"] + np.uint64(base))
+    ctx.close()

@@ -142,6 +142,42 @@ def test_rt_unit_prefetch_vote_matches_reference():
     assert checked > 20
 
 
+def test_port_matches_replay_fixture():
+    """The restatements of the rt_unit helpers and of the remapped traversal against tests/golden/replay_inst1500.npz,
+    recorded from the reference's own bodies (works without /root/reference)."""
+    z, arena, arena2, rays = golden_util.load_replay()
+    budget, stride = int(z["budget"]), int(z["stride"])
+    port = oracles.PortOracle(); port.register(arena); port.form(budget)
+    go, front, unit_offs, lanes, stalled = golden_util.replay_groups(len(rays))
+    for mode in (0, 1):
+        t = port.trace(mode, rays)
+        for method in (0, 1):
+            assert np.array_equal(port.sort_trace(method, t), golden_util.replay_txns(z, "m%d_s%d_" % (mode, method), arena.base)), (mode, method)
+    t = port.trace(1, rays)
+    for h, thr in ((0, 0.0), (1, 0.4), (2, 0.0), (3, 0.0)):
+        for use_meta in (0, 1):
+            p = "h%d_meta%d_" % (h, use_meta)
+            offs, ca, co = golden_util.replay_chunks(z, p, arena.base)
+            for g in range(len(go) - 1):
+                d, a, b = port.prefetch_vote(t, np.arange(go[g], go[g + 1]), h, thr, front, (golden_util.META_BASE, (budget // 64) * 4) if use_meta else None)
+                want = z[p + "dec"][g]
+                assert int(d["root"]) == (int(want["root"]) - 1 + arena.base if want["root"] else 0)
+                assert [int(d[k]) for k in ("votes", "total", "submit", "n_nodes", "first_node", "num_nodes")] == [int(want[k]) for k in ("votes", "total", "submit", "n_nodes", "first_node", "num_nodes")]
+                assert np.array_equal(a, ca[offs[g]:offs[g + 1]]) and np.array_equal(b, co[offs[g]:offs[g + 1]])
+    lp = np.where(z["sched_lp"] != 0, z["sched_lp"] - np.uint64(1) + np.uint64(arena.base), 0).astype(np.uint64)
+    for sched in (0, 1, 2):
+        for u in range(len(unit_offs) - 1):
+            w0, w1 = int(unit_offs[u]), int(unit_offs[u + 1])
+            assert port.schedule_pick(t, sched, int(lp[u]), lanes[32 * w0:32 * w1], stalled[w0:w1], front) == int(z["sched%d_pick" % sched][u])
+    port2 = oracles.PortOracle(); port2.register(arena2); port2.form(budget)
+    base = 0x7e0000000000
+    for mode in (0, 1):
+        r = port2.trace_remapped(mode, rays, base, stride, budget)
+        p = "remap_m%d_" % mode
+        assert np.array_equal(r["offsets"], z[p + "offsets"]) and np.array_equal(r["txns"], golden_util.replay_txns(z, p, base))
+        assert np.array_equal(r["treelet_ids"], z[p + "tid"] + np.uint64(base))
+
+
 def _units(rng, n_rays, n_units):
     """Random RT units: 1-6 warps each, random (possibly repeated, possibly absent) rays per lane, some stalled."""
     offs = [0]; ids = []; st = []

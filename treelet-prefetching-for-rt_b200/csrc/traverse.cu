@@ -44,6 +44,9 @@ VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;
 
 constexpr int THREADS = 128;
 VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef VSRT_K1_FORWARD
+#define VSRT_K1_FORWARD 0   // A/B: taking the next entry from the registers it was just pushed from (no stack load) is slower: 2.32 vs 2.18 ms
+#endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
@@ -188,25 +191,28 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     }
 
     // ================= pop the next entry of every lane that wants one
+    // TAKE: `e` holds the entry just taken from `current` (from_cur_) or from the front of `other`
+#define TAKE(from_cur_) do { \
+      const bool selfroot_ = (e.slot & SLOT_SELFROOT) != 0u, leaf_ = (e.slot & SLOT_LEAF) != 0u; \
+      e.slot &= SLOT_MASK; \
+      if (MODE == VSRT_MODE_TREELET) { \
+        if (from_cur_) { cur_n--; in_cur = true; }       /* entries of `current` were pushed because node_tid == current treelet */ \
+        else { \
+          /* :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST address, */ \
+          /* which equals a treelet's device address only for the root at (host - tlas_delta). */ \
+          oth_n--; \
+          if (av.tlas_delta == 0) { \
+            in_cur = selfroot_; cur_tid = e.slot; tid_known = false; \
+            if (!selfroot_) { cur_tid = root_rank(p.tv, e.slot); tid_known = true; } \
+          } else { uint32_t s2_; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2_) ? root_rank(p.tv, s2_) : VSRT_NO_TID; } \
+        } \
+      } else cur_n--; \
+      st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); } while (0)
     if (st == ST_POP) {
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
         e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
-        const bool selfroot = (e.slot & SLOT_SELFROOT) != 0u, leaf = (e.slot & SLOT_LEAF) != 0u;
-        e.slot &= SLOT_MASK;
-        if (MODE == VSRT_MODE_TREELET) {
-          if (fc) { cur_n--; in_cur = true; }       // entries of `current` were pushed because node_tid == current treelet
-          else {
-            // :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST
-            // address, which equals a treelet's device address only for the root at (host - tlas_delta).
-            oth_n--;
-            if (av.tlas_delta == 0) {
-              in_cur = selfroot; cur_tid = e.slot; tid_known = false;
-              if (!selfroot) { cur_tid = root_rank(p.tv, e.slot); tid_known = true; }
-            } else { uint32_t s2; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2) ? root_rank(p.tv, s2) : VSRT_NO_TID; }
-          }
-        } else cur_n--;
-        st = !leaf ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF);
+        TAKE(fc);
       } else st = ST_FIN;
     }
 
@@ -248,15 +254,23 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
           else {
             int po = STACK_N - 1 - oth_n;
+            Entry lc, lo; lc.slot = lc.meta = lo.slot = lo.meta = 0u;   // last child pushed to `current` / `other` in this node
+            bool hc = false, ho = false;
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
               const uint32_t sel = 0x7770u + bit_index(bit);
               Entry c; c.slot = (child0 + __byte_perm(xlo, xhi, sel)) | ((__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u); c.meta = cmeta;
               const bool ic = (mcur & bit) != 0u;
               stk[ic ? cur_n : po] = c;
-              cur_n += ic ? 1 : 0; po -= ic ? 0 : 1;
+              if (ic) { lc = c; hc = true; cur_n++; } else { lo = c; ho = true; po--; }
             }
             oth_n = STACK_N - 1 - po;
+            // pop forwarding: the entry this lane takes next is usually one it has just pushed -- take it from the registers
+            // instead of waiting for the stack load at the top of the next iteration (the top stall of the kernel)
+#if VSRT_K1_FORWARD
+            if (hc) { e = lc; TAKE(true); }
+            else if (cur_n == 0 && ho) { e = lo; TAKE(false); }
+#endif
           }
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
@@ -315,7 +329,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           ACTIVATE(e_inst(e));
           float thit = 0.0f;
           const bool hit = ray_tri(q, a.ray, thit);
-          const float tw = fdiv(thit, a.tmult);
+          // world t = t_obj / tMult (:2124 / :2840), needed only for a hit; x / 1.0f is x, and a miss leaves thit = 0, which
+          // would send the IEEE division down its slow path for nothing
+          const float tw = !hit ? 0.0f : (a.tmult == 1.0f ? thit : fdiv(thit, a.tmult));
           bool acc = hit && w_tmin <= tw && tw <= w_tmax;                         // :2843
           if (MODE == VSRT_MODE_TREELET) acc = acc && tw < min_thit;              // :2127
           if (acc) {
@@ -336,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #undef EMIT
 #undef PUSH_CUR
 #undef PUSH_OTH
+#undef TAKE
 #undef CUR_TID
 #undef ACTIVATE
 #undef LOAD_WORLD

@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     if (m_leaf && (__popc(m_leaf) >= LEAF_T || __ballot_sync(full, st == ST_INT || st == ST_INST || st == ST_POP) == 0u)) {
       if (st == ST_LEAF) {
         st = ST_POP;
+        const Node64 q = load_node_now(base, e.slot);
         EMIT(e.slot, C_DESC);
-        const Node64 q = load_node(base, e.slot);
         if (((q.w[1] >> 29) & 1u) == 0u) {
           ACTIVATE(e_inst(e));
           float thit = 0.0f;

@@ -27,6 +27,17 @@ VS_DEV Node64 load_node(const uint8_t* base, uint32_t slot) {
   n.w[8] = c.x; n.w[9] = c.y; n.w[10] = c.z; n.w[11] = c.w; n.w[12] = d.x; n.w[13] = d.y; n.w[14] = d.z; n.w[15] = d.w;
   return n;
 }
+// Same, but the four loads are issued here and now: the compiler otherwise sinks three of them below the first branch on
+// the node's contents (leaf type), which costs a BLAS-leaf visit two dependent memory round trips instead of one.
+VS_DEV Node64 load_node_now(const uint8_t* base, uint32_t slot) {
+  const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)slot * 64u);
+  Node64 n;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[0]), "=r"(n.w[1]), "=r"(n.w[2]), "=r"(n.w[3]) : "l"(p));
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[4]), "=r"(n.w[5]), "=r"(n.w[6]), "=r"(n.w[7]) : "l"(p + 1));
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[8]), "=r"(n.w[9]), "=r"(n.w[10]), "=r"(n.w[11]) : "l"(p + 2));
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[12]), "=r"(n.w[13]), "=r"(n.w[14]), "=r"(n.w[15]) : "l"(p + 3));
+  return n;
+}
 // byte i (0..63) of a node held in registers; i must be a compile-time constant after unrolling
 VS_DEV uint32_t node_byte(const Node64& n, int i) { return (n.w[i >> 2] >> ((i & 3) * 8)) & 0xffu; }
 

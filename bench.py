@@ -252,26 +252,54 @@ def run_cuda(args):
 
     red_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     red_state = {"done": None, "out": None}
+    # The NCCL calls are enqueued by a helper thread: their host cost (~0.25 ms per frame for three collectives) would
+    # otherwise sit between two frames with the GPU idle; vsrt_trace_rays_device releases the GIL while it runs.
+    red_q = red_thread = None
+    if world > 1:
+        import queue
+        import threading
+        red_q = queue.Queue()
+
+        def _reducer():
+            torch.cuda.set_device(dev)
+            while True:
+                item = red_q.get()
+                if item is None:
+                    red_q.task_done()
+                    return
+                ready, bufs, done = item
+                with torch.cuda.stream(red_stream):
+                    red_stream.wait_event(ready)
+                    shard.reduce_counters(dist, *bufs)
+                    done.record(red_stream)
+                red_q.task_done()
+        red_thread = threading.Thread(target=_reducer, daemon=True)
+        red_thread.start()
 
     def step():
         with torch.cuda.stream(stream):
             ctx.trace_device(MODE, rays_dev.data_ptr(), n, stream.cuda_stream)
             if reduce_bufs is not None:
                 # the path's only exchange: per-frame reduce of counters + treelet visit histogram, into
-                # scratch copies (the per-rank counters keep their own totals).  It runs on a side stream so that the
-                # reduce of frame i overlaps the traversal of frame i+1; frame i+1's reduce waits for it.
-                s2, m2, h2 = reduce_bufs[0].clone(), reduce_bufs[1].clone(), reduce_bufs[2].clone()
+                # scratch copies taken on the traversal stream (the per-rank counters keep their own totals).  The
+                # collectives run on a side stream, so the reduce of frame i overlaps the traversal of frame i+1.
+                bufs = (reduce_bufs[0].clone(), reduce_bufs[1].clone(), reduce_bufs[2].clone())
                 ready = torch.cuda.Event(); ready.record(stream)
-                with torch.cuda.stream(red_stream):
-                    red_stream.wait_event(ready)
-                    shard.reduce_counters(dist, s2, m2, h2)
-                    red_state["done"] = torch.cuda.Event(); red_state["done"].record(red_stream)
-                red_state["out"] = (s2, m2, h2)
+                done = torch.cuda.Event()
+                red_q.put((ready, bufs, done))
+                red_state["done"] = done
+                red_state["out"] = bufs
         return red_state["out"]
+
+    def drain_reduces():
+        """All queued collectives are enqueued on the side stream; the caller may now wait on red_state['done']."""
+        if red_q is not None:
+            red_q.join()
 
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~100 ms to come up
     for _ in range(args.warmup):
         step()
+    drain_reduces()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -289,6 +317,7 @@ def run_cuda(args):
         reduced = step()
         with torch.cuda.stream(stream):
             if i == args.steps - 1 and red_state["done"] is not None:
+                drain_reduces()
                 stream.wait_event(red_state["done"])   # the last frame's reduce is inside the timed region
             ev[i][1].record(stream)
         r = ctx.device_results()
@@ -298,6 +327,8 @@ def run_cuda(args):
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    if red_q is not None:
+        red_q.put(None)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     res = ctx.device_results()
     n_txn, alg_bytes = res.n_txn, res.algorithmic_bytes

@@ -278,6 +278,22 @@ int vsrt_prefetch_chunks(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uin
 int vsrt_schedule_pick(vsrt_context* ctx, int scheduler, uint64_t n_units, const uint64_t* unit_warp_offsets, const uint64_t* warp_ray_ids,
                        const uint8_t* stalled, const uint64_t* last_prefetched, const uint32_t* front, int64_t* pick);
 
+/* ---- acceleration-structure dump files (VulkanRayTracing::dump_AS, vulkan_ray_tracing.cc:4455-4558, split_files) ----
+ * <prefix>.asmain / .asback / .asfront / .asmetadata: the TLAS descriptor range, the BLAS ranges below and above it and
+ * the offsets findOffsetBounds (:4901) computed.  vsrt_as_dump_write produces them for a TLAS of desc_size bytes whose
+ * BLAS headers are child_addrs[] (the addresses Mesa passes through gpgpusim_pass_child_addr); back/front_buffer are
+ * the slack bytes written after the last backward / forward BLAS start (the reference uses 0 and 20 KiB).
+ * vsrt_as_dump_read rebuilds one 64-byte aligned host image with the original relative placement (free it with
+ * vsrt_as_dump_free); vsrt_register_as_image walks the TLAS in it, registers the TLAS and every BLAS an instance leaf
+ * references (simulated-device address = host address + device_delta) and reports how many BLASes it found.  The TLAS
+ * handle for the trace calls is image + tlas_offset. */
+int vsrt_as_dump_write(const char* prefix, const void* tlas, uint64_t desc_size, const void* const* child_addrs, uint32_t n_children,
+                       uint64_t back_buffer, uint64_t front_buffer);
+int vsrt_as_dump_read(const char* prefix, void** image, uint64_t* image_size, uint64_t* tlas_offset);
+void vsrt_as_dump_free(void* image);
+int vsrt_register_as_image(vsrt_context* ctx, const void* image, uint64_t image_size, uint64_t tlas_offset, int64_t device_delta,
+                           uint32_t* n_blas);
+
 #ifdef __cplusplus
 }
 #endif

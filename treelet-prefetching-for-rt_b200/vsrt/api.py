@@ -27,7 +27,8 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_table", "vsrt_node_map", "vsrt_treelet_remap", "vsrt_set_treelet_layout_base", "vsrt_addr_to_treelet", "vsrt_is_treelet_root",
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
-           "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick"]
+           "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick",
+           "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image"]
 
 
 class VsrtError(RuntimeError):
@@ -66,6 +67,10 @@ def load():
     L.vsrt_trace_rays.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
     L.vsrt_trace_fetch.argtypes = [c_vp, c_vp, c_u64, c_vp]
     L.vsrt_sort_trace.argtypes = [c_vp, c_int]
+    L.vsrt_as_dump_write.argtypes = [ctypes.c_char_p, c_vp, c_u64, c_vp, c_u32, c_u64, c_u64]
+    L.vsrt_as_dump_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]
+    L.vsrt_as_dump_free.argtypes = [c_vp]
+    L.vsrt_register_as_image.argtypes = [c_vp, c_vp, c_u64, c_u64, ctypes.c_int64, ctypes.POINTER(c_u32)]
     L.vsrt_schedule_pick.argtypes = [c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.vsrt_prefetch_vote.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp]
     L.vsrt_prefetch_chunks.argtypes = [c_vp, ctypes.POINTER(_abi.PrefetchConfig), c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
@@ -86,6 +91,40 @@ def parse_config(text):
     L.vsrt_default_config(ctypes.byref(cfg))
     L.vsrt_config_parse(ctypes.byref(cfg), text.encode())
     return cfg
+
+
+def write_as_dump(prefix, arena, desc_size=None, back_buffer=0, front_buffer=20 * 1024):
+    """dump_AS files for a host arena (TLAS at arena.tlas, BLAS headers at arena.blas offsets)."""
+    L = load()
+    kids = (c_vp * len(arena.blas))(*[arena.base + off for off, _ in arena.blas])
+    if desc_size is None:   # the TLAS buffer: up to the first BLAS above it, or the end of the arena
+        above = sorted(off for off, _ in arena.blas if off > arena.tlas_offset)
+        desc_size = (above[0] if above else arena.size) - arena.tlas_offset
+    rc = L.vsrt_as_dump_write(prefix.encode(), arena.tlas, desc_size, kids, len(arena.blas), back_buffer, front_buffer)
+    if rc:
+        raise VsrtError(rc, "vsrt_as_dump_write(%s)" % prefix)
+
+
+class AsImage:
+    """Host image rebuilt from <prefix>.asmain/.asback/.asfront/.asmetadata."""
+
+    def __init__(self, prefix):
+        self.L = load()
+        p, n, t = c_vp(), c_u64(), c_u64()
+        rc = self.L.vsrt_as_dump_read(prefix.encode(), ctypes.byref(p), ctypes.byref(n), ctypes.byref(t))
+        if rc:
+            raise VsrtError(rc, "vsrt_as_dump_read(%s)" % prefix)
+        self.ptr, self.size, self.tlas_offset = p.value, n.value, t.value
+        self.base = self.ptr
+        self.bytes = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(self.size,))
+
+    @property
+    def tlas(self):
+        return self.ptr + self.tlas_offset
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.L.vsrt_as_dump_free(self.ptr); self.ptr = None
 
 
 class Context:
@@ -144,6 +183,14 @@ class Context:
         for i, (off, size) in enumerate(arena.blas):
             d = delta if blas_delta is None else blas_delta[i]
             self.alloc_blas(arena.base + off, size, arena.base + off + d)
+
+    def register_image(self, image, delta=0):
+        """Registers the TLAS and the BLASes of an AsImage; returns the number of BLASes found."""
+        n = c_u32()
+        self._ck(self.L.vsrt_register_as_image(self.h, image.ptr, image.size, image.tlas_offset, delta, ctypes.byref(n)))
+        self.tlas = image.tlas
+        self._image = image
+        return n.value
 
     def commit(self):
         self._ck(self.L.vsrt_commit(self.h))

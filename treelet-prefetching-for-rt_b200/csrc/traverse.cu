@@ -47,6 +47,9 @@ VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 #ifndef VSRT_K1_FORWARD
 #define VSRT_K1_FORWARD 0   // A/B: taking the next entry from the registers it was just pushed from (no stack load) is slower: 2.32 vs 2.18 ms
 #endif
+#ifndef VSRT_K1_INNER
+#define VSRT_K1_INNER 2   // measured: 1 -> 2.19 ms, 2 -> 2.14 ms, 3 -> 2.22 ms, 4 -> 2.31 ms
+#endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
@@ -208,6 +211,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         } \
       } else cur_n--; \
       st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); } while (0)
+    // pop + internal-node phase run up to VSRT_K1_INNER times back to back: the refill and leaf votes around them are
+    // amortised, at the price of idle / leaf lanes waiting a little longer
+#pragma unroll 1
+    for (int inner = 0; inner < VSRT_K1_INNER; inner++) {
     if (st == ST_POP) {
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
@@ -215,6 +222,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         TAKE(fc);
       } else st = ST_FIN;
     }
+    if (VSRT_K1_INNER > 1 && inner && !__any_sync(full, st == ST_INT)) break;
 
     // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
     if (st == ST_INT) {
@@ -297,8 +305,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         }
       }
     }
+    }   // inner
     // ================= phase 2: instance leaves (:1876-1953 / :2602-2677)
-    else if (st == ST_INST) {
+    if (st == ST_INST) {
       st = ST_POP;
       EMIT(e.slot, C_INSTANCE); ray_nodes++;
       uint32_t hdr = 0, broot = 0;

@@ -53,6 +53,7 @@ struct vsrt_context {
   DevBuf<vsrt_ray> d_rays; DevBuf<vsrt_hit> d_hits; DevBuf<uint32_t> d_stage; DevBuf<uint32_t> d_counts;
   DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint8_t> d_scan_tmp;
   uint32_t stage_cap = 128;
+  DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
   DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
@@ -183,8 +184,16 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
+    const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
+    const bool wavefront = !getenv("VSRT_K1_WF") || atoi(getenv("VSRT_K1_WF")) != 0;
+    unsigned wf_grid = 0;
+    if (wavefront && n) {
+      wf_grid = vsrt_wf_grid(n);
+      CUDA_OK(c, c->d_gstack.ensure(vsrt_wf_stack_bytes(wf_grid, stack_entries)));
+      tp.gstack = (uint2*)c->d_gstack.p; tp.stack_n = stack_entries;
+    } else { tp.gstack = nullptr; tp.stack_n = stack_entries; }
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
-    rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, av.force_exact != 0, st);
+    rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, av.force_exact != 0, st) : vsrt_launch_traverse(tp, stack_entries, av.force_exact != 0, st);
     if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     launches += n ? 1 : 0;
     if (!av.force_exact && n) {
@@ -194,7 +203,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       CUDA_OK(c, cudaStreamSynchronize(st));
       if (e1 & EF_NEED_EXACT) {
         tp.only_deferred = 1;
-        rc = vsrt_launch_traverse(tp, c->cfg.stack_entries ? c->cfg.stack_entries : 96, true, st);
+        rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, st);
         if (rc) return fail(c, rc, "exact traversal kernel launch failed");
         launches++;
       }
@@ -301,7 +310,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_treelets(c);
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
-  c->d_rays.release(); c->d_hits.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
+  c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

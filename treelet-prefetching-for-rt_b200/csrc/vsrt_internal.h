@@ -99,9 +99,15 @@ struct TraverseParams {
   uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
   uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
   uint32_t prefetch;              // issue an L1 prefetch for the node a lane will pop next
+  uint2* gstack;                  // wavefront kernel: per-warp stack areas (vsrt_wf_stack_bytes)
+  uint32_t stack_n;               // wavefront kernel: stack entries per ray
   uint32_t magic16;               // 0x64646464 (fp16 1024 in each half), passed as data so it lives in a register (byte_pair_f16)
 };
 int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
+// warp-wavefront formulation (traverse_wf.cu): same results, a pool of 64 rays per warp regrouped by phase every iteration
+unsigned vsrt_wf_grid(uint64_t n_rays);
+size_t vsrt_wf_stack_bytes(unsigned grid, uint32_t stack_entries);
+int vsrt_launch_traverse_wf(const TraverseParams& p, unsigned grid, bool exact, cudaStream_t st);
 
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);

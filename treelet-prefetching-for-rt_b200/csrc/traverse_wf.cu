@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
       } else { uint32_t s2_; bits = (bits & ~B_INCUR) | B_TIDKNOWN; \
         cur_tid = host_to_slot(av, slot_to_host(av, eslot & SLOT_MASK) - (uint64_t)av.tlas_delta, s2_) ? root_rank(p.tv, s2_) : VSRT_NO_TID; } } while (0)
 #define POP_NEXT(have_c_, ent_c_, have_o_, ent_o_) do { \
-      if (have_c_) TAKE_FROM_CUR(ent_c_); \
-      else if (cur_n > 0) { const uint2 t_ = STK(cur_n - 1, s); TAKE_FROM_CUR(t_); } \
-      else if (MODE == VSRT_MODE_TREELET && (have_o_)) TAKE_FROM_OTH(ent_o_); \
-      else if (MODE == VSRT_MODE_TREELET && oth_n > 0) { const uint2 t_ = STK(STACK_N - oth_n, s); TAKE_FROM_OTH(t_); } \
-      else nst = ST_FIN; \
-      if (nst != ST_FIN) { const bool leaf_ = (eslot & SLOT_LEAF) != 0u; eslot &= SLOT_MASK; \
-        nst = !leaf_ ? ST_INT : ((emeta & INST_NONE) == INST_NONE ? ST_INST : ST_LEAF); } } while (0)
+      const bool fc_ = (have_c_) || cur_n > 0; \
+      const bool fo_ = !fc_ && MODE == VSRT_MODE_TREELET && ((have_o_) || oth_n > 0); \
+      if (fc_ || fo_) { \
+        uint2 t_ = fc_ ? (ent_c_) : (ent_o_); \
+        if (fc_ ? !(have_c_) : !(have_o_)) t_ = STK(fc_ ? cur_n - 1 : STACK_N - oth_n, s);   /* older entry: one load */ \
+        if (fc_) TAKE_FROM_CUR(t_); else TAKE_FROM_OTH(t_); \
+        const bool leaf_ = (eslot & SLOT_LEAF) != 0u; eslot &= SLOT_MASK; \
+        nst = !leaf_ ? ST_INT : ((emeta & INST_NONE) == INST_NONE ? ST_INST : ST_LEAF); \
+      } else nst = ST_FIN; } while (0)
 #define CUR_TID() ((bits & B_TIDKNOWN) ? cur_tid : (bits |= B_TIDKNOWN, cur_tid = __ldg(p.tv.node_tid + cur_tid) & VSRT_TID_MASK))
 #define EMIT(slot_, code_) do { if (cnt < cap) rstage[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
   // the ray's record for context `inst_` (INST_NONE = world) into the slot's active-ray words
@@ -111,20 +113,20 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
     __syncwarp();
     // ================= census of the pool: lane l is the home of slots l and l + 32
     const uint32_t s0 = S(F_ST, lane), s1 = S(F_ST, lane + 32);
-    const uint32_t i_lo = __ballot_sync(full, s0 == ST_INT), i_hi = __ballot_sync(full, s1 == ST_INT);
-    const uint32_t l_lo = __ballot_sync(full, s0 == ST_LEAF), l_hi = __ballot_sync(full, s1 == ST_LEAF);
-    const uint32_t n_lo = __ballot_sync(full, s0 == ST_INST), n_hi = __ballot_sync(full, s1 == ST_INST);
     const bool rec0 = s0 == ST_FIN || (s0 == ST_IDLE && !exhausted), rec1 = s1 == ST_FIN || (s1 == ST_IDLE && !exhausted);
-    const uint32_t r_lo = __ballot_sync(full, rec0), r_hi = __ballot_sync(full, rec1);
-    const int n_int = __popc(i_lo) + __popc(i_hi), n_leaf = __popc(l_lo) + __popc(l_hi), n_inst = __popc(n_lo) + __popc(n_hi), n_rec = __popc(r_lo) + __popc(r_hi);
-    if ((n_int | n_leaf | n_inst | n_rec) == 0) break;     // every slot idle and no ray left
+    // how many rays are ready for each phase: one REDUX.ADD over byte counters (a pool has 64 slots)
+    const uint32_t mine = (s0 == ST_INT ? 1u : 0u) + (s1 == ST_INT ? 1u : 0u) + ((s0 == ST_LEAF ? 1u : 0u) + (s1 == ST_LEAF ? 1u : 0u)) * 0x100u +
+                          ((s0 == ST_INST ? 1u : 0u) + (s1 == ST_INST ? 1u : 0u)) * 0x10000u + ((rec0 ? 1u : 0u) + (rec1 ? 1u : 0u)) * 0x1000000u;
+    const uint32_t tot = __reduce_add_sync(full, mine);
+    const int n_int = (int)(tot & 0xffu), n_leaf = (int)((tot >> 8) & 0xffu), n_inst = (int)((tot >> 16) & 0xffu), n_rec = (int)(tot >> 24);
+    if (tot == 0u) break;     // every slot idle and no ray left
     // the phase with the most ready rays (a full warp of internal nodes always wins)
     int phase = PH_INT, best = min(n_int, 32);
     if (min(n_leaf, 32) > best) { phase = PH_LEAF; best = min(n_leaf, 32); }
     if (min(n_rec, 32) > best) { phase = PH_REC; best = min(n_rec, 32); }
     if (min(n_inst, 32) > best) { phase = PH_INST; best = min(n_inst, 32); }
-    const uint32_t m_lo = phase == PH_INT ? i_lo : phase == PH_LEAF ? l_lo : phase == PH_REC ? r_lo : n_lo;
-    const uint32_t m_hi = phase == PH_INT ? i_hi : phase == PH_LEAF ? l_hi : phase == PH_REC ? r_hi : n_hi;
+    const uint32_t want = phase == PH_INT ? ST_INT : phase == PH_LEAF ? ST_LEAF : ST_INST;
+    const uint32_t m_lo = __ballot_sync(full, phase == PH_REC ? rec0 : s0 == want), m_hi = __ballot_sync(full, phase == PH_REC ? rec1 : s1 == want);
     // the first 32 ready slots, one per lane
     {
       const int c_lo = __popc(m_lo);

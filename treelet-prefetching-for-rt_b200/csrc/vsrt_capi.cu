@@ -185,7 +185,9 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
     const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
-    const bool wavefront = !getenv("VSRT_K1_WF") || atoi(getenv("VSRT_K1_WF")) != 0;
+    // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel
+    // (traverse_wf.cu), bit-identical results, measured 10 % slower on the bench workload (profiles/README.md)
+    const bool wavefront = getenv("VSRT_K1_WF") && atoi(getenv("VSRT_K1_WF")) != 0;
     unsigned wf_grid = 0;
     if (wavefront && n) {
       wf_grid = vsrt_wf_grid(n);

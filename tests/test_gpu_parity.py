@@ -84,6 +84,23 @@ def test_random_scenes(api, ntri, nb, ni, flags, fan, budget):
     run_case(api, s, helpers.mixed_rays(1500, ntri), budget)
 
 
+@pytest.mark.parametrize("ntri,nb,ni,flags,budget,delta", [
+    (2000, 2, 3, sc.F_TRANSFORMS | sc.F_HOLES, 512, 0),
+    (20000, 1, 2, sc.F_TRANSFORMS | sc.F_HOLES, 49152, 0),
+    (5000, 2, 4, sc.F_TRANSFORMS, 256, 0x100000),
+])
+def test_wavefront_variant(api, monkeypatch, ntri, nb, ni, flags, budget, delta):
+    """The warp-wavefront formulation of K1 (traverse_wf.cu, VSRT_K1_WF=1): a pool of 64 rays per warp regrouped by
+    phase every iteration.  Same records, treelet ids, hits and counters as the reference; also with non-finite rays
+    (EXACT pass) mixed in."""
+    monkeypatch.setenv("VSRT_K1_WF", "1")
+    s = sc.Scene(ntri, seed=ntri + 1, n_blas=nb, n_instances=ni, flags=flags)
+    rays = helpers.mixed_rays(3000, ntri + 5)
+    rays["origin"][7::97, 1] = np.inf
+    rays["direction"][11::89, 2] = np.nan
+    run_case(api, s, rays, budget, delta=delta)
+
+
 @pytest.mark.parametrize("budget", [256, 1024])
 def test_host_device_offset_quirk(api, budget):
     """Non-zero host->device offset: traceRayWithTreelets stores a HOST address in current_treelet_root

@@ -82,6 +82,9 @@ constexpr int K3_ILP = 4;        // independent 32-record windows in flight per 
 #ifndef VSRT_K3_PERSIST
 #define VSRT_K3_PERSIST 0   // measured: a persistent grid saturates the CTA-private table and is slower (1.10 vs 0.72 ms)
 #endif
+#ifndef VSRT_K3_WARP_TABLE
+#define VSRT_K3_WARP_TABLE 0   // A/B: 1 = every warp has its own slice of the table and flushes it itself (no CTA barrier at the end); slower, 0.77 vs 0.74 ms
+#endif
 constexpr int K3_HASH_BITS = VSRT_K3_HASH_BITS; // CTA-private treelet histogram: 2^bits (key,count) slots in shared memory, flushed once per CTA
 constexpr int K3_CTAS_PER_SM = 4; // only for the persistent-grid A/B variant (VSRT_K3_PERSIST=1)
 
@@ -99,6 +102,10 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
   for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS) { s_hkey[i] = VSRT_NO_TID; s_hcnt[i] = 0; }
   if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
   __syncthreads();
+  // the warp's slice of the table (VSRT_K3_WARP_TABLE) or the whole table
+  constexpr int TBITS = VSRT_K3_WARP_TABLE ? K3_HASH_BITS - 3 : K3_HASH_BITS;
+  unsigned int* const t_key = s_hkey + (VSRT_K3_WARP_TABLE ? (threadIdx.x >> 5) << TBITS : 0);
+  unsigned int* const t_cnt = s_hcnt + (VSRT_K3_WARP_TABLE ? (threadIdx.x >> 5) << TBITS : 0);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const ArenaView& av = p.av;
@@ -189,9 +196,9 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
             // run = lanes up to the next head or the first inactive lane
             const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
             const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
-            const uint32_t h = (tid[u] * 2654435761u) >> (32 - K3_HASH_BITS);
-            const uint32_t old = atomicCAS(&s_hkey[h], VSRT_NO_TID, tid[u]);
-            if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&s_hcnt[h], run);
+            const uint32_t h = (tid[u] * 2654435761u) >> (32 - TBITS);
+            const uint32_t old = atomicCAS(&t_key[h], VSRT_NO_TID, tid[u]);
+            if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&t_cnt[h], run);
             else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
           }
         }
@@ -201,14 +208,30 @@ __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
     for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(packed >> (8 * c)) & 0xffu;
   }
   if (p.treelet_hist) {
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS)
-      if (s_hkey[i] != VSRT_NO_TID && s_hcnt[i]) atomicAdd(p.treelet_hist + s_hkey[i], (unsigned long long)s_hcnt[i]);
+    if (VSRT_K3_WARP_TABLE) {
+      __syncwarp();
+      for (uint32_t i = threadIdx.x & 31; i < (1u << TBITS); i += 32)
+        if (t_key[i] != VSRT_NO_TID && t_cnt[i]) atomicAdd(p.treelet_hist + t_key[i], (unsigned long long)t_cnt[i]);
+    } else {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS)
+        if (s_hkey[i] != VSRT_NO_TID && s_hcnt[i]) atomicAdd(p.treelet_hist + s_hkey[i], (unsigned long long)s_hcnt[i]);
+    }
   }
+  uint32_t mine = 0;
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     const uint32_t s = __reduce_add_sync(0xffffffffu, hc[c]);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_hist[c], s);
+    if (VSRT_K3_WARP_TABLE) { if ((threadIdx.x & 31) == c) mine = s; }
+    else if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_hist[c], s);
+  }
+  if (VSRT_K3_WARP_TABLE) {   // lane c of every warp adds type c straight to the global counters
+    const uint32_t c = threadIdx.x & 31;
+    if (c < 8 && mine) {
+      atomicAdd(p.counters->v + CI_TYPE0 + c, (unsigned long long)mine);
+      atomicAdd(p.counters->v + CI_ACCESSED, (unsigned long long)mine * (c == VSRT_TXN_BVH_INSTANCE_LEAF ? 128ull : (c == VSRT_TXN_BVH_PRIMITIVE_LEAF_DESCRIPTOR ? 8ull : 64ull)));
+    }
+    return;
   }
   __syncthreads();
   if (threadIdx.x < 8 && s_hist[threadIdx.x]) {

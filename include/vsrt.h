@@ -223,8 +223,8 @@ int vsrt_get_counters(vsrt_context* ctx, vsrt_counters* out);
 int vsrt_reset_counters(vsrt_context* ctx);
 /* Device copy of the counters as uint64[VSRT_COUNTERS_N_SUM + VSRT_COUNTERS_N_MAX] followed by the
  * per-treelet visit histogram uint64[n_treelets] (metadata-index order): the buffers a multi-GPU run
- * all-reduces (SUM over the first part and the histogram, MAX over the 2 max fields).
- * vsrt_set_counters_device writes reduced values back. */
+ * all-reduces (SUM over the first part and the histogram, MAX over the 2 max fields).  The pointers alias the library's
+ * own buffers: reduce into copies to keep per-rank totals, or in place to make every rank hold the global ones. */
 int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_hist_dev, uint64_t* n_treelets);
 /* Host copy of the per-treelet visit histogram (records whose node belongs to treelet i, metadata-index order):
  * the popularity data the RT unit's treelet prefetcher votes on (shader.cc:3424-3433), accumulated over every

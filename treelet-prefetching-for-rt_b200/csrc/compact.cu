@@ -97,6 +97,9 @@ __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_
 // offsets, one REDUX.OR builds the bitmap of ray starts inside the window and a popcount of the bits at or below the lane
 // gives the ray (every ray has at least its TLAS-header record; a warp that sees an empty ray counts with shuffles instead).
 __global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
+  // queued by the host before it knows whether the traversal succeeded and how many records there are (see run_batch)
+  if (p.err_flags && (*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.fatal_mask)) return;
+  if (p.offsets[p.n_rays] > p.out_capacity) return;
   __shared__ unsigned int s_hist[8];
   __shared__ unsigned int s_hkey[1 << K3_HASH_BITS], s_hcnt[1 << K3_HASH_BITS];
   for (uint32_t i = threadIdx.x; i < (1u << K3_HASH_BITS); i += K3_THREADS) { s_hkey[i] = VSRT_NO_TID; s_hcnt[i] = 0; }

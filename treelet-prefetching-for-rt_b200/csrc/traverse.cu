@@ -62,6 +62,7 @@ struct ActiveRay { Ray8 ray; Idir idir; float tmult; uint32_t inst; bool nonfini
 
 template <int MODE, int STACK_N, bool EXACT>
 __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const TraverseParams p) {
+  if (p.gate && !(*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.gate)) return;   // nothing was deferred to this pass
   const ArenaView& av = p.av;
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;

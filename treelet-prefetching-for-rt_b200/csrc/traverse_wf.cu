@@ -36,6 +36,7 @@ constexpr uint32_t B_INCUR = 1u, B_TIDKNOWN = 2u, B_NONFINITE = 4u;
 
 template <int MODE, bool EXACT>
 __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(const TraverseParams p) {
+  if (p.gate && !(*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.gate)) return;   // nothing was deferred to this pass
   const ArenaView& av = p.av;
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;

@@ -183,7 +183,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
-    tp.magic16 = 0x64646464u; tp.only_deferred = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
+    tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
     const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
     // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel
     // (traverse_wf.cu), bit-identical results, measured 10 % slower on the bench workload (profiles/README.md)
@@ -199,24 +199,34 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     launches += n ? 1 : 0;
     if (!av.force_exact && n) {
-      // rays (or instances) with non-finite coordinates were deferred by the fast kernel: run the EXACT kernel on them
-      uint32_t e1 = 0;
-      CUDA_OK(c, cudaMemcpyAsync(&e1, c->d_err, 4, cudaMemcpyDeviceToHost, st));
-      CUDA_OK(c, cudaStreamSynchronize(st));
-      if (e1 & EF_NEED_EXACT) {
-        tp.only_deferred = 1;
-        rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, st);
-        if (rc) return fail(c, rc, "exact traversal kernel launch failed");
-        launches++;
-      }
+      // rays (or instances) with non-finite coordinates are deferred by the fast kernel (EF_NEED_EXACT): the EXACT kernel is
+      // queued behind it and returns at once when nothing was deferred -- no flag read-back between the two
+      tp.only_deferred = 1; tp.gate = EF_NEED_EXACT;
+      rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, st);
+      if (rc) return fail(c, rc, "exact traversal kernel launch failed");
+      launches++;
     }
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
     rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
     launches += n ? 3 : 0;   // 3 scan kernels
-    uint32_t h_err = 0;
+    // K3 is queued right away into the buffers of the previous batch; it checks the error flags and the record count on the
+    // device and does nothing if either says no.  One host synchronisation per batch in the steady state.
+    CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
+    cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
+    cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
+    cp.err_flags = c->d_err; cp.fatal_mask = EF_BAD_BVH | EF_STACK | EF_TRACE_CAP;
+    uint64_t queued_cap = std::min(c->d_txns.cap, c->d_tids.cap);
+    if (queued_cap && n) {
+      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = queued_cap;
+      rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
+      launches++;
+    }
+    CUDA_OK(c, cudaEventRecord(c->ev[3], st));
+    uint32_t h_err = 0; DevCounters now;
     CUDA_OK(c, cudaMemcpyAsync(&total, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(&h_err, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
     if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
     if (h_err & EF_STACK) {
@@ -229,22 +239,22 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       c->stage_cap *= 2;
       continue;
     }
-    break;
-  }
-  CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
-  CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
-  cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = c->d_txns.cap; cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
-  cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
-  rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
-  CUDA_OK(c, cudaEventRecord(c->ev[3], st));
-  launches += n ? 1 : 0;
-  {
+    if (!queued_cap || total > queued_cap) {
+      // first batch, or more records than the buffers held: the queued K3 declined; grow and run it now
+      CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
+      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap);
+      if (n) {
+        rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
+        launches++;
+      }
+      CUDA_OK(c, cudaEventRecord(c->ev[3], st));
+      CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(c, cudaStreamSynchronize(st));
+    }
     // rayCount (:1665) advanced by the traversal kernel; accessedDataSize delta of this batch = its algorithmic bytes
-    DevCounters now;
-    CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaStreamSynchronize(st));
     c->last.algorithmic_bytes = now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
     c->h_prev = now;
+    break;
   }
   c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p; c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p;
   c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;

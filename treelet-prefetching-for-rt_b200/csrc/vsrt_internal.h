@@ -98,6 +98,7 @@ struct TraverseParams {
   uint32_t refill_t;              // refill a warp when at least this many lanes are idle
   uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
   uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
+  uint32_t gate;                  // != 0: the kernel returns at once unless (*err_flags & gate) -- lets the host queue the EXACT pass without reading the flags back
   uint32_t prefetch;              // issue an L1 prefetch for the node a lane will pop next
   uint2* gstack;                  // wavefront kernel: per-warp stack areas (vsrt_wf_stack_bytes)
   uint32_t stack_n;               // wavefront kernel: stack entries per ray
@@ -120,6 +121,8 @@ struct CompactParams {
   vsrt_txn* txns; uint32_t* tids; uint64_t out_capacity;
   DevCounters* counters; unsigned long long* treelet_hist;   // may be NULL
   const uint64_t* remap;      // -remap_to_treelet_layout: record address = remap[slot] (NULL = original addresses)
+  const uint32_t* err_flags;  // K3 does nothing if (*err_flags & fatal_mask) or if the batch has more records than out_capacity:
+  uint32_t fatal_mask;        //   the host queues it before it has read either back, and repeats it after growing the buffers
 };
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st);
 

@@ -278,6 +278,32 @@ int vsrt_prefetch_chunks(vsrt_context* ctx, const vsrt_prefetch_config* cfg, uin
 int vsrt_schedule_pick(vsrt_context* ctx, int scheduler, uint64_t n_units, const uint64_t* unit_warp_offsets, const uint64_t* warp_ray_ids,
                        const uint8_t* stalled, const uint64_t* last_prefetched, const uint32_t* front, int64_t* pick);
 
+/* ---- shader-table side effects of the last batch (Baseline tables, -gpgpu_rt_intersection_table_type 0) ----
+ * Every procedural-leaf visit calls intersection_table[cta]->add_intersection (vulkan_ray_tracing.cc:2171-2203 / :2951-2984)
+ * and, in traceRay, every accepted triangle hit of a ray without the Opaque flag calls anyhit_table[cta]->add_intersection
+ * and pushes a Hit_data (:2869-2930).  The Baseline table (intersection_table.cc:165-187) keeps one row counter per thread
+ * and issues two stores per call and no loads, so the load trace is the one vsrt_trace_rays returns.  Rays
+ * [32g, 32g + 32) of the batch are taken as the threads of one CTA (thread index tid_x[r], NULL = r % 32; threads that share
+ * a tid_x share its row counter, in ray order); the tables are empty at the start of the batch.  The Coalescing table
+ * (type 1) is not built.  The reference asserts beyond 100 rows per thread (INTERSECTION_TABLE_MAX_LENGTH); no limit here. */
+typedef struct vsrt_table_event {
+  uint32_t table;            /* 0 intersection_table (procedural leaf), 1 anyhit_table (non-opaque triangle hit, traceRay only) */
+  uint32_t shader_counter;   /* row of the table = index[tid] before the call */
+  uint32_t hit_group_index;  /* InstanceContributionToHitGroupIndex of the instance leaf */
+  uint32_t primitive_id;     /* PrimitiveIndex[0] of the procedural leaf / PrimitiveIndex0 of the quad leaf */
+  uint32_t instance_id;      /* InstanceID */
+  uint32_t tid;              /* thread index the row is written for */
+  uint32_t record;           /* index of the PROCEDURAL_LEAF / QUAD_LEAF_HIT record inside the ray's trace */
+  uint32_t reserved;
+} vsrt_table_event;            /* 32 bytes */
+typedef struct vsrt_store_txn { uint64_t address; uint32_t size; uint32_t type; } vsrt_store_txn;   /* MemoryStoreTransactionRecord, abstract_hardware_model.h:323-329 */
+/* event_offsets[n_rays + 1]: CSR over events, in each ray's traversal order; anyhit (may be NULL) is parallel to events and
+ * holds the Hit_data of table-1 events (world_min_thit = thit / tMult, :2895).  VSRT_E_CAPACITY if capacity < *n_events. */
+int vsrt_table_events(vsrt_context* ctx, const uint8_t* tid_x, uint64_t* event_offsets, vsrt_table_event* events, vsrt_hit* anyhit,
+                      uint64_t capacity, uint64_t* n_events);
+/* The two MemoryStoreTransactionRecords of one event for a table that gpgpusim_alloc placed at table_base. */
+void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vsrt_store_txn out[2]);
+
 /* ---- acceleration-structure dump files (VulkanRayTracing::dump_AS, vulkan_ray_tracing.cc:4455-4558, split_files) ----
  * <prefix>.asmain / .asback / .asfront / .asmetadata: the TLAS descriptor range, the BLAS ranges below and above it and
  * the offsets findOffsetBounds (:4901) computed.  vsrt_as_dump_write produces them for a TLAS of desc_size bytes whose

@@ -30,9 +30,29 @@ static void silence(bool on) {
   }
 }
 
-static warp_intersection_table g_noop_table;
+// ref_trace() keeps the shader tables out of the way (a table holds 100 rows per thread and asserts beyond, and ref_trace runs
+// every ray as thread 0): a table that records nothing.  ref_trace_tables() switches the reference's own Baseline tables in.
+struct noop_intersection_table : public warp_intersection_table {
+  std::pair<std::vector<MemoryTransactionRecord>, std::vector<MemoryStoreTransactionRecord> >
+  add_intersection(uint32_t, uint32_t, uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) {
+    return std::pair<std::vector<MemoryTransactionRecord>, std::vector<MemoryStoreTransactionRecord> >();
+  }
+  void clear(const ptx_instruction*, ptx_thread_info*) {}
+  bool shader_exists(uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) { return false; }
+  bool exit_shaders(uint32_t, uint32_t) { return true; }
+  uint32_t get_primitiveID(uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) { return 0; }
+  uint32_t get_instanceID(uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) { return 0; }
+  uint32_t get_hitGroupIndex(uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) { return 0; }
+  void* get_shader_data_address(uint32_t, uint32_t) { return NULL; }
+};
+static noop_intersection_table g_noop_table;
 static warp_intersection_table* g_row[1] = { &g_noop_table };
 static warp_intersection_table** g_tab[1] = { g_row };
+// one CTA's pair of Baseline tables (vulkan_ray_tracing.cc:424-447): intersection_table[0][0] and anyhit_table[0][0]
+static Baseline_warp_intersection_table* g_itab = NULL;
+static Baseline_warp_intersection_table* g_atab = NULL;
+static warp_intersection_table* g_irow[1]; static warp_intersection_table** g_itab3[1] = { g_irow };
+static warp_intersection_table* g_arow[1]; static warp_intersection_table** g_atab3[1] = { g_arow };
 
 void ref_reset(void) {
   VulkanRayTracing::treelet_roots.clear();
@@ -45,6 +65,9 @@ void ref_reset(void) {
   VulkanRayTracing::blas_addr_map.clear();
   VulkanRayTracing::tlas_addr = NULL;
   VulkanRayTracing::accessedDataSize = 0;
+  if (!g_itab) { g_itab = new Baseline_warp_intersection_table(); g_atab = new Baseline_warp_intersection_table(); }
+  g_itab->clear(NULL, NULL); g_atab->clear(NULL, NULL);
+  g_irow[0] = g_itab; g_arow[0] = g_atab;
   VulkanRayTracing::intersection_table = g_tab;
   VulkanRayTracing::anyhit_table = g_tab;
   rayCount = 0;
@@ -153,6 +176,61 @@ int64_t ref_trace(void* tlas, int mode, uint32_t n, const ref_ray* rays, ref_hit
   }
   if (!keep_stdout) silence(false);
   return overflow ? -(int64_t)total : (int64_t)total;
+}
+
+// ---- shader-table side effects (Baseline tables): rays [32g, 32g+32) are the threads tid.x = i % 32 of one
+// CTA whose two tables start empty.  Per add_intersection call: which table, the row (index[tid] before the call), the
+// values written, and the two MemoryStoreTransactionRecords; per any-hit call the Hit_data pushed to all_hit_data.
+struct ref_table_event { uint32_t table, shader_counter, hit_group_index, primitive_id, instance_id, tid; uint64_t store_addr[2]; uint32_t store_size[2]; };
+void ref_table_bases(uint64_t* itab, uint64_t* atab) { *itab = (uint64_t)g_itab->table; *atab = (uint64_t)g_atab->table; }
+int64_t ref_trace_tables(void* tlas, int mode, uint32_t n, const ref_ray* rays, uint32_t* ev_counts, ref_table_event* ev, ref_hit* anyhit, uint64_t cap) {
+  silence(true);
+  VulkanRayTracing::intersection_table = g_itab3; VulkanRayTracing::anyhit_table = g_atab3;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (i % 32 == 0) { g_itab->clear(NULL, NULL); g_atab->clear(NULL, NULL); }
+    const ref_ray& r = rays[i];
+    ptx_thread_info th; th.tid_x = i % 32;
+    float3 o = { r.origin[0], r.origin[1], r.origin[2] }, d = { r.dir[0], r.dir[1], r.dir[2] };
+    if (mode == 1)
+      VulkanRayTracing::traceRayWithTreelets(tlas, r.flags, r.cull_mask, r.sbt_offset, r.sbt_stride, r.miss_index, o, r.tmin, d, r.tmax, 0, NULL, &th);
+    else
+      VulkanRayTracing::traceRay(tlas, r.flags, r.cull_mask, r.sbt_offset, r.sbt_stride, r.miss_index, o, r.tmin, d, r.tmax, 0, NULL, &th);
+    free(th.data.traversal_data.back());
+    // the Baseline table emits exactly two stores per call (intersection_table.cc:180-181): hitGroupIndex[tid], shader_data[tid]
+    const uint32_t n_ev = (uint32_t)(th.store_txns.size() / 2);
+    uint32_t k_any = 0;
+    for (uint32_t k = 0; k < n_ev; k++) {
+      const MemoryStoreTransactionRecord& s0 = th.store_txns[2 * k]; const MemoryStoreTransactionRecord& s1 = th.store_txns[2 * k + 1];
+      const uint64_t a0 = (uint64_t)s0.address;
+      const bool is_any = a0 >= (uint64_t)g_atab->table && a0 < (uint64_t)(g_atab->table + INTERSECTION_TABLE_MAX_LENGTH);
+      Baseline_warp_intersection_table* t = is_any ? g_atab : g_itab;
+      const uint64_t off = a0 - (uint64_t)t->table;
+      if (total < cap && ev) {
+        ref_table_event& e = ev[total];
+        e.table = is_any ? 1u : 0u; e.shader_counter = (uint32_t)(off / sizeof(Baseline_Entry)); e.tid = (uint32_t)((off % sizeof(Baseline_Entry)) / 4);
+        e.hit_group_index = t->table[e.shader_counter].hitGroupIndex[e.tid];
+        e.primitive_id = t->table[e.shader_counter].shader_data[e.tid].primitiveID; e.instance_id = t->table[e.shader_counter].shader_data[e.tid].instanceID;
+        e.store_addr[0] = a0; e.store_size[0] = s0.size; e.store_addr[1] = (uint64_t)s1.address; e.store_size[1] = s1.size;
+        if (anyhit) {
+          ref_hit& h = anyhit[total]; memset(&h, 0, sizeof(h));
+          if (is_any && k_any < th.data.all_hit_data.size()) {
+            const Hit_data* hd = th.data.all_hit_data[k_any];
+            h.hit = 1; h.t = hd->world_min_thit; h.prim = hd->primitive_index; h.geom = hd->geometry_index; h.instance_id = hd->instance_index;
+            h.bary[0] = hd->barycentric_coordinates.x; h.bary[1] = hd->barycentric_coordinates.y; h.bary[2] = hd->barycentric_coordinates.z;
+            h.point[0] = hd->intersection_point.x; h.point[1] = hd->intersection_point.y; h.point[2] = hd->intersection_point.z;
+          }
+        }
+      }
+      if (is_any) k_any++;
+      total++;
+    }
+    for (auto* p : th.data.all_hit_data) free(p);
+    if (ev_counts) ev_counts[i] = n_ev;
+  }
+  VulkanRayTracing::intersection_table = g_tab; VulkanRayTracing::anyhit_table = g_tab;
+  silence(false);
+  return (int64_t)total;
 }
 
 void ref_get_counters(ref_counters* out) {

@@ -33,6 +33,7 @@ static gpgpu_context* GPGPU_Context() { static gpgpu_context c; return &c; }
 
 struct memory_space {
   void write(void* addr, size_t n, const void* data, ptx_thread_info*, const ptx_instruction*) { memcpy(addr, data, n); }
+  void read(const void* addr, size_t n, void* out) { memcpy(out, addr, n); }
 };
 
 struct ref_rt_thread_data {
@@ -50,25 +51,21 @@ class ptx_thread_info {
   std::vector<Ray> rays; unsigned n_intersect;
   std::vector<MemoryTransactionRecord> txns;
   std::vector<MemoryStoreTransactionRecord> store_txns;
-  ptx_thread_info() : n_intersect(0) { RT_thread_data = &data; }
+  unsigned tid_x;   // lane inside its warp-sized CTA row: what the warp intersection tables are indexed by
+  ptx_thread_info() : n_intersect(0), tid_x(0) { RT_thread_data = &data; }
   void add_ray_properties(Ray r) { rays.push_back(r); }
   void add_ray_intersect() { n_intersect++; }
   void set_rt_transactions(std::vector<MemoryTransactionRecord> t) { txns = t; }
   void set_rt_store_transactions(std::vector<MemoryStoreTransactionRecord> t) { store_txns = t; }
   memory_space* get_global_memory() { return &mem; }
   dim3 get_ctaid() const { return dim3(0, 0, 0); }
-  dim3 get_tid() const { return dim3(0, 0, 0); }
+  dim3 get_tid() const { return dim3(tid_x, 0, 0); }
   unsigned get_uid() const { return 0; }
   unsigned get_hw_tid() const { return 0; }
 };
 
-enum class IntersectionTableType { Baseline, Coalescing };
-struct warp_intersection_table {
-  std::pair<std::vector<MemoryTransactionRecord>, std::vector<MemoryStoreTransactionRecord> >
-  add_intersection(uint32_t, uint32_t, uint32_t, uint32_t, const ptx_instruction*, ptx_thread_info*) {
-    return std::pair<std::vector<MemoryTransactionRecord>, std::vector<MemoryStoreTransactionRecord> >();
-  }
-};
+enum class IntersectionTableType { Baseline, Function_Call_Coalescing };
+class warp_intersection_table;   // the reference's own class (intersection_table.h) is spliced in right after this file
 
 struct DESCRIPTOR_SET_STRUCT;
 

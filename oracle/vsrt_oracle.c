@@ -80,6 +80,7 @@ typedef struct vo_ctx {
   map64 root_idx;                    /* treelet_addr_to_metadata_idx (:1332) */
   uint64_t total_bvh_size;
   vo_counters c;
+  uint64_t* proc_sink; uint64_t proc_cap, proc_n;   /* optional: instance leaf (host address) of every procedural-leaf visit, in trace order (single-threaded traces) */
 } vo_ctx;
 
 vo_ctx* vo_create(void) { vo_ctx* c = (vo_ctx*)calloc(1, sizeof(vo_ctx)); map_init(&c->blas, 16); return c; }
@@ -93,6 +94,12 @@ void vo_destroy(vo_ctx* c) { if (!c) return; vo_clear_treelets(c); map_free(&c->
 void vo_alloc_tlas(vo_ctx* c, const void* host, uint64_t size, uint64_t dev) { (void)host; (void)size; c->tlas_dev = dev; }
 void vo_alloc_blas(vo_ctx* c, const void* host, uint64_t size, uint64_t dev) { (void)size; map_put(&c->blas, (uint64_t)(uintptr_t)host, dev); }
 void vo_reset_counters(vo_ctx* c) { memset(&c->c, 0, sizeof(c->c)); }
+void vo_set_proc_sink(vo_ctx* c, uint64_t* buf, uint64_t cap) { c->proc_sink = buf; c->proc_cap = cap; c->proc_n = 0; }
+uint64_t vo_proc_sink_count(vo_ctx* c) { return c->proc_n; }
+static void proc_visit(vo_ctx* c, const uint8_t* instance_leaf) {
+  if (c->proc_sink && c->proc_n < c->proc_cap) c->proc_sink[c->proc_n] = (uint64_t)(uintptr_t)instance_leaf;
+  c->proc_n++;
+}
 void vo_get_counters(vo_ctx* c, vo_counters* out) { *out = c->c; }
 
 /* ---------------------------------------------------------------- wire-format decode */
@@ -528,7 +535,8 @@ static int trace_treelet(vo_ctx* c, const uint8_t* tlas, const vo_ray* r, vo_hit
           if (terminate) { w->cur.n = 0; w->oth.n = 0; }
         } else { emit(tb, DEV(n.addr), 64, T_QUAD, hist); total_nodes++; }
       } else {
-        emit(tb, DEV(n.addr), 64, T_PROC, hist); total_nodes++;               /* intersection-table txns: not restated */
+        emit(tb, DEV(n.addr), 64, T_PROC, hist); total_nodes++;               /* intersection-table call: vo_table_events */
+        proc_visit(c, w->ic[n.ictx].leaf_addr);
       }
     }
   }
@@ -640,7 +648,7 @@ static int trace_dfs(vo_ctx* c, const uint8_t* tlas, const vo_ray* r, vo_hit* h,
               if (!opaque) { w->c.num_any_hits++; n_all_hits++; }              /* any-hit table txns: not restated */
               if (terminate) st->n = 0;
             } else { emit(tb, DEV(lf), 64, T_QUAD, hist); total_nodes++; }
-          } else { emit(tb, DEV(lf), 64, T_PROC, hist); total_nodes++; }
+          } else { emit(tb, DEV(lf), 64, T_PROC, hist); total_nodes++; proc_visit(c, ic.leaf_addr); }
         }
       }
     }
@@ -851,4 +859,65 @@ int64_t vo_schedule_pick(vo_ctx* c, int scheduler, uint64_t last_prefetched, uin
     if (scheduler == 2 && m > best_n) { best_n = m; best = (int64_t)w; }
   }
   return best >= 0 ? best : first_free;
+}
+
+/* ================================================================ shader-table side effects, Baseline tables
+ * Every procedural-leaf visit (both variants, :2171-2203 / :2951-2984) calls intersection_table[cta]->add_intersection, every
+ * accepted triangle hit of a NON-opaque ray in traceRay (:2869-2930) calls anyhit_table[cta]->add_intersection and pushes a
+ * Hit_data.  The Baseline table (intersection_table.cc:165-187) keeps a row counter per thread (index[tid]) and emits two
+ * stores: &table[row].hitGroupIndex[tid] (4 bytes) and &table[row].shader_data[tid] (8 bytes); no loads, so the load trace is
+ * unaffected.  Restated from the trace: rays [32g, 32g+32) are the threads of one CTA row (tid = tid_x[r] or r % 32), tables
+ * empty at the start of the batch.  Uniform host->device offset only (the record addresses are mapped back with it). */
+typedef struct { uint32_t table, shader_counter, hit_group_index, primitive_id, instance_id, tid; uint64_t store_addr[2]; uint32_t store_size[2]; } vo_table_event;
+enum { VO_BASELINE_ENTRY = 384 };   /* sizeof(Baseline_Entry): 32 x u32 + 32 x {u32, u32}, intersection_table.h:109-116 */
+int64_t vo_table_events(vo_ctx* c, const void* tlas_v, int mode, uint64_t n_rays, const vo_ray* rays, const uint64_t* offsets, const vo_txn* txns,
+                        const uint8_t* tid_x, const uint64_t* proc_inst, uint64_t itab_base, uint64_t atab_base, uint32_t* ev_counts, vo_table_event* ev, vo_hit* anyhit, uint64_t cap) {
+  const int64_t off = (int64_t)(c->tlas_dev - (uint64_t)(uintptr_t)tlas_v);
+  uint32_t rows[2][32];
+  uint64_t total = 0, n_proc = 0;   /* proc_inst: the instance leaf of every procedural visit, in trace order (vo_set_proc_sink) -- the
+                                       treelet-ordered variant interleaves the nodes of different instances, so the trace alone does not tell */
+  for (uint64_t r = 0; r < n_rays; r++) {
+    if (r % 32 == 0) memset(rows, 0, sizeof(rows));
+    const uint32_t tid = tid_x ? tid_x[r] : (uint32_t)(r % 32);
+    const uint8_t* inst = NULL; uint32_t n_ev = 0;
+    for (uint64_t k = offsets[r]; k < offsets[r + 1]; k++) {
+      const uint8_t* node = (const uint8_t*)(uintptr_t)(txns[k].address - (uint64_t)off);
+      if (txns[k].type == T_INSTANCE) { inst = node; continue; }
+      int table = -1;
+      if (txns[k].type == T_PROC) table = 0;
+      else if (txns[k].type == T_QUAD_HIT && mode == 0 && !(rays[r].flags & 0x1u)) table = 1;
+      if (table < 0) continue;
+      const uint8_t* own = table == 0 ? (const uint8_t*)(uintptr_t)proc_inst[n_proc++] : inst;
+      if (!own) continue;
+      ileaf il; unpack_instance(&il, own);
+      if (total < cap && ev) {
+        vo_table_event* e = &ev[total];
+        const uint64_t base = table ? atab_base : itab_base;
+        e->table = (uint32_t)table; e->shader_counter = rows[table][tid]; e->tid = tid;
+        e->hit_group_index = il.hit_group; e->instance_id = il.instance_id;
+        e->primitive_id = table ? ldu32(node + 8) : ldu32(node + 12);                  /* PrimitiveIndex0 / PrimitiveIndex[0] */
+        e->store_addr[0] = base + (uint64_t)e->shader_counter * VO_BASELINE_ENTRY + 4ull * tid; e->store_size[0] = 4;
+        e->store_addr[1] = base + (uint64_t)e->shader_counter * VO_BASELINE_ENTRY + 128ull + 8ull * tid; e->store_size[1] = 8;
+        if (anyhit) {
+          vo_hit* h = &anyhit[total]; memset(h, 0, sizeof(*h));
+          if (table == 1) {
+            /* the any-hit Hit_data (:2886-2922): same transform, triangle test and barycentrics as the traversal itself */
+            rayf wr, orr; float tmult, thit = 0.0f, p[3][3], op[3];
+            for (int a = 0; a < 3; a++) { wr.o[a] = rays[r].origin[a]; wr.d[a] = rays[r].dir[a]; }
+            wr.tmin = rays[r].tmin; wr.tmax = rays[r].tmax;
+            transform_ray(&wr, il.w2o, &orr, &tmult);
+            for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) p[i][a] = ldf(node + 16 + 12 * i + 4 * a);
+            ray_tri(p[0], p[1], p[2], &orr, &thit);
+            const float tw = thit / tmult;
+            h->hit = 1; h->t = tw; h->geom = ldu32(node + 4) & 0x0fffffffu; h->prim = ldu32(node + 8); h->instance_id = il.instance_id;
+            for (int a = 0; a < 3; a++) { h->point[a] = wr.o[a] + wr.d[a] * tw; op[a] = orr.o[a] + orr.d[a] * thit; }
+            barycentric(op, p[0], p[1], p[2], h->bary);
+          }
+        }
+      }
+      rows[table][tid]++; n_ev++; total++;
+    }
+    if (ev_counts) ev_counts[r] = n_ev;
+  }
+  return (int64_t)total;
 }

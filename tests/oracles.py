@@ -34,6 +34,11 @@ PDEC = np.dtype([("root", np.uint64), ("votes", np.uint32), ("total", np.uint32)
                  ("first_node", np.uint32), ("num_nodes", np.uint32)])
 
 
+# one warp_intersection_table::add_intersection call (Baseline table): ref_table_event / vo_table_event
+TEV = np.dtype([("table", np.uint32), ("shader_counter", np.uint32), ("hit_group_index", np.uint32), ("primitive_id", np.uint32),
+                ("instance_id", np.uint32), ("tid", np.uint32), ("store_addr", np.uint64, 2), ("store_size", np.uint32, 2)])
+
+
 class _Base:
     def _finish_trace(self, n, total, hits, counts, txns, tids):
         offsets = np.zeros(n + 1, dtype=np.uint64)
@@ -62,6 +67,9 @@ class RefOracle(_Base):
         L.ref_prefetch_vote.restype = ctypes.c_int64
         L.ref_prefetch_vote.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64]
         L.ref_set_treelet_metadata.argtypes = [c_u64, ctypes.c_uint]
+        L.ref_trace_tables.restype = ctypes.c_int64
+        L.ref_trace_tables.argtypes = [c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64]
+        L.ref_table_bases.argtypes = [c_vp, c_vp]
         L.ref_schedule_pick.restype = ctypes.c_int64
         L.ref_schedule_pick.argtypes = [ctypes.c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp]
         self.L = L
@@ -116,6 +124,21 @@ class RefOracle(_Base):
         self.L.ref_sort_trace(method, len(trace["offsets"]) - 1, _abi.ptr(trace["offsets"]), _abi.ptr(t))
         return t
 
+    def table_bases(self):
+        a, b = c_u64(), c_u64()
+        self.L.ref_table_bases(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def table_events(self, mode, rays):
+        """The reference's own Baseline intersection / any-hit tables while tracing `rays` as CTA rows of 32 threads: per
+        ray the add_intersection calls (rows, values, the two stores) and the any-hit Hit_data."""
+        n = len(rays)
+        counts = np.zeros(n, np.uint32)
+        total = self.L.ref_trace_tables(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(counts), None, None, 0)
+        ev = np.zeros(total, TEV); ah = np.zeros(total, OHIT)
+        self.L.ref_trace_tables(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(counts), _abi.ptr(ev), _abi.ptr(ah), total)
+        return counts, ev, ah
+
     def schedule_pick(self, trace, scheduler, last_prefetched, warp_ray_ids, stalled=None, front=None):
         """rt_unit::schedule_next_warp (shader.cc:4307-4392) for one unit."""
         ids = np.ascontiguousarray(warp_ray_ids, np.uint64)
@@ -165,6 +188,11 @@ class PortOracle(_Base):
         L.vo_get_counters.argtypes = [c_vp, c_vp]
         L.vo_reset_counters.argtypes = [c_vp]
         L.vo_sort_trace.argtypes = [c_vp, ctypes.c_int, c_u64, c_vp, c_vp]
+        L.vo_table_events.restype = ctypes.c_int64
+        L.vo_table_events.argtypes = [c_vp, c_vp, ctypes.c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_vp, c_vp, c_vp, c_u64]
+        L.vo_set_proc_sink.argtypes = [c_vp, c_vp, c_u64]
+        L.vo_proc_sink_count.restype = c_u64
+        L.vo_proc_sink_count.argtypes = [c_vp]
         L.vo_schedule_pick.restype = ctypes.c_int64
         L.vo_schedule_pick.argtypes = [c_vp, ctypes.c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.vo_prefetch_vote.restype = ctypes.c_int64
@@ -250,6 +278,21 @@ class PortOracle(_Base):
         fr = None if front is None else np.ascontiguousarray(front, np.uint32)
         return self.L.vo_schedule_pick(self.h, scheduler, int(last_prefetched), len(ids) // 32, _abi.ptr(ids), _abi.ptr(st), _abi.ptr(trace["offsets"]),
                                        _abi.ptr(fr), _abi.ptr(trace["txns"]))
+
+    def table_events(self, mode, rays, itab_base, atab_base, tid_x=None):
+        sink = np.zeros(max(16, 64 * len(rays)), np.uint64)
+        self.L.vo_set_proc_sink(self.h, _abi.ptr(sink), len(sink))
+        t = self.trace(mode, rays)
+        assert self.L.vo_proc_sink_count(self.h) <= len(sink)
+        self.L.vo_set_proc_sink(self.h, None, 0)
+        n = len(rays)
+        counts = np.zeros(n, np.uint32)
+        tx = None if tid_x is None else np.ascontiguousarray(tid_x, np.uint8)
+        args = (self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(t["offsets"]), _abi.ptr(t["txns"]), _abi.ptr(tx), _abi.ptr(sink), itab_base, atab_base, _abi.ptr(counts))
+        total = self.L.vo_table_events(*args, None, None, 0)
+        ev = np.zeros(total, TEV); ah = np.zeros(total, OHIT)
+        self.L.vo_table_events(*args, _abi.ptr(ev), _abi.ptr(ah), total)
+        return counts, ev, ah
 
     def trace_remapped(self, mode, rays, base, stride, budget):
         """-remap_to_treelet_layout 1 (vulkan_ray_tracing.cc:1682,:1763,...): the same visit sequence with every record

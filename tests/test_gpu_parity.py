@@ -338,6 +338,56 @@ def test_prefetch_vote_and_chunks(api):
     ctx.close()
 
 
+def ctx_offsets(ctx, n):
+    """CSR trace offsets of the last batch, read back from the device through torch (the library keeps them resident)."""
+    import torch
+    r = ctx.device_results()
+
+    class _D:
+        __cuda_array_interface__ = {"shape": ((n + 1) * 8,), "typestr": "|u1", "data": (r.trace_offsets, False), "version": 3}
+    return torch.as_tensor(_D(), device="cuda").cpu().numpy().view(np.uint64).astype(np.int64)
+
+
+@pytest.mark.parametrize("wavefront", ["0", "1"])
+def test_table_events(api, monkeypatch, wavefront):
+    """Shader-table side effects (Baseline tables): procedural-leaf calls in both variants, any-hit calls + Hit_data of
+    non-opaque rays in traceRay, against the reference with its own Baseline tables in the loop; shared thread indices
+    (several threads of a CTA with the same tid.x) against the pinned restatement."""
+    monkeypatch.setenv("VSRT_K1_WF", wavefront)
+    s = sc.Scene(2500, seed=18, n_blas=2, n_instances=4, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(1000, 33, 16, 12)
+    port = oracles.PortOracle(); port.register(s); port.form(512)
+    ref = None
+    if oracles.have_ref():
+        ref = oracles.RefOracle(); ref.register(s); ref.form(512)
+    ib, ab = ref.table_bases() if ref else (0x6000000000, 0x6100000000)
+    ctx = api.Context(max_treelet_size=512, device=0); ctx.register(s); ctx.form_treelets()
+    n_ev = [0, 0]
+    for mode in (0, 1):
+        ctx.trace(mode, rays)
+        for tid_x in (None, (np.arange(len(rays)) % 8).astype(np.uint8)):
+            co, eo, ho = (ref if (ref and tid_x is None) else port).table_events(mode, rays, *(() if (ref and tid_x is None) else (ib, ab, tid_x)))
+            offs, ev, ah = ctx.table_events(tid_x)
+            assert np.array_equal(np.diff(offs).astype(np.uint32), co), (mode, "counts")
+            for k in ("table", "shader_counter", "hit_group_index", "primitive_id", "instance_id", "tid"):
+                assert np.array_equal(eo[k], ev[k]), (mode, k)
+            st = ctx.table_event_stores(ev, (ib, ab))
+            assert np.array_equal(st["address"], eo["store_addr"]) and np.array_equal(st["size"], eo["store_size"])
+            anyh = ev["table"] == 1
+            assert np.array_equal(ho["t"][anyh].view(np.uint32), ah["world_min_thit"][anyh].view(np.uint32))
+            assert np.array_equal(ho["prim"][anyh], ah["primitive_index"][anyh]) and np.array_equal(ho["instance_id"][anyh], ah["instance_index"][anyh])
+            assert np.array_equal(ho["bary"][anyh].view(np.uint32), ah["barycentric"][anyh].view(np.uint32))
+            assert np.array_equal(ho["point"][anyh].view(np.uint32), ah["intersection_point"][anyh].view(np.uint32))
+            # the event's record is the PROCEDURAL_LEAF (6) / QUAD_LEAF_HIT (5) record of its ray
+            t = ctx.fetch_trace()[0]
+            toffs = np.asarray(ctx_offsets(ctx, len(rays)))
+            ray_of = np.repeat(np.arange(len(rays)), np.diff(offs).astype(np.int64))
+            assert np.array_equal(t["type"][toffs[ray_of] + ev["record"]], np.where(ev["table"] == 0, 6, 5))
+            n_ev[0] += int((ev["table"] == 0).sum()); n_ev[1] += int(anyh.sum())
+    assert n_ev[0] > 50 and n_ev[1] > 100
+    ctx.close()
+
+
 def test_schedule_pick(api):
     """rt_unit::schedule_next_warp (shader.cc:4307-4392) for many units at once."""
     from test_oracle import _units

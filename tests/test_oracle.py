@@ -178,6 +178,28 @@ def test_port_matches_replay_fixture():
         assert np.array_equal(r["treelet_ids"], z[p + "tid"] + np.uint64(base))
 
 
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_table_events_match_reference():
+    """Shader-table side effects with the reference's own Baseline tables (intersection_table.cc:165-187) in the loop:
+    procedural leaves in both variants, any-hit calls + Hit_data for non-opaque rays in traceRay."""
+    s = sc.Scene(1500, seed=8, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(1200, 12, 24, 16)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s); ref.form(512); port.register(s); port.form(512)
+    ib, ab = ref.table_bases()
+    seen = [0, 0]
+    for mode in (0, 1):
+        (ca, ea, ha), (cb, eb, hb) = ref.table_events(mode, rays), port.table_events(mode, rays, ib, ab)
+        assert np.array_equal(ca, cb)
+        for k in ("table", "shader_counter", "hit_group_index", "primitive_id", "instance_id", "tid", "store_addr", "store_size"):
+            assert np.array_equal(ea[k], eb[k]), (mode, k)
+        assert same_hits(ha, hb)
+        seen[0] += int((ea["table"] == 0).sum()); seen[1] += int((ea["table"] == 1).sum())
+        if mode == 1:
+            assert not (ea["table"] == 1).any()          # traceRayWithTreelets has no any-hit path
+    assert seen[0] >= 20 and seen[1] > 50 and int(ea["shader_counter"].max()) > 0
+
+
 def _units(rng, n_rays, n_units):
     """Random RT units: 1-6 warps each, random (possibly repeated, possibly absent) rays per lane, some stalled."""
     offs = [0]; ids = []; st = []

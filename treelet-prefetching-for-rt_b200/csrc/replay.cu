@@ -220,6 +220,79 @@ __global__ void k_schedule_pick(const unsigned long long* __restrict__ offsets, 
   if (lane == 0) pick[u] = best >= 0 ? best : first_free;
 }
 
+// ------------------------------------------------------------------ shader-table events (Baseline tables)
+// One thread per ray walks the ray's staged records.  A procedural-leaf record is an intersection-table call (its instance
+// is the j-th word from the end of the staging segment, left there by K1); in traceRay a QUAD_LEAF_HIT record of a ray
+// without the Opaque flag is an any-hit call, whose instance is the last INSTANCE_LEAF record before it (traceRay drains a
+// BLAS before it returns to the TLAS, :2679).  FILL = false counts, FILL = true writes the events and the any-hit Hit_data
+// (same transform, triangle test and barycentrics as the traversal: make_object_ray / ray_tri / barycentric).
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_table_events(const TableParams p) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.n_rays) return;
+  const ArenaView& av = p.av;
+  const uint32_t cnt = min(p.counts[r], p.cap);
+  const uint32_t* seg = p.stage + r * (uint64_t)p.cap;
+  const bool anyhit_ray = p.mode == VSRT_MODE_DFS && !(__ldg(&p.rays[r].ray_flags) & VSRT_RAY_FLAG_OPAQUE);
+  const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
+  if (!FILL) {
+    uint32_t n_any = 0;
+    if (anyhit_ray) for (uint32_t k = 0; k < cnt; k++) n_any += (seg[k] & 7u) == C_QUAD_HIT;
+    p.ev_counts[r] = p.nproc[r] + n_any;
+    return;
+  }
+  const uint32_t tid = p.tid_x ? p.tid_x[r] : (uint32_t)(r & 31u);
+  uint32_t row[2] = { 0u, 0u };
+  if (p.tid_x) {   // threads of the CTA that share this tid_x and come earlier have advanced its row counters
+    for (uint64_t q = r & ~31ull; q < r; q++) if (p.tid_x[q] == tid) { row[0] += p.nproc[q]; row[1] += p.ev_counts[q] - p.nproc[q]; }
+  }
+  unsigned long long o = p.ev_offsets[r];
+  uint32_t last_inst = 0xFFFFFFFFu, j = 0;
+  for (uint32_t k = 0; k < cnt; k++) {
+    const uint32_t rec = seg[k], slot = rec >> 3, code = rec & 7u;
+    if (code == C_INSTANCE) { last_inst = slot; continue; }
+    int table = -1; uint32_t inst_slot = 0;
+    if (code == C_PROC) { table = 0; inst_slot = inst_base + seg[p.cap - 1u - j]; j++; }
+    else if (code == C_QUAD_HIT && anyhit_ray && last_inst != 0xFFFFFFFFu) { table = 1; inst_slot = last_inst; }
+    if (table < 0) continue;
+    if (o < p.capacity) {
+      const uint8_t* il = av.base + (uint64_t)inst_slot * 64u;
+      const uint8_t* leaf = av.base + (uint64_t)slot * 64u;
+      vsrt_table_event e;
+      e.table = (uint32_t)table; e.shader_counter = row[table]; e.tid = tid; e.record = k; e.reserved = 0;
+      e.hit_group_index = __ldg(reinterpret_cast<const uint32_t*>(il + 4)) & 0x00ffffffu;
+      e.instance_id = __ldg(reinterpret_cast<const uint32_t*>(il + 72));
+      e.primitive_id = __ldg(reinterpret_cast<const uint32_t*>(leaf + (table ? 8 : 12)));
+      p.events[o] = e;
+      if (p.anyhit) {
+        vsrt_hit h;
+        h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
+        h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
+        h.intersection_point[0] = h.intersection_point[1] = h.intersection_point[2] = 0.0f;
+        h.n_all_hits = 0; h.instance_leaf_address = 0;
+        if (table == 1) {
+          const vsrt_ray* rp = p.rays + r;
+          Ray8 w;
+          w.ox = __ldg(&rp->origin[0]); w.oy = __ldg(&rp->origin[1]); w.oz = __ldg(&rp->origin[2]); w.tmin = __ldg(&rp->tmin);
+          w.dx = __ldg(&rp->direction[0]); w.dy = __ldg(&rp->direction[1]); w.dz = __ldg(&rp->direction[2]); w.tmax = __ldg(&rp->tmax);
+          InstCtx c; make_object_ray(av.base, inst_slot, w, c);
+          const Node64 q = load_node(av.base, slot);
+          float thit = 0.0f;
+          ray_tri(q, c.ray, thit);
+          const float tw = fdiv(thit, c.tmult);                                     // anyhit_thit, :2895
+          h.hit_geometry = 1; h.world_min_thit = tw;
+          h.geometry_index = q.w[1] & 0x0fffffffu; h.primitive_index = q.w[2]; h.instance_index = e.instance_id;
+          h.intersection_point[0] = fadd(w.ox, fmul(w.dx, tw)); h.intersection_point[1] = fadd(w.oy, fmul(w.dy, tw)); h.intersection_point[2] = fadd(w.oz, fmul(w.dz, tw));
+          barycentric(q, fadd(c.ray.ox, fmul(c.ray.dx, thit)), fadd(c.ray.oy, fmul(c.ray.dy, thit)), fadd(c.ray.oz, fmul(c.ray.dz, thit)), h.barycentric);
+          h.instance_leaf_address = slot_to_host(av, inst_slot);
+        }
+        p.anyhit[o] = h;
+      }
+    }
+    row[table]++; o++;
+  }
+}
+
 // ------------------------------------------------------------------ prefetch chunks
 struct ChunkParams {
   ArenaView av; TreeletView tv;
@@ -350,5 +423,12 @@ int vsrt_launch_schedule_pick(const uint64_t* offsets, const uint32_t* tids, uin
   k_schedule_pick<<<(unsigned)((n_units + 3) / 4), 128, 0, st>>>((const unsigned long long*)offsets, tids, n_rays_batch, (const unsigned long long*)unit_offsets_dev,
                                                                  (const unsigned long long*)warp_ray_ids_dev, stalled_dev, target_tid_dev, front_dev, n_units, scheduler,
                                                                  (long long*)pick_dev);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+int vsrt_launch_table_events(bool fill, const TableParams& p, uint32_t*, cudaStream_t st) {
+  if (p.n_rays == 0) return VSRT_OK;
+  const unsigned grid = (unsigned)((p.n_rays + 127) / 128);
+  if (fill) k_table_events<true><<<grid, 128, 0, st>>>(p); else k_table_events<false><<<grid, 128, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   uint32_t* rstage = p.stage;            // staging segment of ray r
   float w_tmin = 0.0f, w_tmax = 0.0f;   // the world ray's origin/direction are re-read from p.rays[r] when needed
   ActiveRay a; a.ray.ox = a.ray.oy = a.ray.oz = a.ray.dx = a.ray.dy = a.ray.dz = a.ray.tmin = a.ray.tmax = 0.0f; a.idir.x = a.idir.y = a.idir.z = 0.0f; a.tmult = 1.0f; a.inst = INST_NONE; a.nonfinite = false;
+  // ray_nodes: bits 0..19 total_nodes_accessed, bits 20..31 procedural-leaf visits (their instance refs sit at the END of
+  // the ray's staging segment, visit j at [cap - 1 - j], for the shader-table post-pass)
   uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0;
   // TREELET: the current treelet (current_treelet_root, :1707/:1752) is kept lazily.  tid_known: cur_tid is its index;
   // otherwise cur_tid holds the SLOT of the self-rooted node that was moved over from `other`, and the index is looked up
@@ -117,8 +119,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       if (st == ST_FIN) {
         // ---- hit record (:2211-2245 / :2990-3033) and per-ray counters
         st = ST_IDLE;
-        if (cnt > cap) err |= EF_TRACE_CAP;
+        if (cnt + (ray_nodes >> 20) > cap) err |= EF_TRACE_CAP;       // records and procedural-visit words share the segment
         p.counts[r] = cnt;
+        p.nproc[r] = ray_nodes >> 20; ray_nodes &= 0xFFFFFu;
         vsrt_hit h;
         h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
         h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;
@@ -355,7 +358,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             EMIT(e.slot, C_QUAD_HIT); ray_nodes++;
             if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) { cur_n = 0; oth_n = 0; }   // :2151-2155 / :2932-2935
           } else { EMIT(e.slot, C_QUAD); ray_nodes++; }
-        } else { EMIT(e.slot, C_PROC); ray_nodes++; }                             // intersection-table transactions: not built yet
+        } else {
+          EMIT(e.slot, C_PROC); ray_nodes++;
+          // which instance this procedural visit belongs to (:2171-2203 / :2951-2984 use it for the intersection table)
+          const uint32_t j = ray_nodes >> 20;
+          if (cnt + j < cap) rstage[cap - 1u - j] = e_inst(e);
+          if (j < 0xFFFu && (ray_nodes & 0xFFFFFu) != 0xFFFFFu) ray_nodes += 1u << 20; else err |= EF_UNSUPPORTED;
+        }
       }
     }
   }

@@ -243,8 +243,14 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
             EMIT(eslot, C_QUAD_HIT);
             if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) { cur_n = 0; oth_n = 0; }   // :2151-2155 / :2932-2935
           } else EMIT(eslot, C_QUAD);
-        } else EMIT(eslot, C_PROC);                                               // intersection-table transactions: not built
-        S(F_NODES, s) = S(F_NODES, s) + 1u;
+          S(F_NODES, s) = S(F_NODES, s) + 1u;
+        } else {
+          EMIT(eslot, C_PROC);
+          // which instance this procedural visit belongs to: kept at the end of the staging segment (see traverse.cu)
+          const uint32_t nn = S(F_NODES, s) + 1u, j = nn >> 20;
+          if (cnt + j < cap) rstage[cap - 1u - j] = emeta & INST_NONE;
+          if (j < 0xFFFu && (nn & 0xFFFFFu) != 0xFFFFFu) S(F_NODES, s) = nn + (1u << 20); else { S(F_NODES, s) = nn; err |= EF_UNSUPPORTED; }
+        }
         { const uint2 z = make_uint2(0u, 0u); POP_NEXT(false, z, false, z); }
         S(F_ESLOT, s) = eslot; S(F_EMETA, s) = emeta; S(F_BITS, s) = bits; S(F_CNT, s) = cnt; S(F_CTID, s) = cur_tid;
         S(F_STK, s) = (uint32_t)cur_n | ((uint32_t)oth_n << 16);
@@ -286,10 +292,10 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
       // ================= recycle: hit record of a finished ray (:2211-2245 / :2990-3033), then a new ray in the slot
       const bool was_fin = active && S(F_ST, s) == ST_FIN;
       if (was_fin) {
-        const uint32_t r = S(F_R, s), cnt = S(F_CNT, s), ray_nodes = S(F_NODES, s), ray_any = S(F_ANY, s), flags = S(F_BITS, s) >> 8;
+        const uint32_t r = S(F_R, s), cnt = S(F_CNT, s), nproc = S(F_NODES, s) >> 20, ray_nodes = S(F_NODES, s) & 0xFFFFFu, ray_any = S(F_ANY, s), flags = S(F_BITS, s) >> 8;
         const float min_thit = SF(F_MINT, s), min_thit_object = SF(F_MINTO, s), w_tmax = SF(F_WTMAX, s);
-        if (cnt > cap) err |= EF_TRACE_CAP;
-        p.counts[r] = cnt;
+        if (cnt + nproc > cap) err |= EF_TRACE_CAP;
+        p.counts[r] = cnt; p.nproc[r] = nproc;
         vsrt_hit h;
         h.hit_geometry = 0; h.world_min_thit = 0.0f; h.primitive_index = 0; h.geometry_index = 0; h.instance_index = 0;
         h.barycentric[0] = h.barycentric[1] = h.barycentric[2] = 0.0f;

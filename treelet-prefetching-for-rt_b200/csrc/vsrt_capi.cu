@@ -54,6 +54,7 @@ struct vsrt_context {
   DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint8_t> d_scan_tmp;
   uint32_t stage_cap = 128;
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
+  DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
   DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
@@ -64,7 +65,7 @@ struct vsrt_context {
   uint64_t* d_inv_off = nullptr; uint2* d_inv = nullptr;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
-  uint64_t last_tlas = 0; int last_mode = 0;
+  uint64_t last_tlas = 0; int last_mode = 0; const vsrt_ray* last_rays = nullptr;
 };
 
 namespace {
@@ -172,15 +173,15 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   }
   ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
   const TreeletView tv = treelet_view(c);
-  c->last = vsrt_device_results{}; c->last_tlas = tlas; c->last_mode = mode;
+  c->last = vsrt_device_results{}; c->last_tlas = tlas; c->last_mode = mode; c->last_rays = d_rays;
   CUDA_OK(c, c->d_hits.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_counts.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_offsets.ensure(n + 1));
-  CUDA_OK(c, c->d_scan_tmp.ensure(vsrt_scan_tmp_bytes(n)));
+  CUDA_OK(c, c->d_scan_tmp.ensure(vsrt_scan_tmp_bytes(n))); CUDA_OK(c, c->d_nproc.ensure(std::max<uint64_t>(n, 1)));
   uint32_t launches = 0; uint64_t total = 0;
   for (int attempt = 0;; attempt++) {
     CUDA_OK(c, c->d_stage.ensure(std::max<uint64_t>(n, 1) * c->stage_cap));
     CUDA_OK(c, cudaMemcpyAsync(c->d_counters_bak, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
-    TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p;
+    TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; { const char* pf = getenv("VSRT_PREFETCH"); tp.prefetch = pf ? (uint32_t)atoi(pf) : 0u; }
@@ -322,7 +323,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_treelets(c);
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
-  c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
+  c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -715,6 +716,48 @@ int vsrt_schedule_pick(vsrt_context* c, int scheduler, uint64_t n_units, const u
   cudaFree(d_uo); cudaFree(d_ids); cudaFree(d_st); cudaFree(d_tg); cudaFree(d_front); cudaFree(d_pick);
   if (rc) return fail(c, rc, "schedule pick failed: %s", cudaGetErrorString(cudaGetLastError()));
   return VSRT_OK;
+}
+
+int vsrt_table_events(vsrt_context* c, const uint8_t* tid_x, uint64_t* event_offsets, vsrt_table_event* events, vsrt_hit* anyhit,
+                      uint64_t capacity, uint64_t* n_events) {
+  if (!c) return VSRT_E_INVALID;
+  if (n_events) *n_events = 0;
+  if (!c->formed || !c->last.trace_offsets || !c->last_rays) return fail(c, VSRT_E_INVALID, "no trace: call vsrt_trace_rays / vsrt_trace_rays_device first (the rays must still be resident)");
+  cudaSetDevice(c->device);
+  const uint64_t n = c->last.n_rays;
+  if (n == 0) { if (event_offsets) event_offsets[0] = 0; return VSRT_OK; }
+  ArenaView av; int rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
+  cudaStream_t st = c->stream;
+  uint8_t* d_tid = nullptr; uint32_t* d_cnt = nullptr; uint64_t* d_off = nullptr; void* d_tmp = nullptr; vsrt_table_event* d_ev = nullptr; vsrt_hit* d_ah = nullptr;
+  uint64_t total = 0;
+  bool ok = upload(&d_tid, tid_x, n, st) == cudaSuccess && cudaMalloc(&d_cnt, n * 4) == cudaSuccess && cudaMalloc(&d_off, (n + 1) * 8) == cudaSuccess &&
+            cudaMalloc(&d_tmp, vsrt_scan_tmp_bytes(n)) == cudaSuccess;
+  TableParams tp; tp.av = av; tp.rays = c->last_rays; tp.n_rays = n; tp.stage = c->d_stage.p; tp.cap = c->stage_cap; tp.mode = (uint32_t)c->last_mode;
+  tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p; tp.tid_x = d_tid; tp.ev_counts = d_cnt; tp.ev_offsets = d_off; tp.events = nullptr; tp.anyhit = nullptr; tp.capacity = 0;
+  rc = ok ? vsrt_launch_table_events(false, tp, nullptr, st) : VSRT_E_CUDA;
+  if (rc == VSRT_OK) rc = vsrt_launch_scan(d_cnt, n, d_off, d_tmp, st);
+  if (rc == VSRT_OK && (cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)) rc = VSRT_E_CUDA;
+  if (rc == VSRT_OK && event_offsets && cudaMemcpy(event_offsets, d_off, (n + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = VSRT_E_CUDA;
+  if (n_events) *n_events = total;
+  const uint64_t m = std::min(total, capacity);
+  if (rc == VSRT_OK && m && events) {
+    ok = cudaMalloc(&d_ev, total * sizeof(vsrt_table_event)) == cudaSuccess && (!anyhit || cudaMalloc(&d_ah, total * sizeof(vsrt_hit)) == cudaSuccess);
+    tp.events = d_ev; tp.anyhit = d_ah; tp.capacity = total;
+    rc = ok ? vsrt_launch_table_events(true, tp, nullptr, st) : VSRT_E_CUDA;
+    if (rc == VSRT_OK && (cudaMemcpyAsync(events, d_ev, m * sizeof(vsrt_table_event), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                          (anyhit && cudaMemcpyAsync(anyhit, d_ah, m * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
+                          cudaStreamSynchronize(st) != cudaSuccess)) rc = VSRT_E_CUDA;
+  }
+  cudaFree(d_tid); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_ev); cudaFree(d_ah);
+  if (rc) return fail(c, rc, "table event generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return total > capacity ? VSRT_E_CAPACITY : VSRT_OK;
+}
+
+void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vsrt_store_txn out[2]) {
+  // Baseline_warp_intersection_table::add_intersection, intersection_table.cc:180-181; Baseline_Entry = u32 hitGroupIndex[32] + {u32, u32} shader_data[32]
+  const uint64_t row = table_base + (uint64_t)ev->shader_counter * 384ull;
+  out[0].address = row + 4ull * ev->tid; out[0].size = 4; out[0].type = 0;            // &table[row].hitGroupIndex[tid], Intersection_Table_Store
+  out[1].address = row + 128ull + 8ull * ev->tid; out[1].size = 8; out[1].type = 0;   // &table[row].shader_data[tid]
 }
 
 }  // extern "C"

@@ -90,6 +90,7 @@ struct TraverseParams {
   vsrt_hit* hits;
   uint32_t* stage;            // [n_rays * cap]
   uint32_t* counts;           // [n_rays] records emitted per ray
+  uint32_t* nproc;            // [n_rays] procedural-leaf visits per ray (their instance refs: stage[r * cap + cap - 1 - j])
   uint32_t cap;               // staging records per ray
   uint32_t mode;
   DevCounters* counters;
@@ -148,3 +149,16 @@ int vsrt_launch_prefetch_chunks(bool fill, const ArenaView& av, const TreeletVie
 int vsrt_launch_schedule_pick(const uint64_t* offsets, const uint32_t* tids, uint64_t n_rays_batch, const uint64_t* unit_offsets_dev,
                               const uint64_t* warp_ray_ids_dev, const uint8_t* stalled_dev, const uint32_t* target_tid_dev, const uint32_t* front_dev,
                               uint64_t n_units, int scheduler, int64_t* pick_dev, cudaStream_t st);
+
+// ---- shader-table side effects (replay.cu): Baseline warp intersection / any-hit tables, from the staged trace of the last batch
+struct TableParams {
+  ArenaView av;
+  const vsrt_ray* rays; uint64_t n_rays;
+  const uint32_t* stage; uint32_t cap; uint32_t mode;
+  const uint32_t* counts; const uint32_t* nproc;
+  const uint8_t* tid_x;              // [n_rays] or NULL (thread r % 32)
+  uint32_t* ev_counts;               // [n_rays] events per ray: out of the count pass, in of the fill pass
+  const uint64_t* ev_offsets;        // [n_rays + 1] (fill pass)
+  vsrt_table_event* events; vsrt_hit* anyhit; uint64_t capacity;
+};
+int vsrt_launch_table_events(bool fill, const TableParams& p, uint32_t* totals_dev, cudaStream_t st);

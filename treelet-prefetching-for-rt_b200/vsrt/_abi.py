@@ -56,6 +56,12 @@ PDEC = np.dtype([("treelet_root", np.uint64), ("votes", np.uint32), ("total", np
                  ("first_node", np.uint32), ("num_nodes", np.uint32)])
 
 
+# vsrt_table_event, vsrt_store_txn
+TEV = np.dtype([("table", np.uint32), ("shader_counter", np.uint32), ("hit_group_index", np.uint32), ("primitive_id", np.uint32),
+                ("instance_id", np.uint32), ("tid", np.uint32), ("record", np.uint32), ("reserved", np.uint32)])
+STORE = np.dtype([("address", np.uint64), ("size", np.uint32), ("type", np.uint32)])
+
+
 def ptr(a):
     """ctypes void* of a numpy array (or None)."""
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)

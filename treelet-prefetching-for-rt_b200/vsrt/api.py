@@ -28,6 +28,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
            "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick",
+           "vsrt_table_events", "vsrt_table_event_stores",
            "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image"]
 
 
@@ -67,6 +68,9 @@ def load():
     L.vsrt_trace_rays.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
     L.vsrt_trace_fetch.argtypes = [c_vp, c_vp, c_u64, c_vp]
     L.vsrt_sort_trace.argtypes = [c_vp, c_int]
+    L.vsrt_table_events.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
+    L.vsrt_table_event_stores.argtypes = [c_vp, c_u64, c_vp]
+    L.vsrt_table_event_stores.restype = None
     L.vsrt_as_dump_write.argtypes = [ctypes.c_char_p, c_vp, c_u64, c_vp, c_u32, c_u64, c_u64]
     L.vsrt_as_dump_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]
     L.vsrt_as_dump_free.argtypes = [c_vp]
@@ -320,6 +324,24 @@ class Context:
         if n.value:
             self._ck(self.L.vsrt_prefetch_chunks(self.h, ctypes.byref(cfg), len(dec), _abi.ptr(dec), _abi.ptr(offs), _abi.ptr(ca), _abi.ptr(co), n.value, ctypes.byref(n)))
         return offs, ca, co
+
+    def table_events(self, tid_x=None, want_anyhit=True):
+        """Baseline intersection / any-hit table calls of the last batch: (CSR offsets, events, any-hit Hit_data)."""
+        n = self.device_results().n_rays
+        tx = None if tid_x is None else np.ascontiguousarray(tid_x, np.uint8)
+        offs = np.zeros(n + 1, np.uint64); tot = c_u64()
+        self._ck(self.L.vsrt_table_events(self.h, _abi.ptr(tx), _abi.ptr(offs), None, None, 0, ctypes.byref(tot)), allow=(-4,))
+        ev = np.zeros(tot.value, _abi.TEV); ah = np.zeros(tot.value, _abi.HIT) if want_anyhit else None
+        if tot.value:
+            self._ck(self.L.vsrt_table_events(self.h, _abi.ptr(tx), _abi.ptr(offs), _abi.ptr(ev), _abi.ptr(ah), tot.value, ctypes.byref(tot)))
+        return offs, ev, ah
+
+    def table_event_stores(self, events, table_bases):
+        """The two MemoryStoreTransactionRecords of every event; table_bases = (intersection_table, anyhit_table) addresses."""
+        out = np.zeros((len(events), 2), _abi.STORE)
+        for i in range(len(events)):
+            self.L.vsrt_table_event_stores(events[i:i + 1].ctypes.data_as(c_vp), int(table_bases[int(events[i]["table"])]), out[i].ctypes.data_as(c_vp))
+        return out
 
     def schedule_pick(self, scheduler, unit_warp_offsets, warp_ray_ids, stalled=None, last_prefetched=None, front=None):
         uo = np.ascontiguousarray(unit_warp_offsets, np.uint64); ids = np.ascontiguousarray(warp_ray_ids, np.uint64)

@@ -132,6 +132,31 @@ def main_replay():
     print("%s: %d bytes" % (path, os.path.getsize(path)))
 
 
+def main_tables():
+    """tables_proc1200.npz: the reference's Baseline intersection / any-hit tables (intersection_table.cc) in the loop of
+    both traversals on a scene with procedural leaves; rays [32g, 32g+32) = one CTA, tid = r % 32."""
+    ref = oracles.RefOracle()
+    arena = sc.Scene(1200, seed=1200, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(600, 6, 16, 12)
+    out = {"arena": np.array(arena.bytes), "tlas_offset": np.uint64(arena.tlas_offset), "blas": np.array(arena.blas, np.uint64).reshape(-1, 2),
+           "rays": rays, "budget": np.uint32(512)}
+    ref.register(arena); ref.form(512)
+    ib, ab = ref.table_bases()
+    for mode in (0, 1):
+        counts, ev, ah = ref.table_events(mode, rays)
+        p = "m%d_" % mode
+        out[p + "counts"] = counts
+        for k in ("table", "shader_counter", "hit_group_index", "primitive_id", "instance_id", "tid", "store_size"):
+            out[p + k] = ev[k]
+        base = np.where(ev["table"] == 1, np.uint64(ab), np.uint64(ib))
+        out[p + "store_off"] = ev["store_addr"] - base[:, None]             # offsets inside the table
+        out[p + "anyhit"] = ah
+    path = os.path.join(HERE, "tables_proc1200.npz")
+    np.savez_compressed(path, **out)
+    print("%s: %d bytes" % (path, os.path.getsize(path)))
+
+
 if __name__ == "__main__":
     main()
     main_replay()
+    main_tables()

@@ -74,3 +74,13 @@ def replay_chunks(z, prefix, base):
     node = co < np.uint64(META_BASE)
     ca[node] += np.uint64(base); co[node] += np.uint64(base)
     return z[prefix + "chunk_off"], ca, co
+
+
+TABLES = os.path.join(GOLDEN_DIR, "tables_proc1200.npz")
+
+
+def load_tables():
+    z = np.load(TABLES)
+    arena = sc.Arena(z["arena"], int(z["tlas_offset"]), [(int(o), int(s)) for o, s in z["blas"]])
+    rays = z["rays"].view(_abi.RAY) if z["rays"].dtype != _abi.RAY else z["rays"]
+    return z, arena, rays

@@ -493,3 +493,26 @@ def test_cuda_matches_replay_fixture(api):
         assert np.array_equal(g["offsets"], z[p + "offsets"]) and np.array_equal(g["txns"], golden_util.replay_txns(z, p, base))
         assert np.array_equal(g["treelet_ids"], z[p + "tid"] + np.uint64(base))
     ctx.close()
+
+
+def test_cuda_matches_tables_fixture(api):
+    """vsrt_table_events against tests/golden/tables_proc1200.npz (the reference's Baseline tables in the loop)."""
+    z, arena, rays = golden_util.load_tables()
+    ctx = api.Context(max_treelet_size=int(z["budget"]), device=0); ctx.register(arena); ctx.form_treelets()
+    ib, ab = 0x6000000000, 0x6100000000
+    for mode in (0, 1):
+        ctx.trace(mode, rays)
+        offs, ev, ah = ctx.table_events()
+        p = "m%d_" % mode
+        assert np.array_equal(np.diff(offs).astype(np.uint32), z[p + "counts"])
+        for k in ("table", "shader_counter", "hit_group_index", "primitive_id", "instance_id", "tid"):
+            assert np.array_equal(ev[k], z[p + k]), (mode, k)
+        st = ctx.table_event_stores(ev, (ib, ab))
+        base = np.where(ev["table"] == 1, np.uint64(ab), np.uint64(ib))
+        assert np.array_equal(st["address"] - base[:, None], z[p + "store_off"]) and np.array_equal(st["size"], z[p + "store_size"])
+        want = z[p + "anyhit"]
+        anyh = ev["table"] == 1
+        assert np.array_equal(want["t"][anyh].view(np.uint32), ah["world_min_thit"][anyh].view(np.uint32))
+        assert np.array_equal(want["bary"][anyh].view(np.uint32), ah["barycentric"][anyh].view(np.uint32))
+        assert np.array_equal(want["prim"][anyh], ah["primitive_index"][anyh])
+    ctx.close()

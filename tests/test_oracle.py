@@ -200,6 +200,24 @@ def test_table_events_match_reference():
     assert seen[0] >= 20 and seen[1] > 50 and int(ea["shader_counter"].max()) > 0
 
 
+def test_port_matches_tables_fixture():
+    """Shader-table events of the restatement against tests/golden/tables_proc1200.npz (recorded with the reference's own
+    Baseline tables in the loop)."""
+    z, arena, rays = golden_util.load_tables()
+    port = oracles.PortOracle(); port.register(arena); port.form(int(z["budget"]))
+    ib, ab = 0x6000000000, 0x6100000000
+    for mode in (0, 1):
+        counts, ev, ah = port.table_events(mode, rays, ib, ab)
+        p = "m%d_" % mode
+        assert np.array_equal(counts, z[p + "counts"])
+        for k in ("table", "shader_counter", "hit_group_index", "primitive_id", "instance_id", "tid", "store_size"):
+            assert np.array_equal(ev[k], z[p + k]), (mode, k)
+        base = np.where(ev["table"] == 1, np.uint64(ab), np.uint64(ib))
+        assert np.array_equal(ev["store_addr"] - base[:, None], z[p + "store_off"])
+        want = z[p + "anyhit"].view(oracles.OHIT) if z[p + "anyhit"].dtype != oracles.OHIT else z[p + "anyhit"]
+        assert same_hits(want, ah)
+
+
 def _units(rng, n_rays, n_units):
     """Random RT units: 1-6 warps each, random (possibly repeated, possibly absent) rays per lane, some stalled."""
     offs = [0]; ids = []; st = []

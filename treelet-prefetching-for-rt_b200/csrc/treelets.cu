@@ -43,6 +43,20 @@ struct Walker {
       {   // a non-finite node origin lets a NaN reach the slab test: traversal must then keep the ternary MIN/MAX
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u));
         if (!finite3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z))) err |= EF_NONFINITE;
+        // so does a present child whose quantised lower bound exceeds its upper bound on some axis: the fast slab test takes
+        // the near / far plane from the sign of the ray direction, which equals min / max only for ordered bounds
+        const uint4* np = reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u);
+        const uint4 b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3);
+        const uint32_t w[16] = { 0, 0, 0, 0, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w };
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          if (((w[(22 + i) >> 2] >> (((22 + i) & 3) * 8)) & 3u) == 0u) continue;
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) {
+            const int lo = 28 + 12 * ax + i, hi = lo + 6;
+            if (((w[lo >> 2] >> ((lo & 3) * 8)) & 0xffu) > ((w[hi >> 2] >> ((hi & 3) * 8)) & 0xffu)) err |= EF_NONFINITE;
+          }
+        }
       }
       if (kind == K_TLAS_INTERNAL) {   // assert(node.ChildType[i] == NODE_TYPE_INSTANCE) for TLAS leaves, :926
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u) + 1);

@@ -100,42 +100,11 @@ VS_DEV void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;"
 VS_DEV uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 VS_DEV uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 VS_DEV uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// byte -> float conversion of the slab test: 0 = one PRMT per byte (2^23 + q) and a packed add of -2^23 (default, measured
-// faster: 2.25 vs 2.33 ms on the bench workload); 1 = one PRMT per byte PAIR (fp16 1024 + q) and two mixed-precision FHADDs,
-// which moves 18 instructions per node from the ALU pipe to the FMA pipe but costs register-pair moves (profiles/README.md)
-#ifndef VSRT_SLAB_FP16
-#define VSRT_SLAB_FP16 0
-#endif
-// 2^23 + byte i of the node as a float (A/B variant of the conversion, see test_children)
-VS_DEV float byte_magic(const Node64& n, int i, uint32_t magic) {
-  uint32_t d;
-  switch (i & 3) {
-    case 0: asm("prmt.b32 %0, %1, %2, 0x7540;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
-    case 1: asm("prmt.b32 %0, %1, %2, 0x7541;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
-    case 2: asm("prmt.b32 %0, %1, %2, 0x7542;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
-    default: asm("prmt.b32 %0, %1, %2, 0x7543;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic)); break;
-  }
-  return __uint_as_float(d);
-}
-// Bytes (i, i+1) of the node (i even) as two fp16 values 1024 + byte: [b_i, 0x64, b_i+1, 0x64].  `magic16` = 0x64646464
-// held in a register so the byte selector can be the PRMT's immediate.
-VS_DEV uint32_t byte_pair_f16(const Node64& n, int i, uint32_t magic16) {
-  uint32_t d;
-  if (i & 2) asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic16));
-  else asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(d) : "r"(n.w[i >> 2]), "r"(magic16));
-  return d;
-}
-// (float(h2.lo) - 1024, float(h2.hi) - 1024) as a packed pair: two mixed-precision adds (FHADD), both exact
-VS_DEV uint64_t half2_minus_1024(uint32_t h2) {
-  float a, b;
-  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\nadd.rn.f32.f16 %0, l, %3;\nadd.rn.f32.f16 %1, h, %3;\n}" : "=f"(a), "=f"(b) : "r"(h2), "f"(-1024.0f));
-  return pk2(a, b);
-}
-
 // Tests the six child boxes of an internal node; returns the hit mask after the reference's cull
 // `thit >= min_thit * tMult` (:1791,:1989,:2537,:2725).  `cull` = min_thit * tMult computed by the caller.
 // EXACT = true keeps the reference's ternary MIN/MAX (NaN picks the second operand); it is taken for rays or
-// arenas with non-finite coordinates, where a NaN can reach the slab test.  Straight-line code: all six slots are
+// arenas with non-finite coordinates, where a NaN can reach the slab test, and for arenas in which a present child has a
+// quantised lower bound above its upper bound (the fast path reads near/far planes off the ray's direction signs).  Straight-line code: all six slots are
 // evaluated and empty slots (ChildSize == 0) are masked out at the end.
 template <bool EXACT>
 VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull, uint32_t magic16) {
@@ -157,10 +126,14 @@ VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, fl
     }
   } else {
     // Same operations in the same order as ray_box_fast(dequant(..)) for every child, issued two children at a time:
-    //  * bytes (2p, 2p+1) of each of the six bound arrays are one aligned halfword of the node; one PRMT interleaves them
-    //    with 0x64 into two fp16 values 1024 + q, and a mixed-precision add (FHADD, FMA pipe) of -1024 gives (float)q exactly;
-    //  * de-quantisation, origin subtraction and the multiply by idir run as packed f32x2 (a - b is written a + (-b), the
-    //    same IEEE operation); the per-axis constants are broadcast operands;
+    //  * NEAR / FAR instead of min / max per axis.  t_lo = ((q_lo * s + o) - ro) * idir and t_hi are monotone in q (every
+    //    step rounds monotonically, s > 0), so with q_lo <= q_hi -- K0 checks it for every present child and sends arenas that
+    //    break it down the EXACT path -- min(t_lo, t_hi) IS t_lo when idir >= 0 and t_hi when idir < 0 (no NaN can arise: idir
+    //    is finite and non-zero by calculate_idir, node and ray coordinates were checked finite).  The six min/max per child
+    //    become a choice of BYTES made once per node and axis: the axis' twelve bound bytes (lower 0..5, upper 0..5) are
+    //    regrouped by four PRMTs with per-ray selectors into near(0..3), far(0..3) and near(4,5)|far(4,5);
+    //  * one PRMT per byte builds 2^23 + q as fp32 and a packed add of -2^23 gives (float)q exactly; de-quantisation, origin
+    //    subtraction and the multiply by idir run as packed f32x2 (a - b is written a + (-b), the same IEEE operation);
     //  * hit = (mn <= mx) && !(mn >= cull) is read from sign bits: mx - mn is negative exactly when mn > mx, mn - cull is
     //    negative exactly when mn < cull (a zero or NaN difference has a clear sign, like the comparisons being false; the
     //    only NaN possible here is inf - inf, which FADD returns as the positive default NaN).  Children are visited
@@ -168,26 +141,43 @@ VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, fl
     const uint64_t s_x = pk2(sx, sx), s_y = pk2(sy, sy), s_z = pk2(sz, sz), o_x = pk2(ox, ox), o_y = pk2(oy, oy), o_z = pk2(oz, oz);
     const uint64_t nr_x = pk2(-r.ox, -r.ox), nr_y = pk2(-r.oy, -r.oy), nr_z = pk2(-r.oz, -r.oz);
     const uint64_t id_x = pk2(id.x, id.x), id_y = pk2(id.y, id.y), id_z = pk2(id.z, id.z);
-#if VSRT_SLAB_FP16
-#define VS_T2(byte0_, s_, o_, nr_, id_) mul2(add2(fma2(half2_minus_1024(byte_pair_f16(n, (byte0_) + 2 * pp, magic16)), s_, o_), nr_), id_)
-#else   // A/B variant: one PRMT per byte (2^23 + q as fp32) and a packed add of -2^23
-#define VS_T2(byte0_, s_, o_, nr_, id_) mul2(add2(fma2(add2(pk2(byte_magic(n, (byte0_) + 2 * pp, magic16 ^ 0x2F646464u), byte_magic(n, (byte0_) + 2 * pp + 1, magic16 ^ 0x2F646464u)), pk2(-8388608.0f, -8388608.0f)), s_, o_), nr_), id_)
-#endif
+    const uint32_t magic = magic16 ^ 0x2F646464u;   // 0x4B000000 in a register, so the byte selector can be the PRMT's immediate
+    const uint64_t m23 = pk2(-8388608.0f, -8388608.0f);
+    // near4 = bytes of children 0..3 on the side the ray enters, far4 on the side it leaves, nf2 = near(4,5) | far(4,5)
+    uint32_t near4[3], far4[3], nf2[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      const bool neg = (__float_as_uint(ax == 0 ? id.x : (ax == 1 ? id.y : id.z)) >> 31) != 0u;
+      const uint32_t wA = n.w[7 + 3 * ax], wB = n.w[8 + 3 * ax], wC = n.w[9 + 3 * ax];   // lower 0..3 | lower 4,5 upper 0,1 | upper 2..5
+      const uint32_t up4 = __byte_perm(wB, wC, 0x5432);                                   // upper 0..3
+      const uint32_t sn = neg ? 0x7654u : 0x3210u;
+      near4[ax] = __byte_perm(wA, up4, sn); far4[ax] = __byte_perm(wA, up4, sn ^ 0x4444u);
+      nf2[ax] = __byte_perm(wB, wC, neg ? 0x1076u : 0x7610u);
+    }
+#define VS_B2(w_, k_) pk2(__uint_as_float(__byte_perm((w_), magic, 0x7540u + (k_))), __uint_as_float(__byte_perm((w_), magic, 0x7541u + (k_))))
+#define VS_T2(w_, k_, s_, o_, nr_, id_) mul2(add2(fma2(add2(VS_B2(w_, k_), m23), s_, o_), nr_), id_)
 #pragma unroll
     for (int pp = 2; pp >= 0; pp--) {
-      float lx[2], hx[2], ly[2], hy[2], lz[2], hz[2];
-      upk2(VS_T2(28, s_x, o_x, nr_x, id_x), lx[0], lx[1]); upk2(VS_T2(34, s_x, o_x, nr_x, id_x), hx[0], hx[1]);
-      upk2(VS_T2(40, s_y, o_y, nr_y, id_y), ly[0], ly[1]); upk2(VS_T2(46, s_y, o_y, nr_y, id_y), hy[0], hy[1]);
-      upk2(VS_T2(52, s_z, o_z, nr_z, id_z), lz[0], lz[1]); upk2(VS_T2(58, s_z, o_z, nr_z, id_z), hz[0], hz[1]);
+      float nx[2], fx[2], ny[2], fy[2], nz[2], fz[2];
+      if (pp == 2) {
+        upk2(VS_T2(nf2[0], 0, s_x, o_x, nr_x, id_x), nx[0], nx[1]); upk2(VS_T2(nf2[0], 2, s_x, o_x, nr_x, id_x), fx[0], fx[1]);
+        upk2(VS_T2(nf2[1], 0, s_y, o_y, nr_y, id_y), ny[0], ny[1]); upk2(VS_T2(nf2[1], 2, s_y, o_y, nr_y, id_y), fy[0], fy[1]);
+        upk2(VS_T2(nf2[2], 0, s_z, o_z, nr_z, id_z), nz[0], nz[1]); upk2(VS_T2(nf2[2], 2, s_z, o_z, nr_z, id_z), fz[0], fz[1]);
+      } else {
+        upk2(VS_T2(near4[0], 2 * pp, s_x, o_x, nr_x, id_x), nx[0], nx[1]); upk2(VS_T2(far4[0], 2 * pp, s_x, o_x, nr_x, id_x), fx[0], fx[1]);
+        upk2(VS_T2(near4[1], 2 * pp, s_y, o_y, nr_y, id_y), ny[0], ny[1]); upk2(VS_T2(far4[1], 2 * pp, s_y, o_y, nr_y, id_y), fy[0], fy[1]);
+        upk2(VS_T2(near4[2], 2 * pp, s_z, o_z, nr_z, id_z), nz[0], nz[1]); upk2(VS_T2(far4[2], 2 * pp, s_z, o_z, nr_z, id_z), fz[0], fz[1]);
+      }
 #pragma unroll
       for (int k = 1; k >= 0; k--) {
-        const float mn = fmaxf(fminf(lz[k], hz[k]), fmaxf(fminf(ly[k], hy[k]), fmaxf(fminf(lx[k], hx[k]), r.tmin)));
-        const float mx = fminf(fmaxf(lz[k], hz[k]), fminf(fmaxf(ly[k], hy[k]), fminf(fmaxf(lx[k], hx[k]), r.tmax)));
+        const float mn = fmaxf(fmaxf(nx[k], ny[k]), fmaxf(nz[k], r.tmin));
+        const float mx = fminf(fminf(fx[k], fy[k]), fminf(fz[k], r.tmax));
         const uint32_t sb = __float_as_uint(fsub(mn, cull)) & ~__float_as_uint(fsub(mx, mn));   // bit 31 = hit
         mask = __funnelshift_l(sb, mask, 1);
       }
     }
 #undef VS_T2
+#undef VS_B2
     // empty slots (ChildSize == 0) never hit: bit 0 of each info byte = size != 0, gathered into six bits by a multiply
     const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;                  // bytes 22..25 | 26,27
     const uint32_t nz4 = (lo4 | (lo4 >> 1)) & 0x01010101u, nz2 = (hi2 | (hi2 >> 1)) & 0x0101u;

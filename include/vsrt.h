@@ -285,7 +285,8 @@ int vsrt_schedule_pick(vsrt_context* ctx, int scheduler, uint64_t n_units, const
  * and issues two stores per call and no loads, so the load trace is the one vsrt_trace_rays returns.  Rays
  * [32g, 32g + 32) of the batch are taken as the threads of one CTA (thread index tid_x[r], NULL = r % 32; threads that share
  * a tid_x share its row counter, in ray order); the tables are empty at the start of the batch.  The Coalescing table
- * (type 1) is not built.  The reference asserts beyond 100 rows per thread (INTERSECTION_TABLE_MAX_LENGTH); no limit here. */
+ * (type 1) is derived from these events by vsrt_coalescing_events below.  The reference asserts beyond 100 rows per thread
+ * (INTERSECTION_TABLE_MAX_LENGTH); no limit here. */
 typedef struct vsrt_table_event {
   uint32_t table;            /* 0 intersection_table (procedural leaf), 1 anyhit_table (non-opaque triangle hit, traceRay only) */
   uint32_t shader_counter;   /* row of the table = index[tid] before the call */
@@ -303,6 +304,30 @@ int vsrt_table_events(vsrt_context* ctx, const uint8_t* tid_x, uint64_t* event_o
                       uint64_t capacity, uint64_t* n_events);
 /* The two MemoryStoreTransactionRecords of one event for a table that gpgpusim_alloc placed at table_base. */
 void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vsrt_store_txn out[2]);
+
+/* ---- Function_Call_Coalescing intersection table (-gpgpu_rt_intersection_table_type 1) ----
+ * Coalescing_warp_intersection_table::add_intersection (intersection_table.cc:43-98): the rows are shared by the threads of a
+ * CTA.  A call looks at rows 0, 1, ... (one Intersection_Table_Load record {&table[i].hitGroupIndex, 4} per row), claims the
+ * first row of its hit group whose thread_mask[tid] is free (stores: thread_mask[tid], shader_data[tid]) or appends a row
+ * (stores: hitGroupIndex, thread_mask[tid], shader_data[tid]).  traceRay / traceRayWithTreelets append the returned loads to
+ * the ray's transaction list right after the PROCEDURAL_LEAF record unless the address is already in the list
+ * (vulkan_ray_tracing.cc:2186-2200 / :2966-2980), i.e. only rows first_new_load .. n_loads-1.  Only the intersection table
+ * has this type (the any-hit table is always a Baseline table, :441-447): events with table == 1 get an all-zero result.
+ * Input: event_offsets / events as vsrt_table_events returned them (rays [32g, 32g + 32) = one CTA, in lane order, a fresh
+ * table per CTA -- the reference's clear() (:101-111) cannot be followed: its inner loop increments the wrong variable and
+ * never terminates on a non-empty table).  VSRT_E_UNSUPPORTED if a CTA needs more than the 100 rows the reference allocates. */
+typedef struct vsrt_coalescing_event {
+  uint32_t row;             /* row the thread's shader data went to */
+  uint32_t appended;        /* 1: a new row was appended (three stores); 0: an existing row was claimed (two stores) */
+  uint32_t n_loads;         /* Intersection_Table_Load records add_intersection returned: rows 0 .. n_loads-1 */
+  uint32_t first_new_load;  /* rows first_new_load .. n_loads-1 are new to the ray's transaction list and are appended to it */
+} vsrt_coalescing_event;
+int vsrt_coalescing_events(vsrt_context* ctx, uint64_t n_rays, const uint64_t* event_offsets, const vsrt_table_event* events,
+                           vsrt_coalescing_event* out);
+/* The MemoryStoreTransactionRecords of one call (returns how many: 2 or 3) and the load record of one row, for a table that
+ * gpgpusim_alloc placed at table_base (Coalescing_Entry = u32 hitGroupIndex, bool thread_mask[32], {u32, u32} shader_data[32]). */
+uint32_t vsrt_coalescing_event_stores(const vsrt_table_event* ev, const vsrt_coalescing_event* cev, uint64_t table_base, vsrt_store_txn out[3]);
+void vsrt_coalescing_event_load(uint32_t row, uint64_t table_base, vsrt_txn* out);
 
 /* ---- acceleration-structure dump files (VulkanRayTracing::dump_AS, vulkan_ray_tracing.cc:4455-4558, split_files) ----
  * <prefix>.asmain / .asback / .asfront / .asmetadata: the TLAS descriptor range, the BLAS ranges below and above it and

@@ -24,13 +24,16 @@ mkdir -p "$OUT"
   sed -n '5,23p' "$R/gpgpu-sim/vector-math.h"
   grep -v '#include' "$R/gpgpu-sim/vector-math.cc"
   cat "$HERE/ref_shim/shim_post.h"
-  # the warp intersection tables (abstract class + Baseline table); members opened for the test driver (class -> struct)
+  # the warp intersection tables (abstract class, Coalescing and Baseline tables); members opened for the test driver (class -> struct)
   echo '#define class struct'
-  sed -n '42p;52,67p;109,139p' "$R/cuda-sim/intersection_table.h"
+  sed -n '42p;52,67p;70,107p;109,139p' "$R/cuda-sim/intersection_table.h"
   echo '#undef class'
   sed -n '123,129p;136,140p' "$R/cuda-sim/vulkan_ray_tracing.cc"
   sed -n '148,257p;456,510p;823,1520p;1522,2307p;2309,3076p;3089,3130p' "$R/cuda-sim/vulkan_ray_tracing.cc"
   sed -n '155,192p;198,229p' "$R/cuda-sim/intersection_table.cc"
+  # Coalescing table: constructor + add_intersection and the getters; its clear() (:101-111) is NOT taken -- the inner loop
+  # increments i instead of j and never terminates on a non-empty table -- ref_api.cc defines the evident intent instead
+  sed -n '36,99p;113,148p' "$R/cuda-sim/intersection_table.cc"
   cat "$HERE/ref_shim/ref_api.cc"
   # ---- RT-unit replay helpers: RTMemoryTransactionRecord, rt_unit::sort_mem_accesses and the
   # treelet-prefetch vote block of rt_unit::cycle, the latter spliced in as the body of a member function

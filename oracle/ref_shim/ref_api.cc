@@ -233,6 +233,54 @@ int64_t ref_trace_tables(void* tlas, int mode, uint32_t n, const ref_ray* rays, 
   return (int64_t)total;
 }
 
+// ---- Function_Call_Coalescing intersection table (-gpgpu_rt_intersection_table_type 1, intersection_table.cc:36-99): rays
+// [32g, 32g+32) are the threads tid.x = i % 32 of one CTA, traced in order like execute_warp_inst_t does, against a FRESH
+// reference table per CTA.  Returned per ray: its whole transaction list (the Intersection_Table_Load records merged in by
+// :2186-2200 / :2966-2980 included) and its store list; table addresses are reported relative to the table base
+// (| 1 << 63), everything else as is.  mode 0 (traceRay) only: traceRayWithTreelets passes every record of the finished list
+// to addrToTreeletID (:2256-2262), whose assert (:470) fires on the first table address.
+void Coalescing_warp_intersection_table::clear(const ptx_instruction*, ptx_thread_info*) {
+  for (uint32_t i = 0; i < tableSize; i++) for (int j = 0; j < 32; j++) table[i].thread_mask[j] = false;
+  tableSize = 0;
+}
+struct ref_store_rec { uint64_t address; uint32_t size; uint32_t type; };
+int64_t ref_trace_coalescing(void* tlas, int mode, uint32_t n, const ref_ray* rays, uint64_t* txn_offsets, ref_txn* txns, uint64_t txn_cap,
+                             uint64_t* store_offsets, ref_store_rec* stores, uint64_t store_cap, uint32_t* entry_size) {
+  silence(true);
+  static warp_intersection_table* crow[1]; static warp_intersection_table** ctab[1] = { crow };
+  Coalescing_warp_intersection_table* tab = NULL;
+  if (entry_size) *entry_size = (uint32_t)sizeof(Coalescing_Entry);
+  uint64_t nt = 0, ns = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (i % 32 == 0) { if (tab) { free(tab->table); tab->table = NULL; operator delete(tab); } tab = new Coalescing_warp_intersection_table(); crow[0] = tab; }
+    VulkanRayTracing::intersection_table = ctab; VulkanRayTracing::anyhit_table = g_tab;
+    const ref_ray& r = rays[i];
+    ptx_thread_info th; th.tid_x = i % 32;
+    float3 o = { r.origin[0], r.origin[1], r.origin[2] }, d = { r.dir[0], r.dir[1], r.dir[2] };
+    if (mode == 1)
+      VulkanRayTracing::traceRayWithTreelets(tlas, r.flags, r.cull_mask, r.sbt_offset, r.sbt_stride, r.miss_index, o, r.tmin, d, r.tmax, 0, NULL, &th);
+    else
+      VulkanRayTracing::traceRay(tlas, r.flags, r.cull_mask, r.sbt_offset, r.sbt_stride, r.miss_index, o, r.tmin, d, r.tmax, 0, NULL, &th);
+    free(th.data.traversal_data.back());
+    for (auto* p : th.data.all_hit_data) free(p);
+    const uint64_t b0 = (uint64_t)tab->table, b1 = b0 + sizeof(Coalescing_Entry) * INTERSECTION_TABLE_MAX_LENGTH;
+    txn_offsets[i] = nt; store_offsets[i] = ns;
+    for (const MemoryTransactionRecord& t : th.txns) {
+      if (txns && nt < txn_cap) { uint64_t a = (uint64_t)t.address; if (a >= b0 && a < b1) a = (a - b0) | (1ull << 63); txns[nt].address = a; txns[nt].size = t.size; txns[nt].type = (uint32_t)t.type; }
+      nt++;
+    }
+    for (const MemoryStoreTransactionRecord& t : th.store_txns) {
+      if (stores && ns < store_cap) { uint64_t a = (uint64_t)t.address; if (a >= b0 && a < b1) a = (a - b0) | (1ull << 63); stores[ns].address = a; stores[ns].size = t.size; stores[ns].type = (uint32_t)t.type; }
+      ns++;
+    }
+  }
+  txn_offsets[n] = nt; store_offsets[n] = ns;
+  if (tab) { free(tab->table); tab->table = NULL; operator delete(tab); }
+  VulkanRayTracing::intersection_table = g_tab; VulkanRayTracing::anyhit_table = g_tab;
+  silence(false);
+  return (int64_t)nt;
+}
+
 void ref_get_counters(ref_counters* out) {
   ref_func_sim& f = GPGPU_Context()->fs;
   for (int i = 0; i < 9; i++) out->mem_access_type[i] = f.g_rt_mem_access_type[i];

@@ -921,3 +921,37 @@ int64_t vo_table_events(vo_ctx* c, const void* tlas_v, int mode, uint64_t n_rays
   }
   return (int64_t)total;
 }
+
+/* ---- Function_Call_Coalescing intersection table (-gpgpu_rt_intersection_table_type 1).
+ * Coalescing_warp_intersection_table::add_intersection, intersection_table.cc:43-98: the rows are shared by the 32 threads of a
+ * CTA; a call scans rows 0.. (one Intersection_Table_Load record per row looked at), claims the first row of its hit group
+ * whose thread_mask[tid] is free (two stores) or appends a row (three stores).  The caller merges the loads into the ray's
+ * transaction list unless the address is already there (vulkan_ray_tracing.cc:2186-2200 / :2966-2980), i.e. only the rows the
+ * ray has not looked at before.  Input: the table-0 events of a batch in ray order (rays [32g, 32g + 32) = one CTA, fresh
+ * table per CTA); output per event: row, appended, n_loads, first_new_load.  Returns -1 if a CTA needs more than the 100 rows
+ * the reference allocates (INTERSECTION_TABLE_MAX_LENGTH; it would write past its allocation). */
+typedef struct { uint32_t row, appended, n_loads, first_new_load; } vo_coalescing_event;
+enum { VO_COALESCING_ROWS = 100 };
+int vo_coalescing_events(uint64_t n_rays, const uint64_t* event_offsets, const vo_table_event* ev, vo_coalescing_event* out) {
+  uint32_t key[VO_COALESCING_ROWS], mask[VO_COALESCING_ROWS], n_rows = 0;
+  for (uint64_t r = 0; r < n_rays; r++) {
+    if (r % 32 == 0) n_rows = 0;
+    uint32_t seen = 0;                                   /* rows whose load record is already in this ray's list */
+    for (uint64_t k = event_offsets[r]; k < event_offsets[r + 1]; k++) {
+      vo_coalescing_event* o = &out[k];
+      o->row = o->appended = o->n_loads = o->first_new_load = 0;
+      if (ev[k].table != 0) continue;                    /* the any-hit table is a Baseline table whatever the option says (:441-447) */
+      const uint32_t bit = 1u << (ev[k].tid & 31u);
+      uint32_t i = 0, found = 0;
+      for (; i < n_rows; i++) if (key[i] == ev[k].hit_group_index && !(mask[i] & bit)) { found = 1; break; }
+      if (found) { mask[i] |= bit; o->row = i; o->n_loads = i + 1; }
+      else {
+        if (n_rows >= VO_COALESCING_ROWS) return -1;
+        key[n_rows] = ev[k].hit_group_index; mask[n_rows] = bit; o->row = n_rows; o->appended = 1; o->n_loads = n_rows; n_rows++;
+      }
+      o->first_new_load = seen < o->n_loads ? seen : o->n_loads;
+      if (o->n_loads > seen) seen = o->n_loads;
+    }
+  }
+  return 0;
+}

@@ -101,3 +101,38 @@ def assert_tables_equal(to, tg, what=""):
 COUNTER_MAP = {"num_hits": "num_hits", "num_any_hits": "num_any_hits", "n_anyhit_rays": "n_anyhit_rays",
                "n_closesthit_rays": "n_closesthit_rays", "max_nodes_per_ray": "max_nodes_per_ray",
                "tot_nodes_per_ray": "tot_nodes_per_ray", "max_tree_depth": "max_tree_depth", "ray_count": "ray_count"}
+
+
+COALESCING_ENTRY = 292   # sizeof(Coalescing_Entry): u32 hitGroupIndex, bool thread_mask[32], {u32, u32} shader_data[32]
+
+
+def coalescing_splice(offsets, txns, ev_offsets, ev_table, ev_tid, cev, base=1 << 63):
+    """Per-ray transaction / store lists with a Coalescing intersection table at `base`, built from a plain trace, the table
+    events of its rays (table-0 events are the rays' PROCEDURAL_LEAF records, in order) and the replayed table (cev):
+    after the j-th PROCEDURAL_LEAF record come the load records of rows first_new_load .. n_loads-1
+    (vulkan_ray_tracing.cc:2186-2200); stores per call: [hitGroupIndex if appended], thread_mask[tid], shader_data[tid]
+    (intersection_table.cc:73-74, :88-90)."""
+    offsets = np.asarray(offsets, np.int64); eo = np.asarray(ev_offsets, np.int64)
+    t_out, s_out, to, so = [], [], [0], [0]
+    for r in range(len(offsets) - 1):
+        seg = txns[offsets[r]:offsets[r + 1]]
+        ks = [k for k in range(eo[r], eo[r + 1]) if ev_table[k] == 0]
+        procs = np.flatnonzero(seg["type"] == 6)
+        assert len(procs) == len(ks)
+        pos = 0
+        for j, k in enumerate(ks):
+            for rec in seg[pos:procs[j] + 1]:
+                t_out.append((int(rec["address"]), int(rec["size"]), int(rec["type"])))
+            pos = procs[j] + 1
+            for row in range(int(cev[k]["first_new_load"]), int(cev[k]["n_loads"])):
+                t_out.append((base + row * COALESCING_ENTRY, 4, 7))
+            rb = base + int(cev[k]["row"]) * COALESCING_ENTRY
+            if cev[k]["appended"]:
+                s_out.append((rb, 4, 0))
+            s_out.append((rb + 4 + int(ev_tid[k]), 1, 0)); s_out.append((rb + 36 + 8 * int(ev_tid[k]), 8, 0))
+        for rec in seg[pos:]:
+            t_out.append((int(rec["address"]), int(rec["size"]), int(rec["type"])))
+        to.append(len(t_out)); so.append(len(s_out))
+    return (np.array(to, np.uint64), np.array(t_out, dtype=_abi.TXN) if t_out else np.zeros(0, _abi.TXN),
+            np.array(so, np.uint64), np.array(s_out, dtype=_abi.STORE) if s_out else np.zeros(0, _abi.STORE))
+

@@ -70,6 +70,8 @@ class RefOracle(_Base):
         L.ref_trace_tables.restype = ctypes.c_int64
         L.ref_trace_tables.argtypes = [c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_u64]
         L.ref_table_bases.argtypes = [c_vp, c_vp]
+        L.ref_trace_coalescing.restype = ctypes.c_int64
+        L.ref_trace_coalescing.argtypes = [c_vp, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp, c_vp, c_u64, c_vp, c_vp, c_u64, c_vp]
         L.ref_schedule_pick.restype = ctypes.c_int64
         L.ref_schedule_pick.argtypes = [ctypes.c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp]
         self.L = L
@@ -139,6 +141,18 @@ class RefOracle(_Base):
         self.L.ref_trace_tables(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(counts), _abi.ptr(ev), _abi.ptr(ah), total)
         return counts, ev, ah
 
+    def trace_coalescing(self, mode, rays):
+        """The reference traversal with its own Function_Call_Coalescing intersection table in the loop (a fresh table per
+        32 rays): per-ray transaction lists with the Intersection_Table_Load records merged in, and the store lists.  Table
+        addresses come back as (offset from the table base) | 1 << 63.  Returns (txn_offsets, txns, store_offsets, stores,
+        sizeof(Coalescing_Entry))."""
+        n = len(rays)
+        to = np.zeros(n + 1, np.uint64); so = np.zeros(n + 1, np.uint64); es = ctypes.c_uint32()
+        self.L.ref_trace_coalescing(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(to), None, 0, _abi.ptr(so), None, 0, ctypes.byref(es))
+        tx = np.zeros(int(to[n]), _abi.TXN); st = np.zeros(int(so[n]), _abi.STORE)
+        self.L.ref_trace_coalescing(self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(to), _abi.ptr(tx), len(tx), _abi.ptr(so), _abi.ptr(st), len(st), ctypes.byref(es))
+        return to, tx, so, st, es.value
+
     def schedule_pick(self, trace, scheduler, last_prefetched, warp_ray_ids, stalled=None, front=None):
         """rt_unit::schedule_next_warp (shader.cc:4307-4392) for one unit."""
         ids = np.ascontiguousarray(warp_ray_ids, np.uint64)
@@ -191,6 +205,7 @@ class PortOracle(_Base):
         L.vo_table_events.restype = ctypes.c_int64
         L.vo_table_events.argtypes = [c_vp, c_vp, ctypes.c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_vp, c_vp, c_vp, c_u64]
         L.vo_set_proc_sink.argtypes = [c_vp, c_vp, c_u64]
+        L.vo_coalescing_events.argtypes = [c_u64, c_vp, c_vp, c_vp]
         L.vo_proc_sink_count.restype = c_u64
         L.vo_proc_sink_count.argtypes = [c_vp]
         L.vo_schedule_pick.restype = ctypes.c_int64
@@ -293,6 +308,14 @@ class PortOracle(_Base):
         ev = np.zeros(total, TEV); ah = np.zeros(total, OHIT)
         self.L.vo_table_events(*args, _abi.ptr(ev), _abi.ptr(ah), total)
         return counts, ev, ah
+
+    def coalescing_events(self, event_offsets, events):
+        """Coalescing_warp_intersection_table::add_intersection (intersection_table.cc:43-98) replayed over table events
+        (port layout: vo_table_event)."""
+        offs = np.ascontiguousarray(event_offsets, np.uint64); ev = np.ascontiguousarray(events, TEV)
+        out = np.zeros(len(ev), _abi.CEV)
+        assert self.L.vo_coalescing_events(len(offs) - 1, _abi.ptr(offs), _abi.ptr(ev), _abi.ptr(out)) == 0
+        return out
 
     def trace_remapped(self, mode, rays, base, stride, budget):
         """-remap_to_treelet_layout 1 (vulkan_ray_tracing.cc:1682,:1763,...): the same visit sequence with every record

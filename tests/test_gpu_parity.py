@@ -388,6 +388,48 @@ def test_table_events(api, monkeypatch, wavefront):
     ctx.close()
 
 
+def test_coalescing_table(api):
+    """Function_Call_Coalescing intersection table: vsrt_coalescing_events over the CUDA path's own table events against the
+    pinned restatement, and the spliced transaction / store lists against the reference traversal run with its own
+    Coalescing table (oracle/_ref) where that is available."""
+    s = sc.Scene(2500, seed=18, n_blas=2, n_instances=6, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(1000, 33, 16, 12)
+    port = oracles.PortOracle(); port.register(s); port.form(512)
+    ref = None
+    if oracles.have_ref():
+        ref = oracles.RefOracle(); ref.register(s); ref.form(512)
+    ctx = api.Context(max_treelet_size=512, device=0); ctx.register(s); ctx.form_treelets()
+    n_loads = 0
+    for mode in (0, 1):
+        g = ctx.trace(mode, rays)
+        offs, ev, _ = ctx.table_events()
+        cev = ctx.coalescing_events(offs, ev)
+        pev = np.zeros(len(ev), oracles.TEV)
+        for k in ("table", "hit_group_index", "tid"):
+            pev[k] = ev[k]
+        want = port.coalescing_events(offs, pev)
+        for k in ("row", "appended", "n_loads", "first_new_load"):
+            assert np.array_equal(cev[k], want[k]), (mode, k)
+        to, tx, so, st = ctx.coalescing_trace(g["offsets"], g["txns"], offs, ev, cev, 1 << 63)
+        eto, etx, eso, est = helpers.coalescing_splice(g["offsets"], g["txns"], offs, ev["table"], ev["tid"], want)
+        assert np.array_equal(to, eto) and np.array_equal(so, eso)
+        assert np.array_equal(tx, etx) and np.array_equal(st, est)
+        if ref and mode == 0:   # the reference's treelet variant asserts in addrToTreeletID (:470) on the first table address in a list
+            rto, rtx, rso, rst, _ = ref.trace_coalescing(mode, rays)
+            assert np.array_equal(rto, to) and np.array_equal(rso, so), mode
+            for k in ("address", "size", "type"):
+                assert np.array_equal(rtx[k], tx[k]), (mode, k)
+                assert np.array_equal(rst[k], st[k]), (mode, "store", k)
+        n_loads += int((tx["type"] == 7).sum())
+    assert n_loads > 40
+    # more than INTERSECTION_TABLE_MAX_LENGTH rows in one CTA: the reference would write past its allocation
+    many = np.zeros(101, _abi.TEV); many["hit_group_index"] = np.arange(101)
+    with pytest.raises(api.VsrtError) as e:
+        ctx.coalescing_events(np.array([0, 101], np.uint64), many)
+    assert e.value.code == -9
+    ctx.close()
+
+
 def test_schedule_pick(api):
     """rt_unit::schedule_next_warp (shader.cc:4307-4392) for many units at once."""
     from test_oracle import _units

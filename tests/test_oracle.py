@@ -200,6 +200,35 @@ def test_table_events_match_reference():
     assert seen[0] >= 20 and seen[1] > 50 and int(ea["shader_counter"].max()) > 0
 
 
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_coalescing_table_matches_reference():
+    """Function_Call_Coalescing intersection table (intersection_table.cc:43-98): the restatement replays the table over
+    the table events; spliced into the plain trace it must give the transaction and store lists of the reference traversal
+    run with its own Coalescing table (loads merged into the ray's list unless the address is already there)."""
+    s = sc.Scene(1500, seed=8, n_blas=2, n_instances=5, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(1200, 12, 24, 16)
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    ref.register(s); ref.form(512); port.register(s); port.form(512)
+    stats = [0, 0, 0]
+    # traceRay only: traceRayWithTreelets sends every record of the finished list through addrToTreeletID (:2256-2262), which
+    # asserts on a table address (:470) -- the reference cannot run that variant with this table and procedural geometry
+    for mode in (0,):
+        to, tx, so, st, entry = ref.trace_coalescing(mode, rays)
+        assert entry == helpers.COALESCING_ENTRY
+        plain = port.trace(mode, rays)
+        counts, ev, _ = port.table_events(mode, rays, 0, 0)
+        eo = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        cev = port.coalescing_events(eo, ev)
+        eto, etx, eso, est = helpers.coalescing_splice(plain["offsets"], plain["txns"], eo, ev["table"], ev["tid"], cev)
+        assert np.array_equal(to, eto) and np.array_equal(so, eso), mode
+        for k in ("address", "size", "type"):
+            assert np.array_equal(tx[k], etx[k]), (mode, k)
+            assert np.array_equal(st[k], est[k]), (mode, "store", k)
+        t0 = ev["table"] == 0
+        stats[0] += int((tx["type"] == 7).sum()); stats[1] += int(cev["appended"][t0].sum()); stats[2] += int((t0 & (cev["appended"] == 0)).sum())
+    assert stats[0] > 40 and stats[1] > 10 and stats[2] > 10, stats      # loads merged, rows appended, rows shared between threads
+
+
 def test_port_matches_tables_fixture():
     """Shader-table events of the restatement against tests/golden/tables_proc1200.npz (recorded with the reference's own
     Baseline tables in the loop)."""

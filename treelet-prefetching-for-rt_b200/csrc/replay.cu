@@ -426,6 +426,52 @@ int vsrt_launch_schedule_pick(const uint64_t* offsets, const uint32_t* tids, uin
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
+// ------------------------------------------------------------------ Function_Call_Coalescing intersection table
+// Coalescing_warp_intersection_table::add_intersection (intersection_table.cc:43-98) replayed over the table-0 events of a
+// batch.  The rows are shared by the 32 threads of a CTA and filled lane by lane (execute_warp_inst_t runs the lanes in
+// order), so a CTA is a sequential chain: one WARP per CTA, the row scan of one call done by the lanes in parallel -- lane l
+// holds rows l, l + 32, l + 64, l + 96 (key + thread mask) in registers, "first row of this hit group whose thread_mask[tid]
+// is free" is a ballot per 32 rows.
+__global__ void __launch_bounds__(128) k_coalescing(const unsigned long long* __restrict__ ev_off, const vsrt_table_event* __restrict__ ev,
+                                                    uint64_t n_rays, vsrt_coalescing_event* __restrict__ out, uint32_t* __restrict__ err) {
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t r0 = g * 32u;
+  if (r0 >= n_rays) return;
+  const uint64_t r1 = min(r0 + 32u, n_rays);
+  uint32_t key[4] = { 0, 0, 0, 0 }, mask[4] = { 0, 0, 0, 0 }, n_rows = 0;
+  for (uint64_t r = r0; r < r1; r++) {
+    uint32_t seen = 0;
+    for (unsigned long long k = ev_off[r]; k < ev_off[r + 1]; k++) {
+      vsrt_coalescing_event o; o.row = o.appended = o.n_loads = o.first_new_load = 0;
+      if (ev[k].table == 0) {
+        const uint32_t want = ev[k].hit_group_index, bit = 1u << (ev[k].tid & 31u);
+        uint32_t row = 0xFFFFFFFFu;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const unsigned m = __ballot_sync(0xffffffffu, (uint32_t)c * 32u + lane < n_rows && key[c] == want && !(mask[c] & bit));
+          if (m && row == 0xFFFFFFFFu) row = (uint32_t)c * 32u + (uint32_t)(__ffs(m) - 1);
+        }
+        if (row != 0xFFFFFFFFu) { o.row = row; o.n_loads = row + 1u; }
+        else if (n_rows >= 100u) { if (lane == 0) atomicOr(err, (uint32_t)EF_UNSUPPORTED); return; }   // the reference's allocation (INTERSECTION_TABLE_MAX_LENGTH rows) ends here
+        else { row = n_rows; o.row = row; o.appended = 1; o.n_loads = n_rows; n_rows++; }
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (row == (uint32_t)c * 32u + lane) { if (o.appended) { key[c] = want; mask[c] = bit; } else mask[c] |= bit; }
+        o.first_new_load = min(seen, o.n_loads);
+        seen = max(seen, o.n_loads);
+      }
+      if (lane == 0) out[k] = o;
+    }
+  }
+}
+
+int vsrt_launch_coalescing(const uint64_t* ev_off, const vsrt_table_event* ev, uint64_t n_rays, vsrt_coalescing_event* out, uint32_t* err, cudaStream_t st) {
+  if (n_rays == 0) return VSRT_OK;
+  const uint64_t n_groups = (n_rays + 31) / 32;
+  k_coalescing<<<(unsigned)((n_groups + 3) / 4), 128, 0, st>>>((const unsigned long long*)ev_off, ev, n_rays, out, err);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
 int vsrt_launch_table_events(bool fill, const TableParams& p, uint32_t*, cudaStream_t st) {
   if (p.n_rays == 0) return VSRT_OK;
   const unsigned grid = (unsigned)((p.n_rays + 127) / 128);

@@ -760,4 +760,39 @@ void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vs
   out[1].address = row + 128ull + 8ull * ev->tid; out[1].size = 8; out[1].type = 0;   // &table[row].shader_data[tid]
 }
 
+int vsrt_coalescing_events(vsrt_context* c, uint64_t n_rays, const uint64_t* event_offsets, const vsrt_table_event* events, vsrt_coalescing_event* out) {
+  if (!c) return VSRT_E_INVALID;
+  if (n_rays == 0) return VSRT_OK;
+  if (!event_offsets || !out) return fail(c, VSRT_E_INVALID, "event_offsets / out is NULL");
+  const uint64_t n_ev = event_offsets[n_rays];
+  if (n_ev == 0) return VSRT_OK;
+  if (!events) return fail(c, VSRT_E_INVALID, "events is NULL");
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  uint64_t* d_off = nullptr; vsrt_table_event* d_ev = nullptr; vsrt_coalescing_event* d_out = nullptr; uint32_t* d_err = nullptr; uint32_t h_err = 0;
+  bool ok = upload(&d_off, event_offsets, n_rays + 1, st) == cudaSuccess && upload(&d_ev, events, n_ev, st) == cudaSuccess &&
+            cudaMalloc(&d_out, n_ev * sizeof(vsrt_coalescing_event)) == cudaSuccess && cudaMalloc(&d_err, 4) == cudaSuccess &&
+            cudaMemsetAsync(d_err, 0, 4, st) == cudaSuccess;
+  int rc = ok ? vsrt_launch_coalescing(d_off, d_ev, n_rays, d_out, d_err, st) : VSRT_E_CUDA;
+  if (rc == VSRT_OK && (cudaMemcpyAsync(out, d_out, n_ev * sizeof(vsrt_coalescing_event), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                        cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)) rc = VSRT_E_CUDA;
+  cudaFree(d_off); cudaFree(d_ev); cudaFree(d_out); cudaFree(d_err);
+  if (rc) return fail(c, rc, "coalescing table replay failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (h_err & EF_UNSUPPORTED) return fail(c, VSRT_E_UNSUPPORTED, "a CTA needs more than the 100 rows the reference's Coalescing table holds");
+  return VSRT_OK;
+}
+
+uint32_t vsrt_coalescing_event_stores(const vsrt_table_event* ev, const vsrt_coalescing_event* cev, uint64_t table_base, vsrt_store_txn out[3]) {
+  // intersection_table.cc:73-74 (claim) / :88-90 (append); Coalescing_Entry: hitGroupIndex @0, thread_mask[32] @4, shader_data[32] @36, 292 bytes
+  const uint64_t row = table_base + (uint64_t)cev->row * 292ull;
+  uint32_t n = 0;
+  if (cev->appended) { out[n].address = row; out[n].size = 4; out[n].type = 0; n++; }
+  out[n].address = row + 4ull + ev->tid; out[n].size = 1; out[n].type = 0; n++;
+  out[n].address = row + 36ull + 8ull * ev->tid; out[n].size = 8; out[n].type = 0; n++;
+  return n;
+}
+void vsrt_coalescing_event_load(uint32_t row, uint64_t table_base, vsrt_txn* out) {
+  out->address = table_base + (uint64_t)row * 292ull; out->size = 4; out->type = VSRT_TXN_INTERSECTION_TABLE_LOAD;   // :55
+}
+
 }  // extern "C"

@@ -162,3 +162,5 @@ struct TableParams {
   vsrt_table_event* events; vsrt_hit* anyhit; uint64_t capacity;
 };
 int vsrt_launch_table_events(bool fill, const TableParams& p, uint32_t* totals_dev, cudaStream_t st);
+// Function_Call_Coalescing intersection table replayed over table events (device arrays); *err receives EF_UNSUPPORTED if a CTA outgrows the reference's 100 rows
+int vsrt_launch_coalescing(const uint64_t* ev_off, const vsrt_table_event* ev, uint64_t n_rays, vsrt_coalescing_event* out, uint32_t* err, cudaStream_t st);

@@ -60,6 +60,8 @@ PDEC = np.dtype([("treelet_root", np.uint64), ("votes", np.uint32), ("total", np
 TEV = np.dtype([("table", np.uint32), ("shader_counter", np.uint32), ("hit_group_index", np.uint32), ("primitive_id", np.uint32),
                 ("instance_id", np.uint32), ("tid", np.uint32), ("record", np.uint32), ("reserved", np.uint32)])
 STORE = np.dtype([("address", np.uint64), ("size", np.uint32), ("type", np.uint32)])
+# vsrt_coalescing_event
+CEV = np.dtype([("row", np.uint32), ("appended", np.uint32), ("n_loads", np.uint32), ("first_new_load", np.uint32)])
 
 
 def ptr(a):

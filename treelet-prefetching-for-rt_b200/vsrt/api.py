@@ -28,7 +28,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_treelet_metadata_idx", "vsrt_trace_rays", "vsrt_trace_fetch", "vsrt_trace_ray_warp",
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
            "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick",
-           "vsrt_table_events", "vsrt_table_event_stores",
+           "vsrt_table_events", "vsrt_table_event_stores", "vsrt_coalescing_events", "vsrt_coalescing_event_stores", "vsrt_coalescing_event_load",
            "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image"]
 
 
@@ -71,6 +71,11 @@ def load():
     L.vsrt_table_events.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_table_event_stores.argtypes = [c_vp, c_u64, c_vp]
     L.vsrt_table_event_stores.restype = None
+    L.vsrt_coalescing_events.argtypes = [c_vp, c_u64, c_vp, c_vp, c_vp]
+    L.vsrt_coalescing_event_stores.argtypes = [c_vp, c_vp, c_u64, c_vp]
+    L.vsrt_coalescing_event_stores.restype = c_u32
+    L.vsrt_coalescing_event_load.argtypes = [c_u32, c_u64, c_vp]
+    L.vsrt_coalescing_event_load.restype = None
     L.vsrt_as_dump_write.argtypes = [ctypes.c_char_p, c_vp, c_u64, c_vp, c_u32, c_u64, c_u64]
     L.vsrt_as_dump_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]
     L.vsrt_as_dump_free.argtypes = [c_vp]
@@ -342,6 +347,37 @@ class Context:
         for i in range(len(events)):
             self.L.vsrt_table_event_stores(events[i:i + 1].ctypes.data_as(c_vp), int(table_bases[int(events[i]["table"])]), out[i].ctypes.data_as(c_vp))
         return out
+
+    def coalescing_events(self, event_offsets, events):
+        """Function_Call_Coalescing intersection table replayed over the table-0 events of table_events(): one
+        vsrt_coalescing_event (row, appended, n_loads, first_new_load) per event."""
+        offs = np.ascontiguousarray(event_offsets, np.uint64); ev = np.ascontiguousarray(events, _abi.TEV)
+        out = np.zeros(len(ev), _abi.CEV)
+        self._ck(self.L.vsrt_coalescing_events(self.h, len(offs) - 1, _abi.ptr(offs), _abi.ptr(ev), _abi.ptr(out)))
+        return out
+
+    def coalescing_trace(self, offsets, txns, event_offsets, events, cev, table_base):
+        """The per-ray transaction and store lists with a Coalescing intersection table at table_base: the load records of
+        every call spliced in after its PROCEDURAL_LEAF record (rows first_new_load .. n_loads-1), stores in call order.
+        Returns (txn_offsets, txns, store_offsets, stores)."""
+        offsets = np.asarray(offsets, np.int64); eo = np.asarray(event_offsets, np.int64)
+        out_t, out_s, to, so = [np.zeros(0, _abi.TXN)], [np.zeros(0, _abi.STORE)], [0], [0]
+        one = np.zeros(1, _abi.TXN); st3 = np.zeros(3, _abi.STORE)
+        for r in range(len(offsets) - 1):
+            seg = txns[offsets[r]:offsets[r + 1]]
+            pos, nt, ns = 0, 0, 0
+            for k in range(eo[r], eo[r + 1]):
+                if events[k]["table"] != 0:
+                    continue
+                rec = int(events[k]["record"])
+                out_t.append(seg[pos:rec + 1]); nt += rec + 1 - pos; pos = rec + 1
+                for row in range(int(cev[k]["first_new_load"]), int(cev[k]["n_loads"])):
+                    self.L.vsrt_coalescing_event_load(row, int(table_base), one.ctypes.data_as(c_vp)); out_t.append(one.copy()); nt += 1
+                n = self.L.vsrt_coalescing_event_stores(events[k:k + 1].ctypes.data_as(c_vp), cev[k:k + 1].ctypes.data_as(c_vp), int(table_base), st3.ctypes.data_as(c_vp))
+                out_s.append(st3[:n].copy()); ns += n
+            out_t.append(seg[pos:]); nt += len(seg) - pos
+            to.append(to[-1] + nt); so.append(so[-1] + ns)
+        return np.array(to, np.uint64), np.concatenate(out_t), np.array(so, np.uint64), np.concatenate(out_s)
 
     def schedule_pick(self, scheduler, unit_warp_offsets, warp_ray_ids, stalled=None, last_prefetched=None, front=None):
         uo = np.ascontiguousarray(unit_warp_offsets, np.uint64); ids = np.ascontiguousarray(warp_ray_ids, np.uint64)

@@ -43,7 +43,6 @@ VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(one_bit)); return i; }   // FLO
 
 constexpr int THREADS = 128;
-VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_FORWARD
 #define VSRT_K1_FORWARD 0   // A/B: taking the next entry from the registers it was just pushed from (no stack load) is slower: 2.32 vs 2.18 ms
 #endif
@@ -53,7 +52,7 @@ VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
-enum { ST_IDLE = 0, ST_FIN = 1, ST_POP = 2, ST_INT = 3, ST_INST = 4, ST_LEAF = 5 };   // lane state
+enum { ST_IDLE = 0, ST_DEFER = 1, ST_FIN = 2, ST_POP = 3, ST_INT = 4, ST_INST = 5, ST_LEAF = 6 };   // lane state (DEFER: the ray is handed to the EXACT pass at the next refill)
 
 // The ray the lane is currently testing against: the world ray inside the TLAS, the object-space ray of instance
 // `inst` inside a BLAS (make_transformed_ray, :168-181).  Rebuilt only when a popped entry belongs to another
@@ -116,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     // ================= refill: finalize finished rays, fetch new ones
     const unsigned idle = __ballot_sync(full, st <= ST_FIN);
     if (idle == full || (!exhausted && __popc(idle) >= REFILL_T)) {
+      if (st == ST_DEFER) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; st = ST_IDLE; }   // degenerate instance transform: left to the EXACT pass
       if (st == ST_FIN) {
         // ---- hit record (:2211-2245 / :2990-3033) and per-ray counters
         st = ST_IDLE;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       const uint32_t inst = e_inst(e);
       EMIT(e.slot, inst == INST_NONE ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
       ACTIVATE(inst);
-      if (!EXACT && a.nonfinite) { p.counts[r] = RAY_DEFERRED; err |= EF_NEED_EXACT; st = ST_IDLE; }   // degenerate instance transform
+      if (!EXACT && a.nonfinite) st = ST_DEFER;       // degenerate instance transform
       else {
         uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic16);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
         // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             }
           }
           const uint32_t mcur = mask & mc;
-          if (cur_n + oth_n + __popc(mask) > STACK_N) err |= EF_STACK;
+          if (cur_n + oth_n + 6 > STACK_N) err |= EF_STACK;      // room for six children, however many are pushed
           else {
             int po = STACK_N - 1 - oth_n;
             Entry lc, lo; lc.slot = lc.meta = lo.slot = lo.meta = 0u;   // last child pushed to `current` / `other` in this node
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           }
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
-          if (cur_n + __popc(mask) > STACK_N) err |= EF_STACK;
+          if (cur_n + 6 > STACK_N) err |= EF_STACK;
           else {
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
@@ -297,15 +297,6 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               else { c.slot |= fl; stk[cur_n] = c; cur_n++; }
             }
           }
-        }
-        // the entry this lane pops next is known now: start pulling its 64 bytes into L1 while the rest of the
-        // iteration (other phases, refill vote) runs
-        if (p.prefetch) {
-          uint32_t ns = 0xFFFFFFFFu;
-          if (MODE == VSRT_MODE_DFS && st == ST_INT) ns = e.slot;
-          else if (cur_n) ns = stk[cur_n - 1].slot;
-          else if (MODE == VSRT_MODE_TREELET && oth_n) ns = stk[STACK_N - oth_n].slot;
-          if (ns != 0xFFFFFFFFu) prefetch_l1(base + (uint64_t)(ns & SLOT_MASK) * 64u);
         }
       }
     }

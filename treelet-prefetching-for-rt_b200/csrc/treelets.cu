@@ -48,6 +48,9 @@ struct Walker {
         const uint4* np = reinterpret_cast<const uint4*>(av.base + (uint64_t)slot * 64u);
         const uint4 b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3);
         const uint32_t w[16] = { 0, 0, 0, 0, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w };
+        // and a bound exponent below -118 (scale 2^(e-8) is a denormal): the fast path builds the scale from the byte alone
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) if ((int)(int8_t)((w[(18 + ax) >> 2] >> (((18 + ax) & 3) * 8)) & 0xffu) < -118) err |= EF_NONFINITE;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
           if (((w[(22 + i) >> 2] >> (((22 + i) & 3) * 8)) & 3u) == 0u) continue;

@@ -109,10 +109,14 @@ VS_DEV uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.
 template <bool EXACT>
 VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, float cull, uint32_t magic16) {
   const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
-  // 2^(e-8) per axis; exponents below -126 (denormal scales, no sane BVH) take the general path
-  const int kx = (int)(int8_t)node_byte(n, 18) - 8, ky = (int)(int8_t)node_byte(n, 19) - 8, kz = (int)(int8_t)node_byte(n, 20) - 8;
-  float sx = __uint_as_float((uint32_t)(kx + 127) << 23), sy = __uint_as_float((uint32_t)(ky + 127) << 23), sz = __uint_as_float((uint32_t)(kz + 127) << 23);
-  if (min(kx, min(ky, kz)) < -126) { sx = node_scale(n, 18); sy = node_scale(n, 19); sz = node_scale(n, 20); }
+  // 2^(e-8) per axis.  Exponents below -126 (denormal scales, no sane BVH) need the general form: K0 sends an arena that has
+  // one down the EXACT path, so the hot path builds the float from the exponent byte alone: (e + 119) << 23, e >= -118
+  float sx, sy, sz;
+  if (EXACT) { sx = node_scale(n, 18); sy = node_scale(n, 19); sz = node_scale(n, 20); }
+  else {
+    sx = __uint_as_float(((node_byte(n, 18) + 119u) & 0xffu) << 23); sy = __uint_as_float(((node_byte(n, 19) + 119u) & 0xffu) << 23);
+    sz = __uint_as_float(((node_byte(n, 20) + 119u) & 0xffu) << 23);
+  }
   uint32_t mask = 0;
   if (EXACT) {
 #pragma unroll

@@ -365,6 +365,29 @@ def run_cuda(args):
     h2d = n * _abi.RAY.itemsize
     d2h = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 16 + n_txn * 8
 
+    # ---- the same with the packed host form (vsrt_trace_rays_packed): 4-byte records + 4-byte treelet indices, expanded by the
+    # caller where it consumes them (vsrt_unpack_txn).  Reported beside "e2e", which stays the full 24 bytes per record.
+    rec_h = torch.empty(max(n_txn, 1) * 4, dtype=torch.uint8).pin_memory()
+    tix_h = torch.empty(max(n_txn, 1) * 4, dtype=torch.uint8).pin_memory()
+
+    def e2e_packed_step():
+        return ctx.trace_packed_into(MODE, n, rays_pinned.data_ptr(), hits_h.data_ptr(), offs_h.data_ptr(), rec_h.data_ptr(), n_txn, tix_h.data_ptr())
+    e2e_packed_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got = e2e_packed_step()
+    torch.cuda.synchronize()
+    e2ep_s = time.perf_counter() - t0
+    assert got == n_txn
+    ep_all = torch.tensor([e2ep_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ep_all, op=dist.ReduceOp.MAX)
+    e2e_packed_value = total_rays * e2e_steps / float(ep_all.item())
+    d2h_packed = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 8
+
     if rank == 0:
         peak, peak_src = peaks()
         k1_ms = trav_ms / args.steps
@@ -386,6 +409,8 @@ def run_cuda(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                         "api": "vsrt_trace_rays (host pinned buffers; hits + CSR offsets + 16-byte records + 64-bit treelet ids copied back)"},
+                "e2e_packed": {"value": e2e_packed_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_packed), "steps": e2e_steps,
+                               "api": "vsrt_trace_rays_packed (host pinned buffers; hits + CSR offsets + 4-byte packed records + 4-byte treelet indices; the caller expands with vsrt_unpack_txn)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,

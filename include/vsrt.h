@@ -305,6 +305,38 @@ int vsrt_table_events(vsrt_context* ctx, const uint8_t* tid_x, uint64_t* event_o
 /* The two MemoryStoreTransactionRecords of one event for a table that gpgpusim_alloc placed at table_base. */
 void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vsrt_store_txn out[2]);
 
+/* ---- packed trace for host consumers ----
+ * The 16-byte records + 64-bit treelet ids of a 1080p frame are 2.1 GB, and the PCIe link (not the GPU) bounds a host-side
+ * caller at ~46 M rays/s.  A record is a function of 32 bits -- the node's 64-byte slot in the packed arena and a 3-bit code --
+ * and a treelet id is an index into vsrt_treelet_table's ascending root array, so a caller that builds its
+ * MemoryTransactionRecords where it consumes them (trace_ray_impl -> thread->set_rt_transactions, instructions.cc:7235-7254)
+ * can take 8 bytes per record instead of 24 and expand with vsrt_unpack_txn.  Same records, same order, same ids.
+ * Limits: every BLAS registered with the TLAS's host->device offset (the reference's two offset conventions then coincide,
+ * SURVEY A.2), remap_to_treelet_layout off, at most 8 disjoint host spans; otherwise VSRT_E_UNSUPPORTED. */
+typedef struct vsrt_packed_layout {
+  int64_t device_delta;        /* simulated-device address - host address */
+  uint32_t n_spans, reserved;
+  struct { uint64_t host; uint32_t slot0, n_slots; } spans[8];   /* slot s of span i lives at spans[i].host + (s - slot0) * 64 */
+} vsrt_packed_layout;
+int vsrt_packed_layout_get(vsrt_context* ctx, const void* tlas, vsrt_packed_layout* out);
+/* records[i] = slot << 3 | code (code = VSRT_TXN_* type, 7 = an internal node of the TLAS); treelet_index[i] = rank of the
+ * record's treelet root in vsrt_treelet_table's roots[] (0xFFFFFFFF: the address is in no treelet).  Either may be NULL.
+ * Always the traversal order of the last batch (vsrt_sort_trace does not affect it). */
+int vsrt_trace_fetch_packed(vsrt_context* ctx, uint32_t* records, uint64_t capacity, uint32_t* treelet_index);
+/* vsrt_trace_rays with packed outputs (hits and trace_offsets as there) */
+int vsrt_trace_rays_packed(vsrt_context* ctx, const void* tlas, int mode, uint64_t n_rays, const vsrt_ray* rays, vsrt_hit* hits,
+                           uint64_t* trace_offsets, uint32_t* records, uint64_t capacity, uint32_t* treelet_index, uint64_t* n_txn);
+static inline void vsrt_unpack_txn(const vsrt_packed_layout* L, uint32_t record, vsrt_txn* out) {
+  const uint32_t slot = record >> 3, code = record & 7u;
+  uint32_t i = L->n_spans - 1u;
+  while (i > 0u && L->spans[i].slot0 > slot) i--;
+  out->address = L->spans[i].host + (uint64_t)(slot - L->spans[i].slot0) * 64u + (uint64_t)L->device_delta;
+  out->size = code == VSRT_TXN_BVH_INSTANCE_LEAF ? 128u : (code == VSRT_TXN_BVH_PRIMITIVE_LEAF_DESCRIPTOR ? 8u : 64u);
+  out->type = code == 7u ? (uint32_t)VSRT_TXN_BVH_INTERNAL_NODE : code;
+}
+/* the same over an array (exported for bindings that cannot use the inline) */
+void vsrt_unpack_txns(const vsrt_packed_layout* layout, const uint32_t* records, uint64_t n, vsrt_txn* out);
+
 /* ---- Function_Call_Coalescing intersection table (-gpgpu_rt_intersection_table_type 1) ----
  * Coalescing_warp_intersection_table::add_intersection (intersection_table.cc:43-98): the rows are shared by the threads of a
  * CTA.  A call looks at rows 0, 1, ... (one Intersection_Table_Load record {&table[i].hitGroupIndex, 4} per row), claims the

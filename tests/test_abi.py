@@ -21,6 +21,7 @@ def api():
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "vsrt.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline[^{;]*\{.*?\n\}", "", text, flags=re.S)   # header-only helpers are not exports
     return sorted(set(re.findall(r"\b(vsrt_[a-z_0-9]+)\s*\(", text)))
 
 
@@ -37,6 +38,7 @@ def test_struct_sizes():
     assert _abi.RAY.itemsize == 52 and _abi.HIT.itemsize == 56 and _abi.TXN.itemsize == 16
     assert ctypes.sizeof(_abi.Config) == 32 and ctypes.sizeof(_abi.DeviceResults) == 80 and ctypes.sizeof(_abi.TreeletInfo) == 40
     assert _abi.HIT.fields["instance_leaf_address"][1] == 48
+    assert ctypes.sizeof(_abi.PackedLayout) == 144 and _abi.CEV.itemsize == 16
 
 
 def test_config_parser(api):

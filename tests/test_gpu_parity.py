@@ -388,6 +388,39 @@ def test_table_events(api, monkeypatch, wavefront):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_packed_trace(api, mode):
+    """vsrt_trace_rays_packed / vsrt_trace_fetch_packed: 8 bytes per record instead of 24; expanded with vsrt_unpack_txn and the
+    treelet table they must give exactly the records and treelet ids of vsrt_trace_rays (which the other tests pin to the
+    oracle), also for an arena of several host spans and a host->device offset."""
+    s = sc.Scene(3000, seed=21, n_blas=3, n_instances=4, flags=sc.F_TRANSFORMS)
+    rays = helpers.mixed_rays(1500, 21, 24, 16)
+    ctx = api.Context(max_treelet_size=512, device=0); ctx.register(s, delta=0x1000000); ctx.form_treelets()
+    g = ctx.trace(mode, rays)
+    rec, tix = ctx.fetch_packed()
+    assert len(rec) == len(g["txns"])
+    assert np.array_equal(ctx.unpack(rec), g["txns"])
+    roots = ctx.tables()["roots"]
+    ids = np.where(tix == 0xFFFFFFFF, np.uint64(0xFFFFFFFFFFFFFFFF), roots[np.minimum(tix, len(roots) - 1)])
+    assert np.array_equal(ids, g["treelet_ids"])
+    # one call, host buffers
+    n = len(rays)
+    hits = np.zeros(n, _abi.HIT); offs = np.zeros(n + 1, np.uint64); rec2 = np.zeros(len(rec), np.uint32); tix2 = np.zeros(len(rec), np.uint32)
+    r = np.ascontiguousarray(rays, _abi.RAY)
+    got = ctx.trace_packed_into(mode, n, r.ctypes.data, hits.ctypes.data, offs.ctypes.data, rec2.ctypes.data, len(rec2), tix2.ctypes.data)
+    assert got == len(rec) and np.array_equal(rec2, rec) and np.array_equal(tix2, tix) and np.array_equal(offs, g["offsets"])
+    assert np.array_equal(hits["primitive_index"], g["hits"]["primitive_index"])
+    ctx.close()
+    # non-uniform BLAS offsets: the two address conventions of the reference differ, the packed form cannot express them
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.register(s, delta=0x4000, blas_delta=[0x4000, 0x900000, 0x2000000]); ctx.form_treelets()
+    ctx.trace(mode, rays[:64])
+    with pytest.raises(api.VsrtError) as e:
+        ctx.fetch_packed()
+    assert e.value.code == -9
+    ctx.close()
+
+
 def test_coalescing_table(api):
     """Function_Call_Coalescing intersection table: vsrt_coalescing_events over the CUDA path's own table events against the
     pinned restatement, and the spliced transaction / store lists against the reference traversal run with its own

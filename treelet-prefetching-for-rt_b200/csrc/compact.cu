@@ -254,6 +254,17 @@ __global__ void k_tid_to_addr(const ArenaView av, const TreeletView tv, const ui
   else out[i] = remap_pitch ? remap_base + (unsigned long long)t * remap_pitch : slot_to_host(av, __ldg(tv.tl_root + t)) + (uint64_t)av.tlas_delta;
 }
 
+// Packed form of the trace for host consumers that expand records at the point of use: the staged words (slot << 3 | code)
+// of every ray, CSR-compacted.  One warp per ray, lanes over its records (both sides coalesced).
+__global__ void __launch_bounds__(256) k_pack_trace(const uint32_t* __restrict__ stage, uint32_t cap, const unsigned long long* __restrict__ offsets,
+                                                    uint64_t n_rays, uint32_t* __restrict__ out, uint64_t out_capacity) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rays) return;
+  const unsigned long long o0 = offsets[r], o1 = offsets[r + 1];
+  const uint32_t* seg = stage + r * (uint64_t)cap;
+  for (unsigned long long k = threadIdx.x & 31u; o0 + k < o1 && o0 + k < out_capacity; k += 32u) out[o0 + k] = __ldg(seg + k);
+}
+
 }  // namespace
 
 size_t vsrt_scan_tmp_bytes(uint64_t n) { return ((n + SCAN_TILE - 1) / SCAN_TILE + 2) * sizeof(unsigned long long); }
@@ -284,5 +295,11 @@ int vsrt_launch_tid_to_addr(const ArenaView& av, const TreeletView& tv, const ui
                             uint64_t remap_base, uint64_t remap_pitch, cudaStream_t st) {
   if (n == 0) return VSRT_OK;
   k_tid_to_addr<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(av, tv, tids, n, (unsigned long long*)out, remap_base, remap_pitch);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+int vsrt_launch_pack_trace(const uint32_t* stage, uint32_t cap, const uint64_t* offsets, uint64_t n_rays, uint32_t* out, uint64_t out_capacity, cudaStream_t st) {
+  if (n_rays == 0) return VSRT_OK;
+  k_pack_trace<<<(unsigned)((n_rays + 7) / 8), 256, 0, st>>>(stage, cap, (const unsigned long long*)offsets, n_rays, out, out_capacity);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

@@ -51,7 +51,7 @@ struct vsrt_context {
   std::vector<uint32_t> h_node_tid, h_tl_root; std::vector<uint64_t> h_tl_off, h_tl_node; bool mirrors = false;
   // per-batch buffers
   DevBuf<vsrt_ray> d_rays; DevBuf<vsrt_hit> d_hits; DevBuf<uint32_t> d_stage; DevBuf<uint32_t> d_counts;
-  DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint8_t> d_scan_tmp;
+  DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint32_t> d_packed; DevBuf<uint8_t> d_scan_tmp;
   uint32_t stage_cap = 128;
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
   DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
@@ -324,7 +324,7 @@ void vsrt_destroy(vsrt_context* c) {
   free_treelets(c);
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
-  c->d_tids.release(); c->d_tid_addr.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
+  c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -531,6 +531,54 @@ int vsrt_trace_rays(vsrt_context* c, const void* tlas, int mode, uint64_t n, con
   if (txns || treelet_ids) return vsrt_trace_fetch(c, txns, txn_capacity, treelet_ids);
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VSRT_OK;
+}
+
+int vsrt_packed_layout_get(vsrt_context* c, const void* tlas, vsrt_packed_layout* out) {
+  if (!c || !out) return VSRT_E_INVALID;
+  ArenaView av; int rc = make_view(c, (uint64_t)(uintptr_t)tlas, &av); if (rc) return rc;
+  if (!av.uniform_delta) return fail(c, VSRT_E_UNSUPPORTED, "packed traces need every BLAS registered with the TLAS's host->device offset");
+  if (c->cfg.remap_to_treelet_layout) return fail(c, VSRT_E_UNSUPPORTED, "packed traces carry original addresses; remap_to_treelet_layout is on");
+  if (c->spans.size() > 8 || c->spans.empty()) return fail(c, VSRT_E_UNSUPPORTED, "packed traces support 1..8 disjoint host spans (%zu registered)", c->spans.size());
+  memset(out, 0, sizeof(*out));
+  out->device_delta = av.tlas_delta; out->n_spans = (uint32_t)c->spans.size();
+  for (size_t i = 0; i < c->spans.size(); i++) { out->spans[i].host = c->spans[i].host; out->spans[i].slot0 = c->spans[i].slot0; out->spans[i].n_slots = c->spans[i].n_slots; }
+  return VSRT_OK;
+}
+
+int vsrt_trace_fetch_packed(vsrt_context* c, uint32_t* records, uint64_t cap, uint32_t* treelet_index) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->last.trace_offsets) return fail(c, VSRT_E_INVALID, "no trace: call vsrt_trace_rays / vsrt_trace_rays_device first");
+  cudaSetDevice(c->device);
+  vsrt_packed_layout lay; int rc = vsrt_packed_layout_get(c, (const void*)(uintptr_t)c->last_tlas, &lay); if (rc) return rc;
+  const uint64_t total = c->last.n_txn, m = std::min(total, cap);
+  if (records && m) {
+    CUDA_OK(c, c->d_packed.ensure(m));
+    rc = vsrt_launch_pack_trace(c->d_stage.p, c->stage_cap, c->d_offsets.p, c->last.n_rays, c->d_packed.p, m, c->stream); if (rc) return fail(c, rc, "pack kernel launch failed");
+    CUDA_OK(c, cudaMemcpyAsync(records, c->d_packed.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (treelet_index && m) CUDA_OK(c, cudaMemcpyAsync(treelet_index, c->d_tids.p, m * 4, cudaMemcpyDeviceToHost, c->stream));   // traversal order, whatever vsrt_sort_trace did since
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return total > cap ? VSRT_E_CAPACITY : VSRT_OK;
+}
+
+int vsrt_trace_rays_packed(vsrt_context* c, const void* tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
+                           uint32_t* records, uint64_t capacity, uint32_t* treelet_index, uint64_t* n_txn) {
+  if (!c || !tlas || (n && !rays)) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
+  if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));
+  int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, c->d_rays.p, n, c->stream);
+  if (n_txn) *n_txn = c->last.n_txn;
+  if (rc) return rc;
+  if (hits && n) CUDA_OK(c, cudaMemcpyAsync(hits, c->d_hits.p, n * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->stream));
+  if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets, c->d_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (records || treelet_index) return vsrt_trace_fetch_packed(c, records, capacity, treelet_index);
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VSRT_OK;
+}
+
+void vsrt_unpack_txns(const vsrt_packed_layout* layout, const uint32_t* records, uint64_t n, vsrt_txn* out) {
+  for (uint64_t i = 0; i < n; i++) vsrt_unpack_txn(layout, records[i], &out[i]);
 }
 
 int vsrt_trace_ray_warp(vsrt_context* c, const void* tlas, uint32_t active_mask, const vsrt_ray rays[32], vsrt_hit hits[32],

@@ -164,3 +164,5 @@ struct TableParams {
 int vsrt_launch_table_events(bool fill, const TableParams& p, uint32_t* totals_dev, cudaStream_t st);
 // Function_Call_Coalescing intersection table replayed over table events (device arrays); *err receives EF_UNSUPPORTED if a CTA outgrows the reference's 100 rows
 int vsrt_launch_coalescing(const uint64_t* ev_off, const vsrt_table_event* ev, uint64_t n_rays, vsrt_coalescing_event* out, uint32_t* err, cudaStream_t st);
+// CSR-compacted copy of the staged trace words (vsrt_trace_fetch_packed)
+int vsrt_launch_pack_trace(const uint32_t* stage, uint32_t cap, const uint64_t* offsets, uint64_t n_rays, uint32_t* out, uint64_t out_capacity, cudaStream_t st);

@@ -67,3 +67,12 @@ CEV = np.dtype([("row", np.uint32), ("appended", np.uint32), ("n_loads", np.uint
 def ptr(a):
     """ctypes void* of a numpy array (or None)."""
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _PackedSpan(ctypes.Structure):
+    _fields_ = [("host", ctypes.c_uint64), ("slot0", ctypes.c_uint32), ("n_slots", ctypes.c_uint32)]
+
+
+class PackedLayout(ctypes.Structure):   # vsrt_packed_layout
+    _fields_ = [("device_delta", ctypes.c_int64), ("n_spans", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("spans", _PackedSpan * 8)]
+

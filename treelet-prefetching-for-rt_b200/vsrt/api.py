@@ -29,6 +29,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_trace_rays_device", "vsrt_trace_device_results", "vsrt_get_counters", "vsrt_reset_counters",
            "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick",
            "vsrt_table_events", "vsrt_table_event_stores", "vsrt_coalescing_events", "vsrt_coalescing_event_stores", "vsrt_coalescing_event_load",
+           "vsrt_packed_layout_get", "vsrt_trace_fetch_packed", "vsrt_trace_rays_packed", "vsrt_unpack_txns",
            "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image"]
 
 
@@ -72,6 +73,11 @@ def load():
     L.vsrt_table_event_stores.argtypes = [c_vp, c_u64, c_vp]
     L.vsrt_table_event_stores.restype = None
     L.vsrt_coalescing_events.argtypes = [c_vp, c_u64, c_vp, c_vp, c_vp]
+    L.vsrt_packed_layout_get.argtypes = [c_vp, c_vp, ctypes.POINTER(_abi.PackedLayout)]
+    L.vsrt_trace_fetch_packed.argtypes = [c_vp, c_vp, c_u64, c_vp]
+    L.vsrt_trace_rays_packed.argtypes = [c_vp, c_vp, c_int, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, ctypes.POINTER(c_u64)]
+    L.vsrt_unpack_txns.argtypes = [ctypes.POINTER(_abi.PackedLayout), c_vp, c_u64, c_vp]
+    L.vsrt_unpack_txns.restype = None
     L.vsrt_coalescing_event_stores.argtypes = [c_vp, c_vp, c_u64, c_vp]
     L.vsrt_coalescing_event_stores.restype = c_u32
     L.vsrt_coalescing_event_load.argtypes = [c_u32, c_u64, c_vp]
@@ -305,6 +311,32 @@ class Context:
         if n:
             self._ck(self.L.vsrt_trace_fetch(self.h, _abi.ptr(txns), n, _abi.ptr(tids)))
         return txns, tids
+
+    def fetch_packed(self):
+        """Packed records (slot << 3 | code) and treelet indices of the last batch, in traversal order."""
+        n = self.device_results().n_txn
+        rec = np.zeros(n, np.uint32); tix = np.zeros(n, np.uint32)
+        if n:
+            self._ck(self.L.vsrt_trace_fetch_packed(self.h, _abi.ptr(rec), n, _abi.ptr(tix)))
+        return rec, tix
+
+    def packed_layout(self):
+        lay = _abi.PackedLayout()
+        self._ck(self.L.vsrt_packed_layout_get(self.h, self.tlas, ctypes.byref(lay)))
+        return lay
+
+    def unpack(self, records, layout=None):
+        """vsrt_unpack_txn over an array of packed records."""
+        lay = layout or self.packed_layout()
+        rec = np.ascontiguousarray(records, np.uint32); out = np.zeros(len(rec), _abi.TXN)
+        self.L.vsrt_unpack_txns(ctypes.byref(lay), _abi.ptr(rec), len(rec), _abi.ptr(out))
+        return out
+
+    def trace_packed_into(self, mode, n, rays_ptr, hits_ptr, offsets_ptr, rec_ptr, capacity, tix_ptr):
+        """vsrt_trace_rays_packed on caller-owned (e.g. pinned) host buffers given as raw addresses; returns #records."""
+        total = c_u64()
+        self._ck(self.L.vsrt_trace_rays_packed(self.h, self.tlas, mode, n, rays_ptr, hits_ptr, offsets_ptr, rec_ptr, capacity, tix_ptr, ctypes.byref(total)))
+        return total.value
 
     def sort_trace(self, method):
         """rt_unit::sort_mem_accesses over every ray of the last batch; returns the sorted (records, treelet ids)."""

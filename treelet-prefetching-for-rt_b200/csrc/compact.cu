@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __r
 }
 
 // ---------------------------------------------------------------- K3
-constexpr int K3_THREADS = 256;
+#ifndef VSRT_K3_THREADS
+#define VSRT_K3_THREADS 128   // the warps of a CTA wait for each other before the table flush: 512 -> 0.93 ms, 256 -> 0.68, 128 -> 0.64, 64 -> 0.63, 32 -> 0.84
+#endif
+constexpr int K3_THREADS = VSRT_K3_THREADS;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_RAYS = K3_WARPS * 32;   // rays per CTA: every warp owns 32 consecutive rays and their contiguous output range
 constexpr int K3_ILP = 4;        // independent 32-record windows in flight per warp
@@ -96,7 +99,10 @@ __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_
 // single coalesced transactions.  Which ray a record belongs to is found without a search: the lanes hold the 32 start
 // offsets, one REDUX.OR builds the bitmap of ray starts inside the window and a popcount of the bits at or below the lane
 // gives the ray (every ray has at least its TLAS-header record; a warp that sees an empty ray counts with shuffles instead).
-__global__ void __launch_bounds__(K3_THREADS) k_compact(const CompactParams p) {
+#ifndef VSRT_K3_MIN_BLOCKS
+#define VSRT_K3_MIN_BLOCKS 10   // x 128 threads = 1280 threads per SM at 51 registers, no spills (256 x 4: 0.71 ms, 256 x 5: 0.68 ms)
+#endif
+__global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(const CompactParams p) {
   // queued by the host before it knows whether the traversal succeeded and how many records there are (see run_batch)
   if (p.err_flags && (*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.fatal_mask)) return;
   if (p.offsets[p.n_rays] > p.out_capacity) return;

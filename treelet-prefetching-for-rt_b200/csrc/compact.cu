@@ -102,6 +102,8 @@ __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_
 #ifndef VSRT_K3_MIN_BLOCKS
 #define VSRT_K3_MIN_BLOCKS 10   // x 128 threads = 1280 threads per SM at 51 registers, no spills (256 x 4: 0.71 ms, 256 x 5: 0.68 ms)
 #endif
+// SIMPLE = one host span, one host->device offset for every buffer, original addresses: a record's address is one multiply-add
+template <bool SIMPLE>
 __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(const CompactParams p) {
   // queued by the host before it knows whether the traversal succeeded and how many records there are (see run_batch)
   if (p.err_flags && (*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.fatal_mask)) return;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
   const ArenaView& av = p.av;
   const bool one_span = av.n_spans == 1;
   const uint64_t span_host = one_span ? av.spans[0].host : 0ull;
+  const uint64_t simple_base = span_host + (uint64_t)av.tlas_delta;
   uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
   const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
   for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
     const uint32_t nxt = __shfl_down_sync(full, rel, 1);
     const bool any_empty = __ballot_sync(full, rvalid && (((uint32_t)lane + 1u < nr ? nxt : total) == rel)) != 0u;
     const uint32_t* stage_w = p.stage + rw0 * (uint64_t)p.cap;
-    unsigned long long packed = 0; uint32_t since_flush = 0;
+    uint32_t packed_lo = 0, packed_hi = 0, since_flush = 0;
     for (uint32_t wb = 0; wb < total; wb += 32u * K3_ILP) {
       uint32_t pos[K3_ILP], k[K3_ILP], ray[K3_ILP], rec[K3_ILP], tid[K3_ILP]; bool valid[K3_ILP];
 #pragma unroll
@@ -143,7 +146,8 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
         pos[u] = wbase + (uint32_t)lane; valid[u] = pos[u] < total;
         if (!any_empty) {
           const uint32_t nle = __popc(__ballot_sync(full, rel <= wbase));                     // rays that start at or before the window
-          const uint32_t bit = (rel > wbase && rel - wbase < 32u) ? (1u << (rel - wbase)) : 0u;
+          const uint32_t dw = rel - wbase;
+          const uint32_t bit = (dw - 1u < 31u) ? (1u << dw) : 0u;                             // 1 <= rel - wbase <= 31
           const uint32_t starts = __reduce_or_sync(full, bit);                                  // ray starts inside the window
           ray[u] = nle - 1u + __popc(starts & ((2u << lane) - 1u));
         } else {
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
         k[u] = pos[u] - __shfl_sync(full, rel, (int)ray[u]);
       }
 #pragma unroll
-      for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(stage_w + (uint64_t)ray[u] * p.cap + k[u]) : 0u;
+      for (int u = 0; u < K3_ILP; u++) rec[u] = valid[u] ? __ldg(stage_w + (ray[u] * p.cap + k[u])) : 0u;   // < 32 * cap: 32-bit index inside the warp's 32 segments
 #pragma unroll
       for (int u = 0; u < K3_ILP; u++) { tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID; if (tid[u] != VSRT_NO_TID) tid[u] &= VSRT_TID_MASK; }
 #pragma unroll
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
           const uint32_t slot = rec[u] >> 3, code = rec[u] & 7u;
           // host -> simulated-device offset the reference applies to this record
           int64_t delta = av.tlas_delta;
-          if (!av.uniform_delta) {
+          if (!SIMPLE && !av.uniform_delta) {
             const uint32_t* seg = stage_w + (uint64_t)ray[u] * p.cap;
             if (code == C_STRUCT && k[u] > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
             else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k[u] > 0) {
@@ -173,21 +177,22 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
             }
           }
           // original_bvh_to_treelet_bvh_mapping[addr + offset] in every record when the layout is remapped (:1682,:1763,...)
-          const uint64_t address = p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta;
+          const uint64_t address = SIMPLE ? simple_base + (uint64_t)slot * 64u
+                                          : (p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta);
           const uint32_t type = code_type(code);
-          const unsigned long long j = j0 + pos[u];
-          if (j < p.out_capacity) {
-            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
-            p.tids[j] = tid[u];
-          }
-          packed += 1ull << (8u * type);        // g_rt_mem_access_type[type]++, eight 8-bit lanes
+          const unsigned long long j = j0 + pos[u];     // < offsets[n_rays] <= out_capacity (checked on entry)
+          *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
+          p.tids[j] = tid[u];
+          // g_rt_mem_access_type[type]++ as eight 8-bit lanes in two words (types 0..3 | 4..7)
+          const uint32_t inc = 1u << (8u * (type & 3u));
+          packed_lo += (type & 4u) ? 0u : inc; packed_hi += (type & 4u) ? inc : 0u;
         }
       }
       since_flush += K3_ILP;
       if (since_flush > 255u - K3_ILP) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(packed >> (8 * c)) & 0xffu;
-        packed = 0; since_flush = 0;
+        for (int c = 0; c < 4; c++) { hc[c] += (packed_lo >> (8 * c)) & 0xffu; hc[4 + c] += (packed_hi >> (8 * c)) & 0xffu; }
+        packed_lo = packed_hi = 0; since_flush = 0;
       }
       if (p.treelet_hist) {
         // Treelet visit histogram.  The hot bins (the treelets at the top of the tree) receive a record from every
@@ -206,7 +211,8 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
             const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
             const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
             const uint32_t h = (tid[u] * 2654435761u) >> (32 - TBITS);
-            const uint32_t old = atomicCAS(&t_key[h], VSRT_NO_TID, tid[u]);
+            uint32_t old = t_key[h];                                             // hot treelets own their slot already: no CAS
+            if (old == VSRT_NO_TID) old = atomicCAS(&t_key[h], VSRT_NO_TID, tid[u]);
             if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&t_cnt[h], run);
             else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
           }
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(packed >> (8 * c)) & 0xffu;
+    for (int c = 0; c < 4; c++) { hc[c] += (packed_lo >> (8 * c)) & 0xffu; hc[4 + c] += (packed_hi >> (8 * c)) & 0xffu; }
   }
   if (p.treelet_hist) {
     if (VSRT_K3_WARP_TABLE) {
@@ -291,9 +297,10 @@ int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
   static int n_sm = 0;
   if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   int per_sm = K3_CTAS_PER_SM;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact, K3_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact<false>, K3_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   const uint64_t grid = VSRT_K3_PERSIST ? std::min<uint64_t>(n_blocks, (uint64_t)n_sm * (uint64_t)per_sm) : n_blocks;
-  k_compact<<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
+  if (p.av.n_spans == 1 && p.av.uniform_delta && !p.remap) k_compact<true><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
+  else k_compact<false><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 

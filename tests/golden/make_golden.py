@@ -156,7 +156,31 @@ def main_tables():
     print("%s: %d bytes" % (path, os.path.getsize(path)))
 
 
+def main_coalescing():
+    """coalescing_proc1500.npz: the reference's traceRay with its own Function_Call_Coalescing intersection table in the loop
+    (intersection_table.cc:43-98; a fresh table per 32 rays, tid = r % 32): per-ray transaction lists with the
+    Intersection_Table_Load records merged in, and store lists.  Table addresses are offsets from the table base | 1 << 63,
+    BVH addresses are relative to the arena base."""
+    ref = oracles.RefOracle()
+    arena = sc.Scene(1500, seed=8, n_blas=2, n_instances=5, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    rays = helpers.mixed_rays(800, 12, 24, 16)
+    out = {"arena": np.array(arena.bytes), "tlas_offset": np.uint64(arena.tlas_offset), "blas": np.array(arena.blas, np.uint64).reshape(-1, 2),
+           "rays": rays, "budget": np.uint32(512)}
+    ref.register(arena); ref.form(512)
+    to, tx, so, st, entry = ref.trace_coalescing(0, rays)
+    tab = (tx["address"] >> np.uint64(63)) != 0
+    out["txn_offsets"] = to; out["txn_addr"] = np.where(tab, tx["address"], tx["address"] - np.uint64(arena.base))
+    out["txn_size"] = tx["size"].astype(np.uint8); out["txn_type"] = tx["type"].astype(np.uint8)
+    out["store_offsets"] = so; out["store_addr"] = st["address"]; out["store_size"] = st["size"].astype(np.uint8)
+    out["entry_size"] = np.uint32(entry)
+    assert int(tab.sum()) > 25 and (st["address"] >> np.uint64(63)).all()
+    path = os.path.join(HERE, "coalescing_proc1500.npz")
+    np.savez_compressed(path, **out)
+    print("%s: %d bytes (%d table loads, %d stores)" % (path, os.path.getsize(path), int(tab.sum()), len(st)))
+
+
 if __name__ == "__main__":
     main()
     main_replay()
     main_tables()
+    main_coalescing()

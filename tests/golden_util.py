@@ -84,3 +84,20 @@ def load_tables():
     arena = sc.Arena(z["arena"], int(z["tlas_offset"]), [(int(o), int(s)) for o, s in z["blas"]])
     rays = z["rays"].view(_abi.RAY) if z["rays"].dtype != _abi.RAY else z["rays"]
     return z, arena, rays
+
+
+COALESCING = os.path.join(GOLDEN_DIR, "coalescing_proc1500.npz")
+
+
+def load_coalescing():
+    """(fixture, arena, rays, expected transactions with BVH addresses rebased to the arena, expected stores)."""
+    z = np.load(COALESCING)
+    arena = sc.Arena(z["arena"], int(z["tlas_offset"]), [(int(o), int(s)) for o, s in z["blas"]])
+    rays = z["rays"].view(_abi.RAY) if z["rays"].dtype != _abi.RAY else z["rays"]
+    tx = np.zeros(len(z["txn_addr"]), _abi.TXN)
+    tab = (z["txn_addr"] >> np.uint64(63)) != 0
+    tx["address"] = np.where(tab, z["txn_addr"], z["txn_addr"] + np.uint64(arena.base)); tx["size"] = z["txn_size"]; tx["type"] = z["txn_type"]
+    st = np.zeros(len(z["store_addr"]), _abi.STORE)
+    st["address"] = z["store_addr"]; st["size"] = z["store_size"]
+    return z, arena, rays, tx, st
+

@@ -591,3 +591,18 @@ def test_cuda_matches_tables_fixture(api):
         assert np.array_equal(want["bary"][anyh].view(np.uint32), ah["barycentric"][anyh].view(np.uint32))
         assert np.array_equal(want["prim"][anyh], ah["primitive_index"][anyh])
     ctx.close()
+
+
+def test_cuda_matches_coalescing_fixture(api):
+    """vsrt_coalescing_events spliced into the CUDA trace against tests/golden/coalescing_proc1500.npz (the reference's
+    traceRay with its own Coalescing table in the loop)."""
+    z, arena, rays, tx, st = golden_util.load_coalescing()
+    ctx = api.Context(max_treelet_size=int(z["budget"]), device=0); ctx.register(arena); ctx.form_treelets()
+    g = ctx.trace(0, rays)
+    offs, ev, _ = ctx.table_events()
+    cev = ctx.coalescing_events(offs, ev)
+    to, gtx, so, gst = ctx.coalescing_trace(g["offsets"], g["txns"], offs, ev, cev, 1 << 63)
+    assert np.array_equal(to, z["txn_offsets"]) and np.array_equal(so, z["store_offsets"])
+    assert np.array_equal(gtx, tx) and np.array_equal(gst, st)
+    ctx.close()
+

@@ -229,6 +229,21 @@ def test_coalescing_table_matches_reference():
     assert stats[0] > 40 and stats[1] > 10 and stats[2] > 10, stats      # loads merged, rows appended, rows shared between threads
 
 
+def test_port_matches_coalescing_fixture():
+    """The restatement's Coalescing-table replay against tests/golden/coalescing_proc1500.npz (recorded from the reference's
+    traceRay with its own Coalescing table in the loop)."""
+    z, arena, rays, tx, st = golden_util.load_coalescing()
+    port = oracles.PortOracle(); port.register(arena); port.form(int(z["budget"]))
+    plain = port.trace(0, rays)
+    counts, ev, _ = port.table_events(0, rays, 0, 0)
+    eo = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    cev = port.coalescing_events(eo, ev)
+    eto, etx, eso, est = helpers.coalescing_splice(plain["offsets"], plain["txns"], eo, ev["table"], ev["tid"], cev)
+    assert int(z["entry_size"]) == helpers.COALESCING_ENTRY
+    assert np.array_equal(eto, z["txn_offsets"]) and np.array_equal(eso, z["store_offsets"])
+    assert np.array_equal(etx, tx) and np.array_equal(est, st)
+
+
 def test_port_matches_tables_fixture():
     """Shader-table events of the restatement against tests/golden/tables_proc1200.npz (recorded with the reference's own
     Baseline tables in the loop)."""

@@ -43,11 +43,14 @@ VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(one_bit)); return i; }   // FLO
 
 constexpr int THREADS = 128;
-#ifndef VSRT_K1_FORWARD
-#define VSRT_K1_FORWARD 0   // A/B: taking the next entry from the registers it was just pushed from (no stack load) is slower: 2.32 vs 2.18 ms
-#endif
+// pop + internal-node rounds per refill / leaf vote, and the lanes that must be at an internal node for another round.
+// Compile-time on purpose: as kernel parameters the same values cost 2 % (2.05 vs 2.00 ms).  Sweep (runtime knobs, ms):
+// rounds 2: 2.05 (1 lane) .. 2.02 (20 lanes); 3: 2.07 .. 2.00; 4: 2.15 .. 1.99; 6: 2.35 .. 2.00
 #ifndef VSRT_K1_INNER
-#define VSRT_K1_INNER 2   // measured: 1 -> 2.19 ms, 2 -> 2.14 ms, 3 -> 2.22 ms, 4 -> 2.31 ms
+#define VSRT_K1_INNER 2
+#endif
+#ifndef VSRT_K1_INT_T
+#define VSRT_K1_INT_T 20
 #endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   const int lane = threadIdx.x & 31;
   const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
   const int REFILL_T = (int)p.refill_t, LEAF_T = (int)p.leaf_t;
+  constexpr int INT_T = VSRT_K1_INT_T, INNER_N = VSRT_K1_INNER;
   const bool only_deferred = EXACT && p.only_deferred != 0;
 
   // ---- functional counters (cuda-sim.h:155-166): per-CTA accumulators in shared memory, touched only when a ray is
@@ -215,10 +219,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         } \
       } else cur_n--; \
       st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); } while (0)
-    // pop + internal-node phase run up to VSRT_K1_INNER times back to back: the refill and leaf votes around them are
+    // pop + internal-node phase run up to INNER_N times back to back (VSRT_K1_INNER): the refill and leaf votes around them are
     // amortised, at the price of idle / leaf lanes waiting a little longer
 #pragma unroll 1
-    for (int inner = 0; inner < VSRT_K1_INNER; inner++) {
+    for (int inner = 0; inner < INNER_N; inner++) {
     if (st == ST_POP) {
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         TAKE(fc);
       } else st = ST_FIN;
     }
-    if (VSRT_K1_INNER > 1 && inner && !__any_sync(full, st == ST_INT)) break;
+    if (inner && __popc(__ballot_sync(full, st == ST_INT)) < INT_T) break;   // too few lanes at an internal node: let the other phases / the refill bring lanes back first
 
     // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
     if (st == ST_INT) {
@@ -266,23 +270,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (cur_n + oth_n + 6 > STACK_N) err |= EF_STACK;      // room for six children, however many are pushed
           else {
             int po = STACK_N - 1 - oth_n;
-            Entry lc, lo; lc.slot = lc.meta = lo.slot = lo.meta = 0u;   // last child pushed to `current` / `other` in this node
-            bool hc = false, ho = false;
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
               const uint32_t sel = 0x7770u + bit_index(bit);
               Entry c; c.slot = (child0 + __byte_perm(xlo, xhi, sel)) | ((__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u); c.meta = cmeta;
               const bool ic = (mcur & bit) != 0u;
               stk[ic ? cur_n : po] = c;
-              if (ic) { lc = c; hc = true; cur_n++; } else { lo = c; ho = true; po--; }
+              if (ic) cur_n++; else po--;
             }
             oth_n = STACK_N - 1 - po;
-            // pop forwarding: the entry this lane takes next is usually one it has just pushed -- take it from the registers
-            // instead of waiting for the stack load at the top of the next iteration (the top stall of the kernel)
-#if VSRT_K1_FORWARD
-            if (hc) { e = lc; TAKE(true); }
-            else if (cur_n == 0 && ho) { e = lo; TAKE(false); }
-#endif
+            // (taking the entry just pushed from the registers instead of the stack load of the next pop -- the top stall of
+            // the kernel -- was measured twice and is slower: more instructions in divergent code, profiles/README.md)
           }
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order

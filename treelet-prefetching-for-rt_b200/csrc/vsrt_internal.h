@@ -100,7 +100,6 @@ struct TraverseParams {
   uint32_t leaf_t;                // run the leaf phase when at least this many lanes wait at a BLAS leaf
   uint32_t only_deferred;         // EXACT pass: trace only the rays the fast pass marked RAY_DEFERRED
   uint32_t gate;                  // != 0: the kernel returns at once unless (*err_flags & gate) -- lets the host queue the EXACT pass without reading the flags back
-  uint32_t prefetch;              // issue an L1 prefetch for the node a lane will pop next
   uint2* gstack;                  // wavefront kernel: per-warp stack areas (vsrt_wf_stack_bytes)
   uint32_t stack_n;               // wavefront kernel: stack entries per ray
   uint32_t magic16;               // 0x64646464 (fp16 1024 in each half), passed as data so it lives in a register (byte_pair_f16)

@@ -183,7 +183,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
-    { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 6u; }
+    { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 4u; }
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0;
     const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
     // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel

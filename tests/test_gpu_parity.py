@@ -101,6 +101,16 @@ def test_wavefront_variant(api, monkeypatch, ntri, nb, ni, flags, budget, delta)
     run_case(api, s, rays, budget, delta=delta)
 
 
+def test_staging_overflow_regrows(api, monkeypatch):
+    """A ray that outgrows its staging segment: the batch is redone with doubled segments (several times here: 8 records to
+    start with) and the functional counters are rolled back in between -- traces, hits and counters must come out as if
+    nothing had happened.  Procedural visits share the segment (their instance refs sit at its end)."""
+    monkeypatch.setenv("VSRT_STAGE_CAP", "8")
+    s = sc.Scene(2500, seed=31, n_blas=2, n_instances=4, flags=sc.F_TRANSFORMS | sc.F_PROCEDURAL)
+    run_case(api, s, helpers.mixed_rays(700, 31, 16, 12), 512)
+    run_case(api, sc.Scene(1200, seed=32), helpers.mixed_rays(300, 32, 16, 12), 4096, modes=(0,))
+
+
 @pytest.mark.parametrize("budget", [256, 1024])
 def test_host_device_offset_quirk(api, budget):
     """Non-zero host->device offset: traceRayWithTreelets stores a HOST address in current_treelet_root

@@ -56,6 +56,11 @@ struct vsrt_context {
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
   DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
+  // pinned host memory: the per-batch read-backs (record total, error flags, counters) land here without a staging copy, and
+  // small host-buffer calls (a warp's 32 rays) bounce their inputs and outputs through it so that a call is two queues of async
+  // copies and two synchronisations instead of a blocking copy per array
+  uint8_t* h_pin = nullptr;
+  static constexpr size_t PIN_HEAD = 1024, PIN_BYTES = 4u << 20;
   DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
   // -remap_to_treelet_layout: where gpgpusim_malloc put treelet_layout_bvh (:1477), and the per-slot table
@@ -225,10 +230,12 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     }
     CUDA_OK(c, cudaEventRecord(c->ev[3], st));
     uint32_t h_err = 0; DevCounters now;
-    CUDA_OK(c, cudaMemcpyAsync(&total, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaMemcpyAsync(&h_err, c->d_err, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
+    static_assert(16 + sizeof(DevCounters) <= vsrt_context::PIN_HEAD, "read-back block must fit the head of the pinned buffer");
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pin, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 8, c->d_err, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
+    memcpy(&total, c->h_pin, 8); memcpy(&h_err, c->h_pin + 8, 4); memcpy(&now, c->h_pin + 16, sizeof(now));
     if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
     if (h_err & EF_STACK) {
       cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st);
@@ -249,8 +256,9 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
         launches++;
       }
       CUDA_OK(c, cudaEventRecord(c->ev[3], st));
-      CUDA_OK(c, cudaMemcpyAsync(&now, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
       CUDA_OK(c, cudaStreamSynchronize(st));
+      memcpy(&now, c->h_pin + 16, sizeof(now));
     }
     // rayCount (:1665) advanced by the traversal kernel; accessedDataSize delta of this batch = its algorithmic bytes
     c->last.algorithmic_bytes = now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
@@ -310,9 +318,12 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
   ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_pin, vsrt_context::PIN_BYTES) == cudaSuccess;
   for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
   if (c->cfg.max_treelet_size == 0) c->cfg.max_treelet_size = 49152;
+  // initial staging records per ray (doubles, with the batch redone, whenever a ray outgrows it); the knob exists for the tests
+  if (const char* sc = getenv("VSRT_STAGE_CAP")) { const int v = atoi(sc); if (v >= 4 && v <= (1 << 20)) c->stage_cap = (uint32_t)v; }
   *out = c;
   return VSRT_OK;
 }
@@ -327,6 +338,7 @@ void vsrt_destroy(vsrt_context* c) {
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -522,10 +534,40 @@ int vsrt_trace_rays(vsrt_context* c, const void* tlas, int mode, uint64_t n, con
   if (!c || !tlas || (n && !rays)) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
   CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
-  if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));
+  uint8_t* const bounce = c->h_pin + vsrt_context::PIN_HEAD; const size_t bounce_bytes = vsrt_context::PIN_BYTES - vsrt_context::PIN_HEAD;
+  const bool small = n && n * sizeof(vsrt_ray) <= bounce_bytes && n <= 4096;
+  if (small) { memcpy(bounce, rays, n * sizeof(vsrt_ray)); CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, bounce, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream)); }
+  else if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));
   int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, c->d_rays.p, n, c->stream);
   if (n_txn) *n_txn = c->last.n_txn;
   if (rc) return rc;
+  {
+    // small batch (the 32-lane call): every output through the pinned bounce buffer, one synchronisation
+    const uint64_t total = c->last.n_txn, m = std::min(total, txn_capacity);
+    const size_t b_hits = hits ? n * sizeof(vsrt_hit) : 0, b_off = trace_offsets ? (n + 1) * 8 : 0, b_txn = txns ? m * sizeof(vsrt_txn) : 0, b_tid = treelet_ids ? m * 8 : 0;
+    if (small && b_hits + b_off + b_txn + b_tid <= bounce_bytes) {
+      uint8_t* p = bounce;
+      if (b_hits) CUDA_OK(c, cudaMemcpyAsync(p, c->d_hits.p, b_hits, cudaMemcpyDeviceToHost, c->stream));
+      uint8_t* p_off = p + b_hits;
+      if (b_off) CUDA_OK(c, cudaMemcpyAsync(p_off, c->d_offsets.p, b_off, cudaMemcpyDeviceToHost, c->stream));
+      uint8_t* p_txn = p_off + b_off;
+      if (b_txn) CUDA_OK(c, cudaMemcpyAsync(p_txn, c->last.txns, b_txn, cudaMemcpyDeviceToHost, c->stream));
+      uint8_t* p_tid = p_txn + b_txn;
+      if (b_tid) {
+        ArenaView av; rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
+        CUDA_OK(c, c->d_tid_addr.ensure(m));
+        const uint64_t pitch = c->cfg.remap_to_treelet_layout ? (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride : 0;
+        rc = vsrt_launch_tid_to_addr(av, treelet_view(c), (const uint32_t*)c->last.treelet_ids, m, c->d_tid_addr.p, c->layout_base, pitch, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
+        CUDA_OK(c, cudaMemcpyAsync(p_tid, c->d_tid_addr.p, b_tid, cudaMemcpyDeviceToHost, c->stream));
+      }
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      if (b_hits) memcpy(hits, p, b_hits);
+      if (b_off) memcpy(trace_offsets, p_off, b_off);
+      if (b_txn) memcpy(txns, p_txn, b_txn);
+      if (b_tid) memcpy(treelet_ids, p_tid, b_tid);
+      return ((txns || treelet_ids) && total > txn_capacity) ? VSRT_E_CAPACITY : VSRT_OK;
+    }
+  }
   if (hits && n) CUDA_OK(c, cudaMemcpyAsync(hits, c->d_hits.p, n * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->stream));
   if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets, c->d_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   if (txns || treelet_ids) return vsrt_trace_fetch(c, txns, txn_capacity, treelet_ids);

@@ -43,6 +43,12 @@ VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(one_bit)); return i; }   // FLO
 
 constexpr int THREADS = 128;
+#ifndef VSRT_K1_STATS
+#define VSRT_K1_STATS 0   // 1: count, per inner round, how many lanes are in which state (tools/k1_lane_states.py); costs ~10 %
+#endif
+#if VSRT_K1_STATS
+__device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state] lanes in that state at the internal-node phase, [9] rounds that ran it, [10] leaf phases run, [11] lanes in them, [12] refills, [13] lanes refilled
+#endif
 // pop + internal-node rounds per refill / leaf vote, and the lanes that must be at an internal node for another round.
 // Compile-time on purpose: as kernel parameters the same values cost 2 % (2.05 vs 2.00 ms).  Sweep (runtime knobs, ms):
 // rounds 2: 2.05 (1 lane) .. 2.02 (20 lanes); 3: 2.07 .. 2.00; 4: 2.15 .. 1.99; 6: 2.35 .. 2.00
@@ -153,6 +159,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) atomicAdd(&s_cnt[5], 1u);
         atomicAdd(&s_cnt[6], 1u);
       }
+#if VSRT_K1_STATS
+      if (lane == 0) { atomicAdd(&g_k1_stats[12], 1ull); atomicAdd(&g_k1_stats[13], (unsigned long long)__popc(idle)); }
+#endif
       if (!exhausted) {
         const int n_idle = __popc(idle);
         unsigned long long b0 = 0;
@@ -232,6 +241,14 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     }
     if (inner && __popc(__ballot_sync(full, st == ST_INT)) < INT_T) break;   // too few lanes at an internal node: let the other phases / the refill bring lanes back first
 
+#if VSRT_K1_STATS
+    {
+      unsigned long long add[16] = { 0 }; add[0] = 1;
+      for (uint32_t sv = 0; sv <= ST_LEAF; sv++) add[1 + sv] = __popc(__ballot_sync(full, st == sv));
+      add[9] = __any_sync(full, st == ST_INT) ? 1 : 0;
+      if (lane < 10 && add[lane]) atomicAdd(&g_k1_stats[lane], add[lane]);
+    }
+#endif
     // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
     if (st == ST_INT) {
       st = ST_POP;
@@ -323,6 +340,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     // ================= phase 3: BLAS leaves (:2073-2204 / :2789-2985), batched
     const unsigned m_leaf = __ballot_sync(full, st == ST_LEAF);
     if (m_leaf && (__popc(m_leaf) >= LEAF_T || __ballot_sync(full, st == ST_INT || st == ST_INST || st == ST_POP) == 0u)) {
+#if VSRT_K1_STATS
+      if (lane == 0) { atomicAdd(&g_k1_stats[10], 1ull); atomicAdd(&g_k1_stats[11], (unsigned long long)__popc(m_leaf)); }
+#endif
       if (st == ST_LEAF) {
         st = ST_POP;
         const Node64 q = load_node_now(base, e.slot);
@@ -414,3 +434,13 @@ int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool e
   if (stack_entries <= 192) return launch_n<192>(p, exact, st);
   return launch_n<384>(p, exact, st);
 }
+
+#if VSRT_K1_STATS
+// debug build only (not part of include/vsrt.h): reads and clears the lane-state counters
+extern "C" int vsrt_debug_k1_stats(unsigned long long out[16]) {
+  unsigned long long z[16] = { 0 };
+  if (cudaMemcpyFromSymbol(out, g_k1_stats, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_k1_stats, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+

@@ -58,6 +58,15 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_INT_T
 #define VSRT_K1_INT_T 20
 #endif
+// 1 (default) = the stack holds one 16-byte entry per internal node and list -- first child slot, six offset|flag bytes, mask of the
+// still pending hit children, meta -- instead of one 8-byte entry per hit child (0, kept as the A/B variant).  Both reference lists
+// are LIFO and a node's hit children are pushed in slot order (:1810-1869 / :2573), so "highest pending child of the top entry" is
+// the reference's pop order.  No per-child push loop (it ran 3.15 turns per node at 7.6 of 32 lanes), a slightly longer pop:
+// 1.96 -> 1.88 ms on the bench workload, 3.39 -> 3.08 ms in DFS mode.  (Taking the next child straight from the registers on top
+// of this was measured and is slower -- the pop then runs for a few lanes at the cost of all, profiles/README.md.)
+#ifndef VSRT_K1_NODE_ENTRY
+#define VSRT_K1_NODE_ENTRY 1
+#endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
@@ -89,7 +98,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
   // ---- per-lane ray state.  `st` is the lane's whole control state: no ray / ray finished (hit record pending) / entry
   // wanted / an entry of one of the three kinds in `e` waiting for its phase.
+#if VSRT_K1_NODE_ENTRY
+  uint4 stk[STACK_N];     // x first child slot | y, z.lo16: per-child byte = offset (low 4 bits) | K0's flags (bits 7, 6) | z bits 16..21 pending mask | w meta
+#else
   Entry stk[STACK_N];
+#endif
   uint32_t st = ST_IDLE; bool exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
   uint32_t r = 0;
@@ -194,11 +207,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
                 const float* hb = reinterpret_cast<const float*>(base + (uint64_t)av.tlas_slot * 64u + 8u);
                 float th;
                 if (ray_box(__ldg(hb), __ldg(hb + 1), __ldg(hb + 2), __ldg(hb + 3), __ldg(hb + 4), __ldg(hb + 5), a.idir, w, th)) {
+#if VSRT_K1_NODE_ENTRY
+                  uint4 c = make_uint4(top_root, 0u, 1u << 16, (1u << 23) | INST_NONE);   // a one-child entry
+#define SET_SELFROOT(c_) ((c_).y = 0x80u)
+#else
                   Entry c; c.slot = top_root; c.meta = (1u << 23) | INST_NONE;
+#define SET_SELFROOT(c_) ((c_).slot |= SLOT_SELFROOT)
+#endif
                   if (MODE == VSRT_MODE_TREELET) {
                     cur_tid = root_rank(p.tv, av.tlas_slot);                               // current_treelet_root = TLAS + offset, :1707
                     const uint32_t tr = __ldg(p.tv.node_tid + top_root);
-                    if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { c.slot |= (tr & VSRT_TID_SELF_ROOTED) ? SLOT_SELFROOT : 0u; PUSH_OTH(c); }
+                    if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { if (tr & VSRT_TID_SELF_ROOTED) SET_SELFROOT(c); PUSH_OTH(c); }
                   } else PUSH_CUR(c);
                   if (max_level < 1) max_level = 1;
                 }
@@ -216,17 +235,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       const bool selfroot_ = (e.slot & SLOT_SELFROOT) != 0u, leaf_ = (e.slot & SLOT_LEAF) != 0u; \
       e.slot &= SLOT_MASK; \
       if (MODE == VSRT_MODE_TREELET) { \
-        if (from_cur_) { cur_n--; in_cur = true; }       /* entries of `current` were pushed because node_tid == current treelet */ \
+        if (from_cur_) { if (!VSRT_K1_NODE_ENTRY) cur_n--; in_cur = true; }       /* entries of `current` were pushed because node_tid == current treelet */ \
         else { \
           /* :1748-1754 -- the front of `other` moves to `current`; current_treelet_root becomes that node's HOST address, */ \
           /* which equals a treelet's device address only for the root at (host - tlas_delta). */ \
-          oth_n--; \
+          if (!VSRT_K1_NODE_ENTRY) oth_n--; \
           if (av.tlas_delta == 0) { \
             in_cur = selfroot_; cur_tid = e.slot; tid_known = false; \
             if (!selfroot_) { cur_tid = root_rank(p.tv, e.slot); tid_known = true; } \
           } else { uint32_t s2_; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2_) ? root_rank(p.tv, s2_) : VSRT_NO_TID; } \
         } \
-      } else cur_n--; \
+      } else if (!VSRT_K1_NODE_ENTRY) cur_n--; \
       st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); } while (0)
     // pop + internal-node phase run up to INNER_N times back to back (VSRT_K1_INNER): the refill and leaf votes around them are
     // amortised, at the price of idle / leaf lanes waiting a little longer
@@ -235,7 +254,20 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     if (st == ST_POP) {
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
+#if VSRT_K1_NODE_ENTRY
+        const int idx = fc ? cur_n - 1 : STACK_N - oth_n;
+        const uint4 t = stk[idx];
+        uint32_t ci; asm("bfind.u32 %0, %1;" : "=r"(ci) : "r"(t.z));          // highest pending child: the mask is the top of z
+        const uint32_t z2 = t.z ^ (1u << ci);
+        stk[idx].z = z2;                                                          // a removed entry is never read again
+        const int gone = (z2 >> 16) == 0u ? 1 : 0;
+        cur_n -= fc ? gone : 0;
+        if (MODE == VSRT_MODE_TREELET) oth_n -= fc ? 0 : gone;
+        const uint32_t cb = __byte_perm(t.y, t.z, 0x7770u + (ci - 16u));          // the child's byte: offset | flags
+        e.slot = (t.x + (cb & 15u)) | ((cb << 24) & 0xC0000000u); e.meta = t.w;
+#else
         e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
+#endif
         TAKE(fc);
       } else st = ST_FIN;
     }
@@ -285,6 +317,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           }
           const uint32_t mcur = mask & mc;
           if (cur_n + oth_n + 6 > STACK_N) err |= EF_STACK;      // room for six children, however many are pushed
+#if VSRT_K1_NODE_ENTRY
+          else {
+            const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u), moth = mask ^ mcur;
+            if (moth) { oth_n++; stk[STACK_N - oth_n] = make_uint4(child0, ey, ez | (moth << 16), cmeta); }
+            if (mcur) { stk[cur_n] = make_uint4(child0, ey, ez | (mcur << 16), cmeta); cur_n++; }
+          }
+#else
           else {
             int po = STACK_N - 1 - oth_n;
             for (uint32_t m = mask; m; ) {
@@ -299,9 +338,20 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             // (taking the entry just pushed from the registers instead of the stack load of the next pop -- the top stall of
             // the kernel -- was measured twice and is slower: more instructions in divergent code, profiles/README.md)
           }
+#endif
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
           if (cur_n + 6 > STACK_N) err |= EF_STACK;
+#if VSRT_K1_NODE_ENTRY
+          else if (mask) {
+            const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u);
+            const uint32_t lf4 = (lo4 >> 6) & 0x01010101u, lf2 = (hi2 >> 6) & 0x0101u;      // leaf flag of every child -> six bits
+            const uint32_t leaf6 = (((lf4 * 0x00204081u) >> 21) & 15u) | (((lf2 * 0x00204081u) >> 17) & 0x30u);
+            const uint32_t mi = mask & ~leaf6, first = mi & (0u - mi), rest = mask ^ first;
+            if (first) { e.slot = child0 + __byte_perm(xlo, xhi, 0x7770u + bit_index(first)); e.meta = cmeta; st = ST_INT; }
+            if (rest) { stk[cur_n] = make_uint4(child0, ey, ez | (rest << 16), cmeta); cur_n++; }
+          }
+#else
           else {
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
@@ -312,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               else { c.slot |= fl; stk[cur_n] = c; cur_n++; }
             }
           }
+#endif
         }
       }
     }
@@ -326,13 +377,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; st = ST_FIN; }
       else {
         EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
+#if VSRT_K1_NODE_ENTRY
+        uint4 c = make_uint4(broot, 0u, 1u << 16, (e_level(e) << 23) | iref);
+#else
         Entry c; c.slot = broot; c.meta = (e_level(e) << 23) | iref;             // BLAS root inherits the leaf's level (:1944)
+#endif
         if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
         else {
           const uint32_t tb = __ldg(p.tv.node_tid + broot);
           if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
           else if ((tb & VSRT_TID_MASK) == CUR_TID()) PUSH_CUR(c);
-          else { c.slot |= (tb & VSRT_TID_SELF_ROOTED) ? SLOT_SELFROOT : 0u; PUSH_OTH(c); }
+          else { if (tb & VSRT_TID_SELF_ROOTED) SET_SELFROOT(c); PUSH_OTH(c); }
         }
       }
     }
@@ -379,6 +434,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   }
 #undef EMIT
 #undef PUSH_CUR
+#undef SET_SELFROOT
 #undef PUSH_OTH
 #undef TAKE
 #undef CUR_TID

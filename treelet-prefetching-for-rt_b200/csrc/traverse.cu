@@ -231,9 +231,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
     // ================= pop the next entry of every lane that wants one
     // TAKE: `e` holds the entry just taken from `current` (from_cur_) or from the front of `other`
-#define TAKE(from_cur_) do { \
-      const bool selfroot_ = (e.slot & SLOT_SELFROOT) != 0u, leaf_ = (e.slot & SLOT_LEAF) != 0u; \
-      e.slot &= SLOT_MASK; \
+#define TAKE(from_cur_, selfroot_in_, leaf_in_) do { \
+      const bool selfroot_ = (selfroot_in_), leaf_ = (leaf_in_); \
       if (MODE == VSRT_MODE_TREELET) { \
         if (from_cur_) { if (!VSRT_K1_NODE_ENTRY) cur_n--; in_cur = true; }       /* entries of `current` were pushed because node_tid == current treelet */ \
         else { \
@@ -264,11 +263,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         cur_n -= fc ? gone : 0;
         if (MODE == VSRT_MODE_TREELET) oth_n -= fc ? 0 : gone;
         const uint32_t cb = __byte_perm(t.y, t.z, 0x7770u + (ci - 16u));          // the child's byte: offset | flags
-        e.slot = (t.x + (cb & 15u)) | ((cb << 24) & 0xC0000000u); e.meta = t.w;
+        e.slot = t.x + (cb & 15u); e.meta = t.w;
+        TAKE(fc, (cb & 0x80u) != 0u, (cb & 0x40u) != 0u);
 #else
         e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
+        const uint32_t fl = e.slot; e.slot &= SLOT_MASK;
+        TAKE(fc, (fl & SLOT_SELFROOT) != 0u, (fl & SLOT_LEAF) != 0u);
 #endif
-        TAKE(fc);
       } else st = ST_FIN;
     }
     if (inner && __popc(__ballot_sync(full, st == ST_INT)) < INT_T) break;   // too few lanes at an internal node: let the other phases / the refill bring lanes back first

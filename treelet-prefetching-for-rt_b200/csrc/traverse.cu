@@ -43,6 +43,7 @@ VS_DEV bool e_top(const Entry& e) { return e_inst(e) == INST_NONE; }
 VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(one_bit)); return i; }   // FLO
 
 constexpr int THREADS = 128;
+VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_STATS
 #define VSRT_K1_STATS 0   // 1: count, per inner round, how many lanes are in which state (tools/k1_lane_states.py); costs ~10 %
 #endif
@@ -66,6 +67,15 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 // of this was measured and is slower -- the pop then runs for a few lanes at the cost of all, profiles/README.md.)
 #ifndef VSRT_K1_NODE_ENTRY
 #define VSRT_K1_NODE_ENTRY 1
+#endif
+// L1 prefetches (prefetch.global.L1) of node bytes a lane is known to need a little later:
+//   PF_LEAF  the BLAS leaf a lane has just taken -- it waits for the batched leaf phase, the leaf is cold (few rays share it)
+//   PF_NEXT  the child the lane will pop after the internal node it has just tested (node-entry stack only)
+#ifndef VSRT_K1_PF_LEAF
+#define VSRT_K1_PF_LEAF 0
+#endif
+#ifndef VSRT_K1_PF_NEXT
+#define VSRT_K1_PF_NEXT 0
 #endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
@@ -245,7 +255,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           } else { uint32_t s2_; in_cur = false; tid_known = true; cur_tid = host_to_slot(av, slot_to_host(av, e.slot) - (uint64_t)av.tlas_delta, s2_) ? root_rank(p.tv, s2_) : VSRT_NO_TID; } \
         } \
       } else if (!VSRT_K1_NODE_ENTRY) cur_n--; \
-      st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); } while (0)
+      st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); \
+      if (VSRT_K1_PF_LEAF && st == ST_LEAF) prefetch_l1(base + (uint64_t)e.slot * 64u); } while (0)
     // pop + internal-node phase run up to INNER_N times back to back (VSRT_K1_INNER): the refill and leaf votes around them are
     // amortised, at the price of idle / leaf lanes waiting a little longer
 #pragma unroll 1
@@ -323,6 +334,12 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u), moth = mask ^ mcur;
             if (moth) { oth_n++; stk[STACK_N - oth_n] = make_uint4(child0, ey, ez | (moth << 16), cmeta); }
             if (mcur) { stk[cur_n] = make_uint4(child0, ey, ez | (mcur << 16), cmeta); cur_n++; }
+#if VSRT_K1_PF_NEXT
+            {   // the child this lane pops next, if it is one of this node's: highest hit child in `current`, else (nothing older in `current`) in `other`
+              const uint32_t mnext = mcur ? mcur : (cur_n == 0 ? moth : 0u);
+              if (mnext) { uint32_t ti; asm("bfind.u32 %0, %1;" : "=r"(ti) : "r"(mnext)); prefetch_l1(base + (uint64_t)(child0 + (__byte_perm(ey, ez, 0x7770u + ti) & 15u)) * 64u); }
+            }
+#endif
           }
 #else
           else {

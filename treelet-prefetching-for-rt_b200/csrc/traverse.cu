@@ -71,6 +71,11 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 // L1 prefetches (prefetch.global.L1) of node bytes a lane is known to need a little later:
 //   PF_LEAF  the BLAS leaf a lane has just taken -- it waits for the batched leaf phase, the leaf is cold (few rays share it)
 //   PF_NEXT  the child the lane will pop after the internal node it has just tested (node-entry stack only)
+// LEAF_ASYNC: the 64 bytes of a BLAS leaf are copied global -> shared memory with cp.async (no registers, no L1 line to lose)
+// when the lane TAKES the leaf; the batched leaf phase, a round or two later, waits for the lane's own copies and reads them back.
+#ifndef VSRT_K1_LEAF_ASYNC
+#define VSRT_K1_LEAF_ASYNC 0
+#endif
 #ifndef VSRT_K1_PF_LEAF
 #define VSRT_K1_PF_LEAF 0
 #endif
@@ -101,6 +106,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
   // ---- functional counters (cuda-sim.h:155-166): per-CTA accumulators in shared memory, touched only when a ray is
   // finalised (keeps them out of the register file of the hot loop)
+#if VSRT_K1_LEAF_ASYNC
+  __shared__ uint4 s_leaf[4][THREADS];   // quarter j of the leaf of thread t (transposed: consecutive lanes, consecutive 16 bytes)
+#endif
   __shared__ unsigned int s_cnt[8];   // 0 sum_nodes 1 max_nodes 2 max_level 3 n_hit 4 n_any 5 n_term 6 n_rays_done 7 err
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -239,6 +247,16 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       if (__ballot_sync(full, st > ST_FIN) == 0u) { if (exhausted) break; else continue; }
     }
 
+#if VSRT_K1_LEAF_ASYNC
+#define LEAF_FETCH() do { if (st == ST_LEAF) { \
+      const uint8_t* g_ = base + (uint64_t)e.slot * 64u; \
+      _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) { \
+        const uint32_t sa_ = (uint32_t)__cvta_generic_to_shared(&s_leaf[j_][threadIdx.x]); \
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa_), "l"(g_ + 16 * j_) : "memory"); } \
+      asm volatile("cp.async.commit_group;" ::: "memory"); } } while (0)
+#else
+#define LEAF_FETCH() do { } while (0)
+#endif
     // ================= pop the next entry of every lane that wants one
     // TAKE: `e` holds the entry just taken from `current` (from_cur_) or from the front of `other`
 #define TAKE(from_cur_, selfroot_in_, leaf_in_) do { \
@@ -256,7 +274,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         } \
       } else if (!VSRT_K1_NODE_ENTRY) cur_n--; \
       st = !leaf_ ? ST_INT : (e_top(e) ? ST_INST : ST_LEAF); \
-      if (VSRT_K1_PF_LEAF && st == ST_LEAF) prefetch_l1(base + (uint64_t)e.slot * 64u); } while (0)
+      if (VSRT_K1_PF_LEAF && st == ST_LEAF) prefetch_l1(base + (uint64_t)e.slot * 64u); \
+      LEAF_FETCH(); } while (0)
     // pop + internal-node phase run up to INNER_N times back to back (VSRT_K1_INNER): the refill and leaf votes around them are
     // amortised, at the price of idle / leaf lanes waiting a little longer
 #pragma unroll 1
@@ -418,7 +437,15 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #endif
       if (st == ST_LEAF) {
         st = ST_POP;
+#if VSRT_K1_LEAF_ASYNC
+        Node64 q;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        { const uint4 a0 = s_leaf[0][threadIdx.x], a1 = s_leaf[1][threadIdx.x], a2 = s_leaf[2][threadIdx.x], a3 = s_leaf[3][threadIdx.x];
+          q.w[0] = a0.x; q.w[1] = a0.y; q.w[2] = a0.z; q.w[3] = a0.w; q.w[4] = a1.x; q.w[5] = a1.y; q.w[6] = a1.z; q.w[7] = a1.w;
+          q.w[8] = a2.x; q.w[9] = a2.y; q.w[10] = a2.z; q.w[11] = a2.w; q.w[12] = a3.x; q.w[13] = a3.y; q.w[14] = a3.z; q.w[15] = a3.w; }
+#else
         const Node64 q = load_node_now(base, e.slot);
+#endif
         EMIT(e.slot, C_DESC);
         if (((q.w[1] >> 29) & 1u) == 0u) {
           ACTIVATE(e_inst(e));
@@ -452,6 +479,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   }
 #undef EMIT
 #undef PUSH_CUR
+#undef LEAF_FETCH
 #undef SET_SELFROOT
 #undef PUSH_OTH
 #undef TAKE

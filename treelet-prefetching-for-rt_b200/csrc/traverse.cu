@@ -25,6 +25,11 @@
 #include "vsrt_device.cuh"
 #include <algorithm>
 
+#ifndef VSRT_K1_NODE_ENTRY
+#define VSRT_K1_NODE_ENTRY 1   // see below
+#endif
+#define VSRT_K1_NODE_ENTRY_DECL VSRT_K1_NODE_ENTRY
+
 namespace {
 
 // stack entry, two words:
@@ -34,7 +39,9 @@ namespace {
 //         first slot of the TLAS span (INST_NONE = the entry is a TLAS node).
 constexpr uint32_t INST_NONE = 0x7FFFFFu;
 constexpr uint32_t RAY_DEFERRED = 0xFFFFFFFFu;
-constexpr uint32_t SLOT_MASK = 0x1FFFFFFFu, SLOT_LEAF = 0x40000000u, SLOT_SELFROOT = 0x80000000u;
+#if !VSRT_K1_NODE_ENTRY_DECL
+constexpr uint32_t SLOT_MASK = 0x1FFFFFFFu, SLOT_LEAF = 0x40000000u, SLOT_SELFROOT = 0x80000000u;   // per-child stack entries (VSRT_K1_NODE_ENTRY=0) only
+#endif
 struct Entry { uint32_t slot; uint32_t meta; };
 VS_DEV uint32_t e_level(const Entry& e) { return (e.meta >> 23) & 0xffu; }
 VS_DEV uint32_t e_inst(const Entry& e) { return e.meta & INST_NONE; }

@@ -215,7 +215,10 @@ VS_DEV void make_object_ray(const uint8_t* base, uint32_t leaf_slot, const Ray8&
     d[i] = fadd(fadd(fadd(fadd(0.0f, fmul(m[0][i], w.dx)), fmul(m[1][i], w.dy)), fmul(m[2][i], w.dz)), fmul(m[3][i], 0.0f));
   }
   o[3] = fadd(fadd(fadd(fadd(0.0f, fmul(0.0f, w.ox)), fmul(0.0f, w.oy)), fmul(0.0f, w.oz)), fmul(1.0f, 1.0f));
-  c.ray.ox = fdiv(o[0], o[3]); c.ray.oy = fdiv(o[1], o[3]); c.ray.oz = fdiv(o[2], o[3]);
+  // the divide by w of make_transformed_ray (:172): w is exactly 1.0f for the affine matrices an instance leaf can hold (column 3 =
+  // (0,0,0,1): 0*x + 0*y + 0*z + 1*1), and x / 1.0f == x in IEEE arithmetic -- the three divisions run only if it ever is not
+  c.ray.ox = o[0]; c.ray.oy = o[1]; c.ray.oz = o[2];
+  if (o[3] != 1.0f) { c.ray.ox = fdiv(o[0], o[3]); c.ray.oy = fdiv(o[1], o[3]); c.ray.oz = fdiv(o[2], o[3]); }
   float norm = __fsqrt_rn(fadd(fadd(fmul(d[0], d[0]), fmul(d[1], d[1])), fmul(d[2], d[2])));
   c.tmult = norm;
   c.ray.dx = fdiv(d[0], norm); c.ray.dy = fdiv(d[1], norm); c.ray.dz = fdiv(d[2], norm);

@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __r
 constexpr int K3_THREADS = VSRT_K3_THREADS;
 constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_RAYS = K3_WARPS * 32;   // rays per CTA: every warp owns 32 consecutive rays and their contiguous output range
-constexpr int K3_ILP = 4;        // independent 32-record windows in flight per warp
+#ifndef VSRT_K3_ILP
+#define VSRT_K3_ILP 4
+#endif
+constexpr int K3_ILP = VSRT_K3_ILP;        // independent 32-record windows in flight per warp
 #ifndef VSRT_K3_HASH_BITS
 #define VSRT_K3_HASH_BITS 10
 #endif

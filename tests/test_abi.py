@@ -69,3 +69,36 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 text = open(os.path.join(dp, f)).read()
                 assert "libvsrt_oracle" not in text and "libvsrt_ref" not in text and "oracles" not in text, f
+
+
+def test_header_is_c99_and_unpack_inline(tmp_path):
+    """include/vsrt.h (and vsrt_scene.h) compile as strict C99 without warnings, and the header-only vsrt_unpack_txn
+    expands packed records: slot -> span -> address + device offset, size by record type, code 7 = TLAS internal node."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if not cc:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text(r'''
+#include "vsrt.h"
+#include "vsrt_scene.h"
+#include <stdio.h>
+int main(void) {
+  vsrt_packed_layout L; vsrt_txn t;
+  L.device_delta = 0x1000; L.n_spans = 2; L.reserved = 0;
+  L.spans[0].host = 0x10000; L.spans[0].slot0 = 0; L.spans[0].n_slots = 4;
+  L.spans[1].host = 0x80000; L.spans[1].slot0 = 4; L.spans[1].n_slots = 100;
+  vsrt_unpack_txn(&L, (5u << 3) | 7u, &t); printf("%llx %u %u\n", (unsigned long long)t.address, t.size, t.type);
+  vsrt_unpack_txn(&L, (2u << 3) | 2u, &t); printf("%llx %u %u\n", (unsigned long long)t.address, t.size, t.type);
+  vsrt_unpack_txn(&L, (3u << 3) | 3u, &t); printf("%llx %u %u\n", (unsigned long long)t.address, t.size, t.type);
+  return 0;
+}
+''')
+    exe = tmp_path / "hdr"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split()
+    assert out == ["81040", "64", "1", "11080", "128", "2", "110c0", "8", "3"]
+

@@ -150,7 +150,16 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   uint32_t closest_leaf = 0, closest_inst = INST_NONE;
   const uint32_t cap = p.cap;
 
+// A/B: staged records are written once and read once, by K3 -- streaming stores (evict-first) were meant to keep them from
+// displacing node bytes in L2, and are slower
+#ifndef VSRT_K1_EMIT_STREAMING
+#define VSRT_K1_EMIT_STREAMING 0   // measured: 1.887 vs 1.855 ms with st.global.cs
+#endif
+#if VSRT_K1_EMIT_STREAMING
+#define EMIT(slot_, code_) do { if (cnt < cap) __stcs(rstage + cnt, ((slot_) << 3) | (uint32_t)(code_)); cnt++; } while (0)
+#else
 #define EMIT(slot_, code_) do { if (cnt < cap) rstage[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
+#endif
 #define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
 #define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
 #define CUR_TID() (tid_known ? cur_tid : (tid_known = true, cur_tid = __ldg(p.tv.node_tid + cur_tid) & VSRT_TID_MASK))

@@ -53,6 +53,17 @@ def kat_arena(z448=1.0, z512=2.0):
     return sc.Arena(a, 0, [(320, len(a) - 320)])
 
 
+def kat_arena_unordered(z448=1.0, z512=2.0):
+    """kat_arena with the quantised x and z bounds of the BLAS node's second child swapped (lower 1, upper 0): a box the
+    reference still intersects (its slab test orders the planes with min / max, vulkan_ray_tracing.cc:183-257) but whose
+    near / far planes cannot be read off the ray's direction signs."""
+    a = kat_arena(z448, z512)
+    for ax in (0, 2):
+        a.bytes[384 + 28 + 12 * ax + 1] = 1      # lower bound of child 1 on this axis
+        a.bytes[384 + 34 + 12 * ax + 1] = 0      # upper bound
+    return a
+
+
 def kat_ray(flags):
     r = np.zeros(1, _abi.RAY)
     r["origin"][0] = (0, 0, -5); r["direction"][0] = (0, 0, 1); r["tmin"] = 0; r["tmax"] = 100; r["ray_flags"] = flags

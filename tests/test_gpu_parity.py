@@ -101,6 +101,15 @@ def test_wavefront_variant(api, monkeypatch, ntri, nb, ni, flags, budget, delta)
     run_case(api, s, rays, budget, delta=delta)
 
 
+def test_unordered_bounds_take_the_exact_path(api):
+    """A present child with quantised lower > upper bound: the fast slab test reads near / far planes off the ray's
+    direction signs and would miss the box, so K0 flags the arena and every ray runs the EXACT instantiation, which orders
+    the planes with the reference's MIN / MAX.  Traces, hits, treelets and counters against the oracle."""
+    rays = np.concatenate([helpers.kat_ray(0), helpers.kat_ray(1), sc.rays_random(300, seed=41)])
+    for budget in (256, 512):
+        run_case(api, helpers.kat_arena_unordered(), rays, budget)
+
+
 def test_staging_overflow_regrows(api, monkeypatch):
     """A ray that outgrows its staging segment: the batch is redone with doubled segments (several times here: 8 records to
     start with) and the functional counters are rolled back in between -- traces, hits and counters must come out as if

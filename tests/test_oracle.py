@@ -229,6 +229,23 @@ def test_coalescing_table_matches_reference():
     assert stats[0] > 40 and stats[1] > 10 and stats[2] > 10, stats      # loads merged, rows appended, rows shared between threads
 
 
+@pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built (no /root/reference)")
+def test_unordered_child_bounds_match_reference():
+    """A present child whose quantised lower bound exceeds its upper bound: the reference orders the slab planes with
+    min / max, so the box is hit as if it were ordered; the restatement must agree (the CUDA fast path cannot -- K0 sends
+    such an arena down the EXACT path, test_unordered_bounds_take_the_exact_path)."""
+    a = helpers.kat_arena_unordered()
+    rays = np.concatenate([helpers.kat_ray(0), helpers.kat_ray(1), sc.rays_random(200, seed=41)])
+    ref, port = oracles.RefOracle(), oracles.PortOracle()
+    for budget in (256, 512):
+        ref.register(a); ref.form(budget); port.register(a); port.form(budget)
+        for mode in (0, 1):
+            r, q = ref.trace(mode, rays), port.trace(mode, rays)
+            assert np.array_equal(r["offsets"], q["offsets"]) and np.array_equal(r["txns"], q["txns"])
+            assert np.array_equal(r["hits"]["prim"], q["hits"]["prim"])
+            assert int(r["hits"]["hit"][1]) == 1 and int(r["offsets"][2] - r["offsets"][1]) == 9   # the opaque KAT ray still visits both quads and hits
+
+
 def test_port_matches_coalescing_fixture():
     """The restatement's Coalescing-table replay against tests/golden/coalescing_proc1500.npz (recorded from the reference's
     traceRay with its own Coalescing table in the loop)."""

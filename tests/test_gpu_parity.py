@@ -110,6 +110,15 @@ def test_unordered_bounds_take_the_exact_path(api):
         run_case(api, helpers.kat_arena_unordered(), rays, budget)
 
 
+def test_denormal_bound_scale_takes_the_exact_path(api):
+    """Bound exponents below -118 make the scale 2^(e-8) a denormal float: the fast path builds the scale from the exponent
+    byte alone, so K0 flags the arena and the EXACT instantiation (general ldexpf form) runs."""
+    a = helpers.kat_arena()
+    a.bytes[384 + 18:384 + 21] = (-120) & 0xff
+    rays = np.concatenate([helpers.kat_ray(1), sc.rays_random(100, seed=43)])
+    run_case(api, a, rays, 512)
+
+
 def test_staging_overflow_regrows(api, monkeypatch):
     """A ray that outgrows its staging segment: the batch is redone with doubled segments (several times here: 8 records to
     start with) and the functional counters are rolled back in between -- traces, hits and counters must come out as if

@@ -154,7 +154,17 @@ def time_cpu(orc, scene, rays, mode, cores, steps, warmup):
     form_s = time.time() - t0
     n = len(rays)
     times, recs, nbytes = [], 0, 0
-    if orc.kind == "reference":
+    last = None
+    if orc.kind == "reference" and cores == 1:
+        # the reference as it runs: one thread, lane after lane, in this process -- the trace is kept for the parity sample
+        for it in range(warmup + steps):
+            t = time.perf_counter()
+            last = orc.trace(mode, rays, cap_per_ray=256)
+            dt = time.perf_counter() - t
+            if it >= warmup:
+                times.append(dt)
+            recs, nbytes = len(last["txns"]), int(last["txns"]["size"].sum())
+    elif orc.kind == "reference":
         _REF["orc"], _REF["rays"] = orc, rays
         chunks = [(n * i // cores, n * (i + 1) // cores, mode) for i in range(cores)]
         ctx = mp.get_context("fork")
@@ -174,8 +184,28 @@ def time_cpu(orc, scene, rays, mode, cores, steps, warmup):
             if it >= warmup:
                 times.append(dt)
             recs, nbytes = len(r["txns"]), int(r["txns"]["size"].sum())
+            last = r
     return {"rays_per_s": n * len(times) / sum(times), "ms_per_step": 1e3 * sum(times) / len(times), "form_s": form_s,
-            "records_per_ray": recs / max(n, 1), "bytes_per_ray": nbytes / max(n, 1)}
+            "records_per_ray": recs / max(n, 1), "bytes_per_ray": nbytes / max(n, 1), "trace": last}
+
+
+def parity_of(o, g):
+    """Bitwise comparison of an oracle trace (o) with the CUDA path's (g) for the same rays: per-ray record counts, every
+    {address, size, type}, every treelet id, hit flags / ids and the bit patterns of t, barycentrics and hit point."""
+    oh, gh = o["hits"], g["hits"]
+    checks = {
+        "offsets": np.array_equal(o["offsets"], g["offsets"]),
+        "txns": len(o["txns"]) == len(g["txns"]) and np.array_equal(o["txns"]["address"], g["txns"]["address"]) and
+                np.array_equal(o["txns"]["size"], g["txns"]["size"]) and np.array_equal(o["txns"]["type"], g["txns"]["type"]),
+        "treelet_ids": np.array_equal(o["treelet_ids"], g["treelet_ids"]),
+        "hit_ids": np.array_equal(oh["hit"], gh["hit_geometry"]) and np.array_equal(oh["prim"], gh["primitive_index"]) and
+                   np.array_equal(oh["geom"], gh["geometry_index"]) and np.array_equal(oh["instance_id"], gh["instance_index"]),
+        "hit_t_bary_point_bits": np.array_equal(oh["t"].view(np.uint32), gh["world_min_thit"].view(np.uint32)) and
+                                 np.array_equal(oh["bary"].view(np.uint32), gh["barycentric"].view(np.uint32)) and
+                                 np.array_equal(oh["point"].view(np.uint32), gh["intersection_point"].view(np.uint32)),
+    }
+    return {"rays": int(len(o["offsets"]) - 1), "records": int(len(o["txns"])), "equal": bool(all(checks.values())),
+            "checks": {k: bool(v) for k, v in checks.items()}}
 
 
 def run_reference(args):
@@ -242,64 +272,25 @@ def run_cuda(args):
     rays_pinned = torch.from_numpy(rays.view(np.uint8).reshape(-1)).pin_memory()
     rays_dev = rays_pinned.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    cptr, hptr, nt = ctx.counters_device()
-    reduce_bufs = None
+    # The path's only exchange: per-frame reduce of the counters + the treelet visit histogram, done by the library
+    # (vsrt_reduce_counters: snapshot on the traversal stream, one grouped NCCL all-reduce pair on the library's own stream into
+    # buffers it owns, fold into global totals), so the reduce of frame i overlaps the traversal of frame i + 1.
     if world > 1:
-        csum = torch.as_tensor(_DevArray(cptr, 8 * _abi.N_SUM), device=dev).view(torch.int64)
-        cmax = torch.as_tensor(_DevArray(cptr + 8 * _abi.N_SUM, 8 * _abi.N_MAX), device=dev).view(torch.int64)
-        hist = torch.as_tensor(_DevArray(hptr, 8 * nt), device=dev).view(torch.int64)
-        reduce_bufs = (csum, cmax, hist)
-
-    red_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    red_state = {"done": None, "out": None}
-    # The NCCL calls are enqueued by a helper thread: their host cost (~0.25 ms per frame for three collectives) would
-    # otherwise sit between two frames with the GPU idle; vsrt_trace_rays_device releases the GIL while it runs.
-    red_q = red_thread = None
-    if world > 1:
-        import queue
-        import threading
-        red_q = queue.Queue()
-
-        def _reducer():
-            torch.cuda.set_device(dev)
-            while True:
-                item = red_q.get()
-                if item is None:
-                    red_q.task_done()
-                    return
-                ready, bufs, done = item
-                with torch.cuda.stream(red_stream):
-                    red_stream.wait_event(ready)
-                    shard.reduce_counters(dist, *bufs)
-                    done.record(red_stream)
-                red_q.task_done()
-        red_thread = threading.Thread(target=_reducer, daemon=True)
-        red_thread.start()
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+    frames = {"n": 0}
 
     def step():
         with torch.cuda.stream(stream):
             ctx.trace_device(MODE, rays_dev.data_ptr(), n, stream.cuda_stream)
-            if reduce_bufs is not None:
-                # the path's only exchange: per-frame reduce of counters + treelet visit histogram, into
-                # scratch copies taken on the traversal stream (the per-rank counters keep their own totals).  The
-                # collectives run on a side stream, so the reduce of frame i overlaps the traversal of frame i+1.
-                bufs = (reduce_bufs[0].clone(), reduce_bufs[1].clone(), reduce_bufs[2].clone())
-                ready = torch.cuda.Event(); ready.record(stream)
-                done = torch.cuda.Event()
-                red_q.put((ready, bufs, done))
-                red_state["done"] = done
-                red_state["out"] = bufs
-        return red_state["out"]
-
-    def drain_reduces():
-        """All queued collectives are enqueued on the side stream; the caller may now wait on red_state['done']."""
-        if red_q is not None:
-            red_q.join()
+            frames["n"] += 1
+            if world > 1:
+                ctx.reduce_counters(stream.cuda_stream)
 
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~100 ms to come up
     for _ in range(args.warmup):
         step()
-    drain_reduces()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -309,16 +300,14 @@ def run_cuda(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     trav_ms = scan_ms = comp_ms = 0.0
     launches = 0
-    reduced = None
     for i in range(args.steps):
         with torch.cuda.stream(stream):
             flush.zero_()                       # evict the L2 between timed iterations (not timed)
             ev[i][0].record(stream)
-        reduced = step()
+        step()
         with torch.cuda.stream(stream):
-            if i == args.steps - 1 and red_state["done"] is not None:
-                drain_reduces()
-                stream.wait_event(red_state["done"])   # the last frame's reduce is inside the timed region
+            if i == args.steps - 1 and world > 1:
+                ctx.reduce_wait(stream.cuda_stream)    # the last frame's reduce is inside the timed region
             ev[i][1].record(stream)
         r = ctx.device_results()
         trav_ms += r.traverse_ms; scan_ms += r.scan_ms; comp_ms += r.compact_ms; launches += r.kernel_launches
@@ -327,8 +316,22 @@ def run_cuda(args):
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    if red_q is not None:
-        red_q.put(None)
+    reduce_check = None
+    if world > 1:
+        # every rank holds the global totals; they must be exactly world x this rank's (every rank traces a block of the same
+        # size) -- the round-1 bench printed sums that a racy reduce had doubled, so this is asserted, not just printed
+        gtot, ghist = ctx.reduced()
+        mine = ctx.counters()
+        rec_mine = sum(mine["mem_access_type_%d" % i] for i in range(9))
+        rec_glob = sum(gtot["mem_access_type_%d" % i] for i in range(9))
+        rec_all = torch.tensor([rec_mine], dtype=torch.int64, device=dev)
+        dist.all_reduce(rec_all, op=dist.ReduceOp.SUM)
+        reduce_check = {"ray_count": gtot["ray_count"], "expected_ray_count": world * n * frames["n"], "records": rec_glob,
+                        "expected_records": int(rec_all.item()), "treelet_hist_sum": int(ghist.sum()), "frames": frames["n"],
+                        "max_nodes_per_ray": gtot["max_nodes_per_ray"], "max_tree_depth": gtot["max_tree_depth"]}
+        reduce_check["reduce_ok"] = bool(reduce_check["ray_count"] == reduce_check["expected_ray_count"] and rec_glob == reduce_check["expected_records"] and
+                                         reduce_check["treelet_hist_sum"] <= rec_glob and gtot["max_nodes_per_ray"] >= mine["max_nodes_per_ray"])
+        assert reduce_check["reduce_ok"], "multi-GPU counter reduce returned wrong totals: %r" % (reduce_check,)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     res = ctx.device_results()
     n_txn, alg_bytes = res.n_txn, res.algorithmic_bytes
@@ -392,11 +395,13 @@ def run_cuda(args):
         peak, peak_src = peaks()
         k1_ms = trav_ms / args.steps
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_src = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_traverse_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_traverse_dram_bytes_per_launch")
+                traffic_src = "profiles/traffic.json: ncu --set full capture %s at commit %s" % (tj.get("capture"), tj.get("commit"))
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -413,7 +418,7 @@ def run_cuda(args):
                                "api": "vsrt_trace_rays_packed (host pinned buffers; hits + CSR offsets + 4-byte packed records + 4-byte treelet indices; the caller expands with vsrt_unpack_txn)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src,
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k1_ms,
                              "step_breakdown_ms": {"k_traverse": k1_ms, "scan": scan_ms / args.steps, "k_compact": comp_ms / args.steps}},
                 }
@@ -428,15 +433,97 @@ def run_cuda(args):
                                         "sample": "%d rays (every %d-th ray of the frame), 1 pass, single thread as the reference runs; treelet formation %.1f s excluded"
                                                   % (len(sample), stride, r["form_s"]),
                                         "host_cores_available": os.cpu_count()}
+                # the same rays through the CUDA path (host-buffer C-ABI call), compared bit for bit with what the CPU arm just
+                # produced: the headline number is for THIS scene, so its parity is checked on this scene, not extrapolated
+                g_tr = ctx.trace(MODE, sample)
+                line["parity_sample"] = parity_of(r["trace"], g_tr)
+                line["parity_sample"]["oracle"] = orc.kind
+                to, tg = orc.tables(), ctx.tables()
+                line["parity_sample"]["treelet_tables_equal"] = bool(all(np.array_equal(to[k], tg[k]) for k in ("roots", "counts", "node_addr", "node_size", "map_nodes", "map_roots")))
+                line["parity_sample"]["equal"] = bool(line["parity_sample"]["equal"] and line["parity_sample"]["treelet_tables_equal"])
             except Exception as e:   # the baseline is reporting only; never lose the GPU line to it
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        if reduced is not None:
-            line["reduced_counters"] = {"ray_count": int(reduced[0][_abi.COUNTER_FIELDS.index("ray_count")].item()),
-                                        "treelet_hist_sum": int(reduced[2].sum().item())}
+        if reduce_check is not None:
+            line["reduced_counters"] = reduce_check
+        if world == 1 and not args.no_incoherent:
+            try:
+                line["incoherent"] = run_incoherent(api, torch, dev, flush, peak, args.c4_triangles)
+            except Exception as e:   # reporting beside the headline; never lose the line to it
+                line["incoherent"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed_batch(ctx, torch, dev, mode, rays, flush, reps=2):
+    """One untimed pass (sizes the library's buffers), then `reps` passes with the L2 flushed before each; device time of the
+    three stages from the library's CUDA events on the launching stream.  Returns (mean ms dict, device results, hits on host)."""
+    from vsrt import _abi
+    rd = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev)
+    ctx.trace_device(mode, rd.data_ptr(), len(rays))
+    acc = {"k1": 0.0, "scan": 0.0, "k3": 0.0}
+    for _ in range(reps):
+        flush.zero_(); torch.cuda.synchronize()
+        ctx.trace_device(mode, rd.data_ptr(), len(rays))
+        r = ctx.device_results()
+        acc["k1"] += r.traverse_ms / reps; acc["scan"] += r.scan_ms / reps; acc["k3"] += r.compact_ms / reps
+    r = ctx.device_results()
+    src = torch.as_tensor(_DevArray(r.hits, len(rays) * _abi.HIT.itemsize), device=dev)
+    hits = src.cpu().numpy().view(_abi.HIT)
+    return acc, r, hits
+
+
+def run_incoherent(api, torch, dev, flush, peak, c4_triangles):
+    """BASELINE.json configs[2] and configs[3] (the incoherent-ray workloads the north star's target is stated on), one GPU,
+    device-resident, same clocks as the headline: rays/s over K1 + scan + K3 and K1's fraction of the HBM roofline."""
+    from vsrt import scene as sc, _abi
+    out = {}
+    # ---- C3: 2 M-triangle clustered scene, 1080p x 4 spp primary rays, diffuse bounces 1-4 generated from the previous hits
+    s = sc.Scene(2_000_000, seed=0x5EED0001 + 2, kind=sc.CLUSTERED)
+    ctx = api.Context(max_treelet_size=BUDGET, device=dev.index)
+    ctx.register(s); ti = ctx.form_treelets()
+    rays = sc.rays_primary(WIDTH, HEIGHT, spp=4, seed=SCENE_SEED + 1, flags=0)
+    tot = {"rays": 0, "ms": 0.0, "k1": 0.0, "bytes": 0, "records": 0}
+    per = []
+    for bounce in range(5):
+        ms, r, hits = _timed_batch(ctx, torch, dev, _abi.MODE_TREELET, rays, flush)
+        t = ms["k1"] + ms["scan"] + ms["k3"]
+        per.append({"bounce": bounce, "rays": int(len(rays)), "ms": t, "k1_ms": ms["k1"], "k3_ms": ms["k3"], "rays_per_s": len(rays) / t * 1e3,
+                    "records_per_ray": r.n_txn / max(len(rays), 1), "bytes_per_ray": r.algorithmic_bytes / max(len(rays), 1)})
+        if bounce > 0:
+            tot["rays"] += len(rays); tot["ms"] += t; tot["k1"] += ms["k1"]; tot["bytes"] += r.algorithmic_bytes; tot["records"] += r.n_txn
+        if bounce == 4:
+            break
+        rays = s.bounce(rays, hits, 77, bounce, 0)
+        if len(rays) == 0:
+            break
+    ach = tot["bytes"] / max(tot["k1"], 1e-9) / 1e6
+    out["C3"] = {"workload": "synthetic 2M-triangle clustered scene, 1080p x 4 spp, diffuse secondary rays of bounces 1-4 (incoherent), traceRayWithTreelets, %d B treelets" % BUDGET,
+                 "value": tot["rays"] / max(tot["ms"], 1e-9) * 1e3, "unit": "rays/s", "rays": tot["rays"], "ms": tot["ms"],
+                 "records_per_ray": tot["records"] / max(tot["rays"], 1), "bytes_per_ray": tot["bytes"] / max(tot["rays"], 1),
+                 "treelets": int(ti.n_treelets), "treelet_form_ms": float(ti.form_ms), "arena_bytes": int(s.size), "per_bounce": per,
+                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "algorithmic_bytes": int(tot["bytes"]), "kernel_ms": tot["k1"]}}
+    ctx.close(); del s
+    # ---- C4 at the shipped budget: 10 M-triangle scene, bounce-1 rays of a 1080p frame
+    s = sc.Scene(c4_triangles, seed=0x5EED0001 + 3)
+    ctx = api.Context(max_treelet_size=BUDGET, device=dev.index)
+    ctx.register(s); ti = ctx.form_treelets()
+    prim = sc.rays_primary(WIDTH, HEIGHT, flags=0)
+    _, _, hits = _timed_batch(ctx, torch, dev, _abi.MODE_TREELET, prim, flush, reps=1)
+    rays = s.bounce(prim, hits, 5, 1, 0)
+    ms, r, _ = _timed_batch(ctx, torch, dev, _abi.MODE_TREELET, rays, flush)
+    t = ms["k1"] + ms["scan"] + ms["k3"]
+    ach = r.algorithmic_bytes / max(ms["k1"], 1e-9) / 1e6
+    out["C4"] = {"workload": "synthetic %dM-triangle scene, diffuse bounce-1 rays of a 1080p frame (incoherent), traceRayWithTreelets, %d B treelets" % (c4_triangles // 1_000_000, BUDGET),
+                 "value": len(rays) / t * 1e3, "unit": "rays/s", "rays": int(len(rays)), "ms": t, "k1_ms": ms["k1"], "k3_ms": ms["k3"],
+                 "records_per_ray": r.n_txn / len(rays), "bytes_per_ray": r.algorithmic_bytes / len(rays),
+                 "treelets": int(ti.n_treelets), "treelet_form_ms": float(ti.form_ms), "arena_bytes": int(s.size),
+                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                              "algorithmic_bytes": int(r.algorithmic_bytes), "kernel_ms": ms["k1"]}}
+    ctx.close()
+    return out
 
 
 def res_stage_bytes(ctx):
@@ -453,6 +540,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=65536, help="rays of the frame the cpu_baseline leg traces")
     ap.add_argument("--ref-sample", type=int, default=2073600, help="rays per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incoherent", action="store_true", help="skip the C3 / C4 incoherent-ray configs reported beside the headline")
+    ap.add_argument("--c4-triangles", type=int, default=10_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

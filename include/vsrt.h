@@ -33,9 +33,12 @@ enum {
   VSRT_E_CAPACITY = -4,      /* caller buffer too small; required size reported */
   VSRT_E_UNKNOWN_AS = -5,    /* TLAS/BLAS address not registered (reference: abort(), :1568) */
   VSRT_E_BAD_BVH = -6,       /* arena violates an invariant the reference asserts on */
-  VSRT_E_STACK_OVERFLOW = -7,/* a ray exceeded the traversal stack capacity (raise stack_entries) */
+  VSRT_E_STACK_OVERFLOW = -7,/* a ray exceeded the traversal stack capacity (raise stack_entries, at most 384) */
   VSRT_E_BUDGET = -8,        /* treelet byte budget too small (reference: assert(remaining_bytes >= 0)) */
-  VSRT_E_UNSUPPORTED = -9    /* feature of the reference path not built yet (procedural leaves, remap in traces) */
+  VSRT_E_UNSUPPORTED = -9,   /* input beyond a documented limit of this implementation: arena above 32 GiB, instance leaves of one TLAS
+                                spread over more than 512 MiB, a ray with more than 4095 procedural-leaf visits, packed traces with
+                                per-BLAS offsets / remap, a Coalescing table beyond the reference's 100 rows */
+  VSRT_E_COMM = -10          /* NCCL not loadable or an NCCL call failed (multi-GPU counter reduce) */
 };
 
 /* ---- transaction record ABI: abstract_hardware_model.h:201-216, 315-321 ---- */
@@ -230,6 +233,33 @@ int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_
  * the popularity data the RT unit's treelet prefetcher votes on (shader.cc:3424-3433), accumulated over every
  * batch since the last vsrt_reset_counters / vsrt_form_treelets. */
 int vsrt_get_treelet_histogram(vsrt_context* ctx, uint64_t* hist, uint64_t capacity);
+
+/* ---- multi-GPU: the reduce of the functional counters and the treelet visit histogram ----
+ * The path shards by rays (one context per GPU, the BVH and the treelet tables replicated, rank r traces its own ray-id block);
+ * nothing is exchanged on the data path.  What a multi-GPU run has to combine are the counters above (cuda-sim.h:155-166) and the
+ * popularity histogram (shader.cc:3424-3433): SUM over the first VSRT_COUNTERS_N_SUM fields and the histogram, MAX over the last
+ * VSRT_COUNTERS_N_MAX.  The library does it with NCCL, bound at run time (dlopen of libnccl.so.2; VSRT_NCCL_LIB overrides).
+ *   vsrt_comm_unique_id   ncclGetUniqueId: rank 0 calls it and hands the 128 bytes to the other ranks by its own means
+ *   vsrt_comm_init        ncclCommInitRank on the context's device (collective: every rank calls it)
+ *   vsrt_comm_attach      use a communicator the caller already owns (an ncclComm_t); it is not destroyed by the library
+ *   vsrt_reduce_counters  enqueue one reduce of everything this rank traced since the previous one: a snapshot kernel on `stream`
+ *                         (a cudaStream_t, NULL = the context's; it must be the stream the batches ran on), then on the library's
+ *                         own stream one grouped ncclAllReduce pair -- u64 header, u32 histogram deltas -- into buffers the library
+ *                         owns, and a fold into the global totals.  Returns without waiting: the reduce of frame i overlaps the
+ *                         traversal of frame i + 1.  Collective: every rank calls it the same number of times.
+ *   vsrt_reduce_wait      make `stream` wait for the reduces enqueued so far (no host wait); stream == (void*)-1 waits on the host
+ *   vsrt_reduced_get      global totals over all ranks and reduces since vsrt_comm_init / vsrt_reset_counters (host wait included).
+ *                         VSRT_E_CAPACITY if 2^32 or more records were traced between two reduces (a 32-bit delta may have wrapped)
+ *   vsrt_reduced_device   the device copies of the same (valid after vsrt_reduce_wait) */
+#define VSRT_COMM_ID_BYTES 128
+int vsrt_comm_unique_id(uint8_t id[VSRT_COMM_ID_BYTES]);
+int vsrt_comm_init(vsrt_context* ctx, uint32_t n_ranks, uint32_t rank, const uint8_t id[VSRT_COMM_ID_BYTES]);
+int vsrt_comm_attach(vsrt_context* ctx, void* nccl_comm, uint32_t n_ranks, uint32_t rank);
+int vsrt_comm_destroy(vsrt_context* ctx);
+int vsrt_reduce_counters(vsrt_context* ctx, void* stream);
+int vsrt_reduce_wait(vsrt_context* ctx, void* stream);
+int vsrt_reduced_get(vsrt_context* ctx, vsrt_counters* out, uint64_t* treelet_hist, uint64_t capacity);
+int vsrt_reduced_device(vsrt_context* ctx, void** counters_dev, void** treelet_hist_dev, uint64_t* n_treelets);
 
 /* ---- RT-unit replay helpers: what rt_unit (gpgpu-sim/shader.cc) does with the trace, batched over the last batch ----
  * rt_unit::sort_mem_accesses (shader.cc:3012-3089) applied to every ray's list: method = -sort_method (0 strict treelet

@@ -297,8 +297,8 @@ int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
   const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
   if (n_blocks == 0) return VSRT_OK;
-  static int n_sm = 0;
-  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  int n_sm = 148;
+  if (VSRT_K3_PERSIST) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   int per_sm = K3_CTAS_PER_SM;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact<false>, K3_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
   const uint64_t grid = VSRT_K3_PERSIST ? std::min<uint64_t>(n_blocks, (uint64_t)n_sm * (uint64_t)per_sm) : n_blocks;

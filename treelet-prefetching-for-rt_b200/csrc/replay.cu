@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128) k_table_events(const TableParams p) {
   const uint32_t cnt = min(p.counts[r], p.cap);
   const uint32_t* seg = p.stage + r * (uint64_t)p.cap;
   const bool anyhit_ray = p.mode == VSRT_MODE_DFS && !(__ldg(&p.rays[r].ray_flags) & VSRT_RAY_FLAG_OPAQUE);
-  const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
+  const uint32_t inst_base = av.inst_base;   // lowest instance-leaf slot of the TLAS (K0)
   if (!FILL) {
     uint32_t n_any = 0;
     if (anyhit_ray) for (uint32_t k = 0; k < cnt; k++) n_any += (seg[k] & 7u) == C_QUAD_HIT;

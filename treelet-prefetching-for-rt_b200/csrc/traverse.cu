@@ -95,6 +95,7 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
+constexpr int PUSH_MAX = VSRT_K1_NODE_ENTRY ? 2 : 6;   // stack entries one internal node can push in TREELET mode: one per list, or one per child
 enum { ST_IDLE = 0, ST_DEFER = 1, ST_FIN = 2, ST_POP = 3, ST_INT = 4, ST_INST = 5, ST_LEAF = 6 };   // lane state (DEFER: the ray is handed to the EXACT pass at the next refill)
 
 // The ray the lane is currently testing against: the world ray inside the TLAS, the object-space ray of instance
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
+  const uint32_t inst_base = av.inst_base;   // lowest instance-leaf slot of the TLAS (K0)
   const int REFILL_T = (int)p.refill_t, LEAF_T = (int)p.leaf_t;
   constexpr int INT_T = VSRT_K1_INT_T, INNER_N = VSRT_K1_INNER;
   const bool only_deferred = EXACT && p.only_deferred != 0;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             }
           }
           const uint32_t mcur = mask & mc;
-          if (cur_n + oth_n + 6 > STACK_N) err |= EF_STACK;      // room for six children, however many are pushed
+          if (cur_n + oth_n + PUSH_MAX > STACK_N) err |= EF_STACK;      // room for everything this node can push
 #if VSRT_K1_NODE_ENTRY
           else {
             const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u), moth = mask ^ mcur;
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #endif
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
-          if (cur_n + 6 > STACK_N) err |= EF_STACK;
+          if (cur_n + (VSRT_K1_NODE_ENTRY ? 1 : 6) > STACK_N) err |= EF_STACK;
 #if VSRT_K1_NODE_ENTRY
           else if (mask) {
             const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u);
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       uint32_t hdr = 0, broot = 0;
       const uint32_t iref = e.slot - inst_base;
       if (!instance_blas_header(av, e.slot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; st = ST_FIN; }
-      else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; st = ST_FIN; }
+      else if (e.slot < inst_base || iref >= INST_NONE) { err |= EF_BAD_BVH; st = ST_FIN; }   // cannot happen for an arena K0 accepted (it bounds the instance-leaf span)
       else {
         EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
 #if VSRT_K1_NODE_ENTRY
@@ -530,12 +531,14 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
 template <int MODE, int STACK_N, bool EXACT>
 int launch_mode(const TraverseParams& p, cudaStream_t st) {
-  static int blocks_per_sm = 0, n_sm = 0;
-  if (blocks_per_sm == 0) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_traverse<MODE, STACK_N, EXACT>, THREADS, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 4;
+  // occupancy of this instantiation, cached per device (contexts on different GPUs may live in one process)
+  static int s_blocks[64], s_sm[64];
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
+  if (s_blocks[dev] == 0) {
+    cudaDeviceGetAttribute(&s_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_blocks[dev], k_traverse<MODE, STACK_N, EXACT>, THREADS, 0) != cudaSuccess || s_blocks[dev] < 1) s_blocks[dev] = 4;
   }
+  const int blocks_per_sm = s_blocks[dev], n_sm = s_sm[dev];
   // persistent grid (a multiple of the SM count): every resident warp keeps pulling rays until the counter runs out
   const uint64_t want = (p.n_rays + THREADS - 1) / THREADS;
   const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t inst_base = av.spans[av.n_spans == 1 ? 0 : span_of_slot(av, av.tlas_slot)].slot0;
+  const uint32_t inst_base = av.inst_base;   // lowest instance-leaf slot of the TLAS (K0)
   const bool only_deferred = EXACT && p.only_deferred != 0;
   const uint32_t cap = p.cap;
   const int STACK_N = (int)p.stack_n;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(WF_THREADS, VSRT_WF_MIN_BLOCKS) k_traverse_wf(
         const uint32_t iref = eslot - inst_base;
         bool dead = false;
         if (!instance_blas_header(av, eslot, hdr) || !header_root(av, hdr, broot)) { err |= EF_BAD_BVH; dead = true; }
-        else if (eslot < inst_base || iref >= INST_NONE) { err |= EF_UNSUPPORTED; dead = true; }
+        else if (eslot < inst_base || iref >= INST_NONE) { err |= EF_BAD_BVH; dead = true; }   // cannot happen for an arena K0 accepted
         else {
           EMIT(hdr, C_STRUCT);                                                     // BLAS header record, :1913 / :2645
           uint2 c = make_uint2(broot, (((emeta >> 23) & 0xffu) << 23) | iref);     // BLAS root inherits the leaf's level (:1944)

@@ -27,13 +27,14 @@ struct FormState {
   unsigned int* n_roots;
   unsigned long long* total_bvh;
   uint32_t* err;
+  uint32_t* inst_range;        // [0] lowest, [1] highest instance-leaf slot met (K1 names an instance by its slot relative to [0])
 };
 
 VS_DEV uint64_t mk_entry(uint32_t slot, uint32_t kind) { return (uint64_t)slot | ((uint64_t)kind << 32); }
 
 struct Walker {
-  const ArenaView& av; uint64_t* list; uint32_t n; int remaining; uint32_t err; uint32_t n_inst; unsigned long long bytes;
-  VS_DEV Walker(const ArenaView& a, uint64_t* l, int budget) : av(a), list(l), n(0), remaining(budget), err(0), n_inst(0), bytes(0) {}
+  const ArenaView& av; uint64_t* list; uint32_t n; int remaining; uint32_t err; uint32_t n_inst; unsigned long long bytes; uint32_t inst_lo, inst_hi;
+  VS_DEV Walker(const ArenaView& a, uint64_t* l, int budget) : av(a), list(l), n(0), remaining(budget), err(0), n_inst(0), bytes(0), inst_lo(0xFFFFFFFFu), inst_hi(0) {}
   VS_DEV void charge(int b) { remaining -= b; bytes += (unsigned)b; if (remaining < 0) err |= EF_BUDGET; }   // assert(remaining_bytes >= 0)
   // "process" one popped candidate: append to the node list and charge its bytes (:886-1114)
   VS_DEV void process(uint32_t slot, uint32_t kind) {
@@ -70,6 +71,7 @@ struct Walker {
     } else if (kind == K_INSTANCE) {
       if (slot + 1 >= av.n_slots) { err |= EF_BAD_BVH; return; }
       charge(128); list[n++] = mk_entry(slot, K_INSTANCE); n_inst++;
+      inst_lo = min(inst_lo, slot); inst_hi = max(inst_hi, slot);
       uint32_t hdr = 0; int64_t d;
       if (!instance_blas_header(av, slot, hdr)) { err |= EF_BAD_BVH; return; }
       if (!blas_delta_of(av, hdr, d)) { err |= EF_UNKNOWN_AS; return; }                                    // assert :973
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const For
   }
   r_count[begin + t] = n;
   atomicAdd(fs.total_bvh, w.bytes);
+  if (w.n_inst) { atomicMin(fs.inst_range, w.inst_lo); atomicMax(fs.inst_range + 1, w.inst_hi); }
   if (w.err) atomicOr(fs.err, w.err);
 }
 
@@ -283,14 +286,14 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   std::vector<uint64_t*> pools;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_roots = 1, begin = 0, h_err = 0;
-  unsigned long long h_scal[2] = { 0, 0 }, n_entries = 0;
+  unsigned long long h_scal[3] = { 0, 0, 0 }, n_entries = 0;
   memset(out, 0, sizeof(*out)); memset(res, 0, sizeof(*res));
   if (budget < 192) { snprintf(errbuf, errcap, "max_treelet_size %u < 192 (an instance-leaf root is charged 128+64 bytes, reference asserts)", budget); return VSRT_E_BUDGET; }
 
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(cudaMalloc(&claimed, (size_t)nw * 4)); CK(cudaMemsetAsync(claimed, 0, (size_t)nw * 4, st));
   CK(cudaMalloc(&roots, (size_t)ns * sizeof(uint2)));
-  CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 16)); CK(cudaMemsetAsync(scal, 0, 16, st));
+  CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 24)); CK(cudaMemsetAsync(scal, 0, 24, st)); CK(cudaMemsetAsync(scal + 2, 0xff, 4, st));   // [2] = {lowest = ~0, highest = 0} instance-leaf slot
   CK(cudaMalloc(&r_count, (size_t)ns * 4)); CK(cudaMalloc(&r_list, (size_t)ns * 8));
   CK(cudaMemsetAsync(err_flags_dev, 0, 4, st));
   CK(cudaEventRecord(ev0, st));
@@ -304,7 +307,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
     CK(cudaStreamSynchronize(st));
   }
   {
-    FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev };
+    FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev, reinterpret_cast<uint32_t*>(scal + 2) };
     while (begin < n_roots) {
       const uint32_t count = n_roots - begin;
       uint64_t* pool = nullptr;
@@ -349,9 +352,19 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(const_cast<uint8_t*>(av.base), ns, tl_node, n_entries, node_tid);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev1, st));
-  CK(cudaMemcpyAsync(h_scal, scal, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_scal, scal, 24, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&res->ms, ev0, ev1));
+  {
+    // K1's stack entries name an instance leaf by its slot relative to the LOWEST instance leaf of the TLAS, in 23 bits: the
+    // instance leaves of one TLAS (contiguous children of its internal nodes) must span less than 2^23 slots = 512 MiB
+    const uint32_t lo = (uint32_t)h_scal[2], hi = (uint32_t)(h_scal[2] >> 32);
+    res->inst_base = lo == 0xFFFFFFFFu ? 0u : lo;
+    if (lo != 0xFFFFFFFFu && hi - lo >= 0x7FFFFFu) {
+      snprintf(errbuf, errcap, "the instance leaves of this TLAS span %llu bytes; K1 addresses them in 23 bits of 64-byte slots (512 MiB, about 4 M instances)", (unsigned long long)(hi - lo) * 64ull);
+      rc = VSRT_E_UNSUPPORTED; goto done;
+    }
+  }
   res->n_treelets = n_roots; res->n_entries = n_entries; res->n_mapped = h_scal[1]; res->total_bvh = h_scal[0];
   out->node_tid = node_tid; out->root_bits = claimed; out->root_prefix = prefix; out->tl_root = tl_root;
   out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node;

@@ -2,7 +2,7 @@
 // file-scope statics of vulkan_ray_tracing.cc: tlas_addr, blas_addr_map, treeletsFormed, rayCount, the treelet
 // maps), arena upload, and the K1 -> scan -> K3 pipeline.  No CPU implementation of the path exists here: every
 // entry point that computes launches the CUDA kernels of treelets.cu / traverse.cu / compact.cu.
-#include "vsrt_internal.h"
+#include "vsrt_context.h"
 #include <algorithm>
 #include <cstdio>
 #include <cstdarg>
@@ -12,74 +12,18 @@
 #include <vector>
 
 namespace {
-
-struct Reg { uint64_t host, size, dev; bool tlas; };
-
 thread_local char g_create_error[512] = "";
-
-template <typename T> struct DevBuf {
-  T* p = nullptr; size_t cap = 0;
-  cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = nullptr) {
-    if (n <= cap) return cudaSuccess;
-    size_t nc = std::max(n, cap + cap / 2);
-    T* q = nullptr; cudaError_t e = cudaMalloc(&q, nc * sizeof(T));
-    if (e != cudaSuccess) { nc = n; e = cudaMalloc(&q, nc * sizeof(T)); if (e != cudaSuccess) return e; }
-    if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
-    p = q; cap = nc; return cudaSuccess;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
 }  // namespace
 
-struct vsrt_context {
-  vsrt_config cfg;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  // registration (allocTLAS / allocBLAS)
-  std::vector<Reg> regs;
-  bool committed = false;
-  // arena
-  uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
-  std::vector<Span> spans; Span* d_spans = nullptr;
-  std::vector<BlasReg> blas; BlasReg* d_blas = nullptr;
-  // treelets (treeletsFormed + the static maps)
-  bool formed = false; uint64_t formed_tlas = 0; uint32_t formed_budget = 0;
-  FormOutputs fo{}; FormResult fr{};
-  std::vector<uint32_t> h_node_tid, h_tl_root; std::vector<uint64_t> h_tl_off, h_tl_node; bool mirrors = false;
-  // per-batch buffers
-  DevBuf<vsrt_ray> d_rays; DevBuf<vsrt_hit> d_hits; DevBuf<uint32_t> d_stage; DevBuf<uint32_t> d_counts;
-  DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint32_t> d_packed; DevBuf<uint8_t> d_scan_tmp;
-  uint32_t stage_cap = 128;
-  DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
-  DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
-  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
-  // pinned host memory: the per-batch read-backs (record total, error flags, counters) land here without a staging copy, and
-  // small host-buffer calls (a warp's 32 rays) bounce their inputs and outputs through it so that a call is two queues of async
-  // copies and two synchronisations instead of a blocking copy per array
-  uint8_t* h_pin = nullptr;
-  static constexpr size_t PIN_HEAD = 1024, PIN_BYTES = 4u << 20;
-  DevCounters h_prev{};
-  DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
-  // -remap_to_treelet_layout: where gpgpusim_malloc put treelet_layout_bvh (:1477), and the per-slot table
-  uint64_t layout_base = 0; bool layout_base_set = false; DevBuf<uint64_t> d_remap; bool remap_valid = false;
-  // replay helpers: sorted copy of the last trace, inverted treelet lists (slot -> (treelet, position))
-  DevBuf<vsrt_txn> d_txns_sorted; DevBuf<uint32_t> d_tids_sorted; DevBuf<uint64_t> d_sort_keys;
-  uint64_t* d_inv_off = nullptr; uint2* d_inv = nullptr;
-  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-  vsrt_device_results last{};
-  uint64_t last_tlas = 0; int last_mode = 0; const vsrt_ray* last_rays = nullptr;
-};
-
-namespace {
-
-int fail(vsrt_context* c, int code, const char* fmt, ...) {
+int vsrt_fail(vsrt_context* c, int code, const char* fmt, ...) {
   char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
   if (c) c->err = buf; else snprintf(g_create_error, sizeof(g_create_error), "%s", buf);
   return code;
 }
+
+namespace {
+
+template <typename... A> int fail(vsrt_context* c, int code, const char* fmt, A... a) { return vsrt_fail(c, code, fmt, a...); }
 #define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, VSRT_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } while (0)
 
 void free_treelets(vsrt_context* c) {
@@ -87,6 +31,7 @@ void free_treelets(vsrt_context* c) {
   c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
   cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
+  vsrt_comm_treelets_changed(c);
 }
 
 const Reg* find_tlas(const vsrt_context* c, uint64_t host) {
@@ -111,6 +56,7 @@ int make_view(vsrt_context* c, uint64_t tlas_host, ArenaView* av) {
   av->base = c->d_arena; av->n_slots = (uint32_t)(c->arena_bytes / 64); av->n_spans = (uint32_t)c->spans.size(); av->n_blas = (uint32_t)c->blas.size();
   av->tlas_slot = slot; av->spans = c->d_spans; av->blas = c->d_blas; av->tlas_delta = (int64_t)(t->dev - t->host);
   av->uniform_delta = 1; av->force_exact = (c->formed && c->fr.nonfinite) ? 1u : 0u;
+  av->inst_base = c->formed ? c->fr.inst_base : 0u; av->pad2 = 0;
   for (const BlasReg& b : c->blas) if (b.delta != av->tlas_delta) av->uniform_delta = 0;
   return VSRT_OK;
 }
@@ -157,6 +103,8 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
   CUDA_OK(c, c->d_hist.ensure(std::max<size_t>(c->fr.n_treelets, 1)));
   CUDA_OK(c, cudaMemsetAsync(c->d_hist.p, 0, (size_t)c->fr.n_treelets * 8, c->stream));
   c->hist_n = c->fr.n_treelets;
+  // a trace call may run on a caller stream: everything queued on the context's stream above must have landed first
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return VSRT_OK;
 }
 
@@ -221,7 +169,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
     cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
     cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
-    cp.err_flags = c->d_err; cp.fatal_mask = EF_BAD_BVH | EF_STACK | EF_TRACE_CAP;
+    cp.err_flags = c->d_err; cp.fatal_mask = EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED;
     uint64_t queued_cap = std::min(c->d_txns.cap, c->d_tids.cap);
     if (queued_cap && n) {
       cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = queued_cap;
@@ -236,10 +184,14 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
     memcpy(&total, c->h_pin, 8); memcpy(&h_err, c->h_pin + 8, 4); memcpy(&now, c->h_pin + 16, sizeof(now));
-    if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
-    if (h_err & EF_STACK) {
+    if (h_err & (EF_BAD_BVH | EF_STACK | EF_UNSUPPORTED)) {
+      // a failed batch leaves no trace in the counters (rayCount, g_rt_* and accessedDataSize are restored); K3 did not run
       cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st);
-      return fail(c, VSRT_E_STACK_OVERFLOW, "a ray needed more than %u traversal-stack entries; raise vsrt_config.stack_entries", c->cfg.stack_entries ? c->cfg.stack_entries : 96);
+      cudaStreamSynchronize(st);
+      c->last = vsrt_device_results{};
+      if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
+      if (h_err & EF_STACK) return fail(c, VSRT_E_STACK_OVERFLOW, "a ray needed more than %u traversal-stack entries; raise vsrt_config.stack_entries (at most 384)", c->cfg.stack_entries ? c->cfg.stack_entries : 96);
+      return fail(c, VSRT_E_UNSUPPORTED, "a ray visited more than 4095 procedural leaves (or 2^20 - 1 nodes): beyond what the per-ray staging segment records");
     }
     if (h_err & EF_TRACE_CAP) {   // a ray produced more records than its staging segment holds: grow and redo the batch
       if (attempt >= 8) return fail(c, VSRT_E_CAPACITY, "per-ray trace staging overflow");
@@ -322,6 +274,7 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
   if (c->cfg.max_treelet_size == 0) c->cfg.max_treelet_size = 49152;
+  if (c->cfg.stack_entries > 384) { vsrt_destroy(c); return fail(nullptr, VSRT_E_INVALID, "vsrt_config.stack_entries = %u: the traversal kernel is built for at most 384 entries per ray", cfg->stack_entries); }
   // initial staging records per ray (doubles, with the batch redone, whenever a ray outgrows it); the knob exists for the tests
   if (const char* sc = getenv("VSRT_STAGE_CAP")) { const int v = atoi(sc); if (v >= 4 && v <= (1 << 20)) c->stage_cap = (uint32_t)v; }
   *out = c;
@@ -332,6 +285,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  vsrt_comm_release(c);
   free_treelets(c);
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
@@ -650,7 +604,7 @@ int vsrt_reset_counters(vsrt_context* c) {
   CUDA_OK(c, cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
   c->h_prev = DevCounters{};
   if (c->hist_n) CUDA_OK(c, cudaMemset(c->d_hist.p, 0, (size_t)c->hist_n * 8));
-  return VSRT_OK;
+  return vsrt_comm_counters_reset(c);
 }
 int vsrt_get_treelet_histogram(vsrt_context* c, uint64_t* hist, uint64_t capacity) {
   if (!c || !hist) return VSRT_E_INVALID;

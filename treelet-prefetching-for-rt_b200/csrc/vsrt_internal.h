@@ -52,6 +52,8 @@ struct ArenaView {
   int64_t tlas_delta;     // tlas_addr - _topLevelAS
   uint32_t uniform_delta; // 1 if every BLAS delta equals tlas_delta (then both reference conventions coincide)
   uint32_t force_exact;   // 1 if some node origin is not finite: a NaN can reach the slab test, keep the ternary MIN/MAX
+  uint32_t inst_base;     // lowest instance-leaf slot of the formed TLAS (K0): stack entries hold instance slots relative to it
+  uint32_t pad2;
 };
 
 struct TreeletView {
@@ -73,7 +75,7 @@ enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 1
 enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */, EF_NEED_EXACT = 128 /* not an error */ };
 
 // ---- launchers (each file implements its kernels) ----
-struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; };
+struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; uint32_t inst_base; };
 struct FormOutputs {      // device allocations owned by the context
   uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
 };

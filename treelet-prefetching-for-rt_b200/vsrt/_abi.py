@@ -22,7 +22,8 @@ FLAG_TERMINATE_ON_FIRST_HIT = 0x4
 MODE_DFS, MODE_TREELET = 0, 1
 
 ERRORS = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "CAPACITY", -5: "UNKNOWN_AS",
-          -6: "BAD_BVH", -7: "STACK_OVERFLOW", -8: "BUDGET", -9: "UNSUPPORTED"}
+          -6: "BAD_BVH", -7: "STACK_OVERFLOW", -8: "BUDGET", -9: "UNSUPPORTED", -10: "COMM"}
+COMM_ID_BYTES = 128
 
 
 class Config(ctypes.Structure):

@@ -30,7 +30,9 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_counters_device", "vsrt_get_treelet_histogram", "vsrt_sort_trace", "vsrt_prefetch_vote", "vsrt_prefetch_chunks", "vsrt_schedule_pick",
            "vsrt_table_events", "vsrt_table_event_stores", "vsrt_coalescing_events", "vsrt_coalescing_event_stores", "vsrt_coalescing_event_load",
            "vsrt_packed_layout_get", "vsrt_trace_fetch_packed", "vsrt_trace_rays_packed", "vsrt_unpack_txns",
-           "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image"]
+           "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image",
+           "vsrt_comm_unique_id", "vsrt_comm_init", "vsrt_comm_attach", "vsrt_comm_destroy", "vsrt_reduce_counters", "vsrt_reduce_wait",
+           "vsrt_reduced_get", "vsrt_reduced_device"]
 
 
 class VsrtError(RuntimeError):
@@ -96,8 +98,26 @@ def load():
     L.vsrt_reset_counters.argtypes = [c_vp]
     L.vsrt_counters_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
     L.vsrt_get_treelet_histogram.argtypes = [c_vp, c_vp, c_u64]
+    L.vsrt_comm_unique_id.argtypes = [c_vp]
+    L.vsrt_comm_init.argtypes = [c_vp, c_u32, c_u32, c_vp]
+    L.vsrt_comm_attach.argtypes = [c_vp, c_vp, c_u32, c_u32]
+    L.vsrt_comm_destroy.argtypes = [c_vp]
+    L.vsrt_reduce_counters.argtypes = [c_vp, c_vp]
+    L.vsrt_reduce_wait.argtypes = [c_vp, c_vp]
+    L.vsrt_reduced_get.argtypes = [c_vp, c_vp, c_vp, c_u64]
+    L.vsrt_reduced_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
     _lib = L
     return L
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); hand the 128 bytes to the other ranks by any means."""
+    L = load()
+    b = (ctypes.c_uint8 * _abi.COMM_ID_BYTES)()
+    rc = L.vsrt_comm_unique_id(b)
+    if rc:
+        raise VsrtError(rc, L.vsrt_last_error(None).decode())
+    return bytes(b)
 
 
 def parse_config(text):
@@ -434,6 +454,29 @@ class Context:
         h = np.zeros(n, np.uint64)
         self._ck(self.L.vsrt_get_treelet_histogram(self.h, _abi.ptr(h), n))
         return h
+
+    # ---- multi-GPU counter / histogram reduce (NCCL inside the library) ----------------------------------
+    def comm_init(self, n_ranks, rank, unique_id):
+        b = (ctypes.c_uint8 * _abi.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.vsrt_comm_init(self.h, n_ranks, rank, b))
+
+    def comm_destroy(self):
+        self._ck(self.L.vsrt_comm_destroy(self.h))
+
+    def reduce_counters(self, stream=None):
+        """Enqueue one reduce of what this rank traced since the previous one (returns without waiting)."""
+        self._ck(self.L.vsrt_reduce_counters(self.h, stream))
+
+    def reduce_wait(self, stream=None, host=False):
+        self._ck(self.L.vsrt_reduce_wait(self.h, c_vp(-1 & 0xFFFFFFFFFFFFFFFF) if host else stream))
+
+    def reduced(self, want_hist=True):
+        """Global totals over all ranks: (counter dict, treelet histogram)."""
+        a = np.zeros(_abi.N_SUM + _abi.N_MAX, np.uint64)
+        n = self.treelet_info().n_treelets if want_hist else 0
+        h = np.zeros(n, np.uint64) if want_hist else None
+        self._ck(self.L.vsrt_reduced_get(self.h, _abi.ptr(a), _abi.ptr(h), n))
+        return dict(zip(_abi.COUNTER_FIELDS, (int(x) for x in a))), h
 
     def counters_device(self):
         cp, hp, n = c_vp(), c_vp(), c_u64()

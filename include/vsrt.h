@@ -124,9 +124,12 @@ typedef struct vsrt_config {
   uint32_t remap_to_treelet_layout; /* -remap_to_treelet_layout */
   uint32_t treelet_remap_stride;    /* -treelet_remap_stride */
   uint32_t load_treelet_metadata;   /* -load_treelet_metadata */
-  uint32_t stack_entries;           /* per-ray traversal stack capacity (0 = default 96) */
-  uint32_t reserved;
+  uint32_t stack_entries;           /* per-ray traversal stack capacity (0 = default 96, at most 384) */
+  uint32_t ray_order;               /* VSRT_RAY_ORDER_*: the order in which the GPU picks up the rays of a batch.  Results never depend
+                                       on it (every output is indexed by the ray's position in the batch); it only decides which rays
+                                       share a warp.  AUTO sorts a batch by origin cell + direction unless all its rays share one origin */
 } vsrt_config;
+enum { VSRT_RAY_ORDER_AUTO = 0, VSRT_RAY_ORDER_INPUT = 1, VSRT_RAY_ORDER_SORTED = 2 };
 
 typedef struct vsrt_context vsrt_context;
 
@@ -217,7 +220,7 @@ typedef struct vsrt_device_results {
   uint64_t algorithmic_bytes; /* sum of txn.size over the batch == accessedDataSize delta */
   float traverse_ms, scan_ms, compact_ms; /* device time of the three stages of the last batch */
   uint32_t kernel_launches;  /* kernels launched by the last batch */
-  uint32_t reserved;
+  float order_ms;            /* device time of the ray-order sort that preceded the traversal (0 when the batch was not sorted) */
 } vsrt_device_results;
 int vsrt_trace_device_results(vsrt_context* ctx, vsrt_device_results* out);
 

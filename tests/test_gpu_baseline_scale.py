@@ -100,7 +100,7 @@ def test_tlas_far_into_its_span(api):
         for mode in (0, 1):
             o = orc.trace(mode, rays); g = ctx.trace(mode, rays)
             helpers.assert_trace_equal(o, g, "far TLAS mode %d" % mode)
-            assert g["hits"]["hit_geometry"].all() and len(g["txns"]) == 18
+            assert len(g["txns"]) == 18 and g["hits"]["hit_geometry"][1] == 1      # (a ray without the Opaque flag never moves min_thit in traceRay)
     finally:
         ctx.close()
 

@@ -515,6 +515,38 @@ def test_schedule_pick(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("order", ["0", "2"])
+def test_ray_order_never_changes_results(api, monkeypatch, order):
+    """K1 may pick the rays of a batch up in sorted order (rayorder.cu: origin cell + direction key, radix sort); every output is
+    indexed by the ray's own position, so traces, hits and counters are those of the input order and of the reference.  AUTO
+    (0) sorts the incoherent batch and leaves the single-origin camera batch alone; 2 sorts both."""
+    monkeypatch.setenv("VSRT_RAY_ORDER_MIN", "1")
+    s = sc.Scene(20000, seed=31, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    batches = [helpers.mixed_rays(6000, 17), sc.rays_primary(80, 60, flags=1), sc.rays_random(5000, seed=3)[:4097]]
+    orc = all_oracles()[0]
+    orc.register(s); orc.form(512)
+    res = {}
+    for ro in ("1", order):
+        monkeypatch.setenv("VSRT_RAY_ORDER", ro)
+        ctx = api.Context(max_treelet_size=512, device=0)
+        ctx.register(s); ctx.form_treelets()
+        res[ro] = [ctx.trace(mode, b) for b in batches for mode in (0, 1)]
+        if ro == order:
+            r = ctx.device_results()
+            assert r.order_ms > 0.0
+        res[ro + "c"] = ctx.counters()
+        ctx.close()
+    assert res["1c"] == res[order + "c"]
+    i = 0
+    for b in batches:
+        for mode in (0, 1):
+            o = orc.trace(mode, b)
+            helpers.assert_trace_equal(o, res[order][i], "sorted batch %d mode %d" % (i // 2, mode))
+            for k in ("offsets", "txns", "treelet_ids", "hits"):
+                assert np.array_equal(res["1"][i][k], res[order][i][k])
+            i += 1
+
+
 def test_large_scene_properties(api):
     """Full-size style check through size-independent properties (no oracle): both variants agree on hit t
     for opaque closest-hit rays; per-ray records start with the TLAS header; counters equal the trace."""

@@ -58,6 +58,7 @@ VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 #define VSRT_K1_STATS 0   // 1: count, per inner round, how many lanes are in which state (tools/k1_lane_states.py); costs ~10 %
 #endif
 #if VSRT_K1_STATS
+__device__ unsigned long long g_k1_depth[128];   // [d] rays whose stack (both lists) peaked at d entries, [64 + d] peak of `current` alone
 __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state] lanes in that state at the internal-node phase, [9] rounds that ran it, [10] leaf phases run, [11] lanes in them, [12] refills, [13] lanes refilled
 #endif
 // pop + internal-node rounds per refill / leaf vote, and the lanes that must be at an internal node for another round.
@@ -95,6 +96,13 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
+// Shared-memory traversal stack of the hot (EXACT = false) kernel: S 16-byte node entries per lane, [entry][thread] so that a
+// warp's 128-bit accesses are conflict-free whatever the lanes' depths.  0 = the stack lives in local memory (L1-cached, written
+// through to L2).  A ray that needs more than S entries is handed to the EXACT pass, whose stack is the local-memory one
+// (vsrt_config.stack_entries): same results, so no ray is ever refused because of S.
+#ifndef VSRT_K1_SMEM_STACK
+#define VSRT_K1_SMEM_STACK 0
+#endif
 constexpr int PUSH_MAX = VSRT_K1_NODE_ENTRY ? 2 : 6;   // stack entries one internal node can push in TREELET mode: one per list, or one per child
 enum { ST_IDLE = 0, ST_DEFER = 1, ST_FIN = 2, ST_POP = 3, ST_INT = 4, ST_INST = 5, ST_LEAF = 6 };   // lane state (DEFER: the ray is handed to the EXACT pass at the next refill)
 
@@ -110,7 +118,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const uint32_t inst_base = av.inst_base;   // lowest instance-leaf slot of the TLAS (K0)
+  // lowest instance-leaf slot of the TLAS (K0 leaves it behind the root-prefix table).  Read from memory on purpose: taken from
+  // the kernel parameters (av.inst_base) the same value costs this kernel 38 bytes of spills at its 72-register budget
+  const uint32_t inst_base = __ldg(p.tv.root_prefix + ((av.n_slots + 31u) >> 5));
   const int REFILL_T = (int)p.refill_t, LEAF_T = (int)p.leaf_t;
   constexpr int INT_T = VSRT_K1_INT_T, INNER_N = VSRT_K1_INNER;
   const bool only_deferred = EXACT && p.only_deferred != 0;
@@ -127,10 +137,19 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 
   // ---- per-lane ray state.  `st` is the lane's whole control state: no ray / ray finished (hit record pending) / entry
   // wanted / an entry of one of the three kinds in `e` waiting for its phase.
-#if VSRT_K1_NODE_ENTRY
-  uint4 stk[STACK_N];     // x first child slot | y, z.lo16: per-child byte = offset (low 4 bits) | K0's flags (bits 7, 6) | z bits 16..21 pending mask | w meta
+  // x first child slot | y, z.lo16: per-child byte = offset (low 4 bits) | K0's flags (bits 7, 6) | z bits 16..21 pending mask | w meta
+  constexpr bool SMEM = VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY && !EXACT;
+  constexpr int SN = SMEM ? VSRT_K1_SMEM_STACK : STACK_N;          // capacity of the stack this instantiation uses
+#if VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY
+  __shared__ uint4 s_stk[EXACT ? 1 : VSRT_K1_SMEM_STACK][EXACT ? 1 : THREADS];
+  uint4 l_stk[EXACT ? STACK_N : 1];
+#define STK(i_) (*(SMEM ? &s_stk[(i_)][threadIdx.x] : &l_stk[(i_)]))
+#elif VSRT_K1_NODE_ENTRY
+  uint4 stk[STACK_N];
+#define STK(i_) stk[(i_)]
 #else
   Entry stk[STACK_N];
+#define STK(i_) stk[(i_)]
 #endif
   uint32_t st = ST_IDLE; bool exhausted = false;
   Entry e; e.slot = 0; e.meta = 0;
@@ -141,6 +160,12 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   // ray_nodes: bits 0..19 total_nodes_accessed, bits 20..31 procedural-leaf visits (their instance refs sit at the END of
   // the ray's staging segment, visit j at [cap - 1 - j], for the shader-table post-pass)
   uint32_t flags = 0, cnt = 0, ray_nodes = 0, ray_any = 0;
+#if VSRT_K1_STATS
+  int peak_all = 0, peak_cur = 0;
+#define STAT_DEPTH() do { peak_all = max(peak_all, cur_n + oth_n); peak_cur = max(peak_cur, cur_n); } while (0)
+#else
+#define STAT_DEPTH() do { } while (0)
+#endif
   // TREELET: the current treelet (current_treelet_root, :1707/:1752) is kept lazily.  tid_known: cur_tid is its index;
   // otherwise cur_tid holds the SLOT of the self-rooted node that was moved over from `other`, and the index is looked up
   // only when something has to be compared with it (BLAS roots, the rare generic path).
@@ -161,8 +186,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #else
 #define EMIT(slot_, code_) do { if (cnt < cap) rstage[cnt] = ((slot_) << 3) | (uint32_t)(code_); cnt++; } while (0)
 #endif
-#define PUSH_CUR(c_) do { stk[cur_n] = (c_); cur_n++; } while (0)
-#define PUSH_OTH(c_) do { oth_n++; stk[STACK_N - oth_n] = (c_); } while (0)
+#define PUSH_CUR(c_) do { STK(cur_n) = (c_); cur_n++; } while (0)
+#define PUSH_OTH(c_) do { oth_n++; STK(SN - oth_n) = (c_); } while (0)
+  // no room for what one node can push: an error for the local-memory stack, a hand-over to the EXACT pass for the shared one
+#define STACK_FULL() do { if (SMEM) st = ST_DEFER; else err |= EF_STACK; } while (0)
 #define CUR_TID() (tid_known ? cur_tid : (tid_known = true, cur_tid = __ldg(p.tv.node_tid + cur_tid) & VSRT_TID_MASK))
   // switch the active ray to context `inst_` (INST_NONE = world)
 #define LOAD_WORLD(w_) do { const vsrt_ray* rp_ = p.rays + r; \
@@ -209,6 +236,9 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         if (ray_any) atomicAdd(&s_cnt[4], ray_any);
         if (flags & VSRT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) atomicAdd(&s_cnt[5], 1u);
         atomicAdd(&s_cnt[6], 1u);
+#if VSRT_K1_STATS
+        atomicAdd(&g_k1_depth[min(peak_all, 63)], 1ull); atomicAdd(&g_k1_depth[64 + min(peak_cur, 63)], 1ull); peak_all = peak_cur = 0;
+#endif
       }
 #if VSRT_K1_STATS
       if (lane == 0) { atomicAdd(&g_k1_stats[12], 1ull); atomicAdd(&g_k1_stats[13], (unsigned long long)__popc(idle)); }
@@ -220,8 +250,11 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         b0 = __shfl_sync(full, b0, 0);
         if (b0 + (unsigned long long)n_idle >= p.n_rays) exhausted = true;
         if (st == ST_IDLE) {
-          const uint64_t nr = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
-          if (nr < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
+          const uint64_t k = b0 + (uint64_t)__popc(idle & ((1u << lane) - 1u));
+          // rays are handed out in sorted order when rayorder.cu decided so (the decision word is re-read here rather than kept in
+          // a register of the hot loop); every output stays indexed by the ray's own id
+          const uint64_t nr = (k < p.n_rays && p.perm != nullptr && __ldg(p.perm_on) != 0u) ? (uint64_t)__ldg(p.perm + k) : k;
+          if (k < p.n_rays && (!only_deferred || p.counts[nr] == RAY_DEFERRED)) {
             // ---- start ray nr (:1650-1741 / :2411-2484)
             r = (uint32_t)nr; rstage = p.stage + nr * cap;
             const vsrt_ray* rp = p.rays + r;
@@ -304,14 +337,14 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       const bool fc = cur_n != 0;
       if (fc || (MODE == VSRT_MODE_TREELET && oth_n != 0)) {
 #if VSRT_K1_NODE_ENTRY
-        const int idx = fc ? cur_n - 1 : STACK_N - oth_n;
-        const uint4 t = stk[idx];
+        const int idx = fc ? cur_n - 1 : SN - oth_n;
+        const uint4 t = STK(idx);
         uint32_t ci; asm("bfind.u32 %0, %1;" : "=r"(ci) : "r"(t.z));          // highest pending child: the mask is the top of z
         const uint32_t z2 = t.z ^ (1u << ci);
 #ifndef VSRT_K1_POP_STORE_ALWAYS
 #define VSRT_K1_POP_STORE_ALWAYS 0   // 1: write the mask back unconditionally (no predicate): 1.864 vs 1.855 ms
 #endif
-        if (VSRT_K1_POP_STORE_ALWAYS || (z2 >> 16)) stk[idx].z = z2;               // a removed entry is never read again
+        if (VSRT_K1_POP_STORE_ALWAYS || (z2 >> 16)) STK(idx).z = z2;               // a removed entry is never read again
         const int gone = (z2 >> 16) == 0u ? 1 : 0;
         cur_n -= fc ? gone : 0;
         if (MODE == VSRT_MODE_TREELET) oth_n -= fc ? 0 : gone;
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
         e.slot = t.x + (cb & 15u); e.meta = t.w;
         TAKE(fc, (cb & 0x80u) != 0u, (cb & 0x40u) != 0u);
 #else
-        e = stk[fc ? cur_n - 1 : STACK_N - oth_n];
+        e = STK(fc ? cur_n - 1 : SN - oth_n);
         const uint32_t fl = e.slot; e.slot &= SLOT_MASK;
         TAKE(fc, (fl & SLOT_SELFROOT) != 0u, (fl & SLOT_LEAF) != 0u);
 #endif
@@ -370,12 +403,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             }
           }
           const uint32_t mcur = mask & mc;
-          if (cur_n + oth_n + PUSH_MAX > STACK_N) err |= EF_STACK;      // room for everything this node can push
+          if (cur_n + oth_n + PUSH_MAX > SN) STACK_FULL();      // room for everything this node can push
 #if VSRT_K1_NODE_ENTRY
           else {
             const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u), moth = mask ^ mcur;
-            if (moth) { oth_n++; stk[STACK_N - oth_n] = make_uint4(child0, ey, ez | (moth << 16), cmeta); }
-            if (mcur) { stk[cur_n] = make_uint4(child0, ey, ez | (mcur << 16), cmeta); cur_n++; }
+            if (moth) { oth_n++; STK(SN - oth_n) = make_uint4(child0, ey, ez | (moth << 16), cmeta); }
+            if (mcur) { STK(cur_n) = make_uint4(child0, ey, ez | (mcur << 16), cmeta); cur_n++; }
+            STAT_DEPTH();
 #if VSRT_K1_PF_NEXT
             {   // the child this lane pops next, if it is one of this node's: highest hit child in `current`, else (nothing older in `current`) in `other`
               const uint32_t mnext = mcur ? mcur : (cur_n == 0 ? moth : 0u);
@@ -385,23 +419,23 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           }
 #else
           else {
-            int po = STACK_N - 1 - oth_n;
+            int po = SN - 1 - oth_n;
             for (uint32_t m = mask; m; ) {
               const uint32_t bit = m & (0u - m); m ^= bit;
               const uint32_t sel = 0x7770u + bit_index(bit);
               Entry c; c.slot = (child0 + __byte_perm(xlo, xhi, sel)) | ((__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u); c.meta = cmeta;
               const bool ic = (mcur & bit) != 0u;
-              stk[ic ? cur_n : po] = c;
+              STK(ic ? cur_n : po) = c;
               if (ic) cur_n++; else po--;
             }
-            oth_n = STACK_N - 1 - po;
+            oth_n = SN - 1 - po;
             // (taking the entry just pushed from the registers instead of the stack load of the next pop -- the top stall of
             // the kernel -- was measured twice and is slower: more instructions in divergent code, profiles/README.md)
           }
 #endif
         } else {
           // the first hit internal child is followed at once (:2573); every other hit child is pushed in slot order
-          if (cur_n + (VSRT_K1_NODE_ENTRY ? 1 : 6) > STACK_N) err |= EF_STACK;
+          if (cur_n + (VSRT_K1_NODE_ENTRY ? 1 : 6) > SN) STACK_FULL();
 #if VSRT_K1_NODE_ENTRY
           else if (mask) {
             const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u);
@@ -409,7 +443,8 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
             const uint32_t leaf6 = (((lf4 * 0x00204081u) >> 21) & 15u) | (((lf2 * 0x00204081u) >> 17) & 0x30u);
             const uint32_t mi = mask & ~leaf6, first = mi & (0u - mi), rest = mask ^ first;
             if (first) { e.slot = child0 + __byte_perm(xlo, xhi, 0x7770u + bit_index(first)); e.meta = cmeta; st = ST_INT; }
-            if (rest) { stk[cur_n] = make_uint4(child0, ey, ez | (rest << 16), cmeta); cur_n++; }
+            if (rest) { STK(cur_n) = make_uint4(child0, ey, ez | (rest << 16), cmeta); cur_n++; }
+            STAT_DEPTH();
           }
 #else
           else {
@@ -419,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
               const uint32_t fl = (__byte_perm(lo4, hi2, sel) << 24) & 0xC0000000u;
               Entry c; c.slot = child0 + __byte_perm(xlo, xhi, sel); c.meta = cmeta;
               if (!(fl & SLOT_LEAF) && st != ST_INT) { e = c; st = ST_INT; }
-              else { c.slot |= fl; stk[cur_n] = c; cur_n++; }
+              else { c.slot |= fl; STK(cur_n) = c; cur_n++; }
             }
           }
 #endif
@@ -442,10 +477,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #else
         Entry c; c.slot = broot; c.meta = (e_level(e) << 23) | iref;             // BLAS root inherits the leaf's level (:1944)
 #endif
-        if (MODE == VSRT_MODE_DFS) { if (cur_n < STACK_N) PUSH_CUR(c); else err |= EF_STACK; }
+        if (MODE == VSRT_MODE_DFS) { if (cur_n < SN) PUSH_CUR(c); else STACK_FULL(); }
         else {
           const uint32_t tb = __ldg(p.tv.node_tid + broot);
-          if (cur_n + oth_n >= STACK_N) err |= EF_STACK;
+          if (cur_n + oth_n >= SN) STACK_FULL();
           else if ((tb & VSRT_TID_MASK) == CUR_TID()) PUSH_CUR(c);
           else { if (tb & VSRT_TID_SELF_ROOTED) SET_SELFROOT(c); PUSH_OTH(c); }
         }
@@ -501,7 +536,10 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     }
   }
 #undef EMIT
+#undef STAT_DEPTH
 #undef PUSH_CUR
+#undef STACK_FULL
+#undef STK
 #undef LEAF_FETCH
 #undef SET_SELFROOT
 #undef PUSH_OTH
@@ -564,6 +602,11 @@ int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool e
 
 #if VSRT_K1_STATS
 // debug build only (not part of include/vsrt.h): reads and clears the lane-state counters
+extern "C" int vsrt_debug_k1_depth(unsigned long long out[128]) {
+  unsigned long long z[128] = { 0 };
+  if (cudaMemcpyFromSymbol(out, g_k1_depth, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_k1_depth, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
 extern "C" int vsrt_debug_k1_stats(unsigned long long out[16]) {
   unsigned long long z[16] = { 0 };
   if (cudaMemcpyFromSymbol(out, g_k1_stats, sizeof(z)) != cudaSuccess) return -1;

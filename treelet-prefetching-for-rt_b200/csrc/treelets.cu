@@ -334,7 +334,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   }
   // ---- rank roots by address: exclusive popcount prefix over the bitmap
   CK(cudaMalloc(&popc, (size_t)nw * 4)); CK(cudaMalloc(&off64, ((size_t)std::max(nw, n_roots) + 1) * 8)); CK(cudaMalloc(&scan_tmp, vsrt_scan_tmp_bytes(std::max(nw, n_roots))));
-  CK(cudaMalloc(&prefix, (size_t)nw * 4));
+  CK(cudaMalloc(&prefix, ((size_t)nw + 1) * 4));   // [nw] = lowest instance-leaf slot, for K1
   k_popc<<<(nw + 255) / 256, 256, 0, st>>>(claimed, nw, popc);
   if ((rc = vsrt_launch_scan(popc, nw, (uint64_t*)off64, scan_tmp, st)) != VSRT_OK) goto done;
   k_narrow<<<(nw + 255) / 256, 256, 0, st>>>(off64, nw, prefix);
@@ -360,6 +360,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
     // instance leaves of one TLAS (contiguous children of its internal nodes) must span less than 2^23 slots = 512 MiB
     const uint32_t lo = (uint32_t)h_scal[2], hi = (uint32_t)(h_scal[2] >> 32);
     res->inst_base = lo == 0xFFFFFFFFu ? 0u : lo;
+    CK(cudaMemcpyAsync(prefix + nw, &res->inst_base, 4, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
     if (lo != 0xFFFFFFFFu && hi - lo >= 0x7FFFFFu) {
       snprintf(errbuf, errcap, "the instance leaves of this TLAS span %llu bytes; K1 addresses them in 23 bits of 64-byte slots (512 MiB, about 4 M instances)", (unsigned long long)(hi - lo) * 64ull);
       rc = VSRT_E_UNSUPPORTED; goto done;

@@ -137,7 +137,18 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 4u; }
-    tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0;
+    tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; tp.perm = nullptr; tp.perm_on = nullptr;
+    // ray order (rayorder.cu): which rays share a warp; batches too small to fill the GPU twice are left alone
+    uint32_t ray_order = c->cfg.ray_order;
+    if (const char* ro = getenv("VSRT_RAY_ORDER")) ray_order = (uint32_t)atoi(ro);
+    const bool want_order = ray_order != VSRT_RAY_ORDER_INPUT && n >= c->order_min_rays;
+    CUDA_OK(c, cudaEventRecord(c->ev[4], st));
+    if (want_order) {
+      CUDA_OK(c, c->d_order.ensure(vsrt_rayorder_tmp_bytes(n)));
+      rc = vsrt_launch_rayorder(d_rays, n, ray_order == VSRT_RAY_ORDER_SORTED, c->d_order.p, &tp.perm, &tp.perm_on, st);
+      if (rc) return fail(c, rc, "ray-order kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+      launches += 14;   // bounds, keys, 3 x (count, 3 scan kernels, scatter)
+    }
     const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
     // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel
     // (traverse_wf.cu), bit-identical results, measured 10 % slower on the bench workload (profiles/README.md)
@@ -219,6 +230,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   }
   c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p; c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p;
   c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;
+  cudaEventElapsedTime(&c->last.order_ms, c->ev[4], c->ev[0]);
   cudaEventElapsedTime(&c->last.traverse_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->last.scan_ms, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->last.compact_ms, c->ev[2], c->ev[3]);
@@ -271,11 +283,12 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
   ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_pin, vsrt_context::PIN_BYTES) == cudaSuccess;
-  for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
   if (c->cfg.max_treelet_size == 0) c->cfg.max_treelet_size = 49152;
   if (c->cfg.stack_entries > 384) { vsrt_destroy(c); return fail(nullptr, VSRT_E_INVALID, "vsrt_config.stack_entries = %u: the traversal kernel is built for at most 384 entries per ray", cfg->stack_entries); }
   // initial staging records per ray (doubles, with the batch redone, whenever a ray outgrows it); the knob exists for the tests
+  if (const char* om = getenv("VSRT_RAY_ORDER_MIN")) { const long long v = atoll(om); if (v >= 1) c->order_min_rays = (uint64_t)v; }
   if (const char* sc = getenv("VSRT_STAGE_CAP")) { const int v = atoi(sc); if (v >= 4 && v <= (1 << 20)) c->stage_cap = (uint32_t)v; }
   *out = c;
   return VSRT_OK;
@@ -290,8 +303,8 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
-  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release();
-  for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release();
+  for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

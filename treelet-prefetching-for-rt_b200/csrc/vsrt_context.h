@@ -60,7 +60,9 @@ struct vsrt_context {
   // replay helpers: sorted copy of the last trace, inverted treelet lists (slot -> (treelet, position))
   DevBuf<vsrt_txn> d_txns_sorted; DevBuf<uint32_t> d_tids_sorted; DevBuf<uint64_t> d_sort_keys;
   uint64_t* d_inv_off = nullptr; uint2* d_inv = nullptr;
-  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+  uint64_t order_min_rays = 65536;   // smaller batches keep the input order (the sort would cost more than it returns)
+  DevBuf<uint8_t> d_order;    // rayorder.cu scratch: keys, sorted ray ids, decision word
+  cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
   uint64_t last_tlas = 0; int last_mode = 0; const vsrt_ray* last_rays = nullptr;
   CommState* comm = nullptr;   // multi-GPU reduce state (reduce.cu), NULL until vsrt_comm_init / vsrt_comm_attach

@@ -105,12 +105,18 @@ struct TraverseParams {
   uint2* gstack;                  // wavefront kernel: per-warp stack areas (vsrt_wf_stack_bytes)
   uint32_t stack_n;               // wavefront kernel: stack entries per ray
   uint32_t magic16;               // 0x64646464 (fp16 1024 in each half), passed as data so it lives in a register (byte_pair_f16)
+  const uint32_t* perm;           // rayorder.cu: the k-th ray a lane picks up is perm[k] (NULL = input order) ...
+  const uint32_t* perm_on;        // ... if this device word is non-zero (AUTO mode decides on the device)
 };
 int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
 // warp-wavefront formulation (traverse_wf.cu): same results, a pool of 64 rays per warp regrouped by phase every iteration
 unsigned vsrt_wf_grid(uint64_t n_rays);
 size_t vsrt_wf_stack_bytes(unsigned grid, uint32_t stack_entries);
 int vsrt_launch_traverse_wf(const TraverseParams& p, unsigned grid, bool exact, cudaStream_t st);
+
+// ray order for K1 (rayorder.cu): sorted ray ids + the device-side decision word, both inside `tmp` (vsrt_rayorder_tmp_bytes)
+size_t vsrt_rayorder_tmp_bytes(uint64_t n);
+int vsrt_launch_rayorder(const vsrt_ray* rays_dev, uint64_t n, bool force, void* tmp, const uint32_t** perm_out, const uint32_t** decision_out, cudaStream_t st);
 
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);

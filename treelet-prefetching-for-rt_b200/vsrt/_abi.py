@@ -20,6 +20,7 @@ assert len(COUNTER_FIELDS) == N_SUM + N_MAX
 FLAG_OPAQUE = 0x1
 FLAG_TERMINATE_ON_FIRST_HIT = 0x4
 MODE_DFS, MODE_TREELET = 0, 1
+RAY_ORDER_AUTO, RAY_ORDER_INPUT, RAY_ORDER_SORTED = 0, 1, 2
 
 ERRORS = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "CAPACITY", -5: "UNKNOWN_AS",
           -6: "BAD_BVH", -7: "STACK_OVERFLOW", -8: "BUDGET", -9: "UNSUPPORTED", -10: "COMM"}
@@ -30,7 +31,7 @@ class Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("max_treelet_size", ctypes.c_uint32),
                 ("treelet_based_traversal", ctypes.c_uint32), ("remap_to_treelet_layout", ctypes.c_uint32),
                 ("treelet_remap_stride", ctypes.c_uint32), ("load_treelet_metadata", ctypes.c_uint32),
-                ("stack_entries", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("stack_entries", ctypes.c_uint32), ("ray_order", ctypes.c_uint32)]
 
 
 class TreeletInfo(ctypes.Structure):
@@ -44,7 +45,7 @@ class DeviceResults(ctypes.Structure):
                 ("treelet_ids", ctypes.c_void_p), ("n_rays", ctypes.c_uint64), ("n_txn", ctypes.c_uint64),
                 ("algorithmic_bytes", ctypes.c_uint64), ("traverse_ms", ctypes.c_float),
                 ("scan_ms", ctypes.c_float), ("compact_ms", ctypes.c_float),
-                ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("order_ms", ctypes.c_float)]
 
 
 class PrefetchConfig(ctypes.Structure):

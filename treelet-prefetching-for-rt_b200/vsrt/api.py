@@ -16,7 +16,8 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvsrt.so")
+# VSRT_LIB selects another build of the same library (A/B variants compiled beside it; tools/ab_variants.sh)
+LIB_PATH = os.environ.get("VSRT_LIB") or os.path.join(os.path.dirname(_HERE), "libvsrt.so")
 _lib = None
 
 c_u64, c_u32, c_vp, c_int = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int
@@ -164,7 +165,7 @@ class AsImage:
 
 class Context:
     def __init__(self, max_treelet_size=49152, device=-1, treelet_based_traversal=1, remap_to_treelet_layout=0,
-                 treelet_remap_stride=0, stack_entries=96, config=None):
+                 treelet_remap_stride=0, stack_entries=96, ray_order=0, config=None):
         L = load()
         self.L = L
         cfg = _abi.Config()
@@ -178,6 +179,7 @@ class Context:
             cfg.remap_to_treelet_layout = remap_to_treelet_layout
             cfg.treelet_remap_stride = treelet_remap_stride
             cfg.stack_entries = stack_entries
+            cfg.ray_order = ray_order
         self.cfg = cfg
         h = c_vp()
         rc = L.vsrt_create(ctypes.byref(cfg), ctypes.byref(h))

@@ -127,7 +127,8 @@ typedef struct vsrt_config {
   uint32_t stack_entries;           /* per-ray traversal stack capacity (0 = default 96, at most 384) */
   uint32_t ray_order;               /* VSRT_RAY_ORDER_*: the order in which the GPU picks up the rays of a batch.  Results never depend
                                        on it (every output is indexed by the ray's position in the batch); it only decides which rays
-                                       share a warp.  AUTO sorts a batch by origin cell + direction unless all its rays share one origin */
+                                       share a warp.  AUTO sorts a batch by origin cell + direction octant when its consecutive rays are far apart (a sample
+                                       of 256 pairs decides); camera batches and bounce rays generated in pixel order keep their input order */
 } vsrt_config;
 enum { VSRT_RAY_ORDER_AUTO = 0, VSRT_RAY_ORDER_INPUT = 1, VSRT_RAY_ORDER_SORTED = 2 };
 

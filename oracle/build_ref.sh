@@ -34,6 +34,8 @@ mkdir -p "$OUT"
   # Coalescing table: constructor + add_intersection and the getters; its clear() (:101-111) is NOT taken -- the inner loop
   # increments i instead of j and never terminates on a non-empty table -- ref_api.cc defines the evident intent instead
   sed -n '36,99p;113,148p' "$R/cuda-sim/intersection_table.cc"
+  # the AS dumper: dump_descriptor_set_for_AS, pass_child_addr, findOffsetBounds
+  sed -n '4455,4558p;4886,4889p;4901,4945p' "$R/cuda-sim/vulkan_ray_tracing.cc"
   cat "$HERE/ref_shim/ref_api.cc"
   # ---- RT-unit replay helpers: RTMemoryTransactionRecord, rt_unit::sort_mem_accesses and the
   # treelet-prefetch vote block of rt_unit::cycle, the latter spliced in as the body of a member function

@@ -281,6 +281,16 @@ int64_t ref_trace_coalescing(void* tlas, int mode, uint32_t n, const ref_ray* ra
   return (int64_t)nt;
 }
 
+// The reference's own AS dumper: writes <mesa_root>gpgpusimShaders/0_0.asmain / .asback / .asfront / .asmetadata for a TLAS of
+// desc_size bytes whose BLAS headers are kids[] (what Mesa passes through gpgpusim_pass_child_addr).  mesa_root must end in '/'
+// and the directory gpgpusimShaders/ must exist under it.
+void ref_dump_as(const char* mesa_root, void* tlas, uint32_t desc_size, void** kids, uint32_t n_kids) {
+  setenv("MESA_ROOT", mesa_root, 1);
+  VulkanRayTracing::child_addrs_from_driver.clear();
+  for (uint32_t i = 0; i < n_kids; i++) VulkanRayTracing::pass_child_addr(kids[i]);
+  VulkanRayTracing::dump_descriptor_set_for_AS(0, 0, tlas, desc_size, VK_DESCRIPTOR_TYPE_ACCELERATION_STRUCTURE_KHR, 0, 0, true, tlas);
+}
+
 void ref_get_counters(ref_counters* out) {
   ref_func_sim& f = GPGPU_Context()->fs;
   for (int i = 0; i < 9; i++) out->mem_access_type[i] = f.g_rt_mem_access_type[i];

@@ -108,6 +108,12 @@ class VulkanRayTracing {
   static std::vector<StackEntry> treeletIDToChildren(uint8_t* treelet_root);
   static void buildNodeToRootMap();
   static void dump_AS(struct DESCRIPTOR_SET_STRUCT*, VkAccelerationStructureKHR) {}
+  /* the AS dumper: bodies taken from vulkan_ray_tracing.cc:4455-4558, :4886-4889, :4901-4945 */
+  static std::vector<void*> child_addrs_from_driver;
+  static void pass_child_addr(void* address);
+  static void findOffsetBounds(int64_t& max_backwards, int64_t& min_backwards, int64_t& min_forwards, int64_t& max_forwards, VkAccelerationStructureKHR _topLevelAS);
+  static void dump_descriptor_set_for_AS(uint32_t setID, uint32_t descID, void* address, uint32_t desc_size, VkDescriptorType type, uint32_t backwards_range,
+                                         uint32_t forward_range, bool split_files, VkAccelerationStructureKHR _topLevelAS);
   static void* gpgpusim_alloc(uint32_t size) { return calloc(1, size); }
   static void* gpgpusim_malloc(uint32_t size) { return calloc(1, size); }
 };
@@ -118,6 +124,7 @@ void* VulkanRayTracing::launcher_deviceDescriptorSets[MAX_DESCRIPTOR_SETS][MAX_D
 std::map<void*, void*> VulkanRayTracing::blas_addr_map;
 void* VulkanRayTracing::tlas_addr = NULL;
 bool VulkanRayTracing::dumped = false;
+std::vector<void*> VulkanRayTracing::child_addrs_from_driver;
 warp_intersection_table*** VulkanRayTracing::intersection_table = NULL;
 warp_intersection_table*** VulkanRayTracing::anyhit_table = NULL;
 bool use_external_launcher = false;

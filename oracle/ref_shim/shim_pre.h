@@ -25,6 +25,7 @@
 
 typedef void* VkAccelerationStructureKHR;
 enum VkGeometryTypeKHR { VK_GEOMETRY_TYPE_TRIANGLES_KHR = 0, VK_GEOMETRY_TYPE_AABBS_KHR = 1 };
+enum VkDescriptorType { VK_DESCRIPTOR_TYPE_ACCELERATION_STRUCTURE_KHR = 1000150000, VK_DESCRIPTOR_TYPE_ACCELERATION_STRUCTURE_NV = 1000165000 };   /* the two values dump_descriptor_set_for_AS switches on */
 enum {
   SpvRayFlagsOpaqueKHRMask = 0x1,
   SpvRayFlagsTerminateOnFirstHitKHRMask = 0x4,

@@ -126,6 +126,15 @@ class RefOracle(_Base):
         self.L.ref_sort_trace(method, len(trace["offsets"]) - 1, _abi.ptr(trace["offsets"]), _abi.ptr(t))
         return t
 
+    def dump_as(self, out_dir, arena, desc_size):
+        """The reference's own dump_descriptor_set_for_AS(split_files = true) for `arena` (BLAS headers handed over as the driver
+        does through gpgpusim_pass_child_addr): files <out_dir>/gpgpusimShaders/0_0.as{main,back,front,metadata}."""
+        os.makedirs(os.path.join(out_dir, "gpgpusimShaders"), exist_ok=True)
+        kids = (c_vp * len(arena.blas))(*[arena.base + off for off, _ in arena.blas])
+        self.L.ref_dump_as.argtypes = [ctypes.c_char_p, c_vp, ctypes.c_uint32, c_vp, ctypes.c_uint32]
+        self.L.ref_dump_as((out_dir.rstrip("/") + "/").encode(), arena.tlas, desc_size, kids, len(arena.blas))
+        return os.path.join(out_dir, "gpgpusimShaders", "0_0")
+
     def table_bases(self):
         a, b = c_u64(), c_u64()
         self.L.ref_table_bases(ctypes.byref(a), ctypes.byref(b))

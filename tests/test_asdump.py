@@ -46,6 +46,38 @@ def tlas_in_the_middle(s):
     return sc.Arena(bytes(data), new_t, [(0, z0), (new_b1, z1)])
 
 
+def test_writer_matches_the_reference_dumper(tmp_path):
+    """vsrt_as_dump_write against the reference's own dump_descriptor_set_for_AS + findOffsetBounds (compiled into oracle/_ref
+    from vulkan_ray_tracing.cc:4455-4558, :4901-4945): the four files byte for byte, for a TLAS below its BLASes, between them
+    and above them -- the reference's 0 / 20 KiB slack after the last BLAS START included (it truncates a larger last BLAS and
+    reads past a smaller one; the arenas here are padded so that the 20 KiB exist).  CPU only: the writer is host code."""
+    if not oracles.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import vsrt.api as api
+    orc = oracles.RefOracle()
+    s = sc.Scene(1200, seed=21, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    mid = tlas_in_the_middle(s)
+    pad = np.zeros(24 * 1024, np.uint8)
+
+    def padded(a):      # same arena with 24 KiB of zeros behind it, so that "last BLAS start + 20 KiB" stays inside the buffer
+        return sc.Arena(np.concatenate([a.bytes, pad]), a.tlas_offset, list(a.blas))
+    (o0, z0), (o1, z1) = s.blas
+    top = sc.Arena(np.concatenate([s.bytes[o0:], s.bytes[:o0]]), s.size - o0, [])      # [BLAS0 | BLAS1 | TLAS]: only backward offsets
+    top.blas = [(0, z0), (o1 - o0, z1)]
+    for name, arena in (("fwd", padded(s)), ("mid", padded(mid)), ("back", top)):
+        above = sorted(off for off, _ in arena.blas if off > arena.tlas_offset)
+        desc = (above[0] if above else arena.size) - arena.tlas_offset
+        want = orc.dump_as(str(tmp_path / ("ref_" + name)), arena, desc)
+        got = str(tmp_path / ("0_0_" + name))
+        api.write_as_dump(got, arena, desc_size=desc, back_buffer=0, front_buffer=20 * 1024)
+        for ext in (".asmain", ".asback", ".asfront", ".asmetadata"):
+            assert os.path.exists(want + ext) == os.path.exists(got + ext), (name, ext)
+            if os.path.exists(want + ext):
+                assert open(want + ext, "rb").read() == open(got + ext, "rb").read(), (name, ext)
+        kinds = (os.path.exists(got + ".asback"), os.path.exists(got + ".asfront"))
+        assert kinds == {"fwd": (False, True), "mid": (True, True), "back": (True, False)}[name]
+
+
 def test_dump_round_trip(api, tmp_path):
     s = sc.Scene(1200, seed=21, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
     for name, arena in (("fwd", s), ("mid", tlas_in_the_middle(s))):

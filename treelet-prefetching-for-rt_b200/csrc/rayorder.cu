@@ -5,15 +5,18 @@
 // by the ray's own id (staging segment, hit record, count -- all are; K3 never sees the order).  For an incoherent batch
 // (diffuse bounces, BASELINE.json configs[2..4]) the input order puts 32 unrelated rays into a warp: they are at different nodes
 // of different subtrees, every node fetch is a separate line and the warp serialises over its phases.  Sorting the batch by a
-// space-filling key -- Morton code of the origin cell (6 bits per axis, scene box of the TLAS header) followed by the direction
-// (2 bits per axis) -- gives a warp neighbouring rays that walk the same part of the tree.
+// space-filling key -- Morton code of the origin cell (7 bits per axis over the batch's own origin box) followed by the direction
+// octant -- gives a warp neighbouring rays that walk the same part of the tree.  Origin first: rays that start close together
+// share the whole chain of boxes around their origin whatever their directions; measured on bounce rays, a key with coarser
+// origin cells than the input's own neighbourhoods makes K1 slower, which is why AUTO mode (vsrt_capi.cu) sorts only batches
+// whose consecutive rays are far apart.
 //
-//   k_ray_bounds   origin / direction extents of the batch (a coherent camera batch has a single origin: not sorted in AUTO mode)
+//   k_ray_bounds   origin box of the batch
 //   k_ray_keys     24-bit key per ray
 //   3 x (count, scan, scatter)   stable LSD radix sort of (key, ray id), 8 bits per pass, 2048 keys per CTA
 //
-// Every kernel after k_ray_bounds returns at once when the device-side decision word says "keep the input order", so AUTO mode
-// needs no host round trip; K1 reads the same word.
+// Every kernel after k_ray_bounds returns at once when the device-side decision word says "keep the input order" (a batch whose
+// origins all coincide has no origin box to sort by, unless `force`); K1 reads the same word.
 #include "vsrt_device.cuh"
 #include <algorithm>
 
@@ -66,13 +69,11 @@ __global__ void __launch_bounds__(256) k_ray_keys(const vsrt_ray* __restrict__ r
     const float lo = ord2f(ext[a]), hi = ord2f(ext[3 + a]);
     const float v = __ldg(&rays[i].origin[a]);
     const float w = hi > lo ? (v - lo) / (hi - lo) : 0.0f;            // ordering only: no bit-exactness contract here
-    q[a] = (uint32_t)fminf(fmaxf(w * 64.0f, 0.0f), 63.0f);
-    const float dv = __ldg(&rays[i].direction[a]);
-    d[a] = dv != dv ? 0u : (dv < -0.5f ? 0u : (dv < 0.0f ? 1u : (dv < 0.5f ? 2u : 3u)));
+    q[a] = (uint32_t)fminf(fmaxf(w * 128.0f, 0.0f), 127.0f);
+    d[a] = __float_as_uint(__ldg(&rays[i].direction[a])) >> 31;
   }
-  const uint32_t om = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);   // 18 bits
-  const uint32_t dm = spread3(d[0]) | (spread3(d[1]) << 1) | (spread3(d[2]) << 2);   // 6 bits
-  keys[i] = (om << 6) | dm;
+  const uint32_t om = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);   // 21 bits
+  keys[i] = (om << 3) | d[0] | (d[1] << 1) | (d[2] << 2);
   ids[i] = (uint32_t)i;
 }
 

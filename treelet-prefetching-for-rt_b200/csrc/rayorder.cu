@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) k_ray_keys(const vsrt_ray* __restrict__ r
 
 // digit-major table: cnt[digit * n_blocks + block]
 __global__ void __launch_bounds__(RS_THREADS) k_radix_count(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t n_blocks, uint32_t* __restrict__ cnt,
-                                                            const unsigned int* __restrict__ ext) {
-  if (ext[6] == 0u) return;
+                                                            const unsigned int* __restrict__ gate) {
+  if (gate && *gate == 0u) return;
   __shared__ unsigned int h[RS_BINS];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_count(const uint32_t* __re
 // the digit (shared memory, bumped once per round by the lowest lane of each match group) + its position inside the group.
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t n, int shift, uint32_t n_blocks,
                                                               const unsigned long long* __restrict__ off, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
-                                                              const unsigned int* __restrict__ ext) {
-  if (ext[6] == 0u) return;
+                                                              const unsigned int* __restrict__ gate) {
+  if (gate && *gate == 0u) return;
   __shared__ unsigned int wc[RS_WARPS][RS_BINS];
   for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wc[0][0])[i] = 0;
   __syncthreads();
@@ -136,35 +136,53 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
 
 }  // namespace
 
-size_t vsrt_rayorder_tmp_bytes(uint64_t n) {
+// ---- stable LSD radix sort of (key, id) pairs, 8 bits per pass, shared with the treelet-binned traversal (traverse_tb.cu)
+size_t vsrt_radix_tmp_bytes(uint64_t n) {
   const uint64_t n_blocks = (n + RS_TILE - 1) / RS_TILE, m = n_blocks * RS_BINS;
-  // ext (8 words) | keys A, ids A, keys B, ids B | counts | offsets (u64) | scan scratch
-  return 64 + 4 * ((n + 63) & ~63ull) * 4 + ((m + 63) & ~63ull) * 4 + (m + 1) * 8 + vsrt_scan_tmp_bytes(m) + 256;
+  return ((m + 63) & ~63ull) * 4 + (m + 1) * 8 + 256 + vsrt_scan_tmp_bytes(m) + 256;
 }
-
-// Leaves the sorted ray ids in *perm_out (inside tmp) and the decision word in *decision_out; both device pointers.
-int vsrt_launch_rayorder(const vsrt_ray* rays_dev, uint64_t n, bool force, void* tmp, const uint32_t** perm_out, const uint32_t** decision_out, cudaStream_t st) {
-  const uint64_t n_blocks = (n + RS_TILE - 1) / RS_TILE, m = n_blocks * RS_BINS, np = (n + 63) & ~63ull;
+// Sorts by the low 8 * passes bits.  (kA, iA) hold the input, (kB, iB) are scratch of the same size; *keys_out / *ids_out name
+// the buffers the result ends up in.  `gate` (device word, may be NULL): every kernel returns at once when it is zero.
+int vsrt_launch_radix_sort(uint32_t* kA, uint32_t* iA, uint32_t* kB, uint32_t* iB, uint64_t n, int passes, void* tmp, const unsigned int* gate,
+                           uint32_t** keys_out, uint32_t** ids_out, cudaStream_t st) {
+  const uint64_t n_blocks = (n + RS_TILE - 1) / RS_TILE, m = n_blocks * RS_BINS;
   uint8_t* p = (uint8_t*)tmp;
-  unsigned int* ext = (unsigned int*)p; p += 64;
-  uint32_t* kA = (uint32_t*)p; p += np * 4; uint32_t* iA = (uint32_t*)p; p += np * 4;
-  uint32_t* kB = (uint32_t*)p; p += np * 4; uint32_t* iB = (uint32_t*)p; p += np * 4;
   uint32_t* cnt = (uint32_t*)p; p += ((m + 63) & ~63ull) * 4;
   unsigned long long* off = (unsigned long long*)p; p += (m + 1) * 8;
   p = (uint8_t*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
   void* scan_tmp = p;
+  uint32_t* ks = kA; uint32_t* is = iA; uint32_t* kd = kB; uint32_t* id = iB;
+  for (int pass = 0; pass < passes && n; pass++) {
+    k_radix_count<<<(unsigned)n_blocks, RS_THREADS, 0, st>>>(ks, n, 8 * pass, (uint32_t)n_blocks, cnt, gate);
+    const int rc = vsrt_launch_scan(cnt, m, (uint64_t*)off, scan_tmp, st); if (rc) return rc;
+    k_radix_scatter<<<(unsigned)n_blocks, RS_THREADS, 0, st>>>(ks, is, n, 8 * pass, (uint32_t)n_blocks, off, kd, id, gate);
+    std::swap(ks, kd); std::swap(is, id);
+  }
+  if (keys_out) *keys_out = ks;
+  if (ids_out) *ids_out = is;
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
+size_t vsrt_rayorder_tmp_bytes(uint64_t n) {
+  // ext (8 words) | keys A, ids A, keys B, ids B | radix scratch
+  return 64 + 4 * ((n + 63) & ~63ull) * 4 + vsrt_radix_tmp_bytes(n);
+}
+
+// Leaves the sorted ray ids in *perm_out (inside tmp) and the decision word in *decision_out; both device pointers.
+int vsrt_launch_rayorder(const vsrt_ray* rays_dev, uint64_t n, bool force, void* tmp, const uint32_t** perm_out, const uint32_t** decision_out, cudaStream_t st) {
+  const uint64_t np = (n + 63) & ~63ull;
+  uint8_t* p = (uint8_t*)tmp;
+  unsigned int* ext = (unsigned int*)p; p += 64;
+  uint32_t* kA = (uint32_t*)p; p += np * 4; uint32_t* iA = (uint32_t*)p; p += np * 4;
+  uint32_t* kB = (uint32_t*)p; p += np * 4; uint32_t* iB = (uint32_t*)p; p += np * 4;
   const unsigned int init[8] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u };
   if (cudaMemcpyAsync(ext, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return VSRT_E_CUDA;
   const unsigned bgrid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
   k_ray_bounds<<<bgrid, 256, 0, st>>>(rays_dev, n, ext, ext + 7, force ? 1u : 0u);
   k_ray_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rays_dev, n, ext, kA, iA);
-  uint32_t* ks = kA; uint32_t* is = iA; uint32_t* kd = kB; uint32_t* id = iB;
-  for (int pass = 0; pass < 3; pass++) {
-    k_radix_count<<<(unsigned)n_blocks, RS_THREADS, 0, st>>>(ks, n, 8 * pass, (uint32_t)n_blocks, cnt, ext);
-    const int rc = vsrt_launch_scan(cnt, m, (uint64_t*)off, scan_tmp, st); if (rc) return rc;
-    k_radix_scatter<<<(unsigned)n_blocks, RS_THREADS, 0, st>>>(ks, is, n, 8 * pass, (uint32_t)n_blocks, off, kd, id, ext);
-    std::swap(ks, kd); std::swap(is, id);
-  }
+  uint32_t* is = nullptr;
+  const int rc = vsrt_launch_radix_sort(kA, iA, kB, iB, n, 3, p, ext + 6, nullptr, &is, st);
+  if (rc) return rc;
   *perm_out = is; *decision_out = ext + 6;
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

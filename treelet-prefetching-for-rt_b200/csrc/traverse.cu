@@ -54,6 +54,7 @@ VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;
 #endif
 constexpr int THREADS = VSRT_K1_THREADS;
 VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+VS_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef VSRT_K1_STATS
 #define VSRT_K1_STATS 0   // 1: count, per inner round, how many lanes are in which state (tools/k1_lane_states.py); costs ~10 %
 #endif
@@ -92,6 +93,14 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #endif
 #ifndef VSRT_K1_PF_NEXT
 #define VSRT_K1_PF_NEXT 0
+#endif
+// PF_CHILDREN: as soon as an internal node's ChildOffset has arrived, prefetch the block of its children (contiguous, at most six
+// 64-byte slots) -- BEFORE the slab test decides which of them the ray visits.  Unlike PF_NEXT / PF_LEAF (issued once the child is
+// known, i.e. a few dozen instructions before its demand load) this has the whole slab test, push and pop as lead time, and it
+// spends DRAM bandwidth K1 does not use (5-7 % of peak on the incoherent configs, where the kernel waits for load LATENCY).
+// 1 = into L2 only (prefetch.global.L2), 2 = into L1.
+#ifndef VSRT_K1_PF_CHILDREN
+#define VSRT_K1_PF_CHILDREN 0
 #endif
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
@@ -372,6 +381,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     if (st == ST_INT) {
       st = ST_POP;
       const Node64 n = load_node(base, e.slot);
+#if VSRT_K1_PF_CHILDREN
+      {
+        const uint8_t* cb_ = base + (uint64_t)(e.slot + (uint32_t)node_child_offset(n)) * 64u;
+        if (VSRT_K1_PF_CHILDREN == 2) { prefetch_l1(cb_); prefetch_l1(cb_ + 128); prefetch_l1(cb_ + 256); }
+        else { prefetch_l2(cb_); prefetch_l2(cb_ + 128); prefetch_l2(cb_ + 256); }
+      }
+#endif
       const uint32_t inst = e_inst(e);
       EMIT(e.slot, inst == INST_NONE ? C_INTERNAL_TLAS : C_INTERNAL_BLAS); ray_nodes++;
       ACTIVATE(inst);

@@ -121,7 +121,7 @@ int input_order_is_scattered(vsrt_context* c, const vsrt_ray* d_rays, uint64_t n
   vsrt_ray* h = reinterpret_cast<vsrt_ray*>(c->h_pin + vsrt_context::PIN_HEAD);
   CUDA_OK(c, cudaMemcpy2DAsync(h, 2 * sizeof(vsrt_ray), d_rays, stride * sizeof(vsrt_ray), 2 * sizeof(vsrt_ray), S, cudaMemcpyDeviceToHost, st));
   CUDA_OK(c, cudaStreamSynchronize(st));
-  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, consec = 0.0; int pairs = 0;
+  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, dist[S]; int pairs = 0;
   for (int i = 0; i < S; i++) {
     const vsrt_ray& a = h[2 * i]; const vsrt_ray& b = h[2 * i + 1];
     double d = 0.0; bool ok = true;
@@ -131,11 +131,13 @@ int input_order_is_scattered(vsrt_context* c, const vsrt_ray* d_rays, uint64_t n
       lo[k] = std::min(lo[k], std::min(x, y)); hi[k] = std::max(hi[k], std::max(x, y));
       d += x > y ? x - y : y - x;
     }
-    if (ok) { consec += d; pairs++; }
+    if (ok) dist[pairs++] = d;
   }
   if (!pairs) return VSRT_OK;
+  // the MEDIAN distance: pixel-ordered bounce rays jump at every silhouette, and a few long jumps must not outvote the many short steps
+  std::nth_element(dist, dist + pairs / 2, dist + pairs);
   const double extent = (hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2]);
-  *scattered = extent > 0.0 && consec / pairs > extent / 128.0;
+  *scattered = extent > 0.0 && dist[pairs / 2] > extent / 128.0;
   return VSRT_OK;
 }
 

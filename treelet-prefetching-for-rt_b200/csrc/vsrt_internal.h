@@ -118,6 +118,11 @@ int vsrt_launch_traverse_wf(const TraverseParams& p, unsigned grid, bool exact, 
 size_t vsrt_rayorder_tmp_bytes(uint64_t n);
 int vsrt_launch_rayorder(const vsrt_ray* rays_dev, uint64_t n, bool force, void* tmp, const uint32_t** perm_out, const uint32_t** decision_out, cudaStream_t st);
 
+// stable LSD radix sort of (key, id) pairs by the low 8 * passes bits (rayorder.cu); see the definition for the buffer contract
+size_t vsrt_radix_tmp_bytes(uint64_t n);
+int vsrt_launch_radix_sort(uint32_t* kA, uint32_t* iA, uint32_t* kB, uint32_t* iB, uint64_t n, int passes, void* tmp, const unsigned int* gate,
+                           uint32_t** keys_out, uint32_t** ids_out, cudaStream_t st);
+
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);
 int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st);

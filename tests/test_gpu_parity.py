@@ -101,6 +101,47 @@ def test_wavefront_variant(api, monkeypatch, ntri, nb, ni, flags, budget, delta)
     run_case(api, s, rays, budget, delta=delta)
 
 
+@pytest.mark.parametrize("ntri,nb,ni,flags,budget,delta", [
+    (2000, 2, 3, sc.F_TRANSFORMS | sc.F_HOLES, 512, 0),
+    (20000, 1, 2, sc.F_TRANSFORMS | sc.F_HOLES, 49152, 0),
+    (30000, 3, 5, sc.F_TRANSFORMS, 4096, 0),
+    (5000, 2, 4, sc.F_TRANSFORMS, 256, 0x100000),
+    (1200, 1, 1, sc.F_PROCEDURAL, 1024, 0),
+])
+def test_treelet_binned_variant(api, monkeypatch, ntri, nb, ni, flags, budget, delta):
+    """The treelet-binned wavefront formulation of K1 (traverse_tb.cu, VSRT_K1_TB=1): rounds of bin-by-next-treelet, TMA-staged
+    shared treelets, drain.  traceRayWithTreelets records, treelet ids, hits and counters equal the reference's (traceRay runs
+    through the lane-owned kernel either way); non-finite rays go through the EXACT pass; shared BLASes (instances > BLASes)
+    exercise the "not stageable" fallback; a host->device offset exercises the :1752 quirk."""
+    monkeypatch.setenv("VSRT_K1_TB", "1")
+    s = sc.Scene(ntri, seed=ntri + 1, n_blas=nb, n_instances=ni, flags=flags)
+    rays = helpers.mixed_rays(3000, ntri + 5)
+    rays["origin"][7::97, 1] = np.inf
+    rays["direction"][11::89, 2] = np.nan
+    run_case(api, s, rays, budget, delta=delta)
+
+
+def test_treelet_binned_variant_stages_treelets(api, monkeypatch):
+    """At the reference's default 48 KB budget the top treelet is shared by every ray of the batch: the binned kernel must
+    actually serve node visits from TMA-staged shared memory (the statistics say how many), and still match the default kernel."""
+    s = sc.Scene(60000, seed=4)
+    rays = np.concatenate([sc.rays_primary(128, 96, flags=0), sc.rays_random(8000, seed=9)])
+    ctx = api.Context(max_treelet_size=49152, device=0)
+    ctx.register(s); ctx.form_treelets()
+    want = ctx.trace(1, rays)
+    ctx.close()
+    monkeypatch.setenv("VSRT_K1_TB", "1")
+    ctx = api.Context(max_treelet_size=49152, device=0)
+    ctx.register(s); ctx.form_treelets()
+    got = ctx.trace(1, rays)
+    st = ctx.tb_stats()
+    ctx.close()
+    for k in ("offsets", "txns", "treelet_ids", "hits"):
+        assert np.array_equal(want[k], got[k]), k
+    assert st["rounds"] > 2 and st["ctas_staged"] > 0 and st["visits_from_smem"] > 0
+    assert st["visits_from_smem"] + st["visits_from_arena"] >= len(got["txns"]) // 3
+
+
 def test_unordered_bounds_take_the_exact_path(api):
     """A present child with quantised lower > upper bound: the fast slab test reads near / far planes off the ray's
     direction signs and would miss the box, so K0 flags the arena and every ray runs the EXACT instantiation, which orders

@@ -59,7 +59,8 @@ def main():
         r = ctx.device_results()
         out.append({"order_ms": r.order_ms, "k1_ms": r.traverse_ms, "k3_ms": r.compact_ms, "scan_ms": r.scan_ms})
     print(json.dumps({"config": a.config, "budget": a.budget, "rays": int(len(rays)), "records_per_ray": r.n_txn / len(rays), "bytes_per_ray": r.algorithmic_bytes / len(rays),
-                      "treelets": int(ti.n_treelets), "form_ms": ti.form_ms, "arena_bytes": int(s.size), "passes": out}), flush=True)
+                      "treelets": int(ti.n_treelets), "form_ms": ti.form_ms, "arena_bytes": int(s.size), "passes": out,
+                      "tb_stats": ctx.tb_stats() if os.environ.get("VSRT_K1_TB", "0") != "0" else None}), flush=True)
     ctx.close()
 
 

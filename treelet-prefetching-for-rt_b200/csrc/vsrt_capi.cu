@@ -32,6 +32,7 @@ void free_treelets(vsrt_context* c) {
   cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
   vsrt_comm_treelets_changed(c);
+  vsrt_tb_free_layout(c->tb_tables); c->tb_tables = nullptr;
 }
 
 const Reg* find_tlas(const vsrt_context* c, uint64_t host) {
@@ -187,6 +188,13 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel
     // (traverse_wf.cu), bit-identical results, measured 10 % slower on the bench workload (profiles/README.md)
     const bool wavefront = getenv("VSRT_K1_WF") && atoi(getenv("VSRT_K1_WF")) != 0;
+    // VSRT_K1_TB=1: the treelet-binned wavefront kernel (traverse_tb.cu; traceRayWithTreelets only): rounds of "bin the rays by next
+    // treelet, stage shared treelets with TMA, drain"; bit-identical results, measured slower (profiles/README.md)
+    const bool binned = !wavefront && mode == VSRT_MODE_TREELET && !av.force_exact && n && getenv("VSRT_K1_TB") && atoi(getenv("VSRT_K1_TB")) != 0;
+    if (binned) {
+      if (!c->tb_tables) { rc = vsrt_tb_build_layout(av, c->fo, c->fr.n_treelets, &c->tb_tables, st); if (rc) return fail(c, rc, "building the treelet-layout copy failed: %s", cudaGetErrorString(cudaGetLastError())); }
+      CUDA_OK(c, c->d_tb.ensure(vsrt_tb_scratch_bytes(n, stack_entries)));
+    }
     unsigned wf_grid = 0;
     if (wavefront && n) {
       wf_grid = vsrt_wf_grid(n);
@@ -194,7 +202,8 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       tp.gstack = (uint2*)c->d_gstack.p; tp.stack_n = stack_entries;
     } else { tp.gstack = nullptr; tp.stack_n = stack_entries; }
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
-    rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, av.force_exact != 0, st) : vsrt_launch_traverse(tp, stack_entries, av.force_exact != 0, st);
+    if (binned) { tp.perm = nullptr; tp.perm_on = nullptr; rc = vsrt_launch_traverse_tb(tp, c->tb_tables, stack_entries, c->d_tb.p, c->tb_stats, st); }
+    else rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, av.force_exact != 0, st) : vsrt_launch_traverse(tp, stack_entries, av.force_exact != 0, st);
     if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     launches += n ? 1 : 0;
     if (!av.force_exact && n) {
@@ -337,7 +346,7 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
-  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release();
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release();
   for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -661,6 +670,11 @@ int vsrt_get_treelet_histogram(vsrt_context* c, uint64_t* hist, uint64_t capacit
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   CUDA_OK(c, cudaMemcpy(hist, c->d_hist.p, (size_t)c->hist_n * 8, cudaMemcpyDeviceToHost));
   return VSRT_OK;
+}
+// debug export (not in vsrt.h): statistics of the last batch the treelet-binned kernel traced (TbParams::stats + rounds)
+int vsrt_debug_tb_stats(vsrt_context* c, unsigned long long out[8]) {
+  if (!c || !out) return VSRT_E_INVALID;
+  memcpy(out, c->tb_stats, sizeof(c->tb_stats)); return VSRT_OK;
 }
 int vsrt_counters_device(vsrt_context* c, void** counters_dev, void** hist_dev, uint64_t* n_treelets) {
   if (!c) return VSRT_E_INVALID;

@@ -46,6 +46,7 @@ struct vsrt_context {
   DevBuf<uint64_t> d_offsets; DevBuf<vsrt_txn> d_txns; DevBuf<uint32_t> d_tids; DevBuf<uint64_t> d_tid_addr; DevBuf<uint32_t> d_packed; DevBuf<uint8_t> d_scan_tmp;
   uint32_t stage_cap = 128;
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
+  void* tb_tables = nullptr; DevBuf<uint8_t> d_tb; unsigned long long tb_stats[8] = { 0 };   // treelet-binned K1 (traverse_tb.cu): layout copy, scratch, statistics of the last batch
   DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
   // pinned host memory: the per-batch read-backs (record total, error flags, counters) land here without a staging copy, and

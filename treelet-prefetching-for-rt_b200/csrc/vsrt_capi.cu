@@ -109,41 +109,9 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
   return VSRT_OK;
 }
 
-// AUTO ray order: is the batch worth sorting?  256 pairs of consecutive rays, evenly spread over the batch, are read back (one
-// strided copy, ~10 us).  The sort groups rays by origin cells of 1/128 of the batch's extent per axis, so it can only improve on
-// an input whose neighbours are farther apart than that: a camera batch (one origin) and bounce rays generated in pixel order
-// (neighbouring pixels, neighbouring hit points) are left as they are -- measured: sorting those costs K1 15-19 % -- while
-// unordered rays are sorted.
-int input_order_is_scattered(vsrt_context* c, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st, bool* scattered) {
-  constexpr int S = 256;
-  const uint64_t stride = n / S;
-  *scattered = false;
-  if (stride < 2) return VSRT_OK;
-  vsrt_ray* h = reinterpret_cast<vsrt_ray*>(c->h_pin + vsrt_context::PIN_HEAD);
-  CUDA_OK(c, cudaMemcpy2DAsync(h, 2 * sizeof(vsrt_ray), d_rays, stride * sizeof(vsrt_ray), 2 * sizeof(vsrt_ray), S, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(c, cudaStreamSynchronize(st));
-  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, dist[S]; int pairs = 0;
-  for (int i = 0; i < S; i++) {
-    const vsrt_ray& a = h[2 * i]; const vsrt_ray& b = h[2 * i + 1];
-    double d = 0.0; bool ok = true;
-    for (int k = 0; k < 3; k++) {
-      const double x = a.origin[k], y = b.origin[k];
-      if (!(x == x) || !(y == y) || x - x != 0.0 || y - y != 0.0) { ok = false; break; }    // NaN / infinite origins: not counted
-      lo[k] = std::min(lo[k], std::min(x, y)); hi[k] = std::max(hi[k], std::max(x, y));
-      d += x > y ? x - y : y - x;
-    }
-    if (ok) dist[pairs++] = d;
-  }
-  if (!pairs) return VSRT_OK;
-  // the MEDIAN distance: pixel-ordered bounce rays jump at every silhouette, and a few long jumps must not outvote the many short steps
-  std::nth_element(dist, dist + pairs / 2, dist + pairs);
-  const double extent = (hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2]);
-  *scattered = extent > 0.0 && dist[pairs / 2] > extent / 128.0;
-  return VSRT_OK;
-}
-
-// K1 -> scan -> K3 over rays already resident at d_rays
-int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st) {
+// packed_out: K3 writes the 4-byte packed records into d_packed instead of the 16-byte records + treelet indices (the host
+// form of vsrt_trace_rays_packed); ensure_full_records() expands them later if a caller asks for the full form after all
+int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st, bool packed_out = false) {
   if (mode != VSRT_MODE_DFS && mode != VSRT_MODE_TREELET) return fail(c, VSRT_E_INVALID, "mode must be VSRT_MODE_DFS or VSRT_MODE_TREELET");
   if (n >= (1ull << 32) - 1) return fail(c, VSRT_E_INVALID, "a batch holds at most 2^32-2 rays; split the frame");
   int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;   // lazily, like :1593 / :2364
@@ -170,13 +138,15 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
-    { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 4u; }
+    { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 1u; }   // round-2 sweep: leaf threshold 1 is best on the headline (1 %) and on the incoherent configs (6 %)
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; tp.perm = nullptr; tp.perm_on = nullptr;
     // ray order (rayorder.cu): which rays share a warp; batches too small to fill the GPU twice are left alone
     uint32_t ray_order = c->cfg.ray_order;
     if (const char* ro = getenv("VSRT_RAY_ORDER")) ray_order = (uint32_t)atoi(ro);
-    bool want_order = ray_order != VSRT_RAY_ORDER_INPUT && n >= c->order_min_rays;
-    if (want_order && ray_order == VSRT_RAY_ORDER_AUTO) { rc = input_order_is_scattered(c, d_rays, n, st, &want_order); if (rc) return rc; }
+    // AUTO is the input order: on every workload measured (camera rays, pixel-ordered bounce rays, a triangle soup's bounce rays,
+    // uniformly random rays) the sorted order raised K1's L1 / L2 hit rates and cut its DRAM reads by up to 30 %, and still made it
+    // 15-30 % SLOWER (profiles/README.md, round 2) -- so sorting is something a caller asks for, not something the library guesses
+    const bool want_order = ray_order == VSRT_RAY_ORDER_SORTED && n >= c->order_min_rays;
     CUDA_OK(c, cudaEventRecord(c->ev[4], st));
     if (want_order) {
       CUDA_OK(c, c->d_order.ensure(vsrt_rayorder_tmp_bytes(n)));
@@ -224,9 +194,10 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
     cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
     cp.err_flags = c->d_err; cp.fatal_mask = EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED;
-    uint64_t queued_cap = std::min(c->d_txns.cap, c->d_tids.cap);
+    cp.packed = nullptr; cp.count = 1; cp.pad3 = 0;
+    uint64_t queued_cap = packed_out ? c->d_packed.cap : std::min(c->d_txns.cap, c->d_tids.cap);
     if (queued_cap && n) {
-      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = queued_cap;
+      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.packed = packed_out ? c->d_packed.p : nullptr; cp.out_capacity = queued_cap;
       rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
       launches++;
     }
@@ -255,8 +226,11 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     }
     if (!queued_cap || total > queued_cap) {
       // first batch, or more records than the buffers held: the queued K3 declined; grow and run it now
-      CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
-      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap);
+      if (packed_out) { CUDA_OK(c, c->d_packed.ensure(std::max<uint64_t>(total, 1))); cp.packed = c->d_packed.p; cp.out_capacity = c->d_packed.cap; }
+      else {
+        CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
+        cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap);
+      }
       if (n) {
         rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
         launches++;
@@ -271,12 +245,32 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     c->h_prev = now;
     break;
   }
-  c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p; c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p;
+  c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p;
+  c->last.txns = packed_out ? nullptr : c->d_txns.p; c->last.treelet_ids = packed_out ? nullptr : c->d_tids.p;
+  c->last_packed_only = packed_out; c->last_av = av;
   c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;
   cudaEventElapsedTime(&c->last.order_ms, c->ev[4], c->ev[0]);
   cudaEventElapsedTime(&c->last.traverse_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->last.scan_ms, c->ev[1], c->ev[2]);
   cudaEventElapsedTime(&c->last.compact_ms, c->ev[2], c->ev[3]);
+  return VSRT_OK;
+}
+
+// The last batch was delivered in packed form only: expand its staged records into the 16-byte records + treelet indices now
+// (same K3, counters and histogram untouched -- they were accumulated when the batch ran).
+int ensure_full_records(vsrt_context* c) {
+  if (!c->last_packed_only) return VSRT_OK;
+  const uint64_t total = c->last.n_txn, n = c->last.n_rays;
+  CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
+  if (n) {
+    CompactParams cp; cp.av = c->last_av; cp.tv = treelet_view(c); cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)c->last_mode;
+    cp.offsets = c->d_offsets.p; cp.n_rays = n; cp.counters = c->d_counters; cp.treelet_hist = nullptr;
+    cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr; cp.err_flags = nullptr; cp.fatal_mask = 0;
+    cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap); cp.packed = nullptr; cp.count = 0; cp.pad3 = 0;
+    int rc = vsrt_launch_compact(cp, c->stream); if (rc) return fail(c, rc, "compaction kernel launch failed");
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  }
+  c->last.txns = c->d_txns.p; c->last.treelet_ids = c->d_tids.p; c->last_packed_only = false;
   return VSRT_OK;
 }
 
@@ -346,7 +340,10 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
-  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release();
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_hits_alt.release(); c->d_offsets_alt.release(); c->d_packed_alt.release();
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream); if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  for (int i = 0; i < 2; i++) { if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]); if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); }
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -414,7 +411,7 @@ int vsrt_set_treelet_layout_base(vsrt_context* c, uint64_t base) {
 int vsrt_treelet_info_get(vsrt_context* c, vsrt_treelet_info* out) {
   if (!c || !out) return VSRT_E_INVALID;
   if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
-  out->n_treelets = c->fr.n_treelets; out->n_list_entries = c->fr.n_entries; out->n_mapped_nodes = c->fr.n_mapped; out->total_bvh_size = c->fr.total_bvh; out->form_ms = c->fr.ms;
+  out->n_treelets = c->fr.n_treelets; out->n_list_entries = c->fr.n_entries; out->n_mapped_nodes = c->fr.n_mapped; out->total_bvh_size = c->fr.total_bvh; out->form_ms = c->fr.ms; out->scratch_bytes = c->fr.peak_scratch_bytes;
   return VSRT_OK;
 }
 
@@ -520,12 +517,15 @@ int vsrt_trace_rays_device(vsrt_context* c, const void* tlas, int mode, uint64_t
 
 int vsrt_trace_device_results(vsrt_context* c, vsrt_device_results* out) {
   if (!c || !out) return VSRT_E_INVALID;
+  cudaSetDevice(c->device);
+  int rc = ensure_full_records(c); if (rc) return rc;
   *out = c->last; return VSRT_OK;
 }
 
 int vsrt_trace_fetch(vsrt_context* c, vsrt_txn* txns, uint64_t cap, uint64_t* treelet_ids) {
   if (!c) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
+  { int rc0 = ensure_full_records(c); if (rc0) return rc0; }
   const uint64_t total = c->last.n_txn, m = std::min(total, cap);
   if (txns && m) CUDA_OK(c, cudaMemcpyAsync(txns, c->last.txns, m * sizeof(vsrt_txn), cudaMemcpyDeviceToHost, c->stream));
   if (treelet_ids && m) {
@@ -604,28 +604,120 @@ int vsrt_trace_fetch_packed(vsrt_context* c, uint32_t* records, uint64_t cap, ui
   vsrt_packed_layout lay; int rc = vsrt_packed_layout_get(c, (const void*)(uintptr_t)c->last_tlas, &lay); if (rc) return rc;
   const uint64_t total = c->last.n_txn, m = std::min(total, cap);
   if (records && m) {
-    CUDA_OK(c, c->d_packed.ensure(m));
-    rc = vsrt_launch_pack_trace(c->d_stage.p, c->stage_cap, c->d_offsets.p, c->last.n_rays, c->d_packed.p, m, c->stream); if (rc) return fail(c, rc, "pack kernel launch failed");
+    if (!c->last_packed_only) {      // (a batch traced in packed form has its packed records in d_packed already: K3 wrote them)
+      CUDA_OK(c, c->d_packed.ensure(m));
+      rc = vsrt_launch_pack_trace(c->d_stage.p, c->stage_cap, c->d_offsets.p, c->last.n_rays, c->d_packed.p, m, c->stream); if (rc) return fail(c, rc, "pack kernel launch failed");
+    }
     CUDA_OK(c, cudaMemcpyAsync(records, c->d_packed.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
   }
-  if (treelet_index && m) CUDA_OK(c, cudaMemcpyAsync(treelet_index, c->d_tids.p, m * 4, cudaMemcpyDeviceToHost, c->stream));   // traversal order, whatever vsrt_sort_trace did since
+  if (treelet_index && m) {
+    rc = ensure_full_records(c); if (rc) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(treelet_index, c->d_tids.p, m * 4, cudaMemcpyDeviceToHost, c->stream));   // traversal order, whatever vsrt_sort_trace did since
+  }
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return total > cap ? VSRT_E_CAPACITY : VSRT_OK;
 }
+
+}  // extern "C"
+
+namespace {
+__global__ void k_add_base(unsigned long long* __restrict__ off, uint64_t n, unsigned long long base) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) off[i] += base;
+}
+
+// vsrt_trace_rays_packed for a frame-sized batch: the rays are traced in chunks, and while chunk i + 1 is uploaded and traced the
+// hits / offsets / packed records of chunk i go back over PCIe on a second stream (the outputs alternate between two sets of
+// device buffers).  A frame's trace is a few hundred MB even in packed form, so the device->host copy is what bounds a host-side
+// caller; everything else hides beneath it.  Ray ids follow the batch order (chunks are traced in order on one stream).
+int trace_packed_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
+                           uint32_t* records, uint64_t capacity, uint64_t* n_txn, uint64_t chunk) {
+  if (!c->copy_stream) {
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)); CUDA_OK(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)); CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)); }
+    CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  }
+  CUDA_OK(c, c->d_rays.ensure(n));
+  const uint64_t n_chunks = (n + chunk - 1) / chunk;
+  uint64_t base = 0; int rc = VSRT_OK; bool overflow = false;
+  auto swap_sets = [&]() { std::swap(c->d_hits, c->d_hits_alt); std::swap(c->d_offsets, c->d_offsets_alt); std::swap(c->d_packed, c->d_packed_alt); };
+  // upload of chunk 0
+  CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, std::min(chunk, n) * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
+  CUDA_OK(c, cudaEventRecord(c->ev_up[0], c->up_stream));
+  bool set_busy[2] = { false, false };
+  for (uint64_t k = 0; k < n_chunks; k++) {
+    const uint64_t r0 = k * chunk, m = std::min(chunk, n - r0); const int b = (int)(k & 1);
+    CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_up[b], 0));
+    if (k + 1 < n_chunks) {   // next chunk's rays go up while this one is traced
+      const uint64_t r1 = r0 + chunk, m1 = std::min(chunk, n - r1);
+      CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p + r1, rays + r1, m1 * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
+      CUDA_OK(c, cudaEventRecord(c->ev_up[b ^ 1], c->up_stream));
+    }
+    if (set_busy[b]) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copy[b], 0));     // this output set is still being copied out (chunk k - 2)
+    rc = run_batch(c, tlas, mode, c->d_rays.p + r0, m, c->stream, true);             // ends with a host synchronisation of c->stream
+    if (rc) break;
+    const uint64_t total = c->last.n_txn;
+    if (trace_offsets) { k_add_base<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c->stream>>>((unsigned long long*)c->d_offsets.p, m + 1, base); }
+    cudaEvent_t ready = c->ev_ready;                                                // "chunk k's outputs are final"
+    CUDA_OK(c, cudaEventRecord(ready, c->stream));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, ready, 0));
+    if (hits) CUDA_OK(c, cudaMemcpyAsync(hits + r0, c->d_hits.p, m * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets + r0, c->d_offsets.p, (m + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (records && base < capacity) {
+      const uint64_t mrec = std::min(total, capacity - base);
+      if (mrec) CUDA_OK(c, cudaMemcpyAsync(records + base, c->d_packed.p, mrec * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    if (base + total > capacity) overflow = true;
+    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+    set_busy[b] = true;
+    base += total;
+    swap_sets();                                                                    // the next chunk writes into the other output set
+  }
+  cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->up_stream);
+  if (n_chunks & 1) swap_sets();                                                    // leave the sets as they were found
+  if (n_txn) *n_txn = base;
+  // vsrt_trace_device_results / vsrt_trace_fetch* describe single batches: after a chunked call there is no "last batch"
+  c->last = vsrt_device_results{}; c->last_packed_only = false;
+  if (rc) return rc;
+  return (records && overflow) ? VSRT_E_CAPACITY : VSRT_OK;
+}
+}  // namespace
+
+extern "C" {
 
 int vsrt_trace_rays_packed(vsrt_context* c, const void* tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
                            uint32_t* records, uint64_t capacity, uint32_t* treelet_index, uint64_t* n_txn) {
   if (!c || !tlas || (n && !rays)) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
+  // frame-sized batches whose records are wanted without the treelet-index stream (derive it from vsrt_node_treelet_table) are
+  // traced in chunks with the copies overlapped; VSRT_PIPELINE_CHUNK sets the chunk size in rays (0 = never)
+  uint64_t chunk = 524288;
+  if (const char* e = getenv("VSRT_PIPELINE_CHUNK")) chunk = (uint64_t)atoll(e);
+  if (chunk && records && !treelet_index && n >= 2 * chunk) {
+    vsrt_packed_layout lay; int rc0 = vsrt_packed_layout_get(c, tlas, &lay); if (rc0) return rc0;
+    return trace_packed_pipelined(c, (uint64_t)(uintptr_t)tlas, mode, n, rays, hits, trace_offsets, records, capacity, n_txn, chunk);
+  }
   CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
   if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));
-  int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, c->d_rays.p, n, c->stream);
+  const bool packed_only = !treelet_index;
+  int rc = run_batch(c, (uint64_t)(uintptr_t)tlas, mode, c->d_rays.p, n, c->stream, packed_only);
   if (n_txn) *n_txn = c->last.n_txn;
   if (rc) return rc;
   if (hits && n) CUDA_OK(c, cudaMemcpyAsync(hits, c->d_hits.p, n * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->stream));
   if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets, c->d_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   if (records || treelet_index) return vsrt_trace_fetch_packed(c, records, capacity, treelet_index);
   CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return VSRT_OK;
+}
+
+int vsrt_node_treelet_table(vsrt_context* c, uint32_t* treelet_of_slot, uint64_t capacity, uint64_t* n_slots) {
+  if (!c) return VSRT_E_INVALID;
+  if (!c->formed) return fail(c, VSRT_E_INVALID, "treelets not formed");
+  cudaSetDevice(c->device);
+  int rc = ensure_mirrors(c); if (rc) return rc;
+  if (n_slots) *n_slots = c->h_node_tid.size();
+  if (!treelet_of_slot) return VSRT_OK;
+  if (capacity < c->h_node_tid.size()) return fail(c, VSRT_E_CAPACITY, "the table has %zu entries", c->h_node_tid.size());
+  memcpy(treelet_of_slot, c->h_node_tid.data(), c->h_node_tid.size() * 4);
   return VSRT_OK;
 }
 
@@ -690,6 +782,7 @@ int vsrt_sort_trace(vsrt_context* c, int method) {
   if (method != 0 && method != 1) return fail(c, VSRT_E_INVALID, "sort method must be 0 (strict) or 1 (loose), -sort_method of gpgpusim.config");
   if (!c->formed || !c->last.trace_offsets) return fail(c, VSRT_E_INVALID, "no trace to sort: call vsrt_trace_rays / vsrt_trace_rays_device first");
   cudaSetDevice(c->device);
+  { int rc0 = ensure_full_records(c); if (rc0) return rc0; }
   const uint64_t n = c->last.n_rays, total = c->last.n_txn;
   CUDA_OK(c, c->d_txns_sorted.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids_sorted.ensure(std::max<uint64_t>(total, 1)));
   CUDA_OK(c, c->d_sort_keys.ensure(std::max<uint64_t>(total, 1)));
@@ -742,6 +835,7 @@ int vsrt_prefetch_vote(vsrt_context* c, const vsrt_prefetch_config* cfg, uint64_
   if (n_groups == 0) return VSRT_OK;
   cudaSetDevice(c->device);
   int rc = ensure_mirrors(c); if (rc) return rc;
+  rc = ensure_full_records(c); if (rc) return rc;
   const uint64_t n_ids = group_offsets[n_groups];
   if (!ray_ids && n_ids > c->last.n_rays) return fail(c, VSRT_E_INVALID, "groups cover %llu rays, the last batch has %llu", (unsigned long long)n_ids, (unsigned long long)c->last.n_rays);
   uint64_t* d_go = nullptr; uint64_t* d_ids = nullptr; uint32_t* d_front = nullptr; vsrt_prefetch_decision* d_out = nullptr;
@@ -808,6 +902,7 @@ int vsrt_schedule_pick(vsrt_context* c, int scheduler, uint64_t n_units, const u
   if (n_units == 0) return VSRT_OK;
   cudaSetDevice(c->device);
   int rc = ensure_mirrors(c); if (rc) return rc;
+  rc = ensure_full_records(c); if (rc) return rc;
   const uint64_t n_warps = unit_warp_offsets[n_units];
   std::vector<uint32_t> target(n_units, VSRT_NO_TID);
   if (last_prefetched) for (uint64_t u = 0; u < n_units; u++) { uint32_t t; if (last_prefetched[u] && treelet_index_of(c, last_prefetched[u], &t)) target[u] = t; }

@@ -66,6 +66,9 @@ struct vsrt_context {
   cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
   vsrt_device_results last{};
   uint64_t last_tlas = 0; int last_mode = 0; const vsrt_ray* last_rays = nullptr;
+  bool last_packed_only = false; ArenaView last_av{};   // the last batch was delivered as packed records only (vsrt_trace_rays_packed)
+  // chunk pipeline of vsrt_trace_rays_packed: second output set + copy streams
+  DevBuf<vsrt_hit> d_hits_alt; DevBuf<uint64_t> d_offsets_alt; DevBuf<uint32_t> d_packed_alt; cudaStream_t copy_stream = nullptr, up_stream = nullptr; cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_up[2] = { nullptr, nullptr }, ev_ready = nullptr;
   CommState* comm = nullptr;   // multi-GPU reduce state (reduce.cu), NULL until vsrt_comm_init / vsrt_comm_attach
 };
 

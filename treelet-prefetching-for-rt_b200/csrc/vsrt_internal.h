@@ -75,7 +75,7 @@ enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 1
 enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */, EF_NEED_EXACT = 128 /* not an error */ };
 
 // ---- launchers (each file implements its kernels) ----
-struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; uint32_t inst_base; };
+struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; uint32_t inst_base; uint64_t peak_scratch_bytes; };
 struct FormOutputs {      // device allocations owned by the context
   uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
 };
@@ -138,6 +138,8 @@ struct CompactParams {
   const uint32_t* stage; uint32_t cap; uint32_t mode;
   const uint64_t* offsets; uint64_t n_rays;
   vsrt_txn* txns; uint32_t* tids; uint64_t out_capacity;
+  uint32_t* packed;           // != NULL: write 4-byte packed records here instead of txns / tids
+  uint32_t count; uint32_t pad3;   // 0: records only -- counters and histogram were already accumulated for this batch
   DevCounters* counters; unsigned long long* treelet_hist;   // may be NULL
   const uint64_t* remap;      // -remap_to_treelet_layout: record address = remap[slot] (NULL = original addresses)
   const uint32_t* err_flags;  // K3 does nothing if (*err_flags & fatal_mask) or if the batch has more records than out_capacity:

@@ -37,7 +37,7 @@ class Config(ctypes.Structure):
 class TreeletInfo(ctypes.Structure):
     _fields_ = [("n_treelets", ctypes.c_uint64), ("n_list_entries", ctypes.c_uint64),
                 ("n_mapped_nodes", ctypes.c_uint64), ("total_bvh_size", ctypes.c_uint64),
-                ("form_ms", ctypes.c_double)]
+                ("form_ms", ctypes.c_double), ("scratch_bytes", ctypes.c_uint64)]
 
 
 class DeviceResults(ctypes.Structure):

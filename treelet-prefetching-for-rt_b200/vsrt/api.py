@@ -33,7 +33,7 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_packed_layout_get", "vsrt_trace_fetch_packed", "vsrt_trace_rays_packed", "vsrt_unpack_txns",
            "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image",
            "vsrt_comm_unique_id", "vsrt_comm_init", "vsrt_comm_attach", "vsrt_comm_destroy", "vsrt_reduce_counters", "vsrt_reduce_wait",
-           "vsrt_reduced_get", "vsrt_reduced_device"]
+           "vsrt_reduced_get", "vsrt_reduced_device", "vsrt_node_treelet_table"]
 
 
 class VsrtError(RuntimeError):
@@ -99,6 +99,7 @@ def load():
     L.vsrt_reset_counters.argtypes = [c_vp]
     L.vsrt_counters_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
     L.vsrt_get_treelet_histogram.argtypes = [c_vp, c_vp, c_u64]
+    L.vsrt_node_treelet_table.argtypes = [c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
     L.vsrt_comm_unique_id.argtypes = [c_vp]
     L.vsrt_comm_init.argtypes = [c_vp, c_u32, c_u32, c_vp]
     L.vsrt_comm_attach.argtypes = [c_vp, c_vp, c_u32, c_u32]
@@ -353,6 +354,24 @@ class Context:
         rec = np.ascontiguousarray(records, np.uint32); out = np.zeros(len(rec), _abi.TXN)
         self.L.vsrt_unpack_txns(ctypes.byref(lay), _abi.ptr(rec), len(rec), _abi.ptr(out))
         return out
+
+    def node_treelet_table(self):
+        """Treelet index of every slot of the packed arena (0xFFFFFFFF = none): treelet of a packed record = table[record >> 3]."""
+        n = c_u64()
+        self._ck(self.L.vsrt_node_treelet_table(self.h, None, 0, ctypes.byref(n)))
+        t = np.zeros(n.value, np.uint32)
+        self._ck(self.L.vsrt_node_treelet_table(self.h, _abi.ptr(t), n.value, ctypes.byref(n)))
+        return t
+
+    def trace_packed(self, mode, rays, want_index=False):
+        """vsrt_trace_rays_packed on numpy buffers: (hits, offsets, packed records[, treelet indices])."""
+        rays = np.ascontiguousarray(rays, dtype=_abi.RAY)
+        n = len(rays)
+        hits = np.zeros(n, _abi.HIT); offs = np.zeros(n + 1, np.uint64); total = c_u64()
+        self._ck(self.L.vsrt_trace_rays_packed(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(offs), None, 0, None, ctypes.byref(total)), allow=(-4,))
+        rec = np.zeros(total.value, np.uint32); tix = np.zeros(total.value, np.uint32) if want_index else None
+        self._ck(self.L.vsrt_trace_rays_packed(self.h, self.tlas, mode, n, _abi.ptr(rays), _abi.ptr(hits), _abi.ptr(offs), _abi.ptr(rec), total.value, _abi.ptr(tix), ctypes.byref(total)))
+        return hits, offs, rec, tix
 
     def trace_packed_into(self, mode, n, rays_ptr, hits_ptr, offsets_ptr, rec_ptr, capacity, tix_ptr):
         """vsrt_trace_rays_packed on caller-owned (e.g. pinned) host buffers given as raw addresses; returns #records."""

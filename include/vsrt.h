@@ -239,6 +239,13 @@ int vsrt_counters_device(vsrt_context* ctx, void** counters_dev, void** treelet_
  * batch since the last vsrt_reset_counters / vsrt_form_treelets. */
 int vsrt_get_treelet_histogram(vsrt_context* ctx, uint64_t* hist, uint64_t capacity);
 
+/* ---- node-visit histogram (optional) ----
+ * Records per node address, as a count per 64-byte slot of the packed arena (slot -> address: vsrt_packed_layout; slot -> treelet:
+ * vsrt_node_treelet_table): the per-node popularity behind the per-treelet one.  Off by default (one more kernel per batch);
+ * accumulated over every batch traced while it is on, cleared by vsrt_reset_counters; included in vsrt_reduce_counters when on. */
+int vsrt_enable_node_histogram(vsrt_context* ctx, int enable);
+int vsrt_get_node_histogram(vsrt_context* ctx, uint64_t* visits_of_slot, uint64_t capacity, uint64_t* n_slots);
+
 /* ---- multi-GPU: the reduce of the functional counters and the treelet visit histogram ----
  * The path shards by rays (one context per GPU, the BVH and the treelet tables replicated, rank r traces its own ray-id block);
  * nothing is exchanged on the data path.  What a multi-GPU run has to combine are the counters above (cuda-sim.h:155-166) and the
@@ -265,6 +272,7 @@ int vsrt_reduce_counters(vsrt_context* ctx, void* stream);
 int vsrt_reduce_wait(vsrt_context* ctx, void* stream);
 int vsrt_reduced_get(vsrt_context* ctx, vsrt_counters* out, uint64_t* treelet_hist, uint64_t capacity);
 int vsrt_reduced_device(vsrt_context* ctx, void** counters_dev, void** treelet_hist_dev, uint64_t* n_treelets);
+int vsrt_reduced_get_node_histogram(vsrt_context* ctx, uint64_t* visits_of_slot, uint64_t capacity);   /* global node-visit histogram (if enabled on every rank) */
 
 /* ---- RT-unit replay helpers: what rt_unit (gpgpu-sim/shader.cc) does with the trace, batched over the last batch ----
  * rt_unit::sort_mem_accesses (shader.cc:3012-3089) applied to every ray's list: method = -sort_method (0 strict treelet

@@ -36,7 +36,7 @@ def test_exports_every_declared_symbol(api):
 
 def test_struct_sizes():
     assert _abi.RAY.itemsize == 52 and _abi.HIT.itemsize == 56 and _abi.TXN.itemsize == 16
-    assert ctypes.sizeof(_abi.Config) == 32 and ctypes.sizeof(_abi.DeviceResults) == 80 and ctypes.sizeof(_abi.TreeletInfo) == 40
+    assert ctypes.sizeof(_abi.Config) == 32 and ctypes.sizeof(_abi.DeviceResults) == 80 and ctypes.sizeof(_abi.TreeletInfo) == 48
     assert _abi.HIT.fields["instance_leaf_address"][1] == 48
     assert ctypes.sizeof(_abi.PackedLayout) == 144 and _abi.CEV.itemsize == 16
 

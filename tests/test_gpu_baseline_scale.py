@@ -179,12 +179,13 @@ def test_two_gpu_reduce_inside_the_library(api):
         try:
             ctx = api.Context(max_treelet_size=512, device=rank)
             ctx.register(s); ctx.form_treelets()
+            ctx.enable_node_histogram()
             ctx.comm_init(2, rank, uid)
             first, count = shard.shard_range(len(rays), 2, rank)
             for _ in range(frames):
                 ctx.trace(1, rays[first:first + count], want_trace=False)
                 ctx.reduce_counters()
-            out[rank] = ctx.reduced()
+            out[rank] = ctx.reduced() + (ctx.node_histogram(reduced=True),)
             ctx.close()
         except Exception as e:    # noqa: BLE001
             errs.append(e)
@@ -193,11 +194,12 @@ def test_two_gpu_reduce_inside_the_library(api):
     assert not errs, errs
     ctx = api.Context(max_treelet_size=512, device=0)
     ctx.register(s); ctx.form_treelets()
+    ctx.enable_node_histogram()
     for _ in range(frames):
         ctx.trace(1, rays, want_trace=False)
-    want, hist = ctx.counters(), ctx.treelet_histogram()
+    want, hist, nodes = ctx.counters(), ctx.treelet_histogram(), ctx.node_histogram()
     ctx.close()
     for rank in (0, 1):
-        got, ghist = out[rank]
+        got, ghist, gnodes = out[rank]
         assert got == want, (rank, got, want)
-        assert np.array_equal(ghist, hist)
+        assert np.array_equal(ghist, hist) and np.array_equal(gnodes, nodes)

@@ -286,7 +286,34 @@ __global__ void __launch_bounds__(256) k_pack_trace(const uint32_t* __restrict__
   for (unsigned long long k = threadIdx.x & 31u; o0 + k < o1 && o0 + k < out_capacity; k += 32u) out[o0 + k] = __ldg(seg + k);
 }
 
+// Node-visit histogram (optional): records per node address, per 64-byte slot.  One warp takes 32 consecutive rays and
+// walks their staged records row by row (lane = ray, row = k-th record): near the top of the tree the lanes of a row name the
+// same few nodes, so the row is grouped with __match_any_sync and only the first lane of each group adds, with the group's size
+// -- the root gets one atomic per warp instead of one per ray.
+__global__ void __launch_bounds__(256) k_node_hist(const uint32_t* __restrict__ stage, uint32_t cap, const unsigned long long* __restrict__ offsets, uint64_t n_rays,
+                                                   unsigned long long* __restrict__ hist, const uint32_t* __restrict__ err_flags, uint32_t fatal_mask) {
+  if (err_flags && (*reinterpret_cast<const volatile uint32_t*>(err_flags) & fatal_mask)) return;
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cnt = r < n_rays ? (uint32_t)(offsets[r + 1] - offsets[r]) : 0u;
+  const uint32_t rows = __reduce_max_sync(0xffffffffu, cnt);
+  const uint32_t* seg = stage + r * (uint64_t)cap;
+  for (uint32_t k = 0; k < rows; k++) {
+    const bool v = k < cnt;
+    const uint32_t slot = v ? (__ldg(seg + k) >> 3) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    if (v && lane == __ffs(peers) - 1) atomicAdd(hist + slot, (unsigned long long)__popc(peers));
+  }
+}
+
 }  // namespace
+
+int vsrt_launch_node_hist(const uint32_t* stage, uint32_t cap, const uint64_t* offsets, uint64_t n_rays, unsigned long long* hist, const uint32_t* err_flags,
+                          uint32_t fatal_mask, cudaStream_t st) {
+  if (n_rays == 0) return VSRT_OK;
+  k_node_hist<<<(unsigned)((n_rays + 255) / 256), 256, 0, st>>>(stage, cap, (const unsigned long long*)offsets, n_rays, hist, err_flags, fatal_mask);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
 
 size_t vsrt_scan_tmp_bytes(uint64_t n) { return ((n + SCAN_TILE - 1) / SCAN_TILE + 2) * sizeof(unsigned long long); }
 

@@ -60,9 +60,9 @@ __host__ __device__ inline uint32_t hdr_words(uint32_t n_ranks) { return H_SUM +
 
 __global__ void __launch_bounds__(256) k_snapshot(const DevCounters* __restrict__ now, DevCounters* __restrict__ prev, unsigned long long* __restrict__ hdr,
                                                   uint32_t n_ranks, uint32_t rank, const unsigned long long* __restrict__ hist,
-                                                  unsigned long long* __restrict__ hist_prev, uint32_t* __restrict__ dh, uint32_t n_hist) {
+                                                  unsigned long long* __restrict__ hist_prev, uint32_t* __restrict__ dh, uint32_t n_hist, uint32_t with_header) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && with_header) {
     const uint32_t hw = hdr_words(n_ranks);
     for (uint32_t k = threadIdx.x; k + 1u < hw; k += blockDim.x) {   // the last word (overflow mark) was zeroed by the launcher: other blocks raise it
       unsigned long long v = 0;
@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(256) k_snapshot(const DevCounters* __restrict_
 }
 
 __global__ void __launch_bounds__(256) k_fold(const unsigned long long* __restrict__ hdr, uint32_t n_ranks, DevCounters* __restrict__ g, const uint32_t* __restrict__ dh,
-                                              unsigned long long* __restrict__ g_hist, uint32_t n_hist, uint32_t* __restrict__ flags) {
+                                              unsigned long long* __restrict__ g_hist, uint32_t n_hist, uint32_t* __restrict__ flags, uint32_t with_header) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!with_header) { if (i < n_hist) g_hist[i] += dh[i]; return; }
   if (i < H_SUM) g->v[i] += hdr[i];
   else if (i < H_SUM + H_MAX) {
     unsigned long long m = g->v[i];
@@ -109,6 +110,8 @@ struct CommState {
   DevBuf<unsigned long long> hdr[2]; DevBuf<uint32_t> dh[2];
   DevCounters* prev = nullptr; DevCounters* global = nullptr; uint32_t* flags = nullptr;
   DevBuf<unsigned long long> hist_prev, g_hist; uint32_t n_hist = 0;
+  // the optional node-visit histogram (vsrt_enable_node_histogram): same scheme, per 64-byte slot
+  DevBuf<uint32_t> ndh[2]; DevBuf<unsigned long long> node_prev, g_node; uint32_t n_node = 0;
   uint64_t n_reduces = 0;
 };
 
@@ -146,6 +149,17 @@ int comm_hist_setup(vsrt_context* c) {
   s->n_hist = n;
   return VSRT_OK;
 }
+int comm_node_setup(vsrt_context* c) {
+  CommState* s = c->comm;
+  const uint32_t n = c->node_hist_on ? c->node_hist_n : 0u;
+  if (s->n_node == n) return VSRT_OK;
+  CUDA_OK(c, cudaStreamSynchronize(s->rstream)); CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 2; i++) CUDA_OK(c, s->ndh[i].ensure(std::max<uint32_t>(n, 1)));
+  CUDA_OK(c, s->node_prev.ensure(std::max<uint32_t>(n, 1))); CUDA_OK(c, s->g_node.ensure(std::max<uint32_t>(n, 1)));
+  if (n) { CUDA_OK(c, cudaMemcpy(s->node_prev.p, c->d_node_hist.p, (size_t)n * 8, cudaMemcpyDeviceToDevice)); CUDA_OK(c, cudaMemset(s->g_node.p, 0, (size_t)n * 8)); }
+  s->n_node = n;
+  return VSRT_OK;
+}
 
 }  // namespace
 
@@ -154,7 +168,7 @@ void vsrt_comm_release(vsrt_context* c) {
   if (s->rstream) cudaStreamSynchronize(s->rstream);
   if (s->owned && s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   for (int i = 0; i < 2; i++) { if (s->ready[i]) cudaEventDestroy(s->ready[i]); if (s->done[i]) cudaEventDestroy(s->done[i]); s->hdr[i].release(); s->dh[i].release(); }
-  s->hist_prev.release(); s->g_hist.release();
+  s->hist_prev.release(); s->g_hist.release(); s->node_prev.release(); s->g_node.release(); s->ndh[0].release(); s->ndh[1].release();
   cudaFree(s->prev); cudaFree(s->global); cudaFree(s->flags);
   if (s->rstream) cudaStreamDestroy(s->rstream);
   delete s; c->comm = nullptr;
@@ -166,6 +180,7 @@ int vsrt_comm_counters_reset(vsrt_context* c) {
   CUDA_OK(c, cudaStreamSynchronize(s->rstream));
   CUDA_OK(c, cudaMemset(s->prev, 0, sizeof(DevCounters))); CUDA_OK(c, cudaMemset(s->global, 0, sizeof(DevCounters))); CUDA_OK(c, cudaMemset(s->flags, 0, 4));
   if (s->n_hist != 0xFFFFFFFFu && s->n_hist) { CUDA_OK(c, cudaMemset(s->hist_prev.p, 0, (size_t)s->n_hist * 8)); CUDA_OK(c, cudaMemset(s->g_hist.p, 0, (size_t)s->n_hist * 8)); }
+  if (s->n_node) { CUDA_OK(c, cudaMemset(s->node_prev.p, 0, (size_t)s->n_node * 8)); CUDA_OK(c, cudaMemset(s->g_node.p, 0, (size_t)s->n_node * 8)); }
   return VSRT_OK;
 }
 
@@ -215,23 +230,27 @@ int vsrt_reduce_counters(vsrt_context* c, void* stream) {
   cudaSetDevice(c->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   int rc = comm_hist_setup(c); if (rc) return rc;
+  rc = comm_node_setup(c); if (rc) return rc;
   const int b = s->turn; s->turn ^= 1;
-  const uint32_t n = s->n_hist, hw = hdr_words(s->n_ranks);
+  const uint32_t n = s->n_hist, nn = s->n_node, hw = hdr_words(s->n_ranks);
   // the buffer set may still be read by the fold of two reduces ago
   if (s->used[b]) CUDA_OK(c, cudaStreamWaitEvent(st, s->done[b], 0));
   CUDA_OK(c, cudaMemsetAsync(s->hdr[b].p + hw - 1u, 0, 8, st));
   const uint32_t grid = std::max<uint32_t>(1u, (n + 255u) / 256u);
-  k_snapshot<<<grid, 256, 0, st>>>(c->d_counters, s->prev, s->hdr[b].p, s->n_ranks, s->rank, c->d_hist.p, s->hist_prev.p, s->dh[b].p, n);
+  k_snapshot<<<grid, 256, 0, st>>>(c->d_counters, s->prev, s->hdr[b].p, s->n_ranks, s->rank, c->d_hist.p, s->hist_prev.p, s->dh[b].p, n, 1u);
+  if (nn) k_snapshot<<<(nn + 255u) / 256u, 256, 0, st>>>(c->d_counters, s->prev, s->hdr[b].p, s->n_ranks, s->rank, c->d_node_hist.p, s->node_prev.p, s->ndh[b].p, nn, 0u);
   CUDA_OK(c, cudaGetLastError());
   CUDA_OK(c, cudaEventRecord(s->ready[b], st));
   CUDA_OK(c, cudaStreamWaitEvent(s->rstream, s->ready[b], 0));
   NCCL_OK(c, g_nccl.GroupStart());
   ncclResult_t r1 = g_nccl.AllReduce(s->hdr[b].p, s->hdr[b].p, hw, ncclUint64, ncclSum, s->comm, s->rstream);
   ncclResult_t r2 = n ? g_nccl.AllReduce(s->dh[b].p, s->dh[b].p, n, ncclUint32, ncclSum, s->comm, s->rstream) : ncclSuccess;
+  ncclResult_t r2b = nn ? g_nccl.AllReduce(s->ndh[b].p, s->ndh[b].p, nn, ncclUint32, ncclSum, s->comm, s->rstream) : ncclSuccess;
   ncclResult_t r3 = g_nccl.GroupEnd();
-  NCCL_OK(c, r1); NCCL_OK(c, r2); NCCL_OK(c, r3);
+  NCCL_OK(c, r1); NCCL_OK(c, r2); NCCL_OK(c, r2b); NCCL_OK(c, r3);
   const uint32_t fgrid = (std::max<uint32_t>(n, H_SUM + H_MAX + 1u) + 255u) / 256u;
-  k_fold<<<fgrid, 256, 0, s->rstream>>>(s->hdr[b].p, s->n_ranks, s->global, s->dh[b].p, s->g_hist.p, n, s->flags);
+  k_fold<<<fgrid, 256, 0, s->rstream>>>(s->hdr[b].p, s->n_ranks, s->global, s->dh[b].p, s->g_hist.p, n, s->flags, 1u);
+  if (nn) k_fold<<<(nn + 255u) / 256u, 256, 0, s->rstream>>>(s->hdr[b].p, s->n_ranks, s->global, s->ndh[b].p, s->g_node.p, nn, s->flags, 0u);
   CUDA_OK(c, cudaGetLastError());
   CUDA_OK(c, cudaEventRecord(s->done[b], s->rstream));
   s->used[b] = true; s->n_reduces++;
@@ -263,6 +282,18 @@ int vsrt_reduced_get(vsrt_context* c, vsrt_counters* out, uint64_t* treelet_hist
     if (s->n_hist) CUDA_OK(c, cudaMemcpy(treelet_hist, s->g_hist.p, (size_t)s->n_hist * 8, cudaMemcpyDeviceToHost));
   }
   if (flags & 1u) return vsrt_fail(c, VSRT_E_CAPACITY, "2^32 or more records were traced between two reduces: the 32-bit histogram deltas may have wrapped; reduce more often");
+  return VSRT_OK;
+}
+
+int vsrt_reduced_get_node_histogram(vsrt_context* c, uint64_t* visits_of_slot, uint64_t capacity) {
+  if (!c || !visits_of_slot) return VSRT_E_INVALID;
+  CommState* s = c->comm;
+  if (!s) return vsrt_fail(c, VSRT_E_INVALID, "no communicator");
+  if (!s->n_node) return vsrt_fail(c, VSRT_E_INVALID, "the node-visit histogram was not part of any reduce: vsrt_enable_node_histogram(ctx, 1) on every rank before tracing");
+  if (capacity < s->n_node) return vsrt_fail(c, VSRT_E_CAPACITY, "the node histogram has %u entries", s->n_node);
+  cudaSetDevice(c->device);
+  CUDA_OK(c, cudaStreamSynchronize(s->rstream));
+  CUDA_OK(c, cudaMemcpy(visits_of_slot, s->g_node.p, (size_t)s->n_node * 8, cudaMemcpyDeviceToHost));
   return VSRT_OK;
 }
 

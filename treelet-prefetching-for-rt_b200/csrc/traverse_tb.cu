@@ -27,6 +27,7 @@
 #include "vsrt_device.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -72,6 +73,7 @@ struct TbParams {
   uint32_t* keys_next; uint32_t* ids_next;     // what every ray is filed under for the next round (same positions)
   uint32_t n_live;
   unsigned int* n_live_next;  // rays that need another round
+  uint32_t free_run;          // != 0: the last launch -- no binning, no staging, every lane keeps switching treelets until its ray ends
   unsigned long long* stats;  // [0] rays processed, [1] rays served from a staged treelet, [2] CTAs that staged, [3] bytes staged, [4] node visits from shared memory, [5] node visits from the arena
 };
 
@@ -288,12 +290,13 @@ __global__ void __launch_bounds__(TB_THREADS) k_tb_round(const TbParams q) {
   const uint32_t r = live ? q.ids[i] : 0u;
 
   // ---- which treelet does this CTA stage?  The one its middle ray is in, if enough of its rays share it.
+  const bool free_run = q.free_run != 0u;
   const uint32_t mid = min(blockIdx.x * TB_THREADS + TB_THREADS / 2, q.n_live - 1u);
   const uint32_t cand = q.keys[mid];
   const int sharers = __syncthreads_count(live && key == cand);
   if (threadIdx.x == 0) {
     uint32_t units = 0;
-    if (cand < p.tv.n_treelets && sharers >= VSRT_TB_STAGE_MIN_RAYS && (__ldg(q.lay.tflags + cand) & 1u)) {
+    if (!free_run && cand < p.tv.n_treelets && sharers >= VSRT_TB_STAGE_MIN_RAYS && (__ldg(q.lay.tflags + cand) & 1u)) {
       units = __ldg(q.lay.unit_off + cand + 1u) - __ldg(q.lay.unit_off + cand);
       if (units < VSRT_TB_STAGE_MIN_UNITS || units > TB_SMEM_UNITS) units = 0;
     }
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tb_round(const TbParams q) {
           for (uint32_t j = 0; j < ci; j++) { const uint32_t bj = __byte_perm(t.y, t.z, 0x7770u + j); if (bj & 0x10u) pos += (top && (bj & 0x40u)) ? 3u : 1u; }
           spos = pos;
         }
-      } else if (!took_other && oth_n) {
+      } else if ((!took_other || free_run) && oth_n) {
         took_other = true;
         const uint4 t = ost[oth_n - 1u];
         uint32_t ci; asm("bfind.u32 %0, %1;" : "=r"(ci) : "r"(t.z & 0x3F0000u));
@@ -550,6 +553,12 @@ int vsrt_launch_traverse_tb(const TraverseParams& tp, void* tables, uint32_t sta
   k_tb_init<<<(unsigned)((n + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, st>>>(q);
   // bits of the sort key: treelet indices 0 .. n_treelets (the last = "in no treelet"); a finished ray's key is all ones
   int passes = 1; while (passes < 4 && (1ull << (8 * passes)) <= (unsigned long long)tp.tv.n_treelets + 1ull) passes++;
+  // Binned rounds pay while many rays share treelets, i.e. for the first few treelet levels below the root; the tail -- a few
+  // rays each in a treelet of its own, hundreds of rounds deep -- would be nothing but launch and sort overhead, so after
+  // VSRT_TB_ROUNDS binned rounds (default 8; 0 = bin to the end) one last launch lets every remaining ray run to its end.
+  unsigned long long max_rounds = 8;
+  if (const char* e = getenv("VSRT_TB_ROUNDS")) max_rounds = (unsigned long long)atoll(e);
+  q.free_run = 0;
   unsigned int live = 0; unsigned long long rounds = 0;
   if (cudaMemcpyAsync(&live, d_live, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return VSRT_E_CUDA;
   while (live) {
@@ -557,6 +566,8 @@ int vsrt_launch_traverse_tb(const TraverseParams& tp, void* tables, uint32_t sta
     // dead ones in [0, n_prev): sorting puts the dead (key 0xFFFFFFFF -> low 24/32 bits all ones) last
     const uint64_t n_sort = q.n_live;
     uint32_t* ks = nullptr; uint32_t* is = nullptr;
+    q.free_run = (max_rounds && rounds >= max_rounds) ? 1u : 0u;
+    // (the free-running launch still needs the live rays in front of the dead ones: same sort)
     int rc = vsrt_launch_radix_sort(kA, iA, kB, iB, n_sort, passes, radix_tmp, nullptr, &ks, &is, st); if (rc) return rc;
     if (cudaMemsetAsync(d_live, 0, 4, st) != cudaSuccess) return VSRT_E_CUDA;
     q.keys = ks; q.ids = is; q.n_live = live;

@@ -305,7 +305,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   CK(cudaMalloc(&n_roots_d, 4)); CK(cudaMalloc(&scal, 32)); CK(cudaMemsetAsync(scal, 0, 32, st)); CK(cudaMemsetAsync(scal + 2, 0xff, 4, st));   // [2] = {lowest = ~0, highest = 0} instance-leaf slot, [3] store cursor
   CK(cudaMalloc(&r_count, (size_t)ns * 4)); CK(cudaMalloc(&r_off, (size_t)ns * 8));
   // every node is listed once, plus the nodes that share a treelet with more than one instance of their BLAS
-  store_cap = (unsigned long long)ns + ns / 4 + 4096;
+  store_cap = (unsigned long long)ns + ns / 4 + 256;
   CK(cudaMalloc(&store, (size_t)store_cap * 8));
   // scratch for the roots of one launch: at most 256 MiB, whatever the budget
   scratch_roots = std::max<size_t>(4096, ((size_t)256 << 20) / ((size_t)cap * 8));

@@ -188,6 +188,15 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
     launches += n ? 3 : 0;   // 3 scan kernels
+    bool node_hist_queued = false;
+    auto queue_node_hist = [&]() -> int {
+      if (!c->node_hist_on || !n || node_hist_queued) return VSRT_OK;
+      const uint32_t ns = (uint32_t)(c->arena_bytes / 64);
+      if (c->node_hist_n != ns) { if (c->d_node_hist.ensure(std::max<uint32_t>(ns, 1)) != cudaSuccess || cudaMemsetAsync(c->d_node_hist.p, 0, (size_t)ns * 8, st) != cudaSuccess) return VSRT_E_CUDA; c->node_hist_n = ns; }
+      node_hist_queued = true; launches++;
+      return vsrt_launch_node_hist(c->d_stage.p, c->stage_cap, c->d_offsets.p, n, c->d_node_hist.p, c->d_err, EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED, st);
+    };
+    rc = queue_node_hist(); if (rc) return fail(c, rc, "node histogram launch failed");
     // K3 is queued right away into the buffers of the previous batch; it checks the error flags and the record count on the
     // device and does nothing if either says no.  One host synchronisation per batch in the steady state.
     CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
@@ -340,7 +349,7 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
-  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_hits_alt.release(); c->d_offsets_alt.release(); c->d_packed_alt.release();
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_hits_alt.release(); c->d_offsets_alt.release(); c->d_packed_alt.release();
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream); if (c->up_stream) cudaStreamDestroy(c->up_stream);
   for (int i = 0; i < 2; i++) { if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]); if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); }
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -752,6 +761,7 @@ int vsrt_reset_counters(vsrt_context* c) {
   CUDA_OK(c, cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
   c->h_prev = DevCounters{};
   if (c->hist_n) CUDA_OK(c, cudaMemset(c->d_hist.p, 0, (size_t)c->hist_n * 8));
+  if (c->node_hist_n) CUDA_OK(c, cudaMemset(c->d_node_hist.p, 0, (size_t)c->node_hist_n * 8));
   return vsrt_comm_counters_reset(c);
 }
 int vsrt_get_treelet_histogram(vsrt_context* c, uint64_t* hist, uint64_t capacity) {
@@ -767,6 +777,24 @@ int vsrt_get_treelet_histogram(vsrt_context* c, uint64_t* hist, uint64_t capacit
 int vsrt_debug_tb_stats(vsrt_context* c, unsigned long long out[8]) {
   if (!c || !out) return VSRT_E_INVALID;
   memcpy(out, c->tb_stats, sizeof(c->tb_stats)); return VSRT_OK;
+}
+int vsrt_enable_node_histogram(vsrt_context* c, int enable) {
+  if (!c) return VSRT_E_INVALID;
+  c->node_hist_on = enable != 0;
+  return VSRT_OK;
+}
+int vsrt_get_node_histogram(vsrt_context* c, uint64_t* visits_of_slot, uint64_t capacity, uint64_t* n_slots) {
+  if (!c) return VSRT_E_INVALID;
+  const uint64_t ns = c->arena_bytes / 64;
+  if (n_slots) *n_slots = ns;
+  if (!visits_of_slot) return VSRT_OK;
+  if (!c->node_hist_on) return fail(c, VSRT_E_INVALID, "the node-visit histogram is off: vsrt_enable_node_histogram(ctx, 1) before tracing");
+  if (capacity < ns) return fail(c, VSRT_E_CAPACITY, "the node histogram has %llu entries", (unsigned long long)ns);
+  cudaSetDevice(c->device);
+  CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (c->node_hist_n != ns) { memset(visits_of_slot, 0, ns * 8); return VSRT_OK; }      // nothing traced yet
+  CUDA_OK(c, cudaMemcpy(visits_of_slot, c->d_node_hist.p, ns * 8, cudaMemcpyDeviceToHost));
+  return VSRT_OK;
 }
 int vsrt_counters_device(vsrt_context* c, void** counters_dev, void** hist_dev, uint64_t* n_treelets) {
   if (!c) return VSRT_E_INVALID;

@@ -56,6 +56,7 @@ struct vsrt_context {
   static constexpr size_t PIN_HEAD = 1024, PIN_BYTES = 4u << 20;
   DevCounters h_prev{};
   DevBuf<unsigned long long> d_hist; uint32_t hist_n = 0;
+  bool node_hist_on = false; DevBuf<unsigned long long> d_node_hist; uint32_t node_hist_n = 0;   // optional per-slot visit counts
   // -remap_to_treelet_layout: where gpgpusim_malloc put treelet_layout_bvh (:1477), and the per-slot table
   uint64_t layout_base = 0; bool layout_base_set = false; DevBuf<uint64_t> d_remap; bool remap_valid = false;
   // replay helpers: sorted copy of the last trace, inverted treelet lists (slot -> (treelet, position))

@@ -146,6 +146,9 @@ struct CompactParams {
   uint32_t fatal_mask;        //   the host queues it before it has read either back, and repeats it after growing the buffers
 };
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st);
+// optional node-visit histogram over the staged records of a batch (after the scan: offsets give the per-ray counts)
+int vsrt_launch_node_hist(const uint32_t* stage, uint32_t cap, const uint64_t* offsets, uint64_t n_rays, unsigned long long* hist, const uint32_t* err_flags,
+                          uint32_t fatal_mask, cudaStream_t st);
 
 // u32 treelet index -> u64 root device address (addrToTreeletID value)
 // remap_pitch != 0: roots are reported in the treelet layout, remap_base + index * remap_pitch

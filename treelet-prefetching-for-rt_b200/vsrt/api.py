@@ -33,7 +33,8 @@ SYMBOLS = ["vsrt_default_config", "vsrt_create", "vsrt_destroy", "vsrt_last_erro
            "vsrt_packed_layout_get", "vsrt_trace_fetch_packed", "vsrt_trace_rays_packed", "vsrt_unpack_txns",
            "vsrt_as_dump_write", "vsrt_as_dump_read", "vsrt_as_dump_free", "vsrt_register_as_image",
            "vsrt_comm_unique_id", "vsrt_comm_init", "vsrt_comm_attach", "vsrt_comm_destroy", "vsrt_reduce_counters", "vsrt_reduce_wait",
-           "vsrt_reduced_get", "vsrt_reduced_device", "vsrt_node_treelet_table"]
+           "vsrt_reduced_get", "vsrt_reduced_device", "vsrt_node_treelet_table",
+           "vsrt_enable_node_histogram", "vsrt_get_node_histogram", "vsrt_reduced_get_node_histogram"]
 
 
 class VsrtError(RuntimeError):
@@ -100,6 +101,9 @@ def load():
     L.vsrt_counters_device.argtypes = [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]
     L.vsrt_get_treelet_histogram.argtypes = [c_vp, c_vp, c_u64]
     L.vsrt_node_treelet_table.argtypes = [c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
+    L.vsrt_enable_node_histogram.argtypes = [c_vp, c_int]
+    L.vsrt_get_node_histogram.argtypes = [c_vp, c_vp, c_u64, ctypes.POINTER(c_u64)]
+    L.vsrt_reduced_get_node_histogram.argtypes = [c_vp, c_vp, c_u64]
     L.vsrt_comm_unique_id.argtypes = [c_vp]
     L.vsrt_comm_init.argtypes = [c_vp, c_u32, c_u32, c_vp]
     L.vsrt_comm_attach.argtypes = [c_vp, c_vp, c_u32, c_u32]
@@ -506,6 +510,20 @@ class Context:
         self._ck(self.L.vsrt_debug_tb_stats(self.h, a))
         names = ("rays_processed", "rays_in_staged_treelet", "ctas_staged", "bytes_staged", "visits_from_smem", "visits_from_arena", "rounds")
         return {n: int(a[i]) for i, n in enumerate(names)}
+
+    def enable_node_histogram(self, on=True):
+        self._ck(self.L.vsrt_enable_node_histogram(self.h, 1 if on else 0))
+
+    def node_histogram(self, reduced=False):
+        """Records per node address, per slot of the packed arena (this rank's, or the global one after reduce_counters)."""
+        n = c_u64()
+        self._ck(self.L.vsrt_get_node_histogram(self.h, None, 0, ctypes.byref(n)))
+        h = np.zeros(n.value, np.uint64)
+        if reduced:
+            self._ck(self.L.vsrt_reduced_get_node_histogram(self.h, _abi.ptr(h), n.value))
+        else:
+            self._ck(self.L.vsrt_get_node_histogram(self.h, _abi.ptr(h), n.value, ctypes.byref(n)))
+        return h
 
     def counters_device(self):
         cp, hp, n = c_vp(), c_vp(), c_u64()

@@ -54,7 +54,9 @@ VS_DEV uint32_t bit_index(uint32_t one_bit) { uint32_t i; asm("bfind.u32 %0, %1;
 #endif
 constexpr int THREADS = VSRT_K1_THREADS;
 VS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#if defined(VSRT_K1_PF_CHILDREN) && VSRT_K1_PF_CHILDREN
 VS_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 #ifndef VSRT_K1_STATS
 #define VSRT_K1_STATS 0   // 1: count, per inner round, how many lanes are in which state (tools/k1_lane_states.py); costs ~10 %
 #endif
@@ -85,8 +87,10 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 //   PF_NEXT  the child the lane will pop after the internal node it has just tested (node-entry stack only)
 // LEAF_ASYNC: the 64 bytes of a BLAS leaf are copied global -> shared memory with cp.async (no registers, no L1 line to lose)
 // when the lane TAKES the leaf; the batched leaf phase, a round or two later, waits for the lane's own copies and reads them back.
+// Round 2: on by default.  With the leaf threshold at 1 it costs the coherent bench workload nothing (1.923 vs 1.921 ms; traceRay mode
+// 1.6 % slower) and makes the incoherent configs 7-8 % faster (C3 bounce 3.32 -> 3.08 ms, C4 3.02 -> 2.77 ms), where a leaf is a DRAM miss.
 #ifndef VSRT_K1_LEAF_ASYNC
-#define VSRT_K1_LEAF_ASYNC 0
+#define VSRT_K1_LEAF_ASYNC 1
 #endif
 #ifndef VSRT_K1_PF_LEAF
 #define VSRT_K1_PF_LEAF 0

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -23,6 +24,10 @@ int vsrt_fail(vsrt_context* c, int code, const char* fmt, ...) {
 
 namespace {
 
+__global__ void k_add_base(unsigned long long* __restrict__ off, uint64_t n, unsigned long long base) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) off[i] += base;
+}
+
 template <typename... A> int fail(vsrt_context* c, int code, const char* fmt, A... a) { return vsrt_fail(c, code, fmt, a...); }
 #define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, VSRT_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } while (0)
 
@@ -30,7 +35,7 @@ void free_treelets(vsrt_context* c) {
   cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node);
   c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
   cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
-  c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear();
+  c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear(); c->h_root_of_slot.clear();
   vsrt_comm_treelets_changed(c);
   vsrt_tb_free_layout(c->tb_tables); c->tb_tables = nullptr;
 }
@@ -111,7 +116,12 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
 
 // packed_out: K3 writes the 4-byte packed records into d_packed instead of the 16-byte records + treelet indices (the host
 // form of vsrt_trace_rays_packed); ensure_full_records() expands them later if a caller asks for the full form after all
-int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st, bool packed_out = false) {
+// A frame may be traced as several WINDOWS (chunks of consecutive rays, for the pipelined host calls): d_rays / n are the window,
+// r0 its first ray in the frame, frame_n the frame's ray count (0 = the window is the frame) and rec_base the records of the
+// windows before it.  Every per-ray and per-record buffer is frame-sized and a window writes its own slice, so after the last
+// window the context holds the whole frame exactly as a single batch would have left it.
+int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, uint64_t n, cudaStream_t st, bool packed_out = false,
+              uint64_t r0 = 0, uint64_t frame_n = 0, uint64_t rec_base = 0) {
   if (mode != VSRT_MODE_DFS && mode != VSRT_MODE_TREELET) return fail(c, VSRT_E_INVALID, "mode must be VSRT_MODE_DFS or VSRT_MODE_TREELET");
   if (n >= (1ull << 32) - 1) return fail(c, VSRT_E_INVALID, "a batch holds at most 2^32-2 rays; split the frame");
   int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;   // lazily, like :1593 / :2364
@@ -128,15 +138,21 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
   }
   ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
   const TreeletView tv = treelet_view(c);
-  c->last = vsrt_device_results{}; c->last_tlas = tlas; c->last_mode = mode; c->last_rays = d_rays;
-  CUDA_OK(c, c->d_hits.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_counts.ensure(std::max<uint64_t>(n, 1))); CUDA_OK(c, c->d_offsets.ensure(n + 1));
-  CUDA_OK(c, c->d_scan_tmp.ensure(vsrt_scan_tmp_bytes(n))); CUDA_OK(c, c->d_nproc.ensure(std::max<uint64_t>(n, 1)));
+  const uint64_t fn = frame_n ? frame_n : n;
+  const vsrt_device_results before = c->last;
+  if (r0 == 0) c->last = vsrt_device_results{};
+  c->last_tlas = tlas; c->last_mode = mode; c->last_rays = d_rays - r0;
+  CUDA_OK(c, c->d_hits.ensure(std::max<uint64_t>(fn, 1))); CUDA_OK(c, c->d_counts.ensure(std::max<uint64_t>(fn, 1))); CUDA_OK(c, c->d_offsets.ensure(fn + 1));
+  CUDA_OK(c, c->d_scan_tmp.ensure(vsrt_scan_tmp_bytes(n))); CUDA_OK(c, c->d_nproc.ensure(std::max<uint64_t>(fn, 1)));
   uint32_t launches = 0; uint64_t total = 0;
   for (int attempt = 0;; attempt++) {
-    CUDA_OK(c, c->d_stage.ensure(std::max<uint64_t>(n, 1) * c->stage_cap));
+    CUDA_OK(c, c->d_stage.ensure(std::max<uint64_t>(fn, 1) * c->stage_cap));
+    // this window's slices of the frame-sized buffers
+    vsrt_hit* const w_hits = c->d_hits.p + r0; uint32_t* const w_counts = c->d_counts.p + r0; uint64_t* const w_offsets = c->d_offsets.p + r0;
+    uint32_t* const w_nproc = c->d_nproc.p + r0; uint32_t* const w_stage = c->d_stage.p + r0 * c->stage_cap;
     CUDA_OK(c, cudaMemcpyAsync(c->d_counters_bak, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
     CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
-    TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = c->d_hits.p; tp.stage = c->d_stage.p; tp.counts = c->d_counts.p; tp.nproc = c->d_nproc.p;
+    TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = w_hits; tp.stage = w_stage; tp.counts = w_counts; tp.nproc = w_nproc;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 1u; }   // round-2 sweep: leaf threshold 1 is best on the headline (1 %) and on the incoherent configs (6 %)
     tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; tp.perm = nullptr; tp.perm_on = nullptr;
@@ -185,7 +201,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       launches++;
     }
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
-    rc = vsrt_launch_scan(c->d_counts.p, n, c->d_offsets.p, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
+    rc = vsrt_launch_scan(w_counts, n, w_offsets, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
     launches += n ? 3 : 0;   // 3 scan kernels
     bool node_hist_queued = false;
@@ -194,26 +210,27 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       const uint32_t ns = (uint32_t)(c->arena_bytes / 64);
       if (c->node_hist_n != ns) { if (c->d_node_hist.ensure(std::max<uint32_t>(ns, 1)) != cudaSuccess || cudaMemsetAsync(c->d_node_hist.p, 0, (size_t)ns * 8, st) != cudaSuccess) return VSRT_E_CUDA; c->node_hist_n = ns; }
       node_hist_queued = true; launches++;
-      return vsrt_launch_node_hist(c->d_stage.p, c->stage_cap, c->d_offsets.p, n, c->d_node_hist.p, c->d_err, EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED, st);
+      return vsrt_launch_node_hist(w_stage, c->stage_cap, w_offsets, n, c->d_node_hist.p, c->d_err, EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED, st);
     };
     rc = queue_node_hist(); if (rc) return fail(c, rc, "node histogram launch failed");
     // K3 is queued right away into the buffers of the previous batch; it checks the error flags and the record count on the
     // device and does nothing if either says no.  One host synchronisation per batch in the steady state.
-    CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = c->d_stage.p; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = c->d_offsets.p; cp.n_rays = n;
+    CompactParams cp; cp.av = av; cp.tv = tv; cp.stage = w_stage; cp.cap = c->stage_cap; cp.mode = (uint32_t)mode; cp.offsets = w_offsets; cp.n_rays = n;
     cp.counters = c->d_counters; cp.treelet_hist = getenv("VSRT_NO_HIST") ? nullptr : c->d_hist.p;
     cp.remap = c->cfg.remap_to_treelet_layout ? c->d_remap.p : nullptr;
     cp.err_flags = c->d_err; cp.fatal_mask = EF_BAD_BVH | EF_STACK | EF_TRACE_CAP | EF_UNSUPPORTED;
     cp.packed = nullptr; cp.count = 1; cp.pad3 = 0;
-    uint64_t queued_cap = packed_out ? c->d_packed.cap : std::min(c->d_txns.cap, c->d_tids.cap);
+    const uint64_t have_cap = packed_out ? c->d_packed.cap : std::min(c->d_txns.cap, c->d_tids.cap);
+    uint64_t queued_cap = have_cap > rec_base ? have_cap - rec_base : 0;
     if (queued_cap && n) {
-      cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.packed = packed_out ? c->d_packed.p : nullptr; cp.out_capacity = queued_cap;
+      cp.txns = c->d_txns.p + rec_base; cp.tids = c->d_tids.p + rec_base; cp.packed = packed_out ? c->d_packed.p + rec_base : nullptr; cp.out_capacity = queued_cap;
       rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
       launches++;
     }
     CUDA_OK(c, cudaEventRecord(c->ev[3], st));
     uint32_t h_err = 0; DevCounters now;
     static_assert(16 + sizeof(DevCounters) <= vsrt_context::PIN_HEAD, "read-back block must fit the head of the pinned buffer");
-    CUDA_OK(c, cudaMemcpyAsync(c->h_pin, c->d_offsets.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pin, w_offsets + n, 8, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 8, c->d_err, 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
@@ -223,6 +240,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st);
       cudaStreamSynchronize(st);
       c->last = vsrt_device_results{};
+      (void)before;
       if (h_err & EF_BAD_BVH) return fail(c, VSRT_E_BAD_BVH, "traversal met a malformed node");
       if (h_err & EF_STACK) return fail(c, VSRT_E_STACK_OVERFLOW, "a ray needed more than %u traversal-stack entries; raise vsrt_config.stack_entries (at most 384)", c->cfg.stack_entries ? c->cfg.stack_entries : 96);
       return fail(c, VSRT_E_UNSUPPORTED, "a ray visited more than 4095 procedural leaves (or 2^20 - 1 nodes): beyond what the per-ray staging segment records");
@@ -235,10 +253,14 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     }
     if (!queued_cap || total > queued_cap) {
       // first batch, or more records than the buffers held: the queued K3 declined; grow and run it now
-      if (packed_out) { CUDA_OK(c, c->d_packed.ensure(std::max<uint64_t>(total, 1))); cp.packed = c->d_packed.p; cp.out_capacity = c->d_packed.cap; }
+      // (the first window of a chunked frame sizes the buffers for the whole frame from its own records per ray)
+      uint64_t need = rec_base + total;
+      if (r0 == 0 && fn > n && n) need = (uint64_t)((double)total * ((double)fn / (double)n) * 1.15) + 4096;
+      need = std::max<uint64_t>(need, 1);
+      if (packed_out) { CUDA_OK(c, c->d_packed.ensure(need, rec_base > 0, st)); cp.packed = c->d_packed.p + rec_base; cp.out_capacity = c->d_packed.cap - rec_base; }
       else {
-        CUDA_OK(c, c->d_txns.ensure(std::max<uint64_t>(total, 1))); CUDA_OK(c, c->d_tids.ensure(std::max<uint64_t>(total, 1)));
-        cp.txns = c->d_txns.p; cp.tids = c->d_tids.p; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap);
+        CUDA_OK(c, c->d_txns.ensure(need, rec_base > 0, st)); CUDA_OK(c, c->d_tids.ensure(need, rec_base > 0, st));
+        cp.txns = c->d_txns.p + rec_base; cp.tids = c->d_tids.p + rec_base; cp.out_capacity = std::min(c->d_txns.cap, c->d_tids.cap) - rec_base;
       }
       if (n) {
         rc = vsrt_launch_compact(cp, st); if (rc) return fail(c, rc, "compaction kernel launch failed");
@@ -250,20 +272,26 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       memcpy(&now, c->h_pin + 16, sizeof(now));
     }
     // rayCount (:1665) advanced by the traversal kernel; accessedDataSize delta of this batch = its algorithmic bytes
-    c->last.algorithmic_bytes = now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
+    c->last.algorithmic_bytes = (r0 ? before.algorithmic_bytes : 0) + now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
     c->h_prev = now;
+    // a later window's offsets continue where the earlier ones ended (K3 and the node histogram have read them window-relative)
+    if (rec_base && n) k_add_base<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>((unsigned long long*)(c->d_offsets.p + r0), n + 1, rec_base);
     break;
   }
   c->last.hits = c->d_hits.p; c->last.trace_offsets = c->d_offsets.p;
   c->last.txns = packed_out ? nullptr : c->d_txns.p; c->last.treelet_ids = packed_out ? nullptr : c->d_tids.p;
   c->last_packed_only = packed_out; c->last_av = av;
-  c->last.n_rays = n; c->last.n_txn = total; c->last.kernel_launches = launches;
-  cudaEventElapsedTime(&c->last.order_ms, c->ev[4], c->ev[0]);
-  cudaEventElapsedTime(&c->last.traverse_ms, c->ev[0], c->ev[1]);
-  cudaEventElapsedTime(&c->last.scan_ms, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&c->last.compact_ms, c->ev[2], c->ev[3]);
+  c->last.n_rays = r0 + n; c->last.n_txn = rec_base + total; c->last.kernel_launches = (r0 ? before.kernel_launches : 0) + launches;
+  float t_order = 0, t_trav = 0, t_scan = 0, t_comp = 0;
+  cudaEventElapsedTime(&t_order, c->ev[4], c->ev[0]); cudaEventElapsedTime(&t_trav, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&t_scan, c->ev[1], c->ev[2]); cudaEventElapsedTime(&t_comp, c->ev[2], c->ev[3]);
+  c->last.order_ms = (r0 ? before.order_ms : 0.0f) + t_order; c->last.traverse_ms = (r0 ? before.traverse_ms : 0.0f) + t_trav;
+  c->last.scan_ms = (r0 ? before.scan_ms : 0.0f) + t_scan; c->last.compact_ms = (r0 ? before.compact_ms : 0.0f) + t_comp;
   return VSRT_OK;
 }
+
+int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
+                          bool packed, void* records_out, uint64_t capacity, uint64_t* treelet_ids, uint64_t* n_txn, uint64_t chunk);
 
 // The last batch was delivered in packed form only: expand its staged records into the 16-byte records + treelet indices now
 // (same K3, counters and histogram untouched -- they were accumulated when the batch ran).
@@ -349,7 +377,7 @@ void vsrt_destroy(vsrt_context* c) {
   cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
-  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_hits_alt.release(); c->d_offsets_alt.release(); c->d_packed_alt.release();
+  c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_frame_bak.release();
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream); if (c->up_stream) cudaStreamDestroy(c->up_stream);
   for (int i = 0; i < 2; i++) { if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]); if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); }
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -552,6 +580,15 @@ int vsrt_trace_rays(vsrt_context* c, const void* tlas, int mode, uint64_t n, con
                     vsrt_txn* txns, uint64_t txn_capacity, uint64_t* treelet_ids, uint64_t* n_txn) {
   if (!c || !tlas || (n && !rays)) return VSRT_E_INVALID;
   cudaSetDevice(c->device);
+  {
+    // frame-sized batches: traced in windows with the copies overlapped, treelet ids derived on the host (see trace_frame_pipelined)
+    uint64_t chunk = 524288;
+    if (const char* e = getenv("VSRT_PIPELINE_CHUNK")) chunk = (uint64_t)atoll(e);
+    if (chunk && txns && n >= 2 * chunk) {
+      const int rcp = trace_frame_pipelined(c, (uint64_t)(uintptr_t)tlas, mode, n, rays, hits, trace_offsets, false, txns, txn_capacity, treelet_ids, n_txn, chunk);
+      if (rcp != VSRT_E_UNSUPPORTED) return rcp;
+    }
+  }
   CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
   uint8_t* const bounce = c->h_pin + vsrt_context::PIN_HEAD; const size_t bounce_bytes = vsrt_context::PIN_BYTES - vsrt_context::PIN_HEAD;
   const bool small = n && n * sizeof(vsrt_ray) <= bounce_bytes && n <= 4096;
@@ -630,64 +667,139 @@ int vsrt_trace_fetch_packed(vsrt_context* c, uint32_t* records, uint64_t cap, ui
 }  // extern "C"
 
 namespace {
-__global__ void k_add_base(unsigned long long* __restrict__ off, uint64_t n, unsigned long long base) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) off[i] += base;
+
+// The host-buffer calls for a frame-sized batch: the rays are traced in windows of `chunk` rays, and while window k + 1 is uploaded
+// and traced the hits / offsets / records of window k go back over PCIe on a second stream.  A frame's trace is hundreds of MB
+// even in packed form, so the device->host copy is what bounds a host-side caller; everything else hides beneath it.
+//   packed form   records = 4-byte packed records
+//   full form     txns = 16-byte records; the 64-bit treelet ids -- a pure function of a record's address -- are not copied
+//                 (8 of every 24 bytes) but filled in on the host from a slot -> root table, by worker threads that follow
+//                 the copy front (layouts with one span, one host->device offset and no remap; otherwise they are copied)
+// Ray ids follow the batch order (windows are traced in order on one stream); every window writes its slice of the frame-sized
+// device buffers, so afterwards the context holds the frame as a single batch would have left it.
+struct FrameJob {   // one window's treelet ids to derive on the host
+  cudaEvent_t copied; const vsrt_txn* txns; uint64_t* ids; uint64_t n;
+};
+void derive_ids(const vsrt_context* c, const std::vector<uint64_t>& root_of_slot, uint64_t addr0, const vsrt_txn* txns, uint64_t* ids, uint64_t n, unsigned threads) {
+  auto work = [&](uint64_t lo, uint64_t hi) {
+    const uint64_t ns = root_of_slot.size();
+    for (uint64_t j = lo; j < hi; j++) { const uint64_t slot = (txns[j].address - addr0) >> 6; ids[j] = slot < ns ? root_of_slot[slot] : ~0ull; }
+  };
+  (void)c;
+  if (threads <= 1 || n < 65536) { work(0, n); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < threads; t++) th.emplace_back(work, n * t / threads, n * (t + 1) / threads);
+  for (auto& x : th) x.join();
 }
 
-// vsrt_trace_rays_packed for a frame-sized batch: the rays are traced in chunks, and while chunk i + 1 is uploaded and traced the
-// hits / offsets / packed records of chunk i go back over PCIe on a second stream (the outputs alternate between two sets of
-// device buffers).  A frame's trace is a few hundred MB even in packed form, so the device->host copy is what bounds a host-side
-// caller; everything else hides beneath it.  Ray ids follow the batch order (chunks are traced in order on one stream).
-int trace_packed_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
-                           uint32_t* records, uint64_t capacity, uint64_t* n_txn, uint64_t chunk) {
+int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
+                          bool packed, void* records_out, uint64_t capacity, uint64_t* treelet_ids, uint64_t* n_txn, uint64_t chunk) {
   if (!c->copy_stream) {
     CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)); CUDA_OK(c, cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)); CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)); }
     CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
   }
   CUDA_OK(c, c->d_rays.ensure(n));
+  int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
-  uint64_t base = 0; int rc = VSRT_OK; bool overflow = false;
-  auto swap_sets = [&]() { std::swap(c->d_hits, c->d_hits_alt); std::swap(c->d_offsets, c->d_offsets_alt); std::swap(c->d_packed, c->d_packed_alt); };
-  // upload of chunk 0
-  CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, std::min(chunk, n) * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
-  CUDA_OK(c, cudaEventRecord(c->ev_up[0], c->up_stream));
-  bool set_busy[2] = { false, false };
-  for (uint64_t k = 0; k < n_chunks; k++) {
-    const uint64_t r0 = k * chunk, m = std::min(chunk, n - r0); const int b = (int)(k & 1);
-    CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_up[b], 0));
-    if (k + 1 < n_chunks) {   // next chunk's rays go up while this one is traced
-      const uint64_t r1 = r0 + chunk, m1 = std::min(chunk, n - r1);
-      CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p + r1, rays + r1, m1 * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
-      CUDA_OK(c, cudaEventRecord(c->ev_up[b ^ 1], c->up_stream));
+  // host-derived treelet ids: slot -> root address table (once per formation), addresses start at the span's first byte
+  const bool derive = !packed && treelet_ids && c->spans.size() == 1 && !c->cfg.remap_to_treelet_layout;
+  uint64_t addr0 = 0; unsigned threads = 1;
+  if (derive) {
+    ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
+    if (!av.uniform_delta) return VSRT_E_UNSUPPORTED;       // (the caller falls back to the one-batch path)
+    rc = ensure_mirrors(c); if (rc) return rc;
+    if (c->h_root_of_slot.size() != c->h_node_tid.size()) {
+      c->h_root_of_slot.resize(c->h_node_tid.size());
+      const int64_t d = formed_delta(c);
+      for (size_t sl = 0; sl < c->h_node_tid.size(); sl++) {
+        const uint32_t t = c->h_node_tid[sl];
+        c->h_root_of_slot[sl] = t == VSRT_NO_TID ? ~0ull : slot_to_host_h(c, c->h_tl_root[t]) + (uint64_t)d;
+      }
     }
-    if (set_busy[b]) CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copy[b], 0));     // this output set is still being copied out (chunk k - 2)
-    rc = run_batch(c, tlas, mode, c->d_rays.p + r0, m, c->stream, true);             // ends with a host synchronisation of c->stream
-    if (rc) break;
-    const uint64_t total = c->last.n_txn;
-    if (trace_offsets) { k_add_base<<<(unsigned)((m + 1 + 255) / 256), 256, 0, c->stream>>>((unsigned long long*)c->d_offsets.p, m + 1, base); }
-    cudaEvent_t ready = c->ev_ready;                                                // "chunk k's outputs are final"
-    CUDA_OK(c, cudaEventRecord(ready, c->stream));
-    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, ready, 0));
-    if (hits) CUDA_OK(c, cudaMemcpyAsync(hits + r0, c->d_hits.p, m * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets + r0, c->d_offsets.p, (m + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-    if (records && base < capacity) {
-      const uint64_t mrec = std::min(total, capacity - base);
-      if (mrec) CUDA_OK(c, cudaMemcpyAsync(records + base, c->d_packed.p, mrec * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-    }
-    if (base + total > capacity) overflow = true;
-    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
-    set_busy[b] = true;
-    base += total;
-    swap_sets();                                                                    // the next chunk writes into the other output set
+    addr0 = c->spans[0].host + (uint64_t)av.tlas_delta;
+    threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (const char* e = getenv("VSRT_HOST_THREADS")) threads = (unsigned)std::max(1, atoi(e));
   }
-  cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->up_stream);
-  if (n_chunks & 1) swap_sets();                                                    // leave the sets as they were found
-  if (n_txn) *n_txn = base;
-  // vsrt_trace_device_results / vsrt_trace_fetch* describe single batches: after a chunked call there is no "last batch"
-  c->last = vsrt_device_results{}; c->last_packed_only = false;
-  if (rc) return rc;
-  return (records && overflow) ? VSRT_E_CAPACITY : VSRT_OK;
+  // a stage-capacity change in a later window invalidates the earlier windows' staging: the frame is restarted then, from a
+  // copy of the counters and histograms taken here (cheap: a few MB device-to-device)
+  const size_t bak_bytes = sizeof(DevCounters) + (size_t)c->hist_n * 8 + (c->node_hist_on ? (size_t)c->node_hist_n * 8 : 0);
+  CUDA_OK(c, c->d_frame_bak.ensure(bak_bytes));
+  CUDA_OK(c, cudaMemcpyAsync(c->d_frame_bak.p, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, c->stream));
+  if (c->hist_n) CUDA_OK(c, cudaMemcpyAsync(c->d_frame_bak.p + sizeof(DevCounters), c->d_hist.p, (size_t)c->hist_n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->node_hist_on && c->node_hist_n) CUDA_OK(c, cudaMemcpyAsync(c->d_frame_bak.p + sizeof(DevCounters) + (size_t)c->hist_n * 8, c->d_node_hist.p, (size_t)c->node_hist_n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  const DevCounters h_prev_bak = c->h_prev;
+  std::vector<cudaEvent_t> win_ev;
+  std::vector<FrameJob> jobs;
+  const uint64_t rec_size = packed ? 4 : sizeof(vsrt_txn);
+  for (int attempt = 0; attempt < 12; attempt++) {
+    uint64_t base = 0; bool overflow = false, restart = false;
+    jobs.clear();
+    CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, std::min(chunk, n) * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
+    CUDA_OK(c, cudaEventRecord(c->ev_up[0], c->up_stream));
+    for (uint64_t k = 0; k < n_chunks; k++) {
+      const uint64_t r0 = k * chunk, m = std::min(chunk, n - r0); const int b = (int)(k & 1);
+      CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_up[b], 0));
+      if (k + 1 < n_chunks) {   // next window's rays go up while this one is traced
+        const uint64_t r1 = r0 + chunk, m1 = std::min(chunk, n - r1);
+        CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p + r1, rays + r1, m1 * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->up_stream));
+        CUDA_OK(c, cudaEventRecord(c->ev_up[b ^ 1], c->up_stream));
+      }
+      const uint32_t cap_before = c->stage_cap;
+      rc = run_batch(c, tlas, mode, c->d_rays.p + r0, m, c->stream, packed, r0, n, base);      // ends with a host synchronisation of c->stream
+      if (rc) break;
+      if (c->stage_cap != cap_before && k > 0) { restart = true; break; }
+      const uint64_t total = c->last.n_txn - base;
+      CUDA_OK(c, cudaEventRecord(c->ev_ready, c->stream));
+      CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
+      if (hits) CUDA_OK(c, cudaMemcpyAsync(hits + r0, c->d_hits.p + r0, m * sizeof(vsrt_hit), cudaMemcpyDeviceToHost, c->copy_stream));
+      // (the window's last offset is the next window's first and is rewritten by it: only the last window copies it)
+      if (trace_offsets) CUDA_OK(c, cudaMemcpyAsync(trace_offsets + r0, c->d_offsets.p + r0, (m + (k + 1 == n_chunks ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+      uint64_t mrec = 0;
+      if (records_out && base < capacity) {
+        mrec = std::min(total, capacity - base);
+        const void* src = packed ? (const void*)(c->d_packed.p + base) : (const void*)(c->d_txns.p + base);
+        if (mrec) CUDA_OK(c, cudaMemcpyAsync((uint8_t*)records_out + base * rec_size, src, mrec * rec_size, cudaMemcpyDeviceToHost, c->copy_stream));
+      }
+      if (base + total > capacity) overflow = true;
+      if (win_ev.size() <= k) { cudaEvent_t e; CUDA_OK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); win_ev.push_back(e); }
+      CUDA_OK(c, cudaEventRecord(win_ev[k], c->copy_stream));
+      if (derive && mrec) {
+        // ids of the PREVIOUS window are derived now, while this window's copy is in flight (the workers need its records in host memory)
+        jobs.push_back(FrameJob{ win_ev[k], (const vsrt_txn*)records_out + base, treelet_ids + base, mrec });
+        if (jobs.size() >= 2) { const FrameJob& j = jobs[jobs.size() - 2]; cudaEventSynchronize(j.copied); derive_ids(c, c->h_root_of_slot, addr0, j.txns, j.ids, j.n, threads); }
+      }
+      base += total;
+    }
+    if (!rc && !restart && derive && !jobs.empty()) { const FrameJob& j = jobs.back(); cudaEventSynchronize(j.copied); derive_ids(c, c->h_root_of_slot, addr0, j.txns, j.ids, j.n, threads); }
+    cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->up_stream);
+    if (restart) {
+      CUDA_OK(c, cudaMemcpyAsync(c->d_counters, c->d_frame_bak.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, c->stream));
+      if (c->hist_n) CUDA_OK(c, cudaMemcpyAsync(c->d_hist.p, c->d_frame_bak.p + sizeof(DevCounters), (size_t)c->hist_n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      if (c->node_hist_on && c->node_hist_n) CUDA_OK(c, cudaMemcpyAsync(c->d_node_hist.p, c->d_frame_bak.p + sizeof(DevCounters) + (size_t)c->hist_n * 8, (size_t)c->node_hist_n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      c->h_prev = h_prev_bak;
+      continue;
+    }
+    for (cudaEvent_t e : win_ev) cudaEventDestroy(e);
+    if (n_txn) *n_txn = rc ? 0 : base;
+    if (rc) return rc;
+    if (!packed && treelet_ids && !derive) {
+      // layouts the host table does not cover: ids expanded on the device and copied (8 more bytes per record over the link)
+      const uint64_t m = std::min(base, capacity);
+      if (m) {
+        ArenaView av; rc = make_view(c, c->last_tlas, &av); if (rc) return rc;
+        CUDA_OK(c, c->d_tid_addr.ensure(m));
+        const uint64_t pitch = c->cfg.remap_to_treelet_layout ? (uint64_t)c->formed_budget + c->cfg.treelet_remap_stride : 0;
+        rc = vsrt_launch_tid_to_addr(av, treelet_view(c), (const uint32_t*)c->last.treelet_ids, m, c->d_tid_addr.p, c->layout_base, pitch, c->stream); if (rc) return fail(c, rc, "tid_to_addr launch failed");
+        CUDA_OK(c, cudaMemcpyAsync(treelet_ids, c->d_tid_addr.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+      }
+    }
+    return (records_out && overflow) ? VSRT_E_CAPACITY : VSRT_OK;
+  }
+  for (cudaEvent_t e : win_ev) cudaEventDestroy(e);
+  return fail(c, VSRT_E_CAPACITY, "per-ray trace staging kept growing");
 }
 }  // namespace
 
@@ -703,7 +815,7 @@ int vsrt_trace_rays_packed(vsrt_context* c, const void* tlas, int mode, uint64_t
   if (const char* e = getenv("VSRT_PIPELINE_CHUNK")) chunk = (uint64_t)atoll(e);
   if (chunk && records && !treelet_index && n >= 2 * chunk) {
     vsrt_packed_layout lay; int rc0 = vsrt_packed_layout_get(c, tlas, &lay); if (rc0) return rc0;
-    return trace_packed_pipelined(c, (uint64_t)(uintptr_t)tlas, mode, n, rays, hits, trace_offsets, records, capacity, n_txn, chunk);
+    return trace_frame_pipelined(c, (uint64_t)(uintptr_t)tlas, mode, n, rays, hits, trace_offsets, true, records, capacity, nullptr, n_txn, chunk);
   }
   CUDA_OK(c, c->d_rays.ensure(std::max<uint64_t>(n, 1)));
   if (n) CUDA_OK(c, cudaMemcpyAsync(c->d_rays.p, rays, n * sizeof(vsrt_ray), cudaMemcpyHostToDevice, c->stream));

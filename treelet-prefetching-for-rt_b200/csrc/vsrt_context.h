@@ -17,7 +17,7 @@ template <typename T> struct DevBuf {
     T* q = nullptr; cudaError_t e = cudaMalloc(&q, nc * sizeof(T));
     if (e != cudaSuccess) { nc = n; e = cudaMalloc(&q, nc * sizeof(T)); if (e != cudaSuccess) return e; }
     if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+    if (p) { if (keep) cudaDeviceSynchronize(); else cudaStreamSynchronize(st); cudaFree(p); }   // keep: copies on other streams may still read the old block
     p = q; cap = nc; return cudaSuccess;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -68,8 +68,8 @@ struct vsrt_context {
   vsrt_device_results last{};
   uint64_t last_tlas = 0; int last_mode = 0; const vsrt_ray* last_rays = nullptr;
   bool last_packed_only = false; ArenaView last_av{};   // the last batch was delivered as packed records only (vsrt_trace_rays_packed)
-  // chunk pipeline of vsrt_trace_rays_packed: second output set + copy streams
-  DevBuf<vsrt_hit> d_hits_alt; DevBuf<uint64_t> d_offsets_alt; DevBuf<uint32_t> d_packed_alt; cudaStream_t copy_stream = nullptr, up_stream = nullptr; cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_up[2] = { nullptr, nullptr }, ev_ready = nullptr;
+  // window pipeline of the host-buffer calls: frame-level backup of counters / histograms, slot -> treelet root table, copy streams
+  DevBuf<uint8_t> d_frame_bak; std::vector<uint64_t> h_root_of_slot; cudaStream_t copy_stream = nullptr, up_stream = nullptr; cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_up[2] = { nullptr, nullptr }, ev_ready = nullptr;
   CommState* comm = nullptr;   // multi-GPU reduce state (reduce.cu), NULL until vsrt_comm_init / vsrt_comm_attach
 };
 

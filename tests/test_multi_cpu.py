@@ -37,9 +37,26 @@ def _worker(rank, world, port, out_dir):
     flat = torch.tensor([vals[k] for k in _abi.COUNTER_FIELDS], dtype=torch.int64)
     csum, cmax = flat[:_abi.N_SUM].clone(), flat[_abi.N_SUM:].clone()
     shard.reduce_counters(dist, csum, cmax, hist)
+    # the scheme the CUDA library uses (csrc/reduce.cu): ONE sum-reduce of a packed header per frame -- deltas of the SUM counters,
+    # every rank's MAX counters in its own pair of a world-wide table -- and u32 histogram deltas, folded into running totals.
+    # Two "frames": the first half of the shard, then the rest.
+    totals = np.zeros(_abi.N_SUM + _abi.N_MAX, np.int64); prev = np.zeros_like(totals); ghist = np.zeros(len(t["roots"]), np.int64); hprev = np.zeros_like(ghist)
+    orc2 = oracles.PortOracle(); orc2.register(s); orc2.form(512)
+    half = (count // 64) * 32
+    for lo, hi in ((0, half), (half, count)):
+        rr = orc2.trace(1, rays[lo:hi])
+        cc = orc2.counters()
+        now = np.array([{**{"mem_access_type_%d" % i: cc["mem_access_type_%d" % i] for i in range(9)}, **cc}[k] for k in _abi.COUNTER_FIELDS], dtype=np.int64)
+        hdr = torch.from_numpy(shard.pack_reduce_header(now, prev, world, rank)); prev = now.copy()
+        hnow = hprev + np.bincount(np.searchsorted(t["roots"], rr["treelet_ids"]), minlength=len(t["roots"]))
+        dh = torch.from_numpy((hnow - hprev).astype(np.int32)); hprev = hnow
+        dist.all_reduce(hdr, op=dist.ReduceOp.SUM); dist.all_reduce(dh, op=dist.ReduceOp.SUM)
+        totals, overflow = shard.fold_reduce_header(totals, hdr.numpy(), world)
+        assert not overflow
+        ghist += dh.numpy()
     r["txns"]["address"] -= np.uint64(s.base)      # every process maps the (identical) arena at its own host address
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), first=first, count=count, offsets=r["offsets"], txns=r["txns"],
-             csum=csum.numpy(), cmax=cmax.numpy(), hist=hist.numpy())
+             csum=csum.numpy(), cmax=cmax.numpy(), hist=hist.numpy(), packed_totals=totals, packed_hist=ghist)
     dist.destroy_process_group()
 
 
@@ -79,3 +96,8 @@ def test_two_rank_reduce_matches_single_process(tmp_path):
         got = dict(zip(_abi.COUNTER_FIELDS, list(p["csum"]) + list(p["cmax"])))
         for k in _abi.COUNTER_FIELDS:
             assert got[k] == c[k], k
+        # the packed single-reduce scheme over two frames arrives at the same totals (sums, maxima, histogram)
+        got2 = dict(zip(_abi.COUNTER_FIELDS, list(p["packed_totals"])))
+        for k in _abi.COUNTER_FIELDS:
+            assert got2[k] == c[k], ("packed", k)
+        assert np.array_equal(p["packed_hist"], hist)

@@ -10,6 +10,9 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <vector>
 
 namespace {
@@ -683,7 +686,18 @@ struct FrameJob {   // one window's treelet ids to derive on the host
 void derive_ids(const vsrt_context* c, const std::vector<uint64_t>& root_of_slot, uint64_t addr0, const vsrt_txn* txns, uint64_t* ids, uint64_t n, unsigned threads) {
   auto work = [&](uint64_t lo, uint64_t hi) {
     const uint64_t ns = root_of_slot.size();
-    for (uint64_t j = lo; j < hi; j++) { const uint64_t slot = (txns[j].address - addr0) >> 6; ids[j] = slot < ns ? root_of_slot[slot] : ~0ull; }
+    for (uint64_t j = lo; j < hi; j++) {
+      const uint64_t slot = (txns[j].address - addr0) >> 6;
+      const uint64_t v = slot < ns ? root_of_slot[slot] : ~0ull;
+#if defined(__x86_64__)
+      _mm_stream_si64(reinterpret_cast<long long*>(ids + j), (long long)v);      // written once, never read here: no read-for-ownership
+#else
+      ids[j] = v;
+#endif
+    }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
   };
   (void)c;
   if (threads <= 1 || n < 65536) { work(0, n); return; }

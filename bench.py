@@ -324,13 +324,13 @@ def run_cuda(args):
         mine = ctx.counters()
         rec_mine = sum(mine["mem_access_type_%d" % i] for i in range(9))
         rec_glob = sum(gtot["mem_access_type_%d" % i] for i in range(9))
-        rec_all = torch.tensor([rec_mine], dtype=torch.int64, device=dev)
+        rec_all = torch.tensor([rec_mine, int(ctx.treelet_histogram().sum())], dtype=torch.int64, device=dev)
         dist.all_reduce(rec_all, op=dist.ReduceOp.SUM)
         reduce_check = {"ray_count": gtot["ray_count"], "expected_ray_count": world * n * frames["n"], "records": rec_glob,
-                        "expected_records": int(rec_all.item()), "treelet_hist_sum": int(ghist.sum()), "frames": frames["n"],
+                        "expected_records": int(rec_all[0].item()), "treelet_hist_sum": int(ghist.sum()), "expected_treelet_hist_sum": int(rec_all[1].item()), "frames": frames["n"],
                         "max_nodes_per_ray": gtot["max_nodes_per_ray"], "max_tree_depth": gtot["max_tree_depth"]}
         reduce_check["reduce_ok"] = bool(reduce_check["ray_count"] == reduce_check["expected_ray_count"] and rec_glob == reduce_check["expected_records"] and
-                                         reduce_check["treelet_hist_sum"] <= rec_glob and gtot["max_nodes_per_ray"] >= mine["max_nodes_per_ray"])
+                                         reduce_check["treelet_hist_sum"] == reduce_check["expected_treelet_hist_sum"] and gtot["max_nodes_per_ray"] >= mine["max_nodes_per_ray"])
         assert reduce_check["reduce_ok"], "multi-GPU counter reduce returned wrong totals: %r" % (reduce_check,)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     res = ctx.device_results()

@@ -137,26 +137,37 @@ int comm_setup(vsrt_context* c, ncclComm_t comm, bool owned, uint32_t n_ranks, u
   return VSRT_OK;
 }
 
-// (re)size the histogram side for the current treelet tables; the baseline is what the rank's histogram holds now
-int comm_hist_setup(vsrt_context* c) {
+// (re)size the histogram side for the current treelet tables.  Baseline: at vsrt_comm_init what the rank's histogram holds at that
+// moment (the reduce covers what is traced from then on); when the tables appear or change later, zero -- formation zeroes the
+// rank's histogram, and everything counted since belongs to the next reduce.
+int comm_hist_setup(vsrt_context* c, bool at_init = false) {
   CommState* s = c->comm;
   const uint32_t n = c->hist_n;
   if (s->n_hist == n && s->g_hist.p) return VSRT_OK;
   CUDA_OK(c, cudaStreamSynchronize(s->rstream)); CUDA_OK(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 2; i++) CUDA_OK(c, s->dh[i].ensure(std::max<uint32_t>(n, 1)));
   CUDA_OK(c, s->hist_prev.ensure(std::max<uint32_t>(n, 1))); CUDA_OK(c, s->g_hist.ensure(std::max<uint32_t>(n, 1)));
-  if (n) { CUDA_OK(c, cudaMemcpy(s->hist_prev.p, c->d_hist.p, (size_t)n * 8, cudaMemcpyDeviceToDevice)); CUDA_OK(c, cudaMemset(s->g_hist.p, 0, (size_t)n * 8)); }
+  if (n) {
+    if (at_init) CUDA_OK(c, cudaMemcpy(s->hist_prev.p, c->d_hist.p, (size_t)n * 8, cudaMemcpyDeviceToDevice));
+    else CUDA_OK(c, cudaMemset(s->hist_prev.p, 0, (size_t)n * 8));
+    CUDA_OK(c, cudaMemset(s->g_hist.p, 0, (size_t)n * 8));
+  }
   s->n_hist = n;
   return VSRT_OK;
 }
-int comm_node_setup(vsrt_context* c) {
+int comm_node_setup(vsrt_context* c, bool at_init = false) {
   CommState* s = c->comm;
   const uint32_t n = c->node_hist_on ? c->node_hist_n : 0u;
   if (s->n_node == n) return VSRT_OK;
   CUDA_OK(c, cudaStreamSynchronize(s->rstream)); CUDA_OK(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 2; i++) CUDA_OK(c, s->ndh[i].ensure(std::max<uint32_t>(n, 1)));
   CUDA_OK(c, s->node_prev.ensure(std::max<uint32_t>(n, 1))); CUDA_OK(c, s->g_node.ensure(std::max<uint32_t>(n, 1)));
-  if (n) { CUDA_OK(c, cudaMemcpy(s->node_prev.p, c->d_node_hist.p, (size_t)n * 8, cudaMemcpyDeviceToDevice)); CUDA_OK(c, cudaMemset(s->g_node.p, 0, (size_t)n * 8)); }
+  // (the node histogram is allocated, zeroed, by the first batch traced with it on: whatever it holds now belongs to this reduce)
+  if (n) {
+    if (at_init) CUDA_OK(c, cudaMemcpy(s->node_prev.p, c->d_node_hist.p, (size_t)n * 8, cudaMemcpyDeviceToDevice));
+    else CUDA_OK(c, cudaMemset(s->node_prev.p, 0, (size_t)n * 8));
+    CUDA_OK(c, cudaMemset(s->g_node.p, 0, (size_t)n * 8));
+  }
   s->n_node = n;
   return VSRT_OK;
 }
@@ -205,7 +216,9 @@ int vsrt_comm_init(vsrt_context* c, uint32_t n_ranks, uint32_t rank, const uint8
   ncclUniqueId u; memcpy(&u, id, VSRT_COMM_ID_BYTES);
   ncclComm_t comm = nullptr;
   NCCL_OK(c, g_nccl.CommInitRank(&comm, (int)n_ranks, u, (int)rank));
-  return comm_setup(c, comm, true, n_ranks, rank);
+  int rc = comm_setup(c, comm, true, n_ranks, rank); if (rc) return rc;
+  rc = comm_hist_setup(c, true); if (rc) return rc;
+  return comm_node_setup(c, true);
 }
 
 int vsrt_comm_attach(vsrt_context* c, void* nccl_comm, uint32_t n_ranks, uint32_t rank) {
@@ -213,7 +226,9 @@ int vsrt_comm_attach(vsrt_context* c, void* nccl_comm, uint32_t n_ranks, uint32_
   if (c->comm) return vsrt_fail(c, VSRT_E_INVALID, "this context already has a communicator");
   if (!load_nccl()) return vsrt_fail(c, VSRT_E_COMM, "%s", g_nccl.err);
   cudaSetDevice(c->device);
-  return comm_setup(c, (ncclComm_t)nccl_comm, false, n_ranks, rank);
+  int rc = comm_setup(c, (ncclComm_t)nccl_comm, false, n_ranks, rank); if (rc) return rc;
+  rc = comm_hist_setup(c, true); if (rc) return rc;
+  return comm_node_setup(c, true);
 }
 
 int vsrt_comm_destroy(vsrt_context* c) {

@@ -7,7 +7,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 tail -c 1500 gpurun_out/r2j_bench_${N}gpu.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/r2j_bench_${N}gpu.json")); b=d["roofline"]["step_breakdown_ms"]
+d=json.loads([l for l in open("gpurun_out/r2j_bench_${N}gpu.json") if l.startswith("{")][-1]); b=d["roofline"]["step_breakdown_ms"]
 print("N=%d value %.1f M ms/step %.3f k1 %.3f k3 %.3f e2e %.1f M e2e_packed %.1f M" % (d["n_gpus"], d["value"]/1e6, d["ms_per_step"], b["k_traverse"], b["k_compact"], d["e2e"]["value"]/1e6, d["e2e_packed"]["value"]/1e6))
 print(d.get("reduced_counters"))
 PY

@@ -224,14 +224,16 @@ def run_reference(args):
     c = time_cpu(orc, scene, cal, MODE, cores, 1, 0)
     target_s = min(10.0, 150.0 / max(1, args.steps + args.warmup))
     sample_n = int(min(len(rays), args.ref_sample, max(16384, c["rays_per_s"] * target_s)))
-    stride = max(1, len(rays) // sample_n)
-    sample = np.ascontiguousarray(rays[::stride][:sample_n])
+    # evenly spaced over the WHOLE frame (round 1 took the first sample_n rays when the stride rounded down to 1)
+    idx = (np.arange(sample_n, dtype=np.int64) * len(rays)) // sample_n
+    stride = len(rays) / sample_n
+    sample = np.ascontiguousarray(rays[idx])
     r = time_cpu(orc, scene, sample, MODE, cores, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+u64", "data": "synthetic", "config": workload_config(args.gpus, {"step": "bounded sample: %d rays (every %d-th ray of the frame)" % (len(sample), stride)}),
+            "dtype": "f32+u64", "data": "synthetic", "config": workload_config(args.gpus),      # the same keys as the CUDA arm's workload description
             "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": cores, "kind": orc.kind,
-                             "sample": "%d rays (every %d-th of the 1080p frame) per step, %d worker %s; treelet formation %.1f s excluded"
+                             "sample": "bounded sample per step: %d rays evenly spaced over the frame (one in %.2f), %d worker %s; treelet formation %.1f s excluded"
                                        % (len(sample), stride, cores, "processes (fork, maps shared copy-on-write)" if orc.kind == "reference" else "OpenMP threads", r["form_s"])},
             "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "records_per_ray": r["records_per_ray"], "bytes_per_ray": r["bytes_per_ray"], "gpu_launches": 0}

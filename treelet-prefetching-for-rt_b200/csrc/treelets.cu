@@ -96,12 +96,13 @@ struct Walker {
 __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const FormState fs, uint32_t begin, uint32_t count, int budget,
                                                    uint32_t cap, uint64_t* __restrict__ pool, uint32_t* __restrict__ r_count) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const uint2 root = fs.roots[begin + t];
-  uint64_t* list = pool + (uint64_t)t * cap;
+  const bool active = t < count;                                   // (no early return: the whole warp allocates store space together below)
+  const uint2 root = active ? fs.roots[begin + t] : make_uint2(0u, 0xFFFFFFFFu);
+  uint64_t* list = pool + (uint64_t)(active ? t : 0u) * cap;
   Walker w(av, list, budget);
   uint32_t p = 0;
-  if (root.y == K_TLAS_HEADER) {                                   // :846-862
+  if (!active) { }
+  else if (root.y == K_TLAS_HEADER) {                                   // :846-862
     w.charge(64); list[w.n++] = mk_entry(root.x, K_TLAS_HEADER);
     uint32_t rs = 0;
     if (!header_root(av, root.x, rs)) w.err |= EF_BAD_BVH; else w.process(rs, K_TLAS_INTERNAL);
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const For
 
   // queue cursor: children of list[p] from child index ci on
   uint32_t ci = 0, child = 0; uint64_t info6 = 0; bool loaded = false; bool closing = false;
-  while (p < w.n && !(w.err & (EF_BAD_BVH | EF_UNKNOWN_AS))) {
+  while (active && p < w.n && !(w.err & (EF_BAD_BVH | EF_UNKNOWN_AS))) {
     const uint64_t ent = list[p];
     const uint32_t eslot = (uint32_t)ent, ekind = (uint32_t)(ent >> 32);
     uint32_t cslot = 0, ckind = 0, csz = 0; bool found = false;
@@ -162,8 +163,21 @@ __global__ void __launch_bounds__(128) k_form_wave(const ArenaView av, const For
     n = o;
   }
   if (w.err) atomicOr(fs.err, w.err);
-  if (w.err & (EF_BAD_BVH | EF_UNKNOWN_AS | EF_BUDGET)) return;
-  const unsigned long long off = atomicAdd(fs.cursor, (unsigned long long)n);
+  const bool keep = active && !(w.err & (EF_BAD_BVH | EF_UNKNOWN_AS | EF_BUDGET));
+  if (!keep) n = 0;
+  // space in the compact store: one atomic per WARP (a cursor bumped once per root serialises in L2 -- 0.6 M same-address atomics
+  // cost 3 ms of a 5 ms formation), the lanes take consecutive pieces of the warp's range
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long wbase = 0;
+  if (lane == 31 && warp_total) wbase = atomicAdd(fs.cursor, (unsigned long long)warp_total);
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
+  if (!keep) return;
+  const unsigned long long off = wbase + (incl - n);
   if (off + n > fs.store_cap) { atomicOr(fs.err, (uint32_t)EF_TRACE_CAP); return; }
   for (uint32_t i = 0; i < n; i++) fs.store[off + i] = list[i];
   fs.r_off[begin + t] = off;
@@ -325,23 +339,25 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   {
     FormState fs = { claimed, roots, n_roots_d, scal, err_flags_dev, reinterpret_cast<uint32_t*>(scal + 2), store, scal + 3, store_cap, r_off };
     unsigned long long peak = (unsigned long long)scratch_roots * cap * 8;
+    unsigned long long before[4] = { 0, 0, 0, 0 }, after[4] = { 0, 0, 0, 0 };     // [0] total_bvh, [3] store cursor: before / after a launch
+    uint32_t n_roots_now = n_roots;
     while (begin < n_roots) {
       // one generation of roots, in launches of at most scratch_roots
       const uint32_t wave_end = n_roots;
       while (begin < wave_end) {
         const uint32_t count = (uint32_t)std::min<size_t>(wave_end - begin, scratch_roots);
-        unsigned long long before[4] = { 0, 0, 0, 0 };          // [0] total_bvh and [3] cursor as they are before this launch
-        CK(cudaMemcpyAsync(before, scal, 32, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-        const unsigned long long cursor_before = before[3];
         k_form_wave<<<(count + 127) / 128, 128, 0, st>>>(av, fs, begin, count, (int)budget, cap, scratch, r_count);
         CK(cudaGetLastError());
+        // one read-back per launch: flags, roots discovered so far, totals and cursor
         CK(cudaMemcpyAsync(&h_err, err_flags_dev, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_roots_now, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(after, scal, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (h_err & EF_TRACE_CAP) {
-          // the compact store is full: double it, rewind the cursor to where this launch started and repeat the launch
+          // the compact store is full: double it, rewind cursor and totals to where this launch started and repeat the launch
           uint64_t* bigger = nullptr; const unsigned long long ncap = store_cap * 2;
           CK(cudaMalloc(&bigger, (size_t)ncap * 8));
-          CK(cudaMemcpyAsync(bigger, store, (size_t)cursor_before * 8, cudaMemcpyDeviceToDevice, st));
+          CK(cudaMemcpyAsync(bigger, store, (size_t)before[3] * 8, cudaMemcpyDeviceToDevice, st));
           CK(cudaStreamSynchronize(st));
           cudaFree(store); store = bigger; store_cap = ncap; fs.store = store; fs.store_cap = store_cap;
           CK(cudaMemcpyAsync(scal + 3, &before[3], 8, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(scal, &before[0], 8, cudaMemcpyHostToDevice, st));
@@ -351,11 +367,11 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
           continue;
         }
         if (h_err & ~EF_NONFINITE) break;
+        before[0] = after[0]; before[3] = after[3];
         begin += count;
       }
       if (h_err & ~EF_NONFINITE) break;
-      CK(cudaMemcpyAsync(&n_roots, n_roots_d, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      n_roots = n_roots_now;
     }
     res->peak_scratch_bytes = peak + store_cap * 8;
   }

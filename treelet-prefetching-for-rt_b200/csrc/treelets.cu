@@ -321,8 +321,8 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   // every node is listed once, plus the nodes that share a treelet with more than one instance of their BLAS
   store_cap = (unsigned long long)ns + ns / 4 + 256;
   CK(cudaMalloc(&store, (size_t)store_cap * 8));
-  // scratch for the roots of one launch: at most 256 MiB, whatever the budget
-  scratch_roots = std::max<size_t>(4096, ((size_t)256 << 20) / ((size_t)cap * 8));
+  // scratch for the roots of one launch: at most 1 GiB, whatever the budget
+  scratch_roots = std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)cap * 8));
   scratch_roots = std::min<size_t>(scratch_roots, (size_t)ns);
   CK(cudaMalloc(&scratch, scratch_roots * cap * 8));
   CK(cudaMemsetAsync(err_flags_dev, 0, 4, st));

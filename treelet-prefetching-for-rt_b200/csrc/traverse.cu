@@ -313,7 +313,18 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       if (__ballot_sync(full, st > ST_FIN) == 0u) { if (exhausted) break; else continue; }
     }
 
-#if VSRT_K1_LEAF_ASYNC
+#if VSRT_K1_LEAF_ASYNC == 2
+// predicated form: the four copies are issued by every popping lane under a predicate instead of inside a branch that a lane or
+// two of the warp takes -- the same dozen instructions per pop round whether one lane took a leaf or twenty
+#define LEAF_FETCH() do { \
+      const uint8_t* g_ = base + (uint64_t)e.slot * 64u; \
+      const uint32_t sa_ = (uint32_t)__cvta_generic_to_shared(&s_leaf[0][threadIdx.x]); \
+      asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, %0, %1;\n" \
+                   " @p cp.async.ca.shared.global [%2], [%3], 16;\n @p cp.async.ca.shared.global [%2+%4], [%3+16], 16;\n" \
+                   " @p cp.async.ca.shared.global [%2+%5], [%3+32], 16;\n @p cp.async.ca.shared.global [%2+%6], [%3+48], 16;\n}" \
+                   ::"r"(st), "r"((uint32_t)ST_LEAF), "r"(sa_), "l"(g_), "n"(THREADS * 16), "n"(THREADS * 32), "n"(THREADS * 48) : "memory"); \
+      asm volatile("cp.async.commit_group;" ::: "memory"); } while (0)
+#elif VSRT_K1_LEAF_ASYNC
 #define LEAF_FETCH() do { if (st == ST_LEAF) { \
       const uint8_t* g_ = base + (uint64_t)e.slot * 64u; \
       _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) { \

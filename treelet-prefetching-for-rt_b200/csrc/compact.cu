@@ -6,6 +6,7 @@
 // (:2257-2261) and the per-treelet visit histogram the prefetcher's popularity vote is built from (shader.cc:3424-3433).
 #include "vsrt_device.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -84,6 +85,9 @@ constexpr int K3_RAYS = K3_WARPS * 32;   // rays per CTA: every warp owns 32 con
 constexpr int K3_ILP = VSRT_K3_ILP;        // independent 32-record windows in flight per warp
 #ifndef VSRT_K3_HASH_BITS
 #define VSRT_K3_HASH_BITS 10
+#endif
+#ifndef VSRT_K3_HIST2
+#define VSRT_K3_HIST2 0   // A/B: run heads from one ballot over an index sentinel, bucket = low bits of the treelet index
 #endif
 #ifndef VSRT_K3_PERSIST
 #define VSRT_K3_PERSIST 0   // measured: a persistent grid saturates the CTA-private table and is slower (1.10 vs 0.72 ms)
@@ -184,11 +188,18 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
           // original_bvh_to_treelet_bvh_mapping[addr + offset] in every record when the layout is remapped (:1682,:1763,...)
           const uint64_t address = SIMPLE ? simple_base + (uint64_t)slot * 64u
                                           : (p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta);
-          const uint32_t type = code_type(code);
+#if VSRT_K3_HIST2
+          // size and type of a code from two byte tables: PRMT picks byte `code`; selector nibbles 9 replicate the sign of byte 1
+          // (0x40 / 0x01: positive) into the upper three bytes, i.e. clear them
+          const uint32_t sel = code | 0x9990u;
+          const uint32_t type = __byte_perm(0x03020100u, 0x01060504u, sel), size = __byte_perm(0x08804040u, 0x40404040u, sel);
+#else
+          const uint32_t type = code_type(code), size = code_size(code);
+#endif
           const unsigned long long j = j0 + pos[u];     // < offsets[n_rays] <= out_capacity (checked on entry)
           if (PACKED) p.packed[j] = rec[u];
           else {
-            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), type);
+            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), size, type);
             p.tids[j] = tid[u];
           }
           // g_rt_mem_access_type[type]++ as eight 8-bit lanes in two words (types 0..3 | 4..7)
@@ -209,6 +220,18 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
         // shared-memory hash table and flushes it once at the end; only table collisions go straight to L2.
 #pragma unroll
         for (int u = 0; u < K3_ILP; u++) {
+#if VSRT_K3_HIST2
+          // a lane without a record (or a node outside every treelet) holds NO_TID, which differs from every real index: a run
+          // starts wherever the index changes, and only runs of a real index are counted -- one ballot, no activity mask
+          const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
+          const bool first = lane == 0 || prev != tid[u];
+          const unsigned bnd = __ballot_sync(full, first);
+          const bool head = first && tid[u] != VSRT_NO_TID;
+          if (head) {
+            const unsigned above = (bnd >> lane) >> 1;
+            const uint32_t run = above ? (uint32_t)__ffs(above) : 32u - (uint32_t)lane;
+            const uint32_t h = tid[u] & ((1u << TBITS) - 1u);   // treelets near each other in the tree have nearby indices: distinct buckets
+#else
           const bool a = valid[u] && tid[u] != VSRT_NO_TID;
           const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
           const unsigned act = __ballot_sync(full, a);
@@ -219,6 +242,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
             const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
             const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
             const uint32_t h = (tid[u] * 2654435761u) >> (32 - TBITS);
+#endif
             uint32_t old = t_key[h];                                             // hot treelets own their slot already: no CAS
             if (old == VSRT_NO_TID) old = atomicCAS(&t_key[h], VSRT_NO_TID, tid[u]);
             if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&t_cnt[h], run);
@@ -258,6 +282,150 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
     return;
   }
   __syncthreads();
+  if (threadIdx.x < 8 && s_hist[threadIdx.x]) {
+    const unsigned long long n = s_hist[threadIdx.x];
+    atomicAdd(p.counters->v + CI_TYPE0 + threadIdx.x, n);
+    const unsigned long long bytes = n * (threadIdx.x == VSRT_TXN_BVH_INSTANCE_LEAF ? 128ull : (threadIdx.x == VSRT_TXN_BVH_PRIMITIVE_LEAF_DESCRIPTOR ? 8ull : 64ull));
+    atomicAdd(p.counters->v + CI_ACCESSED, bytes);
+  }
+}
+
+// ---------------------------------------------------------------- K3, ray-chunk formulation (variant: VSRT_K3_RAYS=1 in the environment)
+// The window kernel above spends a fifth of its instructions finding out which ray a record belongs to and a third on the hash
+// table of the treelet histogram.  Here a warp still owns 32 consecutive rays and their contiguous output range, but walks it as
+// CHUNKS: chunk = 32 consecutive records of ONE ray (the last chunk of a ray is partly empty).  Ray and record index of a lane are
+// then a popcount and an add -- no search, no bitmap -- and the staged read, the 16-byte store and the 4-byte store of a chunk
+// stay single coalesced transactions.  The chunks of the warp's 32 rays are numbered through (a warp scan of chunks per ray), so
+// VSRT_K3V2_ILP of them are in flight whatever the ray lengths.  The grid is persistent (CTAs stride over the ray blocks): the
+// CTA-private histogram table is loaded and flushed once per CTA, not once per 128 rays, and it is direct-mapped with STATIC keys
+// chosen by K0 (vsrt_internal.h, VSRT_HOT_N): a run of records of treelet t adds to the shared-memory counter of bucket
+// t & (N - 1) if K0 gave that bucket to t, and to the global histogram otherwise -- one compare instead of a CAS protocol, and the
+// treelets near the top of the tree, which every ray visits, can never lose their bucket to a treelet that happened to come first.
+// MEASURED (B200, bench workload, profiles/README.md): 0.77 ms against 0.59 ms for the window kernel; without the histogram 0.60
+// against 0.46 ms.  A chunk is two thirds full on average (42 records per ray), so the kernel issues 1.5 x the loads and stores
+// for the same records, which costs more than the ray search it saves; and the deep treelets -- most records -- are shared by
+// NEIGHBOURING rays, which a table private to 128 consecutive rays captures and a static top-of-tree table sends to L2 atomics.
+// ILP 8: 0.86 ms, 10 CTAs per SM: 0.85 ms.  Kept as a variant; the window kernel stays the default.
+#ifndef VSRT_K3_V2
+#define VSRT_K3_V2 1
+#endif
+#ifndef VSRT_K3V2_MIN_BLOCKS
+#define VSRT_K3V2_MIN_BLOCKS 8
+#endif
+#ifndef VSRT_K3V2_ILP
+#define VSRT_K3V2_ILP 4
+#endif
+template <bool SIMPLE, bool PACKED>
+__global__ void __launch_bounds__(K3_THREADS, VSRT_K3V2_MIN_BLOCKS) k_compact_rays(const CompactParams p) {
+  if (p.err_flags && (*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.fatal_mask)) return;
+  if (p.offsets[p.n_rays] > p.out_capacity) return;
+  constexpr int ILP = VSRT_K3V2_ILP;
+  __shared__ unsigned int s_key[VSRT_HOT_N], s_cnt[VSRT_HOT_N];
+  __shared__ unsigned int s_hist[8];
+  const bool do_hist = p.treelet_hist != nullptr && p.count != 0;
+  for (uint32_t i = threadIdx.x; i < VSRT_HOT_N; i += K3_THREADS) { s_key[i] = do_hist ? __ldg(p.tv.hot_keys + i) : VSRT_NO_TID; s_cnt[i] = 0; }
+  if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const ArenaView& av = p.av;
+  const bool one_span = av.n_spans == 1;
+  const uint64_t span_host = one_span ? av.spans[0].host : 0ull;
+  const uint64_t simple_base = span_host + (uint64_t)av.tlas_delta;
+  uint32_t hc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };      // records per CODE seen by this lane (code 7 = TLAS internal is folded into type 1 at the end)
+  unsigned long long pk = 0; uint32_t since_flush = 0;   // the same as eight 8-bit counters, spilled into hc[] before they can wrap
+  const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const uint64_t rw0 = blk * K3_RAYS + (uint64_t)(threadIdx.x >> 5) * 32u;
+    if (rw0 >= p.n_rays) continue;
+    const uint32_t nr = (uint32_t)min((uint64_t)32, p.n_rays - rw0);
+    const unsigned long long my_off = p.offsets[rw0 + min((uint32_t)lane, nr)];
+    const unsigned long long j0 = __shfl_sync(full, my_off, 0);
+    const uint32_t total = (uint32_t)(__shfl_sync(full, my_off, 31) - j0) + 0u;   // lane 31 holds offsets[rw0 + min(31, nr)]
+    const uint32_t end = nr < 32u ? total : (uint32_t)(p.offsets[rw0 + 32u] - j0);  // records of the warp's rays
+    const uint32_t rel = (uint32_t)lane < nr ? (uint32_t)(my_off - j0) : end;
+    uint32_t nxt = __shfl_down_sync(full, rel, 1); if (lane == 31) nxt = end;
+    const uint32_t cntl = nxt - rel;                                 // records of this lane's ray (0 beyond the last ray)
+    const uint32_t nch = (cntl + 31u) >> 5;                          // its chunks
+    uint32_t incl = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
+    const uint32_t excl = incl - nch, n_chunks = __shfl_sync(full, incl, 31);
+    const uint32_t* stage_w = p.stage + rw0 * (uint64_t)p.cap;
+    for (uint32_t t0 = 0; t0 < n_chunks; t0 += ILP) {
+      uint32_t ray[ILP], k[ILP], pos[ILP], rec[ILP], tid[ILP]; bool valid[ILP];
+#pragma unroll
+      for (int u = 0; u < ILP; u++) {
+        const uint32_t t = t0 + (uint32_t)u;
+        ray[u] = min((uint32_t)__popc(__ballot_sync(full, incl <= t)), 31u);     // the ray chunk t belongs to: all rays before it are complete
+        const uint32_t ex = __shfl_sync(full, excl, (int)ray[u]), c = __shfl_sync(full, cntl, (int)ray[u]), o = __shfl_sync(full, rel, (int)ray[u]);
+        k[u] = ((t - ex) << 5) + (uint32_t)lane; valid[u] = t < n_chunks && k[u] < c; pos[u] = o + k[u];
+      }
+#pragma unroll
+      for (int u = 0; u < ILP; u++) rec[u] = valid[u] ? __ldg(stage_w + (ray[u] * p.cap + k[u])) : 0u;
+#pragma unroll
+      for (int u = 0; u < ILP; u++) { tid[u] = valid[u] ? __ldg(p.tv.node_tid + (rec[u] >> 3)) : VSRT_NO_TID; if (tid[u] != VSRT_NO_TID) tid[u] &= VSRT_TID_MASK; }
+#pragma unroll
+      for (int u = 0; u < ILP; u++) {
+        if (valid[u]) {
+          const uint32_t slot = rec[u] >> 3, code = rec[u] & 7u;
+          const unsigned long long j = j0 + pos[u];     // < offsets[n_rays] <= out_capacity (checked on entry)
+          if (PACKED) p.packed[j] = rec[u];
+          else {
+            int64_t delta = av.tlas_delta;                // host -> simulated-device offset the reference applies to this record
+            if (!SIMPLE && !av.uniform_delta) {
+              const uint32_t* seg = stage_w + (uint64_t)ray[u] * p.cap;
+              if (code == C_STRUCT && k[u] > 0) { int64_t d; if (blas_delta_of(av, slot, d)) delta = d; }          // :1908-1913 / :2640-2645
+              else if (p.mode == VSRT_MODE_DFS && code != C_INTERNAL_TLAS && code != C_INSTANCE && k[u] > 0) {
+                // traceRay keeps device_offset = offset of the BLAS it is inside (:2640) until the next TLAS node (:2503,:2605)
+                for (uint32_t b = k[u]; b-- > 0;) { const uint32_t pr = __ldg(seg + b); if ((pr & 7u) == C_STRUCT && b > 0) { int64_t d; if (blas_delta_of(av, pr >> 3, d)) delta = d; break; } }
+              }
+            }
+            const uint64_t address = SIMPLE ? simple_base + (uint64_t)slot * 64u
+                                            : (p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta);
+            *reinterpret_cast<uint4*>(p.txns + j) = make_uint4((uint32_t)address, (uint32_t)(address >> 32), code_size(code), code_type(code));
+            p.tids[j] = tid[u];
+          }
+          pk += 1ull << (code << 3);
+        }
+      }
+      since_flush += ILP;
+      if (since_flush > 255u - ILP) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(pk >> (8 * c)) & 0xffu;
+        pk = 0; since_flush = 0;
+      }
+      if (do_hist) {
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+          // lanes hold consecutive records of one ray: a run of one treelet is folded into its first lane
+          const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
+          const bool first = lane == 0 || prev != tid[u];
+          const unsigned bnd = __ballot_sync(full, first);
+          if (first && tid[u] != VSRT_NO_TID) {
+            const unsigned above = (bnd >> lane) >> 1;
+            const uint32_t run = above ? (uint32_t)__ffs(above) : 32u - (uint32_t)lane;
+            const uint32_t h = tid[u] & (VSRT_HOT_N - 1u);
+            if (s_key[h] == tid[u]) atomicAdd(&s_cnt[h], run);
+            else atomicAdd(p.treelet_hist + tid[u], (unsigned long long)run);
+          }
+        }
+      }
+    }
+  }
+  if (!p.count) return;          // records only (a later full expansion of a batch that was first delivered packed)
+#pragma unroll
+  for (int c = 0; c < 8; c++) hc[c] += (uint32_t)(pk >> (8 * c)) & 0xffu;
+  hc[VSRT_TXN_BVH_INTERNAL_NODE] += hc[C_INTERNAL_TLAS]; hc[C_INTERNAL_TLAS] = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint32_t s = __reduce_add_sync(0xffffffffu, hc[c]);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_hist[c], s);
+  }
+  __syncthreads();
+  if (do_hist)
+    for (uint32_t i = threadIdx.x; i < VSRT_HOT_N; i += K3_THREADS)
+      if (s_cnt[i]) atomicAdd(p.treelet_hist + s_key[i], (unsigned long long)s_cnt[i]);
   if (threadIdx.x < 8 && s_hist[threadIdx.x]) {
     const unsigned long long n = s_hist[threadIdx.x];
     atomicAdd(p.counters->v + CI_TYPE0 + threadIdx.x, n);
@@ -327,9 +495,29 @@ int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
+template <bool SIMPLE, bool PACKED>
+static int launch_compact_rays(const CompactParams& p, uint64_t n_blocks, cudaStream_t st) {
+  static int s_blocks[64], s_sm[64];      // occupancy of this instantiation, per device
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
+  if (s_blocks[dev] == 0) {
+    cudaDeviceGetAttribute(&s_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_blocks[dev], k_compact_rays<SIMPLE, PACKED>, K3_THREADS, 0) != cudaSuccess || s_blocks[dev] < 1) s_blocks[dev] = 4;
+  }
+  const unsigned grid = (unsigned)std::min<uint64_t>(n_blocks, (uint64_t)s_blocks[dev] * (uint64_t)s_sm[dev]);
+  k_compact_rays<SIMPLE, PACKED><<<grid, K3_THREADS, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
+}
+
 int vsrt_launch_compact(const CompactParams& p, cudaStream_t st) {
   const uint64_t n_blocks = (p.n_rays + K3_RAYS - 1) / K3_RAYS;
   if (n_blocks == 0) return VSRT_OK;
+  // the window kernel is the default; VSRT_K3_RAYS=1 picks the ray-chunk kernel (measured: 0.77 vs 0.59 ms, see its header)
+  static const bool chunks = VSRT_K3_V2 && getenv("VSRT_K3_RAYS") && atoi(getenv("VSRT_K3_RAYS")) != 0;
+  if (chunks) {
+    if (p.packed) return launch_compact_rays<true, true>(p, n_blocks, st);
+    if (p.av.n_spans == 1 && p.av.uniform_delta && !p.remap) return launch_compact_rays<true, false>(p, n_blocks, st);
+    return launch_compact_rays<false, false>(p, n_blocks, st);
+  }
   int n_sm = 148;
   if (VSRT_K3_PERSIST) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   int per_sm = K3_CTAS_PER_SM;

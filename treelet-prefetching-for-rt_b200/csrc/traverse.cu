@@ -109,6 +109,14 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_MIN_BLOCKS
 #define VSRT_K1_MIN_BLOCKS 7
 #endif
+// 1 (default): the hot kernel traverses a second copy of the arena in which K0 has re-laid-out every internal node (treelets.cu,
+// k_child_mask: absolute first-child slot, per-child offset|flag bytes, present / leaf / same-treelet masks as fields, bound bytes
+// grouped so that near / far planes are whole words) instead of deriving all of that from the Mesa layout at every visit.  It is
+// a full copy, leaves included, so that an internal node and its leaf siblings still share cache lines and pages: with only the
+// internal nodes in a separate array the coherent headline gained 2 % and the incoherent configs LOST 12 % (two address ranges).
+#ifndef VSRT_K1_TNODES
+#define VSRT_K1_TNODES 1
+#endif
 // Shared-memory traversal stack of the hot (EXACT = false) kernel: S 16-byte node entries per lane, [entry][thread] so that a
 // warp's 128-bit accesses are conflict-free whatever the lanes' depths.  0 = the stack lives in local memory (L1-cached, written
 // through to L2).  A ray that needs more than S entries is handed to the EXACT pass, whose stack is the local-memory one
@@ -146,12 +154,13 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   __shared__ unsigned int s_cnt[8];   // 0 sum_nodes 1 max_nodes 2 max_level 3 n_hit 4 n_any 5 n_term 6 n_rays_done 7 err
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  uint32_t max_level = 0, err = 0;
+  uint32_t max_meta = 0, err = 0;   // max_meta: the largest child meta word seen; its level field (bits 23..30) is g_max_tree_depth's candidate
 
   // ---- per-lane ray state.  `st` is the lane's whole control state: no ray / ray finished (hit record pending) / entry
   // wanted / an entry of one of the three kinds in `e` waiting for its phase.
   // x first child slot | y, z.lo16: per-child byte = offset (low 4 bits) | K0's flags (bits 7, 6) | z bits 16..21 pending mask | w meta
   constexpr bool SMEM = VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY && !EXACT;
+  constexpr bool TN = VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT;   // internal nodes come from the traversal-layout copy
   constexpr int SN = SMEM ? VSRT_K1_SMEM_STACK : STACK_N;          // capacity of the stack this instantiation uses
 #if VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY
   __shared__ uint4 s_stk[EXACT ? 1 : VSRT_K1_SMEM_STACK][EXACT ? 1 : THREADS];
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
                     const uint32_t tr = __ldg(p.tv.node_tid + top_root);
                     if ((tr & VSRT_TID_MASK) == cur_tid) PUSH_CUR(c); else { if (tr & VSRT_TID_SELF_ROOTED) SET_SELFROOT(c); PUSH_OTH(c); }
                   } else PUSH_CUR(c);
-                  if (max_level < 1) max_level = 1;
+                  if (max_meta < (1u << 23)) max_meta = 1u << 23;
                 }
               }
             }
@@ -395,10 +404,12 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
     // ================= phase 1: internal nodes (TLAS :1759-1875 / :2500-2599, BLAS :1954-2072 / :2687-2786)
     if (st == ST_INT) {
       st = ST_POP;
+      // the hot kernel runs over the traversal copy of the arena (the launcher put it into av.base): internal nodes are in the
+      // layout K0 prepared (TN), everything else is the arena's own bytes; the EXACT pass and the other K1 variants read the arena
       const Node64 n = load_node(base, e.slot);
 #if VSRT_K1_PF_CHILDREN
       {
-        const uint8_t* cb_ = base + (uint64_t)(e.slot + (uint32_t)node_child_offset(n)) * 64u;
+        const uint8_t* cb_ = base + (uint64_t)(TN ? n.w[3] : e.slot + (uint32_t)node_child_offset(n)) * 64u;
         if (VSRT_K1_PF_CHILDREN == 2) { prefetch_l1(cb_); prefetch_l1(cb_ + 128); prefetch_l1(cb_ + 256); }
         else { prefetch_l2(cb_); prefetch_l2(cb_ + 128); prefetch_l2(cb_ + 256); }
       }
@@ -408,36 +419,43 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       ACTIVATE(inst);
       if (!EXACT && a.nonfinite) st = ST_DEFER;       // degenerate instance transform
       else {
-        uint32_t mask = test_children<EXACT>(n, a.ray, a.idir, fmul(min_thit, a.tmult), p.magic16);   // cull: :1791 / :1989 (tMult is 1 in the TLAS)
-        // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
-        // bytes: prefix sums of the sizes by one multiply; K0 left two flags in the bits the reference ignores (& 0x3f):
-        // bit 7 "this child is the root of its own treelet", bit 6 "leaf" (type != 0) -- exactly bits 31/30 of an entry's slot
-        const uint32_t lo4 = __byte_perm(n.w[5], n.w[6], 0x5432), hi2 = n.w[6] >> 16;
-        const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;                       // byte j = size_0 + .. + size_j
-        const uint32_t t4 = pre4 >> 24, xlo = pre4 << 8, xhi = t4 | ((t4 + (hi2 & 3u)) << 8);   // byte i of {xlo, xhi} = offset of child i
-        const uint32_t child0 = e.slot + (uint32_t)node_child_offset(n);
-        const uint32_t level = e_level(e), clevel = level < 255u ? level + 1u : 255u;
-        if (mask && clevel > max_level) max_level = clevel;
-        const uint32_t cmeta = (clevel << 23) | inst;
+        const float cull = fmul(min_thit, a.tmult);                                     // :1791 / :1989 (tMult is 1 in the TLAS)
+        uint32_t mask, child0, lo4 = 0, hi2 = 0, xlo = 0, xhi = 0;
+        uint32_t ey, ez;       // byte i of {ey, ez.lo16} = offset of child i from the first child | K0's two flags (bit 7 self-rooted, bit 6 leaf)
+        if (TN) { mask = test_children_t(n, a.ray, a.idir, cull, p.magic16); child0 = n.w[3]; ey = n.w[4]; ez = n.w[5] & 0xffffu; }
+        else {
+          mask = test_children<EXACT>(n, a.ray, a.idir, cull, p.magic16);
+          // child i lives at first_child + sum_{j<i} ChildSize[j] (:1868).  The six info bytes (22..27) are handled as packed
+          // bytes: prefix sums of the sizes by one multiply; K0 left two flags in the bits the reference ignores (& 0x3f):
+          // bit 7 "this child is the root of its own treelet", bit 6 "leaf" (type != 0) -- exactly bits 31/30 of an entry's slot
+          lo4 = __byte_perm(n.w[5], n.w[6], 0x5432); hi2 = n.w[6] >> 16;
+          const uint32_t pre4 = (lo4 & 0x03030303u) * 0x01010101u;                       // byte j = size_0 + .. + size_j
+          const uint32_t t4 = pre4 >> 24; xlo = pre4 << 8; xhi = t4 | ((t4 + (hi2 & 3u)) << 8);   // byte i of {xlo, xhi} = offset of child i
+          child0 = e.slot + (uint32_t)node_child_offset(n);
+          ey = xlo | (lo4 & 0xC0C0C0C0u); ez = xhi | (hi2 & 0xC0C0u);
+        }
+        // children are one level down; the 8-bit level saturates at 255: a carry out of the field lands in bit 31 and is taken back
+        const uint32_t cm_ = e.meta + (1u << 23), cmeta = cm_ - ((cm_ >> 31) << 23);
+        if (mask && cmeta > max_meta) max_meta = cmeta;
         // hit children in slot order (:1810-1869): one loop turn per hit child (a node rarely has more than two)
         if (MODE == VSRT_MODE_TREELET) {
           // which children belong to the CURRENT treelet (:1832): K0 left "child i is in this node's treelet" in the
           // node's pad byte (+17), valid whenever the node itself is in the current treelet; otherwise (a node taken from
           // `other` that is not the root of its treelet, or the host/device offset quirk) look the children up
-          uint32_t mc = node_byte(n, 17);
+          uint32_t mc = TN ? n.w[6] >> 24 : node_byte(n, 17);
           if (!in_cur) {
             mc = 0;
             const uint32_t ct = CUR_TID();
             for (uint32_t m = mask; m; m &= m - 1u) {
               const uint32_t sel = 0x7770u + bit_index(m & (0u - m));
-              if ((__ldg(p.tv.node_tid + child0 + __byte_perm(xlo, xhi, sel)) & VSRT_TID_MASK) == ct) mc |= m & (0u - m);
+              if ((__ldg(p.tv.node_tid + child0 + (__byte_perm(ey, ez, sel) & 15u)) & VSRT_TID_MASK) == ct) mc |= m & (0u - m);
             }
           }
           const uint32_t mcur = mask & mc;
           if (cur_n + oth_n + PUSH_MAX > SN) STACK_FULL();      // room for everything this node can push
 #if VSRT_K1_NODE_ENTRY
           else {
-            const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u), moth = mask ^ mcur;
+            const uint32_t moth = mask ^ mcur;
             if (moth) { oth_n++; STK(SN - oth_n) = make_uint4(child0, ey, ez | (moth << 16), cmeta); }
             if (mcur) { STK(cur_n) = make_uint4(child0, ey, ez | (mcur << 16), cmeta); cur_n++; }
             STAT_DEPTH();
@@ -469,11 +487,14 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
           if (cur_n + (VSRT_K1_NODE_ENTRY ? 1 : 6) > SN) STACK_FULL();
 #if VSRT_K1_NODE_ENTRY
           else if (mask) {
-            const uint32_t ey = xlo | (lo4 & 0xC0C0C0C0u), ez = xhi | (hi2 & 0xC0C0u);
-            const uint32_t lf4 = (lo4 >> 6) & 0x01010101u, lf2 = (hi2 >> 6) & 0x0101u;      // leaf flag of every child -> six bits
-            const uint32_t leaf6 = (((lf4 * 0x00204081u) >> 21) & 15u) | (((lf2 * 0x00204081u) >> 17) & 0x30u);
+            uint32_t leaf6;                                                                   // leaf flag of every child -> six bits
+            if (TN) leaf6 = n.w[5] >> 24;
+            else {
+              const uint32_t lf4 = (lo4 >> 6) & 0x01010101u, lf2 = (hi2 >> 6) & 0x0101u;
+              leaf6 = (((lf4 * 0x00204081u) >> 21) & 15u) | (((lf2 * 0x00204081u) >> 17) & 0x30u);
+            }
             const uint32_t mi = mask & ~leaf6, first = mi & (0u - mi), rest = mask ^ first;
-            if (first) { e.slot = child0 + __byte_perm(xlo, xhi, 0x7770u + bit_index(first)); e.meta = cmeta; st = ST_INT; }
+            if (first) { e.slot = child0 + (__byte_perm(ey, ez, 0x7770u + bit_index(first)) & 15u); e.meta = cmeta; st = ST_INT; }
             if (rest) { STK(cur_n) = make_uint4(child0, ey, ez | (rest << 16), cmeta); cur_n++; }
             STAT_DEPTH();
           }
@@ -580,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
 #undef LOAD_WORLD
 
   // ---- functional counters: one set of atomics per CTA
-  atomicMax(&s_cnt[2], max_level);
+  atomicMax(&s_cnt[2], (max_meta >> 23) & 0xffu);
   if (err) atomicOr(&s_cnt[7], err);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -613,6 +634,11 @@ int launch_mode(const TraverseParams& p, cudaStream_t st) {
   const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);
   if (grid == 0) return VSRT_OK;
   if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
+  if (VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT) {
+    // the hot kernel traverses the traversal copy: the same slots, internal nodes re-laid-out by K0, leaves and headers verbatim
+    TraverseParams q = p; q.av.base = p.tv.tnodes;
+    k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(q);
+  } else
   k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -193,12 +194,16 @@ __global__ void k_narrow(const unsigned long long* __restrict__ in, uint32_t n, 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = (uint32_t)in[i];
 }
 // rank of every discovered root + scatter of (slot, count) into rank order
+// ... and the owner of every bucket of K3's hot table: the treelet discovered first (lowest i: roots are appended generation by
+// generation, starting at the TLAS) among those whose index falls into the bucket
 __global__ void k_rank(const uint2* __restrict__ roots, const uint32_t* __restrict__ r_count, uint32_t n, const uint32_t* __restrict__ bits,
-                       const uint32_t* __restrict__ prefix, uint32_t* __restrict__ r_rank, uint32_t* __restrict__ tl_root, uint32_t* __restrict__ tl_count) {
+                       const uint32_t* __restrict__ prefix, uint32_t* __restrict__ r_rank, uint32_t* __restrict__ tl_root, uint32_t* __restrict__ tl_count,
+                       unsigned long long* __restrict__ hot64) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   const uint32_t s = roots[i].x, w = bits[s >> 5], b = 1u << (s & 31);
   const uint32_t rk = prefix[s >> 5] + __popc(w & (b - 1));
   r_rank[i] = rk; tl_root[rk] = s; tl_count[rk] = r_count[i];
+  atomicMin(hot64 + (rk & (VSRT_HOT_N - 1u)), ((unsigned long long)i << 32) | rk);
 }
 // copy each root's list into the rank-ordered CSR and fold the node -> highest-root map (rank + 1, 0 = unmapped)
 __global__ void k_gather(const uint64_t* __restrict__ store, const unsigned long long* __restrict__ r_off, const uint32_t* __restrict__ r_count, const uint32_t* __restrict__ r_rank, uint32_t n,
@@ -235,8 +240,16 @@ __global__ void k_fix_tid(uint32_t* __restrict__ node_tid, uint32_t n, const uin
 //     it is mapped to (VSRT_TID_SELF_ROOTED of node_tid[child]; also set for an unmapped child, like the flag itself);
 //   bit 6 of the same byte: child i is a leaf (ChildType != 0).  Bits 7/6 are bits 31/30 of a traversal-stack entry.
 // One thread per list entry; a node listed by several treelets (shared BLAS) gets the same value from each.
+//
+// The same thread also writes the node in K1's TRAVERSAL LAYOUT into `tnodes`, a second copy of the arena (same slots; leaves, instance
+// leaves and headers verbatim): everything the hot kernel derives from an internal node per visit with byte shuffles is laid down once --
+//   w0..2 origin | w3 slot of the first child (absolute) | w4 per-child byte "offset | leaf << 6 | self-rooted << 7", children 0..3
+//   w5 the same bytes of children 4,5 | present mask << 16 | leaf mask << 24
+//   w6 bytes 0..2: (exponent + 119) & 255 per axis, i.e. bits 23..30 of the scale 2^(e-8) as a float; byte 3: the same-treelet mask
+//   w7 + 3 * axis: lower bounds of children 0..3 | upper bounds of children 0..3 | lower 4, lower 5, upper 4, upper 5
+// so that near / far planes are whole words chosen by the sign of the ray direction.
 __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, const uint64_t* __restrict__ tl_node, unsigned long long n_entries,
-                             const uint32_t* __restrict__ node_tid) {
+                             const uint32_t* __restrict__ node_tid, uint4* __restrict__ tnodes) {
   const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_entries) return;
   const uint64_t e = tl_node[k];
@@ -246,7 +259,8 @@ __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, cons
   const uint4* np = reinterpret_cast<const uint4*>(node);
   const uint4 a = np[0], b = np[1];
   const uint32_t own = node_tid[slot];
-  uint32_t child = slot + a.w, m = 0;
+  uint32_t child = slot + a.w, m = 0, present = 0, leaf6 = 0, off = 0;
+  uint64_t cbytes = 0;                                    // byte i: offset of child i | leaf << 6 | self-rooted << 7
   const uint64_t info6 = ((uint64_t)b.z << 16) | (b.y >> 16);
 #pragma unroll
   for (int i = 0; i < 6; i++) {
@@ -257,10 +271,33 @@ __global__ void k_child_mask(uint8_t* __restrict__ arena, uint32_t n_slots, cons
       if (own != VSRT_NO_TID && t != VSRT_NO_TID && ((t ^ own) & VSRT_TID_MASK) == 0u) m |= 1u << i;
       self = (t & VSRT_TID_SELF_ROOTED) ? 0x80u : 0u;
     }
-    node[22 + i] = (uint8_t)((info & 0x3fu) | ((info & 0x3cu) ? 0x40u : 0u) | self);
-    child += sz;
+    const uint32_t leaf = (info & 0x3cu) ? 0x40u : 0u;
+    node[22 + i] = (uint8_t)((info & 0x3fu) | leaf | self);
+    cbytes |= (uint64_t)((off & 15u) | leaf | self) << (8 * i);
+    if (sz) present |= 1u << i;
+    if (leaf) leaf6 |= 1u << i;
+    child += sz; off += sz;
   }
   node[17] = (uint8_t)m;
+  if (tnodes) {
+    const uint4 c = np[2], d = np[3];
+    const uint32_t w[16] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w };
+    auto byte_at = [&](int i) -> uint32_t { return (w[i >> 2] >> ((i & 3) * 8)) & 0xffu; };
+    uint32_t t[16];
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = slot + a.w;
+    t[4] = (uint32_t)cbytes; t[5] = (uint32_t)(cbytes >> 32) | (present << 16) | (leaf6 << 24);
+    t[6] = ((byte_at(18) + 119u) & 0xffu) | (((byte_at(19) + 119u) & 0xffu) << 8) | (((byte_at(20) + 119u) & 0xffu) << 16) | (m << 24);
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      const int lo = 28 + 12 * ax, hi = lo + 6;
+      t[7 + 3 * ax] = byte_at(lo) | (byte_at(lo + 1) << 8) | (byte_at(lo + 2) << 16) | (byte_at(lo + 3) << 24);
+      t[8 + 3 * ax] = byte_at(hi) | (byte_at(hi + 1) << 8) | (byte_at(hi + 2) << 16) | (byte_at(hi + 3) << 24);
+      t[9 + 3 * ax] = byte_at(lo + 4) | (byte_at(lo + 5) << 8) | (byte_at(hi + 4) << 16) | (byte_at(hi + 5) << 24);
+    }
+    uint4* o = tnodes + (uint64_t)slot * 4u;
+    o[0] = make_uint4(t[0], t[1], t[2], t[3]); o[1] = make_uint4(t[4], t[5], t[6], t[7]);
+    o[2] = make_uint4(t[8], t[9], t[10], t[11]); o[3] = make_uint4(t[12], t[13], t[14], t[15]);
+  }
 }
 // ---- remapBVHToTreeletLayout (:1473-1509) as a per-slot table: treelet t (ascending root order) starts at base + t * pitch,
 // its root first, then its list entries in order; an entry keeps the mapping of the FIRST treelet (lowest index) that lists
@@ -306,7 +343,7 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   uint64_t* scratch = nullptr; uint64_t* store = nullptr; unsigned long long store_cap = 0; size_t scratch_roots = 0;
   uint32_t* popc = nullptr; unsigned long long* off64 = nullptr; void* scan_tmp = nullptr;
   uint32_t* prefix = nullptr; uint32_t* tl_root = nullptr; uint32_t* tl_count = nullptr; unsigned long long* tl_off = nullptr;
-  uint64_t* tl_node = nullptr; uint32_t* node_tid = nullptr;
+  uint64_t* tl_node = nullptr; uint32_t* node_tid = nullptr; uint4* tnodes = nullptr; unsigned long long* hot64 = nullptr; uint32_t* hot_keys = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_roots = 1, begin = 0, h_err = 0;
   unsigned long long h_scal[3] = { 0, 0, 0 }, n_entries = 0;
@@ -393,7 +430,10 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   k_narrow<<<(nw + 255) / 256, 256, 0, st>>>(off64, nw, prefix);
   CK(cudaMalloc(&r_rank, (size_t)n_roots * 4)); CK(cudaMalloc(&tl_root, (size_t)n_roots * 4)); CK(cudaMalloc(&tl_count, (size_t)n_roots * 4));
   CK(cudaMalloc(&tl_off, ((size_t)n_roots + 1) * 8));
-  k_rank<<<(n_roots + 255) / 256, 256, 0, st>>>(roots, r_count, n_roots, claimed, prefix, r_rank, tl_root, tl_count);
+  CK(cudaMalloc(&hot64, (size_t)VSRT_HOT_N * 8)); CK(cudaMemsetAsync(hot64, 0xff, (size_t)VSRT_HOT_N * 8, st));
+  CK(cudaMalloc(&hot_keys, (size_t)VSRT_HOT_N * 4));
+  k_rank<<<(n_roots + 255) / 256, 256, 0, st>>>(roots, r_count, n_roots, claimed, prefix, r_rank, tl_root, tl_count, hot64);
+  k_narrow<<<(VSRT_HOT_N + 255) / 256, 256, 0, st>>>(hot64, VSRT_HOT_N, hot_keys);   // low word = treelet index; an empty bucket keeps ~0 = VSRT_NO_TID
   if ((rc = vsrt_launch_scan(tl_count, n_roots, (uint64_t*)tl_off, scan_tmp, st)) != VSRT_OK) goto done;
   CK(cudaMemcpyAsync(&n_entries, tl_off + n_roots, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -402,7 +442,18 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   k_gather<<<(n_roots + 127) / 128, 128, 0, st>>>(store, r_off, r_count, r_rank, n_roots, tl_off, tl_node, node_tid, scal + 1);
   k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns, claimed, prefix);
   // the arena copy is private to the context; its pad bytes are ours (data layout)
-  if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(const_cast<uint8_t*>(av.base), ns, tl_node, n_entries, node_tid);
+  // Two copies of the arena from here on: the Mesa-layout one (with K0's flag bits) that every other consumer reads, and K1's
+  // traversal copy with the internal nodes re-laid-out.  VSRT_TN_SWAP=1 (A/B) lets the traversal copy keep the allocation the
+  // arena was uploaded into and moves the Mesa-layout copy to the new one (the caller swaps the pointers, FormOutputs::arena_moved).
+  CK(cudaMalloc(&tnodes, (size_t)std::max(ns, 1u) * 64));
+  CK(cudaMemcpyAsync(tnodes, av.base, (size_t)ns * 64, cudaMemcpyDeviceToDevice, st));
+  {
+    const bool swap = getenv("VSRT_TN_SWAP") && atoi(getenv("VSRT_TN_SWAP")) != 0;
+    uint8_t* mesa = swap ? reinterpret_cast<uint8_t*>(tnodes) : const_cast<uint8_t*>(av.base);
+    uint4* trav = swap ? reinterpret_cast<uint4*>(const_cast<uint8_t*>(av.base)) : tnodes;
+    if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(mesa, ns, tl_node, n_entries, node_tid, trav);
+    out->arena_moved = swap ? 1u : 0u;
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev1, st));
   CK(cudaMemcpyAsync(h_scal, scal, 24, cudaMemcpyDeviceToHost, st));
@@ -421,13 +472,14 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   }
   res->n_treelets = n_roots; res->n_entries = n_entries; res->n_mapped = h_scal[1]; res->total_bvh = h_scal[0];
   out->node_tid = node_tid; out->root_bits = claimed; out->root_prefix = prefix; out->tl_root = tl_root;
-  out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node;
+  out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node; out->tnodes = reinterpret_cast<uint8_t*>(tnodes); tnodes = nullptr;
+  out->hot_keys = hot_keys; hot_keys = nullptr;
   node_tid = nullptr; claimed = nullptr; prefix = nullptr; tl_root = nullptr; tl_off = nullptr; tl_node = nullptr;
 done:
   cudaFree(scratch); cudaFree(store);
   cudaFree(claimed); cudaFree(roots); cudaFree(n_roots_d); cudaFree(scal); cudaFree(r_count); cudaFree(r_off); cudaFree(r_rank);
   cudaFree(popc); cudaFree(off64); cudaFree(scan_tmp); cudaFree(prefix); cudaFree(tl_root); cudaFree(tl_count); cudaFree(tl_off);
-  cudaFree(tl_node); cudaFree(node_tid);
+  cudaFree(tl_node); cudaFree(node_tid); cudaFree(tnodes); cudaFree(hot64); cudaFree(hot_keys);
   if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
   return rc;
 }

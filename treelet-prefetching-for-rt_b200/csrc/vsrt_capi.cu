@@ -35,7 +35,7 @@ template <typename... A> int fail(vsrt_context* c, int code, const char* fmt, A.
 #define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, VSRT_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } while (0)
 
 void free_treelets(vsrt_context* c) {
-  cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node);
+  cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node); cudaFree(c->fo.tnodes); cudaFree(c->fo.hot_keys);
   c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
   cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear(); c->h_root_of_slot.clear();
@@ -71,7 +71,7 @@ int make_view(vsrt_context* c, uint64_t tlas_host, ArenaView* av) {
 }
 TreeletView treelet_view(const vsrt_context* c) {
   TreeletView tv; tv.node_tid = c->fo.node_tid; tv.root_bits = c->fo.root_bits; tv.root_prefix = c->fo.root_prefix; tv.tl_root = c->fo.tl_root;
-  tv.n_treelets = c->fr.n_treelets; tv.pad = 0; return tv;
+  tv.n_treelets = c->fr.n_treelets; tv.pad = 0; tv.tnodes = c->fo.tnodes; tv.hot_keys = c->fo.hot_keys; return tv;
 }
 
 int ensure_mirrors(vsrt_context* c) {
@@ -108,6 +108,7 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
   char eb[400] = "";
   rc = vsrt_launch_form_treelets(av, budget, c->stream, &c->fo, &c->fr, c->d_err, eb, sizeof(eb));
   if (rc) return fail(c, rc, "%s", eb);
+  if (c->fo.arena_moved) { uint8_t* t = c->d_arena; c->d_arena = c->fo.tnodes; c->fo.tnodes = t; c->fo.arena_moved = 0; }
   c->formed = true; c->formed_tlas = tlas; c->formed_budget = budget;
   CUDA_OK(c, c->d_hist.ensure(std::max<size_t>(c->fr.n_treelets, 1)));
   CUDA_OK(c, cudaMemsetAsync(c->d_hist.p, 0, (size_t)c->fr.n_treelets * 8, c->stream));

@@ -190,6 +190,53 @@ VS_DEV uint32_t test_children(const Node64& n, const Ray8& r, const Idir& id, fl
   }
   return mask;
 }
+// The hot slab test over a node in K1's TRAVERSAL LAYOUT (treelets.cu, k_child_mask): the same operations on the same values as
+// test_children<false> -- only the byte shuffles that prepare them are gone.  Near / far planes of children 0..3 are whole words
+// picked by the sign of the ray direction, those of children 4,5 one word rotated by 16 bits; the scale's exponent bits are
+// stored ready to shift; the present mask is a field.
+VS_DEV uint32_t test_children_t(const Node64& n, const Ray8& r, const Idir& id, float cull, uint32_t magic16) {
+  const float ox = __uint_as_float(n.w[0]), oy = __uint_as_float(n.w[1]), oz = __uint_as_float(n.w[2]);
+  const float sx = __uint_as_float((n.w[6] & 0xffu) << 23), sy = __uint_as_float((n.w[6] << 15) & 0x7F800000u), sz = __uint_as_float((n.w[6] << 7) & 0x7F800000u);
+  const uint64_t s_x = pk2(sx, sx), s_y = pk2(sy, sy), s_z = pk2(sz, sz), o_x = pk2(ox, ox), o_y = pk2(oy, oy), o_z = pk2(oz, oz);
+  const uint64_t nr_x = pk2(-r.ox, -r.ox), nr_y = pk2(-r.oy, -r.oy), nr_z = pk2(-r.oz, -r.oz);
+  const uint64_t id_x = pk2(id.x, id.x), id_y = pk2(id.y, id.y), id_z = pk2(id.z, id.z);
+  const uint32_t magic = magic16 ^ 0x2F646464u;   // 0x4B000000 in a register, so the byte selector can be the PRMT's immediate
+  const uint64_t m23 = pk2(-8388608.0f, -8388608.0f);
+  uint32_t near4[3], far4[3], nf2[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const bool neg = (int32_t)__float_as_uint(ax == 0 ? id.x : (ax == 1 ? id.y : id.z)) < 0;
+    const uint32_t lo4 = n.w[7 + 3 * ax], up4 = n.w[8 + 3 * ax], w45 = n.w[9 + 3 * ax];   // lower 0..3 | upper 0..3 | lower 4,5 upper 4,5
+    near4[ax] = neg ? up4 : lo4; far4[ax] = neg ? lo4 : up4;
+    nf2[ax] = __funnelshift_l(w45, w45, neg ? 16u : 0u);                                    // near(4,5) | far(4,5)
+  }
+#define VS_B2(w_, k_) pk2(__uint_as_float(__byte_perm((w_), magic, 0x7540u + (k_))), __uint_as_float(__byte_perm((w_), magic, 0x7541u + (k_))))
+#define VS_T2(w_, k_, s_, o_, nr_, id_) mul2(add2(fma2(add2(VS_B2(w_, k_), m23), s_, o_), nr_), id_)
+  uint32_t mask = 0;
+#pragma unroll
+  for (int pp = 2; pp >= 0; pp--) {
+    float nx[2], fx[2], ny[2], fy[2], nz[2], fz[2];
+    if (pp == 2) {
+      upk2(VS_T2(nf2[0], 0, s_x, o_x, nr_x, id_x), nx[0], nx[1]); upk2(VS_T2(nf2[0], 2, s_x, o_x, nr_x, id_x), fx[0], fx[1]);
+      upk2(VS_T2(nf2[1], 0, s_y, o_y, nr_y, id_y), ny[0], ny[1]); upk2(VS_T2(nf2[1], 2, s_y, o_y, nr_y, id_y), fy[0], fy[1]);
+      upk2(VS_T2(nf2[2], 0, s_z, o_z, nr_z, id_z), nz[0], nz[1]); upk2(VS_T2(nf2[2], 2, s_z, o_z, nr_z, id_z), fz[0], fz[1]);
+    } else {
+      upk2(VS_T2(near4[0], 2 * pp, s_x, o_x, nr_x, id_x), nx[0], nx[1]); upk2(VS_T2(far4[0], 2 * pp, s_x, o_x, nr_x, id_x), fx[0], fx[1]);
+      upk2(VS_T2(near4[1], 2 * pp, s_y, o_y, nr_y, id_y), ny[0], ny[1]); upk2(VS_T2(far4[1], 2 * pp, s_y, o_y, nr_y, id_y), fy[0], fy[1]);
+      upk2(VS_T2(near4[2], 2 * pp, s_z, o_z, nr_z, id_z), nz[0], nz[1]); upk2(VS_T2(far4[2], 2 * pp, s_z, o_z, nr_z, id_z), fz[0], fz[1]);
+    }
+#pragma unroll
+    for (int k = 1; k >= 0; k--) {
+      const float mn = fmaxf(fmaxf(nx[k], ny[k]), fmaxf(nz[k], r.tmin));
+      const float mx = fminf(fminf(fx[k], fy[k]), fminf(fz[k], r.tmax));
+      const uint32_t sb = __float_as_uint(fsub(mn, cull)) & ~__float_as_uint(fsub(mx, mn));   // bit 31 = hit
+      mask = __funnelshift_l(sb, mask, 1);
+    }
+  }
+#undef VS_T2
+#undef VS_B2
+  return mask & (n.w[5] >> 16);      // present children only (the leaf mask above bit 7 cannot reach the six mask bits: mask < 64)
+}
 VS_DEV bool finite3(float a, float b, float c) { return (fabsf(a) <= 3.402823466e38f) && (fabsf(b) <= 3.402823466e38f) && (fabsf(c) <= 3.402823466e38f); }
 // true if a NaN could reach the slab test for this ray: any non-finite origin/direction, NaN tmin/tmax
 VS_DEV bool ray_needs_exact(const Ray8& r) { return !(finite3(r.ox, r.oy, r.oz) && finite3(r.dx, r.dy, r.dz) && r.tmin == r.tmin && r.tmax == r.tmax); }

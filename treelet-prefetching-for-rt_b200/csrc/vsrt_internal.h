@@ -19,6 +19,13 @@
 #define VSRT_TID_SELF_ROOTED 0x80000000u   // flag in node_tid[]: the slot is the root of the treelet it is mapped to
 #define VSRT_TID_MASK 0x7FFFFFFFu
 #define VSRT_NO_INST 0x7FFFFFFFu
+// K3 keeps a CTA-private counter for VSRT_HOT_N treelets: bucket h = index & (VSRT_HOT_N - 1) belongs to the treelet K0 found
+// EARLIEST among those that map to it (formation runs in generations from the TLAS root, so earlier = nearer the top of the tree =
+// visited by more rays); every other treelet of the bucket counts straight into the global histogram
+#ifndef VSRT_HOT_BITS
+#define VSRT_HOT_BITS 11
+#endif
+#define VSRT_HOT_N (1u << VSRT_HOT_BITS)
 #define VSRT_MAX_SPANS_INLINE 8
 
 // compact trace-record codes: the TransactionType (0..6) except that a TLAS internal node is tagged 7 so the
@@ -63,6 +70,8 @@ struct TreeletView {
   const uint32_t* tl_root;      // [n_treelets] slot of each treelet root, ascending
   uint32_t n_treelets;
   uint32_t pad;
+  const uint8_t* tnodes;        // [n_slots * 64] K1's traversal copy of the arena (internal nodes re-laid-out, the rest verbatim)
+  const uint32_t* hot_keys;     // [VSRT_HOT_N]
 };
 
 struct DevCounters {            // mirrors vsrt_counters (uint64 each)
@@ -78,6 +87,9 @@ enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_
 struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; uint32_t inst_base; uint64_t peak_scratch_bytes; };
 struct FormOutputs {      // device allocations owned by the context
   uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
+  uint8_t* tnodes;        // K1's traversal copy of the arena: internal nodes in the traversal layout (treelets.cu, k_child_mask), the rest verbatim
+  uint32_t arena_moved;   // 1: `tnodes` holds the Mesa-layout copy and the arena's own allocation the traversal copy -- the caller swaps the two pointers
+  uint32_t* hot_keys;     // [VSRT_HOT_N] K3's CTA-private histogram table: bucket h counts treelet hot_keys[h] (NO_TID = nobody)
 };
 // Forms treelets for `budget`; allocates outputs with cudaMalloc (caller frees).  Returns VSRT_* code.
 int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,

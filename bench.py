@@ -256,6 +256,8 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line and nothing else (NCCL prints its version there)
     if world > 1:
+        # the host-buffer calls use worker threads (record expansion / treelet ids); the ranks of one box share its cores
+        os.environ.setdefault("VSRT_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     if rank == 0:
@@ -369,7 +371,11 @@ def run_cuda(args):
         dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
     e2e_value = total_rays * e2e_steps / float(e_all.item())
     h2d = n * _abi.RAY.itemsize
-    d2h = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 16 + n_txn * 8
+    # what the caller receives (hits, offsets, 16-byte records, 64-bit treelet ids) and what crosses the link for it: with host
+    # expansion (the library's default for this layout) a record travels as 4 packed bytes and worker threads write the 24
+    delivered = n * _abi.HIT.itemsize + (n + 1) * 8 + n_txn * 16 + n_txn * 8
+    host_expand = os.environ.get("VSRT_HOST_EXPAND", "1") != "0"
+    d2h = n * _abi.HIT.itemsize + (n + 1) * 8 + (n_txn * 4 if host_expand else n_txn * 16)
 
     # ---- the same with the packed host form (vsrt_trace_rays_packed): 4-byte records + 4-byte treelet indices, expanded by the
     # caller where it consumes them (vsrt_unpack_txn).  Reported beside "e2e", which stays the full 24 bytes per record.
@@ -403,6 +409,8 @@ def run_cuda(args):
     txn_dev, tid_dev = ctx.fetch_trace()
     tix_dev = np.searchsorted(ctx.tables()["roots"], tid_dev).astype(np.uint32)
     lean_ok = bool(np.array_equal(ctx.unpack(rec_np[:1 << 20]), txn_dev[:1 << 20]) and np.array_equal(node_table[rec_np >> 3], tix_dev))
+    # ... and what the full host form delivered (the e2e call above): every record and every treelet id of the frame
+    e2e_ok = bool(np.array_equal(txn_h.numpy().view(_abi.TXN)[:n_txn], txn_dev) and np.array_equal(tid_h.numpy().view(np.uint64)[:n_txn], tid_dev))
     # the PCIe link this box gives a pinned device->host copy (the floor of any host-buffer call)
     big = torch.empty(1 << 30, dtype=torch.uint8, device=dev); big_h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
     big_h.copy_(big); torch.cuda.synchronize()
@@ -431,12 +439,15 @@ def run_cuda(args):
                                                   "records_per_ray": n_txn / n, "bytes_per_ray": alg_bytes / n, "arena_bytes": int(scene.size)}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                        "api": "vsrt_trace_rays (host pinned buffers; hits + CSR offsets + 16-byte records + 64-bit treelet ids copied back)"},
+                        "host_bytes_delivered_per_step": int(delivered), "matches_device_records": e2e_ok,
+                        "api": "vsrt_trace_rays (host pinned buffers in, hits + CSR offsets + 16-byte records + 64-bit treelet ids in host buffers out; "
+                               + ("the frame is traced in 524,288-ray windows whose records cross the link as 4 packed bytes and are expanded to the 24 bytes by the library's host threads behind the copy front)"
+                                  if host_expand else "records copied as 16-byte records, ids derived on the host)")},
                 "e2e_packed": {"value": e2e_packed_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_packed), "steps": e2e_steps,
                                "api": "vsrt_trace_rays_packed, lean form (host pinned buffers; hits + CSR offsets + 4-byte packed records, traced in 524,288-ray chunks with the copies overlapped; the caller expands with vsrt_unpack_txn and takes treelet ids from vsrt_node_treelet_table)",
                                "matches_device_records": lean_ok},
                 "pcie": {"d2h_gbs_measured": d2h_gbs, "e2e_floor_ms": d2h / d2h_gbs / 1e6, "e2e_packed_floor_ms": d2h_packed / d2h_gbs / 1e6,
-                         "note": "floor = bytes copied back per frame / measured pinned D2H bandwidth; e2e is at that floor, so the full 24-byte-per-record host form cannot go faster on this link"},
+                         "note": "floor = bytes that cross the link per frame / measured pinned D2H bandwidth; the full form is bound by the host threads that write 24 bytes per record, the lean form by the link"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_traverse<TREELET>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -557,9 +557,15 @@ def test_packed_pipeline_and_treelet_table(api, monkeypatch):
     txn_dev, tid_dev = ctx.fetch_trace()
     assert np.array_equal(txn_dev, full["txns"]) and np.array_equal(tid_dev, full["treelet_ids"])
     # the full host form, pipelined: records copied window by window, treelet ids derived on the host from the slot -> root table
-    again = ctx.trace(1, rays, capacity=len(full["txns"]))
-    assert np.array_equal(again["offsets"], full["offsets"]) and np.array_equal(again["hits"], full["hits"])
-    assert np.array_equal(again["txns"], full["txns"]) and np.array_equal(again["treelet_ids"], full["treelet_ids"])
+    # (VSRT_HOST_EXPAND=0), or -- the default -- windows delivered as 4-byte packed records and expanded to records + ids by host threads
+    for expand in ("0", "1"):
+        monkeypatch.setenv("VSRT_HOST_EXPAND", expand)
+        again = ctx.trace(1, rays, capacity=len(full["txns"]))
+        assert np.array_equal(again["offsets"], full["offsets"]) and np.array_equal(again["hits"], full["hits"]), expand
+        assert np.array_equal(again["txns"], full["txns"]) and np.array_equal(again["treelet_ids"], full["treelet_ids"]), expand
+        txn_dev, tid_dev = ctx.fetch_trace()          # the device-side frame is complete either way
+        assert np.array_equal(txn_dev, full["txns"]) and np.array_equal(tid_dev, full["treelet_ids"]), expand
+    monkeypatch.delenv("VSRT_HOST_EXPAND")
     sorted_txns, _ = ctx.sort_trace(1)
     monkeypatch.setenv("VSRT_PIPELINE_CHUNK", "0")
     ctx.trace(1, rays)

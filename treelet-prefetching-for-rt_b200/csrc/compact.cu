@@ -86,9 +86,6 @@ constexpr int K3_ILP = VSRT_K3_ILP;        // independent 32-record windows in f
 #ifndef VSRT_K3_HASH_BITS
 #define VSRT_K3_HASH_BITS 10
 #endif
-#ifndef VSRT_K3_HIST2
-#define VSRT_K3_HIST2 0   // A/B: run heads from one ballot over an index sentinel, bucket = low bits of the treelet index
-#endif
 #ifndef VSRT_K3_PERSIST
 #define VSRT_K3_PERSIST 0   // measured: a persistent grid saturates the CTA-private table and is slower (1.10 vs 0.72 ms)
 #endif
@@ -188,14 +185,7 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
           // original_bvh_to_treelet_bvh_mapping[addr + offset] in every record when the layout is remapped (:1682,:1763,...)
           const uint64_t address = SIMPLE ? simple_base + (uint64_t)slot * 64u
                                           : (p.remap ? __ldg(p.remap + slot) : (one_span ? span_host + (uint64_t)slot * 64u : slot_to_host(av, slot)) + (uint64_t)delta);
-#if VSRT_K3_HIST2
-          // size and type of a code from two byte tables: PRMT picks byte `code`; selector nibbles 9 replicate the sign of byte 1
-          // (0x40 / 0x01: positive) into the upper three bytes, i.e. clear them
-          const uint32_t sel = code | 0x9990u;
-          const uint32_t type = __byte_perm(0x03020100u, 0x01060504u, sel), size = __byte_perm(0x08804040u, 0x40404040u, sel);
-#else
           const uint32_t type = code_type(code), size = code_size(code);
-#endif
           const unsigned long long j = j0 + pos[u];     // < offsets[n_rays] <= out_capacity (checked on entry)
           if (PACKED) p.packed[j] = rec[u];
           else {
@@ -220,18 +210,6 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
         // shared-memory hash table and flushes it once at the end; only table collisions go straight to L2.
 #pragma unroll
         for (int u = 0; u < K3_ILP; u++) {
-#if VSRT_K3_HIST2
-          // a lane without a record (or a node outside every treelet) holds NO_TID, which differs from every real index: a run
-          // starts wherever the index changes, and only runs of a real index are counted -- one ballot, no activity mask
-          const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
-          const bool first = lane == 0 || prev != tid[u];
-          const unsigned bnd = __ballot_sync(full, first);
-          const bool head = first && tid[u] != VSRT_NO_TID;
-          if (head) {
-            const unsigned above = (bnd >> lane) >> 1;
-            const uint32_t run = above ? (uint32_t)__ffs(above) : 32u - (uint32_t)lane;
-            const uint32_t h = tid[u] & ((1u << TBITS) - 1u);   // treelets near each other in the tree have nearby indices: distinct buckets
-#else
           const bool a = valid[u] && tid[u] != VSRT_NO_TID;
           const uint32_t prev = __shfl_up_sync(full, tid[u], 1);
           const unsigned act = __ballot_sync(full, a);
@@ -242,7 +220,6 @@ __global__ void __launch_bounds__(K3_THREADS, VSRT_K3_MIN_BLOCKS) k_compact(cons
             const unsigned above = (lane == 31) ? 0u : ((heads | ~act) & (0xffffffffu << (lane + 1)));
             const uint32_t run = (above ? (uint32_t)(__ffs(above) - 1) : 32u) - (uint32_t)lane;
             const uint32_t h = (tid[u] * 2654435761u) >> (32 - TBITS);
-#endif
             uint32_t old = t_key[h];                                             // hot treelets own their slot already: no CAS
             if (old == VSRT_NO_TID) old = atomicCAS(&t_key[h], VSRT_NO_TID, tid[u]);
             if (old == VSRT_NO_TID || old == tid[u]) atomicAdd(&t_cnt[h], run);

@@ -92,6 +92,8 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_LEAF_ASYNC
 #define VSRT_K1_LEAF_ASYNC 1
 #endif
+// (L1 hints measured in round 2 and dropped: leaf copies that bypass L1 -- cp.async.cg -- and internal-node loads with
+// L1::evict_last moved K1 by less than the run-to-run noise on all three workloads, profiles/README.md.)
 #ifndef VSRT_K1_PF_LEAF
 #define VSRT_K1_PF_LEAF 0
 #endif

@@ -387,6 +387,8 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  delete c->pool; c->pool = nullptr;
+  for (HostStage& hs : c->h_stage) if (hs.p) cudaFreeHost(hs.p);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -681,30 +683,58 @@ namespace {
 //                 the copy front (layouts with one span, one host->device offset and no remap; otherwise they are copied)
 // Ray ids follow the batch order (windows are traced in order on one stream); every window writes its slice of the frame-sized
 // device buffers, so afterwards the context holds the frame as a single batch would have left it.
-struct FrameJob {   // one window's treelet ids to derive on the host
-  cudaEvent_t copied; const vsrt_txn* txns; uint64_t* ids; uint64_t n;
+struct FrameJob {   // one window's host-side work: treelet ids derived from the copied records, or records and ids expanded from packed records
+  cudaEvent_t copied; const vsrt_txn* txns; uint64_t* ids; uint64_t n; const uint32_t* packed;
 };
-void derive_ids(const vsrt_context* c, const std::vector<uint64_t>& root_of_slot, uint64_t addr0, const vsrt_txn* txns, uint64_t* ids, uint64_t n, unsigned threads) {
-  auto work = [&](uint64_t lo, uint64_t hi) {
-    const uint64_t ns = root_of_slot.size();
-    for (uint64_t j = lo; j < hi; j++) {
-      const uint64_t slot = (txns[j].address - addr0) >> 6;
+void derive_ids(const std::vector<uint64_t>& root_of_slot, uint64_t addr0, const vsrt_txn* txns, uint64_t* ids, uint64_t lo, uint64_t hi) {
+  const uint64_t ns = root_of_slot.size();
+  for (uint64_t j = lo; j < hi; j++) {
+    const uint64_t slot = (txns[j].address - addr0) >> 6;
+    const uint64_t v = slot < ns ? root_of_slot[slot] : ~0ull;
+#if defined(__x86_64__)
+    _mm_stream_si64(reinterpret_cast<long long*>(ids + j), (long long)v);      // written once, never read here: no read-for-ownership
+#else
+    ids[j] = v;
+#endif
+  }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
+}
+
+// Full records written on the host from the 4-byte packed records of a window: {address, size, type} is arithmetic on
+// (slot, code) for layouts with one span, one host->device offset and no remap, and the 64-bit treelet id a table lookup by
+// slot.  The link then carries 4 bytes per record instead of 16 (or 24); the 24 bytes per record the caller asked for are
+// produced by worker threads with streaming stores, behind the copy front.
+void expand_records(const std::vector<uint64_t>& root_of_slot, uint64_t addr0, const uint32_t* packed, vsrt_txn* txns, uint64_t* ids, uint64_t lo, uint64_t hi) {
+  const uint64_t ns = root_of_slot.size();
+  static const uint32_t size_of[8] = { 64, 64, 128, 8, 64, 64, 64, 64 };                 // by compact code (vsrt_internal.h): instance leaf 128, descriptor 8
+  static const uint32_t type_of[8] = { 0, 1, 2, 3, 4, 5, 6, 1 };                        // code 7 = TLAS internal node -> BVH_INTERNAL_NODE
+#if defined(__x86_64__)
+  const bool aligned = (reinterpret_cast<uintptr_t>(txns) & 15u) == 0;
+#endif
+  for (uint64_t j = lo; j < hi; j++) {
+    const uint32_t rec = packed[j], code = rec & 7u; const uint64_t slot = rec >> 3;
+    const uint64_t address = addr0 + slot * 64u;
+    if (txns) {
+#if defined(__x86_64__)
+      if (aligned) _mm_stream_si128(reinterpret_cast<__m128i*>(txns + j), _mm_set_epi32((int)type_of[code], (int)size_of[code], (int)(address >> 32), (int)(uint32_t)address));
+      else
+#endif
+      { txns[j].address = address; txns[j].size = size_of[code]; txns[j].type = type_of[code]; }
+    }
+    if (ids) {
       const uint64_t v = slot < ns ? root_of_slot[slot] : ~0ull;
 #if defined(__x86_64__)
-      _mm_stream_si64(reinterpret_cast<long long*>(ids + j), (long long)v);      // written once, never read here: no read-for-ownership
+      _mm_stream_si64(reinterpret_cast<long long*>(ids + j), (long long)v);
 #else
       ids[j] = v;
 #endif
     }
+  }
 #if defined(__x86_64__)
-    _mm_sfence();
+  _mm_sfence();
 #endif
-  };
-  (void)c;
-  if (threads <= 1 || n < 65536) { work(0, n); return; }
-  std::vector<std::thread> th;
-  for (unsigned t = 0; t < threads; t++) th.emplace_back(work, n * t / threads, n * (t + 1) / threads);
-  for (auto& x : th) x.join();
 }
 
 int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, const vsrt_ray* rays, vsrt_hit* hits, uint64_t* trace_offsets,
@@ -718,7 +748,11 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
   int rc = do_form(c, tlas, c->cfg.max_treelet_size); if (rc) return rc;
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
   // host-derived treelet ids: slot -> root address table (once per formation), addresses start at the span's first byte
-  const bool derive = !packed && treelet_ids && c->spans.size() == 1 && !c->cfg.remap_to_treelet_layout;
+  // full form, simple layout: the windows run in packed form and the host expands them (VSRT_HOST_EXPAND=0: records copied as
+  // 16-byte records, ids derived from their addresses -- the first round-2 scheme, kept for A/B)
+  bool host_expand = !packed && records_out && c->spans.size() == 1 && !c->cfg.remap_to_treelet_layout;
+  if (const char* e = getenv("VSRT_HOST_EXPAND")) host_expand = host_expand && atoi(e) != 0;
+  const bool derive = !packed && (treelet_ids || host_expand) && c->spans.size() == 1 && !c->cfg.remap_to_treelet_layout;
   uint64_t addr0 = 0; unsigned threads = 1;
   if (derive) {
     ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
@@ -733,7 +767,9 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
       }
     }
     addr0 = c->spans[0].host + (uint64_t)av.tlas_delta;
-    threads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    // three quarters of the cores: the thread that launches the next window and the copy engine's completion path need the rest
+    // (16-core box, e2e M rays/s at 4 / 8 / 12 / 15 / 16 / 20 workers: 42 / 59 / 92 / 86 / 88 / 75)
+    { const unsigned hc = std::max(1u, std::thread::hardware_concurrency()); threads = std::max(1u, std::min(hc - hc / 4, 48u)); }
     if (const char* e = getenv("VSRT_HOST_THREADS")) threads = (unsigned)std::max(1, atoi(e));
   }
   // a stage-capacity change in a later window invalidates the earlier windows' staging: the frame is restarted then, from a
@@ -746,6 +782,20 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
   const DevCounters h_prev_bak = c->h_prev;
   std::vector<cudaEvent_t> win_ev;
   std::vector<FrameJob> jobs;
+  // a window's host-side work goes to the context's worker pool and this thread carries on with the next window; the workers
+  // wait for the window's copy themselves.  One job at a time: submitting waits for the previous window's job, which is also
+  // what makes a staging buffer free again by the time the window after next is copied into it.
+  if (derive && (!c->pool || c->pool->th.size() != threads)) { delete c->pool; c->pool = new HostPool(threads); }
+  const std::vector<uint64_t>* const rtab = &c->h_root_of_slot; const int device = c->device;
+  auto run_job = [&](const FrameJob& j) {
+    c->pool->submit([j, rtab, addr0, device](unsigned t, unsigned nt) {
+      cudaSetDevice(device);
+      cudaEventSynchronize(j.copied);
+      const uint64_t lo = j.n * t / nt, hi = j.n * (t + 1) / nt;
+      if (j.packed) expand_records(*rtab, addr0, j.packed, const_cast<vsrt_txn*>(j.txns), j.ids, lo, hi);
+      else if (j.ids) derive_ids(*rtab, addr0, j.txns, j.ids, lo, hi);
+    });
+  };
   const uint64_t rec_size = packed ? 4 : sizeof(vsrt_txn);
   for (int attempt = 0; attempt < 12; attempt++) {
     uint64_t base = 0; bool overflow = false, restart = false;
@@ -761,7 +811,7 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
         CUDA_OK(c, cudaEventRecord(c->ev_up[b ^ 1], c->up_stream));
       }
       const uint32_t cap_before = c->stage_cap;
-      rc = run_batch(c, tlas, mode, c->d_rays.p + r0, m, c->stream, packed, r0, n, base);      // ends with a host synchronisation of c->stream
+      rc = run_batch(c, tlas, mode, c->d_rays.p + r0, m, c->stream, packed || host_expand, r0, n, base);      // ends with a host synchronisation of c->stream
       if (rc) break;
       if (c->stage_cap != cap_before && k > 0) { restart = true; break; }
       const uint64_t total = c->last.n_txn - base;
@@ -773,20 +823,32 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
       uint64_t mrec = 0;
       if (records_out && base < capacity) {
         mrec = std::min(total, capacity - base);
-        const void* src = packed ? (const void*)(c->d_packed.p + base) : (const void*)(c->d_txns.p + base);
-        if (mrec) CUDA_OK(c, cudaMemcpyAsync((uint8_t*)records_out + base * rec_size, src, mrec * rec_size, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (host_expand) {
+          // the window's packed records land in one of two pinned staging buffers of the library; the workers expand from there
+          HostStage& hs = c->h_stage[b];
+          if (hs.cap < mrec) {
+            if (hs.p) cudaFreeHost(hs.p);
+            hs.p = nullptr; hs.cap = 0;
+            const uint64_t want = mrec + mrec / 4 + 4096;
+            CUDA_OK(c, cudaMallocHost(&hs.p, want * 4)); hs.cap = want;
+          }
+          if (mrec) CUDA_OK(c, cudaMemcpyAsync(hs.p, c->d_packed.p + base, mrec * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        } else {
+          const void* src = packed ? (const void*)(c->d_packed.p + base) : (const void*)(c->d_txns.p + base);
+          if (mrec) CUDA_OK(c, cudaMemcpyAsync((uint8_t*)records_out + base * rec_size, src, mrec * rec_size, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
       }
       if (base + total > capacity) overflow = true;
       if (win_ev.size() <= k) { cudaEvent_t e; CUDA_OK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); win_ev.push_back(e); }
       CUDA_OK(c, cudaEventRecord(win_ev[k], c->copy_stream));
       if (derive && mrec) {
-        // ids of the PREVIOUS window are derived now, while this window's copy is in flight (the workers need its records in host memory)
-        jobs.push_back(FrameJob{ win_ev[k], (const vsrt_txn*)records_out + base, treelet_ids + base, mrec });
-        if (jobs.size() >= 2) { const FrameJob& j = jobs[jobs.size() - 2]; cudaEventSynchronize(j.copied); derive_ids(c, c->h_root_of_slot, addr0, j.txns, j.ids, j.n, threads); }
+        // the PREVIOUS window is expanded (or its ids derived) now, while this window's copy is in flight: the workers need its records in host memory
+        jobs.push_back(FrameJob{ win_ev[k], (const vsrt_txn*)records_out + base, treelet_ids ? treelet_ids + base : nullptr, mrec, host_expand ? c->h_stage[b].p : nullptr });
+        run_job(jobs.back());
       }
       base += total;
     }
-    if (!rc && !restart && derive && !jobs.empty()) { const FrameJob& j = jobs.back(); cudaEventSynchronize(j.copied); derive_ids(c, c->h_root_of_slot, addr0, j.txns, j.ids, j.n, threads); }
+    if (c->pool) c->pool->wait();
     cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->up_stream);
     if (restart) {
       CUDA_OK(c, cudaMemcpyAsync(c->d_counters, c->d_frame_bak.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, c->stream));

@@ -4,7 +4,11 @@
 #pragma once
 #include "vsrt_internal.h"
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct Reg { uint64_t host, size, dev; bool tlas; };
@@ -23,7 +27,28 @@ template <typename T> struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Worker threads of the host-buffer calls (record expansion, treelet ids): started once per context, one job at a time; every
+// worker runs job(t, n_threads) and the submitter carries on -- the frame pipeline launches the next window meanwhile.
+struct HostPool {
+  std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
+  std::function<void(unsigned, unsigned)> job; uint64_t gen = 0; unsigned running = 0; bool stop = false;
+  explicit HostPool(unsigned n) {
+    for (unsigned t = 0; t < n; t++) th.emplace_back([this, t, n] {
+      uint64_t seen = 0;
+      for (;;) {
+        std::function<void(unsigned, unsigned)> f;
+        { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; f = job; }
+        f(t, n);
+        { std::lock_guard<std::mutex> l(m); if (--running == 0) cv_done.notify_all(); }
+      }
+    });
+  }
+  void wait() { std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return running == 0; }); }
+  void submit(std::function<void(unsigned, unsigned)> f) { wait(); { std::lock_guard<std::mutex> l(m); job = std::move(f); running = (unsigned)th.size(); gen++; } cv.notify_all(); }
+  ~HostPool() { wait(); { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& x : th) x.join(); }
+};
 struct CommState;   // reduce.cu
+struct HostStage { uint32_t* p = nullptr; uint64_t cap = 0; };   // pinned staging for one window's packed records (host-side expansion)
 
 struct vsrt_context {
   vsrt_config cfg;
@@ -70,6 +95,7 @@ struct vsrt_context {
   bool last_packed_only = false; ArenaView last_av{};   // the last batch was delivered as packed records only (vsrt_trace_rays_packed)
   // window pipeline of the host-buffer calls: frame-level backup of counters / histograms, slot -> treelet root table, copy streams
   DevBuf<uint8_t> d_frame_bak; std::vector<uint64_t> h_root_of_slot; cudaStream_t copy_stream = nullptr, up_stream = nullptr; cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_up[2] = { nullptr, nullptr }, ev_ready = nullptr;
+  HostStage h_stage[2]; HostPool* pool = nullptr;
   CommState* comm = nullptr;   // multi-GPU reduce state (reduce.cu), NULL until vsrt_comm_init / vsrt_comm_attach
 };
 

@@ -197,7 +197,12 @@ int vsrt_treelet_metadata_idx(vsrt_context* ctx, uint64_t root, uint32_t* idx);
  *   treelet_ids[]      addrToTreeletID(txn.address) (the values of the "RayID,..." line, :2256-2262, 64-bit)
  * txn_capacity counts records; *n_txn gets the number the batch produced.  If it exceeds the capacity the
  * call returns VSRT_E_CAPACITY after filling hits/trace_offsets; the trace stays on the device and
- * vsrt_trace_fetch() can still copy it out. */
+ * vsrt_trace_fetch() can still copy it out.
+ * A frame-sized batch (>= 2^20 rays) is traced in windows whose results return while the next window runs; for the common
+ * layout (one host span, one host->device offset, no remap) txns[] and treelet_ids[] are written by worker threads of the
+ * library from 4-byte packed records, so that 4 rather than 24 bytes per record cross the PCIe link.  Environment:
+ * VSRT_HOST_THREADS (workers, default 3/4 of the cores), VSRT_PIPELINE_CHUNK (rays per window, 0 = never),
+ * VSRT_HOST_EXPAND=0 (copy the 16-byte records instead). */
 int vsrt_trace_rays(vsrt_context* ctx, const void* tlas, int mode, uint64_t n_rays, const vsrt_ray* rays,
                     vsrt_hit* hits, uint64_t* trace_offsets, vsrt_txn* txns, uint64_t txn_capacity,
                     uint64_t* treelet_ids, uint64_t* n_txn);
@@ -349,8 +354,8 @@ int vsrt_table_events(vsrt_context* ctx, const uint8_t* tid_x, uint64_t* event_o
 void vsrt_table_event_stores(const vsrt_table_event* ev, uint64_t table_base, vsrt_store_txn out[2]);
 
 /* ---- packed trace for host consumers ----
- * The 16-byte records + 64-bit treelet ids of a 1080p frame are 2.1 GB, and the PCIe link (not the GPU) bounds a host-side
- * caller at ~46 M rays/s.  A record is a function of 32 bits -- the node's 64-byte slot in the packed arena and a 3-bit code --
+ * The 16-byte records + 64-bit treelet ids of a 1080p frame are 2.1 GB; a host-side caller that wants them in host memory
+ * is bounded by the link or by the host's memory bandwidth (vsrt_trace_rays: ~90 M rays/s), not by the GPU.  A record is a function of 32 bits -- the node's 64-byte slot in the packed arena and a 3-bit code --
  * and a treelet id is an index into vsrt_treelet_table's ascending root array, so a caller that builds its
  * MemoryTransactionRecords where it consumes them (trace_ray_impl -> thread->set_rt_transactions, instructions.cc:7235-7254)
  * can take 8 bytes per record instead of 24 and expand with vsrt_unpack_txn.  Same records, same order, same ids.

@@ -297,6 +297,19 @@ def test_empty_and_ragged_batches(api):
     ctx.close()
 
 
+def test_scan_tile_boundaries(api):
+    """Batches whose ray counts sit on and around the tile size of the one-pass offset scan (8192 counts per tile; the look-back
+    walks 32 tiles at a time): offsets, records and hits against the oracle."""
+    s = sc.Scene(1500, seed=21, n_blas=2, n_instances=2)
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.register(s); ctx.form_treelets()
+    orc = oracles.PortOracle(); orc.register(s); orc.form(512)
+    for n in (8191, 8192, 8193, 3 * 8192 + 1, 33 * 8192 + 7):
+        rays = sc.rays_random(n, seed=n & 0xffff)
+        helpers.assert_trace_equal(orc.trace(1, rays), ctx.trace(1, rays), "n=%d" % n)
+    ctx.close()
+
+
 def test_warp_call_and_queries(api):
     s = sc.Scene(4000, seed=8, n_blas=2, n_instances=2)
     orc = oracles.PortOracle(); orc.register(s); orc.form(512)

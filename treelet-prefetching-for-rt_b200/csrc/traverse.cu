@@ -637,6 +637,7 @@ int launch_mode(const TraverseParams& p, cudaStream_t st) {
   if (grid == 0) return VSRT_OK;
   if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
   if (VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT) {
+    if (!p.tv.tnodes) return VSRT_E_INVALID;      // (formation always fills the traversal copy)
     // the hot kernel traverses the traversal copy: the same slots, internal nodes re-laid-out by K0, leaves and headers verbatim
     TraverseParams q = p; q.av.base = p.tv.tnodes;
     k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(q);

@@ -334,7 +334,7 @@ __global__ void k_remap_assign(const uint32_t* __restrict__ tl_root, const unsig
 }  // namespace
 
 int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,
-                              uint32_t* err_flags_dev, char* errbuf, size_t errcap) {
+                              uint32_t* err_flags_dev, char* errbuf, size_t errcap, uint8_t* tarena) {
   int rc = VSRT_OK;
   const uint32_t ns = av.n_slots, nw = (ns + 31) / 32;
   const uint32_t cap = budget / 64 + 2;
@@ -443,17 +443,11 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   k_fix_tid<<<(ns + 255) / 256, 256, 0, st>>>(node_tid, ns, claimed, prefix);
   // the arena copy is private to the context; its pad bytes are ours (data layout)
   // Two copies of the arena from here on: the Mesa-layout one (with K0's flag bits) that every other consumer reads, and K1's
-  // traversal copy with the internal nodes re-laid-out.  VSRT_TN_SWAP=1 (A/B) lets the traversal copy keep the allocation the
-  // arena was uploaded into and moves the Mesa-layout copy to the new one (the caller swaps the pointers, FormOutputs::arena_moved).
-  CK(cudaMalloc(&tnodes, (size_t)std::max(ns, 1u) * 64));
-  CK(cudaMemcpyAsync(tnodes, av.base, (size_t)ns * 64, cudaMemcpyDeviceToDevice, st));
-  {
-    const bool swap = getenv("VSRT_TN_SWAP") && atoi(getenv("VSRT_TN_SWAP")) != 0;
-    uint8_t* mesa = swap ? reinterpret_cast<uint8_t*>(tnodes) : const_cast<uint8_t*>(av.base);
-    uint4* trav = swap ? reinterpret_cast<uint4*>(const_cast<uint8_t*>(av.base)) : tnodes;
-    if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(mesa, ns, tl_node, n_entries, node_tid, trav);
-    out->arena_moved = swap ? 1u : 0u;
-  }
+  // traversal copy -- every slot verbatim, then the internal nodes overwritten in the traversal layout.  (Which of the two keeps
+  // the allocation the arena was uploaded into makes no difference to K1: measured both ways.)
+  tnodes = reinterpret_cast<uint4*>(tarena);     // allocated with the arena (vsrt_commit): no allocation inside the timed formation
+  if (tnodes) CK(cudaMemcpyAsync(tnodes, av.base, (size_t)ns * 64, cudaMemcpyDeviceToDevice, st));
+  if (n_entries) k_child_mask<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(const_cast<uint8_t*>(av.base), ns, tl_node, n_entries, node_tid, tnodes);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev1, st));
   CK(cudaMemcpyAsync(h_scal, scal, 24, cudaMemcpyDeviceToHost, st));
@@ -472,14 +466,14 @@ int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t
   }
   res->n_treelets = n_roots; res->n_entries = n_entries; res->n_mapped = h_scal[1]; res->total_bvh = h_scal[0];
   out->node_tid = node_tid; out->root_bits = claimed; out->root_prefix = prefix; out->tl_root = tl_root;
-  out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node; out->tnodes = reinterpret_cast<uint8_t*>(tnodes); tnodes = nullptr;
+  out->tl_off = (uint64_t*)tl_off; out->tl_node = tl_node; out->tnodes = reinterpret_cast<uint8_t*>(tnodes);   // not owned: the context's traversal copy
   out->hot_keys = hot_keys; hot_keys = nullptr;
   node_tid = nullptr; claimed = nullptr; prefix = nullptr; tl_root = nullptr; tl_off = nullptr; tl_node = nullptr;
 done:
   cudaFree(scratch); cudaFree(store);
   cudaFree(claimed); cudaFree(roots); cudaFree(n_roots_d); cudaFree(scal); cudaFree(r_count); cudaFree(r_off); cudaFree(r_rank);
   cudaFree(popc); cudaFree(off64); cudaFree(scan_tmp); cudaFree(prefix); cudaFree(tl_root); cudaFree(tl_count); cudaFree(tl_off);
-  cudaFree(tl_node); cudaFree(node_tid); cudaFree(tnodes); cudaFree(hot64); cudaFree(hot_keys);
+  cudaFree(tl_node); cudaFree(node_tid); cudaFree(hot64); cudaFree(hot_keys);
   if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
   return rc;
 }

@@ -35,7 +35,7 @@ template <typename... A> int fail(vsrt_context* c, int code, const char* fmt, A.
 #define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, VSRT_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } while (0)
 
 void free_treelets(vsrt_context* c) {
-  cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node); cudaFree(c->fo.tnodes); cudaFree(c->fo.hot_keys);
+  cudaFree(c->fo.node_tid); cudaFree(c->fo.root_bits); cudaFree(c->fo.root_prefix); cudaFree(c->fo.tl_root); cudaFree(c->fo.tl_off); cudaFree(c->fo.tl_node); cudaFree(c->fo.hot_keys);
   c->fo = FormOutputs{}; c->formed = false; c->mirrors = false; c->hist_n = 0; c->remap_valid = false;
   cudaFree(c->d_inv_off); cudaFree(c->d_inv); c->d_inv_off = nullptr; c->d_inv = nullptr;
   c->h_node_tid.clear(); c->h_tl_root.clear(); c->h_tl_off.clear(); c->h_tl_node.clear(); c->h_root_of_slot.clear();
@@ -106,9 +106,8 @@ int do_form(vsrt_context* c, uint64_t tlas, uint32_t budget) {
   free_treelets(c);
   ArenaView av; rc = make_view(c, tlas, &av); if (rc) return rc;
   char eb[400] = "";
-  rc = vsrt_launch_form_treelets(av, budget, c->stream, &c->fo, &c->fr, c->d_err, eb, sizeof(eb));
+  rc = vsrt_launch_form_treelets(av, budget, c->stream, &c->fo, &c->fr, c->d_err, eb, sizeof(eb), c->d_tarena);
   if (rc) return fail(c, rc, "%s", eb);
-  if (c->fo.arena_moved) { uint8_t* t = c->d_arena; c->d_arena = c->fo.tnodes; c->fo.tnodes = t; c->fo.arena_moved = 0; }
   c->formed = true; c->formed_tlas = tlas; c->formed_budget = budget;
   CUDA_OK(c, c->d_hist.ensure(std::max<size_t>(c->fr.n_treelets, 1)));
   CUDA_OK(c, cudaMemsetAsync(c->d_hist.p, 0, (size_t)c->fr.n_treelets * 8, c->stream));
@@ -172,7 +171,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       CUDA_OK(c, c->d_order.ensure(vsrt_rayorder_tmp_bytes(n)));
       rc = vsrt_launch_rayorder(d_rays, n, true, c->d_order.p, &tp.perm, &tp.perm_on, st);
       if (rc) return fail(c, rc, "ray-order kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
-      launches += 14;   // bounds, keys, 3 x (count, 3 scan kernels, scatter)
+      launches += 8;   // bounds, keys, 3 x (count, scan, scatter) -- approximate
     }
     const uint32_t stack_entries = c->cfg.stack_entries ? c->cfg.stack_entries : 96;
     // K1 variant: the lane-owned kernel (traverse.cu) is the default; VSRT_K1_WF=1 selects the warp-wavefront kernel
@@ -207,7 +206,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
     rc = vsrt_launch_scan(w_counts, n, w_offsets, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
-    launches += n ? 3 : 0;   // 3 scan kernels
+    launches += n ? 1 : 0;   // the one-pass scan
     bool node_hist_queued = false;
     auto queue_node_hist = [&]() -> int {
       if (!c->node_hist_on || !n || node_hist_queued) return VSRT_OK;
@@ -378,7 +377,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   vsrt_comm_release(c);
   free_treelets(c);
-  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
+  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_frame_bak.release();
@@ -421,9 +420,10 @@ int vsrt_commit(vsrt_context* c) {
   c->spans.clear(); uint64_t slots = 0;
   for (auto& x : mg) { Span s; s.host = x.first; s.size = x.second - x.first; s.slot0 = (uint32_t)slots; s.n_slots = (uint32_t)(s.size / 64); c->spans.push_back(s); slots += s.size / 64; }
   if (slots >= (1ull << 29)) return fail(c, VSRT_E_UNSUPPORTED, "arena of %llu bytes exceeds the 32 GiB the 29-bit trace record addresses", (unsigned long long)(slots * 64));
-  cudaFree(c->d_arena); cudaFree(c->d_spans); cudaFree(c->d_blas); c->d_arena = nullptr; c->d_spans = nullptr; c->d_blas = nullptr;
+  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); c->d_arena = nullptr; c->d_tarena = nullptr; c->d_spans = nullptr; c->d_blas = nullptr;
   c->arena_bytes = slots * 64;
   CUDA_OK(c, cudaMalloc(&c->d_arena, c->arena_bytes));
+  CUDA_OK(c, cudaMalloc(&c->d_tarena, c->arena_bytes));   // K1's traversal copy (filled by formation)
   for (const Span& s : c->spans) CUDA_OK(c, cudaMemcpyAsync(c->d_arena + (uint64_t)s.slot0 * 64, (const void*)(uintptr_t)s.host, s.size, cudaMemcpyHostToDevice, c->stream));
   c->blas.clear();
   for (const Reg& r : c->regs) if (!r.tlas) { BlasReg b; uint32_t slot = 0; host_to_slot_h(c, r.host, &slot); b.hdr_slot = slot; b.pad = 0; b.delta = (int64_t)(r.dev - r.host); c->blas.push_back(b); }

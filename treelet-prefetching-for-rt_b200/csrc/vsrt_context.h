@@ -60,6 +60,7 @@ struct vsrt_context {
   bool committed = false;
   // arena
   uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
+  uint8_t* d_tarena = nullptr;   // K1's traversal copy of the arena, filled by treelet formation (same size, same slots)
   std::vector<Span> spans; Span* d_spans = nullptr;
   std::vector<BlasReg> blas; BlasReg* d_blas = nullptr;
   // treelets (treeletsFormed + the static maps)

@@ -88,12 +88,12 @@ struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; 
 struct FormOutputs {      // device allocations owned by the context
   uint32_t* node_tid; uint32_t* root_bits; uint32_t* root_prefix; uint32_t* tl_root; uint64_t* tl_off; uint64_t* tl_node;
   uint8_t* tnodes;        // K1's traversal copy of the arena: internal nodes in the traversal layout (treelets.cu, k_child_mask), the rest verbatim
-  uint32_t arena_moved;   // 1: `tnodes` holds the Mesa-layout copy and the arena's own allocation the traversal copy -- the caller swaps the two pointers
   uint32_t* hot_keys;     // [VSRT_HOT_N] K3's CTA-private histogram table: bucket h counts treelet hot_keys[h] (NO_TID = nobody)
 };
 // Forms treelets for `budget`; allocates outputs with cudaMalloc (caller frees).  Returns VSRT_* code.
+// `tarena` = the caller's arena-sized buffer for K1's traversal copy (FormOutputs::tnodes points at it afterwards; may be NULL).
 int vsrt_launch_form_treelets(const ArenaView& av, uint32_t budget, cudaStream_t st, FormOutputs* out, FormResult* res,
-                              uint32_t* err_flags_dev, char* errbuf, size_t errcap);
+                              uint32_t* err_flags_dev, char* errbuf, size_t errcap, uint8_t* tarena);
 
 // remapBVHToTreeletLayout as a device table: remap_dev[slot] = address of the node in the treelet layout (0 = unmapped)
 int vsrt_launch_remap(const FormOutputs& fo, uint32_t n_treelets, uint32_t n_slots, uint64_t base, uint64_t pitch, uint64_t* remap_dev, cudaStream_t st);

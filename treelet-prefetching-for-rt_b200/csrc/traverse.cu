@@ -94,6 +94,9 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #endif
 // (L1 hints measured in round 2 and dropped: leaf copies that bypass L1 -- cp.async.cg -- and internal-node loads with
 // L1::evict_last moved K1 by less than the run-to-run noise on all three workloads, profiles/README.md.)
+#ifndef VSRT_K1_NODE_NA
+#define VSRT_K1_NODE_NA 0   // A/B: internal-node loads do not allocate in L1
+#endif
 #ifndef VSRT_K1_PF_LEAF
 #define VSRT_K1_PF_LEAF 0
 #endif
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       st = ST_POP;
       // the hot kernel runs over the traversal copy of the arena (the launcher put it into av.base): internal nodes are in the
       // layout K0 prepared (TN), everything else is the arena's own bytes; the EXACT pass and the other K1 variants read the arena
-      const Node64 n = load_node(base, e.slot);
+      const Node64 n = VSRT_K1_NODE_NA ? load_node_na(base, e.slot) : load_node(base, e.slot);
 #if VSRT_K1_PF_CHILDREN
       {
         const uint8_t* cb_ = base + (uint64_t)(TN ? n.w[3] : e.slot + (uint32_t)node_child_offset(n)) * 64u;

@@ -24,6 +24,7 @@
 // (compact.cu) turn them into the reference's 16-byte MemoryTransactionRecords in CSR order.
 #include "vsrt_device.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 #ifndef VSRT_K1_NODE_ENTRY
 #define VSRT_K1_NODE_ENTRY 1   // see below
@@ -93,10 +94,8 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #define VSRT_K1_LEAF_ASYNC 1
 #endif
 // (L1 hints measured in round 2 and dropped: leaf copies that bypass L1 -- cp.async.cg -- and internal-node loads with
-// L1::evict_last moved K1 by less than the run-to-run noise on all three workloads, profiles/README.md.)
-#ifndef VSRT_K1_NODE_NA
-#define VSRT_K1_NODE_NA 0   // A/B: internal-node loads do not allocate in L1
-#endif
+// L1::evict_last moved K1 by less than the run-to-run noise on all three workloads; internal-node loads that do not allocate in
+// L1 cost 14 % on the headline and 10-28 % on the incoherent configs, profiles/README.md.)
 #ifndef VSRT_K1_PF_LEAF
 #define VSRT_K1_PF_LEAF 0
 #endif
@@ -137,9 +136,10 @@ enum { ST_IDLE = 0, ST_DEFER = 1, ST_FIN = 2, ST_POP = 3, ST_INT = 4, ST_INST = 
 // context, so the hot loop never selects between two register sets.
 struct ActiveRay { Ray8 ray; Idir idir; float tmult; uint32_t inst; bool nonfinite; };
 
-template <int MODE, int STACK_N, bool EXACT>
+template <int MODE, int STACK_N, bool EXACT, bool TNP>
 __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const TraverseParams p) {
   if (p.gate && !(*reinterpret_cast<const volatile uint32_t*>(p.err_flags) & p.gate)) return;   // nothing was deferred to this pass
+  if (p.sel && *reinterpret_cast<const volatile uint32_t*>(p.sel) != p.sel_want) return;        // the batch was given to the other node layout (k_ray_coherence)
   const ArenaView& av = p.av;
   const uint8_t* __restrict__ base = av.base;
   const unsigned full = 0xffffffffu;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   // wanted / an entry of one of the three kinds in `e` waiting for its phase.
   // x first child slot | y, z.lo16: per-child byte = offset (low 4 bits) | K0's flags (bits 7, 6) | z bits 16..21 pending mask | w meta
   constexpr bool SMEM = VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY && !EXACT;
-  constexpr bool TN = VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT;   // internal nodes come from the traversal-layout copy
+  constexpr bool TN = TNP && VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT;   // internal nodes come from the traversal-layout copy
   constexpr int SN = SMEM ? VSRT_K1_SMEM_STACK : STACK_N;          // capacity of the stack this instantiation uses
 #if VSRT_K1_SMEM_STACK > 0 && VSRT_K1_NODE_ENTRY
   __shared__ uint4 s_stk[EXACT ? 1 : VSRT_K1_SMEM_STACK][EXACT ? 1 : THREADS];
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
       st = ST_POP;
       // the hot kernel runs over the traversal copy of the arena (the launcher put it into av.base): internal nodes are in the
       // layout K0 prepared (TN), everything else is the arena's own bytes; the EXACT pass and the other K1 variants read the arena
-      const Node64 n = VSRT_K1_NODE_NA ? load_node_na(base, e.slot) : load_node(base, e.slot);
+      const Node64 n = load_node(base, e.slot);
 #if VSRT_K1_PF_CHILDREN
       {
         const uint8_t* cb_ = base + (uint64_t)(TN ? n.w[3] : e.slot + (uint32_t)node_child_offset(n)) * 64u;
@@ -624,14 +624,17 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   }
 }
 
-template <int MODE, int STACK_N, bool EXACT>
+template <int MODE, int STACK_N, bool EXACT, bool TNP>
 int launch_mode(const TraverseParams& p, cudaStream_t st) {
   // occupancy of this instantiation, cached per device (contexts on different GPUs may live in one process)
   static int s_blocks[64], s_sm[64];
   int dev = 0; cudaGetDevice(&dev); dev &= 63;
   if (s_blocks[dev] == 0) {
     cudaDeviceGetAttribute(&s_sm[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_blocks[dev], k_traverse<MODE, STACK_N, EXACT>, THREADS, 0) != cudaSuccess || s_blocks[dev] < 1) s_blocks[dev] = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_blocks[dev], k_traverse<MODE, STACK_N, EXACT, TNP>, THREADS, 0) != cudaSuccess || s_blocks[dev] < 1) s_blocks[dev] = 4;
+    // the smallest shared-memory carve-out that holds the resident CTAs; the rest of the 256 KB is L1, which the node and stack
+    // lines live in (vsrt_internal.h).  VSRT_K1_CARVEOUT = percent of the maximum, -1 = the driver's default (A/B).
+    { const char* e = getenv("VSRT_K1_CARVEOUT"); vsrt_min_carveout(k_traverse<MODE, STACK_N, EXACT, TNP>, s_blocks[dev], dev, e ? atoi(e) : -2); }
   }
   const int blocks_per_sm = s_blocks[dev], n_sm = s_sm[dev];
   // persistent grid (a multiple of the SM count): every resident warp keeps pulling rays until the counter runs out
@@ -639,28 +642,57 @@ int launch_mode(const TraverseParams& p, cudaStream_t st) {
   const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);
   if (grid == 0) return VSRT_OK;
   if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
-  if (VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT) {
+  if (TNP && VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT) {
     if (!p.tv.tnodes) return VSRT_E_INVALID;      // (formation always fills the traversal copy)
-    // the hot kernel traverses the traversal copy: the same slots, internal nodes re-laid-out by K0, leaves and headers verbatim
+    // this instantiation traverses the traversal copy: the same slots, internal nodes re-laid-out by K0, leaves and headers verbatim
     TraverseParams q = p; q.av.base = p.tv.tnodes;
-    k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(q);
+    k_traverse<MODE, STACK_N, EXACT, TNP><<<grid, THREADS, 0, st>>>(q);
   } else
-  k_traverse<MODE, STACK_N, EXACT><<<grid, THREADS, 0, st>>>(p);
+  k_traverse<MODE, STACK_N, EXACT, TNP><<<grid, THREADS, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
 template <int STACK_N>
-int launch_n(const TraverseParams& p, bool exact, cudaStream_t st) {
-  if (p.mode == VSRT_MODE_TREELET) return exact ? launch_mode<VSRT_MODE_TREELET, STACK_N, true>(p, st) : launch_mode<VSRT_MODE_TREELET, STACK_N, false>(p, st);
-  return exact ? launch_mode<VSRT_MODE_DFS, STACK_N, true>(p, st) : launch_mode<VSRT_MODE_DFS, STACK_N, false>(p, st);
+int launch_n(const TraverseParams& p, bool exact, bool trav_layout, cudaStream_t st) {
+  if (p.mode == VSRT_MODE_TREELET) {
+    if (exact) return launch_mode<VSRT_MODE_TREELET, STACK_N, true, false>(p, st);
+    return trav_layout ? launch_mode<VSRT_MODE_TREELET, STACK_N, false, true>(p, st) : launch_mode<VSRT_MODE_TREELET, STACK_N, false, false>(p, st);
+  }
+  if (exact) return launch_mode<VSRT_MODE_DFS, STACK_N, true, false>(p, st);
+  return trav_layout ? launch_mode<VSRT_MODE_DFS, STACK_N, false, true>(p, st) : launch_mode<VSRT_MODE_DFS, STACK_N, false, false>(p, st);
+}
+
+// Coherence of a batch from 256 pairs of consecutive rays spread evenly over it: *out = 1 if at least three quarters of the pairs
+// point the same way to within ~2.5 degrees (cos > 0.999) -- camera rays of neighbouring pixels do, diffuse bounce rays do not
+// (neighbouring origins, unrelated directions).  One warp-sized block; decides which node layout K1 reads for this batch.
+__global__ void __launch_bounds__(256) k_ray_coherence(const vsrt_ray* __restrict__ rays, uint64_t n, uint32_t* __restrict__ out) {
+  __shared__ unsigned int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint64_t i = n < 512 ? (uint64_t)threadIdx.x * 2u : (uint64_t)threadIdx.x * ((n - 1) / 256u);
+  bool ok = false;
+  if (i + 1 < n) {
+    const float ax = __ldg(&rays[i].direction[0]), ay = __ldg(&rays[i].direction[1]), az = __ldg(&rays[i].direction[2]);
+    const float bx = __ldg(&rays[i + 1].direction[0]), by = __ldg(&rays[i + 1].direction[1]), bz = __ldg(&rays[i + 1].direction[2]);
+    const float d = ax * bx + ay * by + az * bz, na = ax * ax + ay * ay + az * az, nb = bx * bx + by * by + bz * bz;   // scheduling only: no bit-exactness contract here
+    ok = d > 0.0f && d * d > 0.998f * na * nb;
+  } else ok = true;
+  if (ok) atomicAdd(&s_n, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_n >= 192u ? 1u : 0u;
 }
 
 }  // namespace
 
-int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st) {
-  if (stack_entries <= 96) return launch_n<96>(p, exact, st);
-  if (stack_entries <= 192) return launch_n<192>(p, exact, st);
-  return launch_n<384>(p, exact, st);
+int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, bool trav_layout, cudaStream_t st) {
+  if (stack_entries <= 96) return launch_n<96>(p, exact, trav_layout, st);
+  if (stack_entries <= 192) return launch_n<192>(p, exact, trav_layout, st);
+  return launch_n<384>(p, exact, trav_layout, st);
+}
+
+int vsrt_launch_ray_coherence(const vsrt_ray* rays, uint64_t n, uint32_t* out, cudaStream_t st) {
+  k_ray_coherence<<<1, 256, 0, st>>>(rays, n, out);
+  return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 
 #if VSRT_K1_STATS

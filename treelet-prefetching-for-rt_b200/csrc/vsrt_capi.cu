@@ -158,7 +158,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = w_hits; tp.stage = w_stage; tp.counts = w_counts; tp.nproc = w_nproc;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 1u; }   // round-2 sweep: leaf threshold 1 is best on the headline (1 %) and on the incoherent configs (6 %)
-    tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; tp.perm = nullptr; tp.perm_on = nullptr;
+    tp.magic16 = 0x64646464u; tp.only_deferred = 0; tp.gate = 0; tp.perm = nullptr; tp.perm_on = nullptr; tp.sel = nullptr; tp.sel_want = 0;
     // ray order (rayorder.cu): which rays share a warp; batches too small to fill the GPU twice are left alone
     uint32_t ray_order = c->cfg.ray_order;
     if (const char* ro = getenv("VSRT_RAY_ORDER")) ray_order = (uint32_t)atoi(ro);
@@ -192,14 +192,33 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     } else { tp.gstack = nullptr; tp.stack_n = stack_entries; }
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
     if (binned) { tp.perm = nullptr; tp.perm_on = nullptr; rc = vsrt_launch_traverse_tb(tp, c->tb_tables, stack_entries, c->d_tb.p, c->tb_stats, st); }
-    else rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, av.force_exact != 0, st) : vsrt_launch_traverse(tp, stack_entries, av.force_exact != 0, st);
+    else if (wavefront) rc = vsrt_launch_traverse_wf(tp, wf_grid, av.force_exact != 0, st);
+    else if (av.force_exact) rc = vsrt_launch_traverse(tp, stack_entries, true, false, st);
+    else {
+      // Which node layout the hot kernel reads: the traversal copy saves the byte shuffles of every node visit and
+      // wins where K1 is issue-bound (camera rays: 1.9 %); where it waits for load latency (bounce rays) the Mesa-layout kernel is
+      // 3-8 % faster.  A frame-sized batch is therefore sampled on the device (256 pairs of consecutive rays: do they point the same
+      // way?) and BOTH instantiations are queued, each gated on the sample's verdict -- no read-back; the one that is not picked
+      // returns at once.  VSRT_K1_LAYOUT = 0 / 1 forces the Mesa layout / the traversal copy; small batches take the traversal copy.
+      int layout = -1;
+      if (const char* e = getenv("VSRT_K1_LAYOUT")) layout = atoi(e);
+      if (layout < 0 && n >= 65536) {
+        rc = vsrt_launch_ray_coherence(d_rays, n, c->d_sel, st);
+        tp.sel = c->d_sel; tp.sel_want = 1;
+        if (!rc) rc = vsrt_launch_traverse(tp, stack_entries, false, true, st);
+        tp.sel_want = 0;
+        if (!rc) rc = vsrt_launch_traverse(tp, stack_entries, false, false, st);
+        tp.sel = nullptr;
+        launches += 2;
+      } else rc = vsrt_launch_traverse(tp, stack_entries, false, layout != 0, st);
+    }
     if (rc) return fail(c, rc, "traversal kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     launches += n ? 1 : 0;
     if (!av.force_exact && n) {
       // rays (or instances) with non-finite coordinates are deferred by the fast kernel (EF_NEED_EXACT): the EXACT kernel is
       // queued behind it and returns at once when nothing was deferred -- no flag read-back between the two
       tp.only_deferred = 1; tp.gate = EF_NEED_EXACT;
-      rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, st);
+      rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, false, st);
       if (rc) return fail(c, rc, "exact traversal kernel launch failed");
       launches++;
     }
@@ -357,7 +376,7 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device);
   if (prop.major < 10) { delete c; return fail(nullptr, VSRT_E_NO_DEVICE, "device %d is sm_%d%d; libvsrt is built for sm_100a only", c->device, prop.major, prop.minor); }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess && cudaMalloc(&c->d_sel, 4) == cudaSuccess;
   ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_pin, vsrt_context::PIN_BYTES) == cudaSuccess;
   for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
@@ -377,7 +396,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   vsrt_comm_release(c);
   free_treelets(c);
-  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_next_ray);
+  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_sel); cudaFree(c->d_next_ray);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_frame_bak.release();

@@ -74,7 +74,7 @@ struct vsrt_context {
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
   void* tb_tables = nullptr; DevBuf<uint8_t> d_tb; unsigned long long tb_stats[8] = { 0 };   // treelet-binned K1 (traverse_tb.cu): layout copy, scratch, statistics of the last batch
   DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
-  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; unsigned long long* d_next_ray = nullptr;
+  DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; uint32_t* d_sel = nullptr; unsigned long long* d_next_ray = nullptr;
   // pinned host memory: the per-batch read-backs (record total, error flags, counters) land here without a staging copy, and
   // small host-buffer calls (a warp's 32 rays) bounce their inputs and outputs through it so that a call is two queues of async
   // copies and two synchronisations instead of a blocking copy per array

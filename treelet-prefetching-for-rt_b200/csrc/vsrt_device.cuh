@@ -38,16 +38,6 @@ VS_DEV Node64 load_node_now(const uint8_t* base, uint32_t slot) {
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[12]), "=r"(n.w[13]), "=r"(n.w[14]), "=r"(n.w[15]) : "l"(p + 3));
   return n;
 }
-// Same, without allocating the lines in L1 (A/B knob VSRT_K1_NODE_NA: rays that share no nodes only evict each other's stack lines)
-VS_DEV Node64 load_node_na(const uint8_t* base, uint32_t slot) {
-  const uint4* p = reinterpret_cast<const uint4*>(base + (uint64_t)slot * 64u);
-  Node64 n;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[0]), "=r"(n.w[1]), "=r"(n.w[2]), "=r"(n.w[3]) : "l"(p));
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[4]), "=r"(n.w[5]), "=r"(n.w[6]), "=r"(n.w[7]) : "l"(p + 1));
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[8]), "=r"(n.w[9]), "=r"(n.w[10]), "=r"(n.w[11]) : "l"(p + 2));
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n.w[12]), "=r"(n.w[13]), "=r"(n.w[14]), "=r"(n.w[15]) : "l"(p + 3));
-  return n;
-}
 // byte i (0..63) of a node held in registers; i must be a compile-time constant after unrolling
 VS_DEV uint32_t node_byte(const Node64& n, int i) { return (n.w[i >> 2] >> ((i & 3) * 8)) & 0xffu; }
 

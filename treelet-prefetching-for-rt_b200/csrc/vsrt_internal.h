@@ -83,6 +83,25 @@ enum { CI_TYPE0 = 0, CI_NUM_HITS = 9, CI_NUM_ANY_HITS = 10, CI_N_ANYHIT_RAYS = 1
 // error flags raised by kernels (OR-ed into a device word)
 enum { EF_BAD_BVH = 1, EF_UNKNOWN_AS = 2, EF_STACK = 4, EF_BUDGET = 8, EF_TRACE_CAP = 16, EF_UNSUPPORTED = 32, EF_NONFINITE = 64 /* not an error */, EF_NEED_EXACT = 128 /* not an error */ };
 
+// L1 and shared memory share 256 KB per SM, and the driver's default split gave K1 a 132 KB shared-memory carve-out for the
+// 64 KB its resident CTAs use (ncu launch__shared_mem_config_size; K3 likewise, 132 for 92 KB, but K3 does not care: measured).  Asks for the smallest carve-out that holds
+// `blocks_per_sm` CTAs of `func` and leaves the rest to L1.  pct_override >= 0: that percentage; -1: leave the driver's default.
+template <typename F>
+inline void vsrt_min_carveout(F func, int blocks_per_sm, int dev, int pct_override = -2) {
+  int pct = pct_override;
+  cudaFuncAttributes fa; int max_smem = 0;
+  if (pct == -2 && cudaFuncGetAttributes(&fa, func) == cudaSuccess &&
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && max_smem > 0) {
+    const size_t per_block = (fa.sharedSizeBytes + 1024 + 127) / 128 * 128;         // + the driver's 1 KB per block, 128-byte granules
+    const size_t need = per_block * (size_t)blocks_per_sm;
+    const size_t kb[] = { 0, 8, 16, 32, 64, 100, 132, 164, 196, 228 };              // the carve-outs sm_100 supports
+    size_t pick = 228;
+    for (size_t k : kb) if (k * 1024 >= need) { pick = k; break; }
+    pct = (int)(pick * 1024 * 100 / (size_t)max_smem);                              // rounded down: the driver rounds a request up to the next supported size
+  }
+  if (pct >= 0) cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 // ---- launchers (each file implements its kernels) ----
 struct FormResult { uint32_t n_treelets; uint64_t n_entries; uint64_t n_mapped; uint64_t total_bvh; float ms; uint32_t nonfinite; uint32_t inst_base; uint64_t peak_scratch_bytes; };
 struct FormOutputs {      // device allocations owned by the context
@@ -119,8 +138,13 @@ struct TraverseParams {
   uint32_t magic16;               // 0x64646464 (fp16 1024 in each half), passed as data so it lives in a register (byte_pair_f16)
   const uint32_t* perm;           // rayorder.cu: the k-th ray a lane picks up is perm[k] (NULL = input order) ...
   const uint32_t* perm_on;        // ... if this device word is non-zero (AUTO mode decides on the device)
+  const uint32_t* sel;            // != NULL: the kernel returns at once unless *sel == sel_want (two hot instantiations are queued for a
+  uint32_t sel_want;              //   batch, one per node layout, and k_ray_coherence's device word picks the one that runs)
 };
-int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, cudaStream_t st);
+// trav_layout: the hot kernel reads K1's traversal copy of the arena (TreeletView::tnodes) instead of the Mesa-layout arena
+int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool exact, bool trav_layout, cudaStream_t st);
+// *out = 1 if the batch's consecutive rays point the same way (camera rays), 0 otherwise (bounce rays)
+int vsrt_launch_ray_coherence(const vsrt_ray* rays, uint64_t n, uint32_t* out, cudaStream_t st);
 // warp-wavefront formulation (traverse_wf.cu): same results, a pool of 64 rays per warp regrouped by phase every iteration
 unsigned vsrt_wf_grid(uint64_t n_rays);
 size_t vsrt_wf_stack_bytes(unsigned grid, uint32_t stack_entries);

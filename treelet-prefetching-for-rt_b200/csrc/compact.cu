@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned long long block_scan_excl(unsigned long long
 // 2 M-ray frame); `tmp` = [ticket][status per tile], zeroed by the launcher.
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VALUE = (1ull << 62) - 1ull;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(const uint32_t* __restrict__ counts, uint64_t n, unsigned long long* __restrict__ tmp,
-                                                              unsigned long long* __restrict__ offsets) {
+                                                              unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ total_out) {
   __shared__ unsigned long long sh[32];
   __shared__ unsigned long long s_tile, s_prefix;
   unsigned long long* const status = tmp + 1;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(const uint32_t* _
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) offsets[base + i] = o; o += c[i]; }
   }
-  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) offsets[n] = o;          // the thread that holds the last element also writes the grand total
+  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) { offsets[n] = o; if (total_out) *total_out = o; }   // the thread that holds the last element also writes the grand total
 }
 
 // ---------------------------------------------------------------- K3
@@ -491,11 +491,11 @@ int vsrt_launch_node_hist(const uint32_t* stage, uint32_t cap, const uint64_t* o
 
 size_t vsrt_scan_tmp_bytes(uint64_t n) { return ((n + SCAN_TILE - 1) / SCAN_TILE + 2) * sizeof(unsigned long long); }
 
-int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st) {
+int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st, unsigned long long* total_out) {
   const uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (n_tiles == 0) { cudaMemsetAsync(offsets, 0, 8, st); return VSRT_OK; }
+  if (n_tiles == 0) { cudaMemsetAsync(offsets, 0, 8, st); if (total_out) cudaMemsetAsync(total_out, 0, 8, st); return VSRT_OK; }
   if (cudaMemsetAsync(tmp, 0, (size_t)(n_tiles + 1) * 8, st) != cudaSuccess) return VSRT_E_CUDA;
-  k_scan_onepass<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, (unsigned long long*)tmp, (unsigned long long*)offsets);
+  k_scan_onepass<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, (unsigned long long*)tmp, (unsigned long long*)offsets, total_out);
   return cudaGetLastError() == cudaSuccess ? VSRT_OK : VSRT_E_CUDA;
 }
 

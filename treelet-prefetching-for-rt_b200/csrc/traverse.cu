@@ -641,7 +641,7 @@ int launch_mode(const TraverseParams& p, cudaStream_t st) {
   const uint64_t want = (p.n_rays + THREADS - 1) / THREADS;
   const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)blocks_per_sm * (uint64_t)n_sm);
   if (grid == 0) return VSRT_OK;
-  if (cudaMemsetAsync(p.next_ray, 0, sizeof(unsigned long long), st) != cudaSuccess) return VSRT_E_CUDA;
+  // p.next_ray: this launch's ray counter, zeroed by the caller (k_batch_prepare)
   if (TNP && VSRT_K1_TNODES && VSRT_K1_NODE_ENTRY && !EXACT) {
     if (!p.tv.tnodes) return VSRT_E_INVALID;      // (formation always fills the traversal copy)
     // this instantiation traverses the traversal copy: the same slots, internal nodes re-laid-out by K0, leaves and headers verbatim

@@ -4,6 +4,7 @@
 // entry point that computes launches the CUDA kernels of treelets.cu / traverse.cu / compact.cu.
 #include "vsrt_context.h"
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdarg>
 #include <cstdlib>
@@ -29,6 +30,15 @@ namespace {
 
 __global__ void k_add_base(unsigned long long* __restrict__ off, uint64_t n, unsigned long long base) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) off[i] += base;
+}
+
+// one launch instead of a device-to-device copy and three memsets: counter backup (restored if the batch fails), flags, record
+// total, and the ray counters of the traversal launches queued for the batch (each launch pulls from its own)
+__global__ void k_batch_prepare(BatchCtl* ctl) {
+  const unsigned t = threadIdx.x;
+  if (t < VSRT_COUNTERS_N_SUM + VSRT_COUNTERS_N_MAX) ctl->bak.v[t] = ctl->counters.v[t];
+  if (t < 4) ctl->next_ray[t] = 0ull;
+  if (t == 4) { ctl->err = 0u; ctl->total = 0ull; }
 }
 
 template <typename... A> int fail(vsrt_context* c, int code, const char* fmt, A... a) { return vsrt_fail(c, code, fmt, a...); }
@@ -153,8 +163,7 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     // this window's slices of the frame-sized buffers
     vsrt_hit* const w_hits = c->d_hits.p + r0; uint32_t* const w_counts = c->d_counts.p + r0; uint64_t* const w_offsets = c->d_offsets.p + r0;
     uint32_t* const w_nproc = c->d_nproc.p + r0; uint32_t* const w_stage = c->d_stage.p + r0 * c->stage_cap;
-    CUDA_OK(c, cudaMemcpyAsync(c->d_counters_bak, c->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st));
-    CUDA_OK(c, cudaMemsetAsync(c->d_err, 0, 4, st));
+    k_batch_prepare<<<1, 32, 0, st>>>(c->d_ctl);
     TraverseParams tp; tp.av = av; tp.tv = tv; tp.rays = d_rays; tp.n_rays = n; tp.hits = w_hits; tp.stage = w_stage; tp.counts = w_counts; tp.nproc = w_nproc;
     tp.cap = c->stage_cap; tp.mode = (uint32_t)mode; tp.counters = c->d_counters; tp.err_flags = c->d_err; tp.next_ray = c->d_next_ray;
     { const char* a = getenv("VSRT_REFILL_T"); const char* b = getenv("VSRT_LEAF_T"); tp.refill_t = a ? (uint32_t)atoi(a) : 8u; tp.leaf_t = b ? (uint32_t)atoi(b) : 1u; }   // round-2 sweep: leaf threshold 1 is best on the headline (1 %) and on the incoherent configs (6 %)
@@ -206,9 +215,9 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
         rc = vsrt_launch_ray_coherence(d_rays, n, c->d_sel, st);
         tp.sel = c->d_sel; tp.sel_want = 1;
         if (!rc) rc = vsrt_launch_traverse(tp, stack_entries, false, true, st);
-        tp.sel_want = 0;
+        tp.sel_want = 0; tp.next_ray = c->d_next_ray + 1;
         if (!rc) rc = vsrt_launch_traverse(tp, stack_entries, false, false, st);
-        tp.sel = nullptr;
+        tp.sel = nullptr; tp.next_ray = c->d_next_ray;
         launches += 2;
       } else rc = vsrt_launch_traverse(tp, stack_entries, false, layout != 0, st);
     }
@@ -217,13 +226,13 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     if (!av.force_exact && n) {
       // rays (or instances) with non-finite coordinates are deferred by the fast kernel (EF_NEED_EXACT): the EXACT kernel is
       // queued behind it and returns at once when nothing was deferred -- no flag read-back between the two
-      tp.only_deferred = 1; tp.gate = EF_NEED_EXACT;
+      tp.only_deferred = 1; tp.gate = EF_NEED_EXACT; tp.next_ray = c->d_next_ray + 2;
       rc = wavefront ? vsrt_launch_traverse_wf(tp, wf_grid, true, st) : vsrt_launch_traverse(tp, stack_entries, true, false, st);
       if (rc) return fail(c, rc, "exact traversal kernel launch failed");
       launches++;
     }
     CUDA_OK(c, cudaEventRecord(c->ev[1], st));
-    rc = vsrt_launch_scan(w_counts, n, w_offsets, c->d_scan_tmp.p, st); if (rc) return fail(c, rc, "scan launch failed");
+    rc = vsrt_launch_scan(w_counts, n, w_offsets, c->d_scan_tmp.p, st, &c->d_ctl->total); if (rc) return fail(c, rc, "scan launch failed");
     CUDA_OK(c, cudaEventRecord(c->ev[2], st));
     launches += n ? 1 : 0;   // the one-pass scan
     bool node_hist_queued = false;
@@ -252,11 +261,10 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
     CUDA_OK(c, cudaEventRecord(c->ev[3], st));
     uint32_t h_err = 0; DevCounters now;
     static_assert(16 + sizeof(DevCounters) <= vsrt_context::PIN_HEAD, "read-back block must fit the head of the pinned buffer");
-    CUDA_OK(c, cudaMemcpyAsync(c->h_pin, w_offsets + n, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 8, c->d_err, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
+    static_assert(offsetof(BatchCtl, total) == sizeof(DevCounters) && offsetof(BatchCtl, err) == sizeof(DevCounters) + 8, "read-back block layout");
+    CUDA_OK(c, cudaMemcpyAsync(c->h_pin, c->d_ctl, sizeof(DevCounters) + 16, cudaMemcpyDeviceToHost, st));     // counters | record total (the scan left it there) | error flags
     CUDA_OK(c, cudaStreamSynchronize(st));
-    memcpy(&total, c->h_pin, 8); memcpy(&h_err, c->h_pin + 8, 4); memcpy(&now, c->h_pin + 16, sizeof(now));
+    memcpy(&now, c->h_pin, sizeof(now)); memcpy(&total, c->h_pin + sizeof(DevCounters), 8); memcpy(&h_err, c->h_pin + sizeof(DevCounters) + 8, 4);
     if (h_err & (EF_BAD_BVH | EF_STACK | EF_UNSUPPORTED)) {
       // a failed batch leaves no trace in the counters (rayCount, g_rt_* and accessedDataSize are restored); K3 did not run
       cudaMemcpyAsync(c->d_counters, c->d_counters_bak, sizeof(DevCounters), cudaMemcpyDeviceToDevice, st);
@@ -289,9 +297,9 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
         launches++;
       }
       CUDA_OK(c, cudaEventRecord(c->ev[3], st));
-      CUDA_OK(c, cudaMemcpyAsync(c->h_pin + 16, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(c, cudaMemcpyAsync(c->h_pin, c->d_counters, sizeof(now), cudaMemcpyDeviceToHost, st));
       CUDA_OK(c, cudaStreamSynchronize(st));
-      memcpy(&now, c->h_pin + 16, sizeof(now));
+      memcpy(&now, c->h_pin, sizeof(now));
     }
     // rayCount (:1665) advanced by the traversal kernel; accessedDataSize delta of this batch = its algorithmic bytes
     c->last.algorithmic_bytes = (r0 ? before.algorithmic_bytes : 0) + now.v[CI_ACCESSED] - c->h_prev.v[CI_ACCESSED];
@@ -376,8 +384,8 @@ int vsrt_create(const vsrt_config* cfg, vsrt_context** out) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device);
   if (prop.major < 10) { delete c; return fail(nullptr, VSRT_E_NO_DEVICE, "device %d is sm_%d%d; libvsrt is built for sm_100a only", c->device, prop.major, prop.minor); }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaMalloc(&c->d_next_ray, 8) == cudaSuccess && cudaMalloc(&c->d_counters, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_counters_bak, sizeof(DevCounters)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess && cudaMalloc(&c->d_sel, 4) == cudaSuccess;
-  ok = ok && cudaMemset(c->d_counters, 0, sizeof(DevCounters)) == cudaSuccess && cudaMemset(c->d_err, 0, 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_ctl, sizeof(BatchCtl)) == cudaSuccess && cudaMemset(c->d_ctl, 0, sizeof(BatchCtl)) == cudaSuccess;
+  if (ok) { c->d_counters = &c->d_ctl->counters; c->d_counters_bak = &c->d_ctl->bak; c->d_err = &c->d_ctl->err; c->d_sel = &c->d_ctl->sel; c->d_next_ray = c->d_ctl->next_ray; }
   ok = ok && cudaMallocHost(&c->h_pin, vsrt_context::PIN_BYTES) == cudaSuccess;
   for (int i = 0; i < 5 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   if (!ok) { const char* m = cudaGetErrorString(cudaGetLastError()); vsrt_destroy(c); return fail(nullptr, VSRT_E_NO_DEVICE, "CUDA initialisation failed: %s", m); }
@@ -396,7 +404,7 @@ void vsrt_destroy(vsrt_context* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   vsrt_comm_release(c);
   free_treelets(c);
-  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_counters); cudaFree(c->d_counters_bak); cudaFree(c->d_err); cudaFree(c->d_sel); cudaFree(c->d_next_ray);
+  cudaFree(c->d_arena); cudaFree(c->d_tarena); cudaFree(c->d_spans); cudaFree(c->d_blas); cudaFree(c->d_ctl);
   c->d_rays.release(); c->d_hits.release(); c->d_gstack.release(); c->d_nproc.release(); c->d_stage.release(); c->d_counts.release(); c->d_offsets.release(); c->d_txns.release();
   c->d_tids.release(); c->d_tid_addr.release(); c->d_packed.release(); c->d_scan_tmp.release(); c->d_hist.release(); c->d_remap.release();
   c->d_txns_sorted.release(); c->d_tids_sorted.release(); c->d_sort_keys.release(); c->d_order.release(); c->d_tb.release(); c->d_node_hist.release(); c->d_frame_bak.release();

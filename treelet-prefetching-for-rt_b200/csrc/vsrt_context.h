@@ -47,6 +47,10 @@ struct HostPool {
   void submit(std::function<void(unsigned, unsigned)> f) { wait(); { std::lock_guard<std::mutex> l(m); job = std::move(f); running = (unsigned)th.size(); gen++; } cv.notify_all(); }
   ~HostPool() { wait(); { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& x : th) x.join(); }
 };
+// Per-batch control words of a context, one device allocation: what a batch reads back (counters, record total, error flags) is
+// its first DevCounters + 16 bytes -- one copy --, and one small kernel prepares all of it for a batch (counter backup for the
+// rollback of a failed batch, flags, the ray counters of the queued traversal launches).
+struct BatchCtl { DevCounters counters; unsigned long long total; uint32_t err; uint32_t sel; DevCounters bak; unsigned long long next_ray[4]; };
 struct CommState;   // reduce.cu
 struct HostStage { uint32_t* p = nullptr; uint64_t cap = 0; };   // pinned staging for one window's packed records (host-side expansion)
 
@@ -74,6 +78,7 @@ struct vsrt_context {
   DevBuf<uint8_t> d_gstack;   // wavefront kernel: per-warp stack areas
   void* tb_tables = nullptr; DevBuf<uint8_t> d_tb; unsigned long long tb_stats[8] = { 0 };   // treelet-binned K1 (traverse_tb.cu): layout copy, scratch, statistics of the last batch
   DevBuf<uint32_t> d_nproc;   // procedural-leaf visits per ray
+  BatchCtl* d_ctl = nullptr;   // the pointers below point into it
   DevCounters* d_counters = nullptr; DevCounters* d_counters_bak = nullptr; uint32_t* d_err = nullptr; uint32_t* d_sel = nullptr; unsigned long long* d_next_ray = nullptr;
   // pinned host memory: the per-batch read-backs (record total, error flags, counters) land here without a staging copy, and
   // small host-buffer calls (a warp's 32 rays) bounce their inputs and outputs through it so that a call is two queues of async

@@ -167,7 +167,8 @@ int vsrt_launch_traverse_tb(const TraverseParams& tp, void* tables, uint32_t sta
 
 // exclusive scan of u32 counts into u64 offsets[n+1]; `tmp` must hold vsrt_scan_tmp_bytes(n) bytes
 size_t vsrt_scan_tmp_bytes(uint64_t n);
-int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st);
+// total_out (optional, device): also receives the grand total offsets[n]
+int vsrt_launch_scan(const uint32_t* counts, uint64_t n, uint64_t* offsets, void* tmp, cudaStream_t st, unsigned long long* total_out = nullptr);
 
 struct CompactParams {
   ArenaView av; TreeletView tv;

@@ -310,6 +310,28 @@ def test_scan_tile_boundaries(api):
     ctx.close()
 
 
+def test_node_layout_is_picked_per_batch(api, monkeypatch):
+    """Frame-sized batches queue both hot instantiations of K1 (traversal copy of the arena / Mesa layout) behind a device-side
+    coherence sample; either layout, forced or picked, must give the oracle's traces -- for camera rays (picked: traversal copy)
+    and for rays without any coherence (picked: Mesa layout)."""
+    s = sc.Scene(6000, seed=23, n_blas=2, n_instances=3, flags=sc.F_TRANSFORMS)
+    ctx = api.Context(max_treelet_size=512, device=0)
+    ctx.register(s); ctx.form_treelets()
+    orc = oracles.PortOracle(); orc.register(s); orc.form(512)
+    cam = sc.rays_primary(320, 240)                # 76,800 rays: above the 65,536-ray threshold of the dispatch
+    rnd = sc.rays_random(70000, seed=77)
+    for rays, tag in ((cam, "camera"), (rnd, "random")):
+        want = orc.trace(1, rays)
+        for layout in (None, "0", "1"):
+            if layout is None:
+                monkeypatch.delenv("VSRT_K1_LAYOUT", raising=False)
+            else:
+                monkeypatch.setenv("VSRT_K1_LAYOUT", layout)
+            helpers.assert_trace_equal(want, ctx.trace(1, rays), "%s rays, layout %s" % (tag, layout))
+    monkeypatch.delenv("VSRT_K1_LAYOUT", raising=False)
+    ctx.close()
+
+
 def test_warp_call_and_queries(api):
     s = sc.Scene(4000, seed=8, n_blas=2, n_instances=2)
     orc = oracles.PortOracle(); orc.register(s); orc.form(512)

@@ -35,11 +35,16 @@ SCENE_SEED = 0x5EED0001 + 1
 BUDGET = int(os.environ.get("VSRT_BENCH_BUDGET", "512"))   # configs/tested-cfgs/treelet_prefetching/gpgpusim.config:219
 MODE = int(os.environ.get("VSRT_BENCH_MODE", "1"))          # -treelet_based_traversal 1 (gpgpusim.config:225)
 METRIC = "rays/s (traversal + access trace + treelet ids)"
+# Order of the frame's ray ids: "8x4" = pixel tiles of 8 x 4, the order in which the reference's raygen launch hands rays to
+# traceRay (one-warp CTAs of 8 x 4 pixels, warp_pixel_mapping WARP_8X4, vulkan_ray_tracing.cc:3505); "0" = scanlines
+_t = os.environ.get("VSRT_BENCH_TILE", "8x4").lower()
+TILE = tuple(int(v) for v in _t.split("x")) if "x" in _t else None
 
 
 def workload_config(n_gpus, extra=None):
     cfg = {"workload": "synthetic %dM-triangle scene, %dx%d primary rays %d spp (%d rays/GPU), traceRayWithTreelets, max_treelet_size %d B, full access trace + treelet ids"
            % (N_TRI // 1_000_000, WIDTH, HEIGHT, n_gpus, WIDTH * HEIGHT, BUDGET),
+           "ray_order": ("%dx%d pixel tiles (the reference's WARP_8X4 raygen mapping, vulkan_ray_tracing.cc:3505)" % TILE) if TILE else "scanlines",
            "triangles": N_TRI, "rays_per_gpu": WIDTH * HEIGHT, "mode": "treelet", "max_treelet_size": BUDGET,
            "sharding": "rays: contiguous ray-id block per GPU; BVH replicated"}
     if extra:
@@ -118,7 +123,7 @@ def build_scene_and_rays(n_gpus, rank, flags=0):
     s = sc.Scene(N_TRI, seed=SCENE_SEED)
     from vsrt import shard
     first, count = shard.shard_range(WIDTH * HEIGHT * n_gpus, n_gpus, rank)     # contiguous ray-id block of this rank
-    rays = sc.rays_primary(WIDTH, HEIGHT, spp=n_gpus, seed=SCENE_SEED, flags=flags, first=first, count=count)
+    rays = sc.rays_primary(WIDTH, HEIGHT, spp=n_gpus, seed=SCENE_SEED, flags=flags, first=first, count=count, tile=TILE)
     return s, rays, time.time() - t0
 
 
@@ -515,7 +520,7 @@ def run_incoherent(api, torch, dev, flush, peak, c4_triangles):
     s = sc.Scene(2_000_000, seed=0x5EED0001 + 2, kind=sc.CLUSTERED)
     ctx = api.Context(max_treelet_size=BUDGET, device=dev.index)
     ctx.register(s); ti = ctx.form_treelets()
-    rays = sc.rays_primary(WIDTH, HEIGHT, spp=4, seed=SCENE_SEED + 1, flags=0)
+    rays = sc.rays_primary(WIDTH, HEIGHT, spp=4, seed=SCENE_SEED + 1, flags=0, tile=TILE)
     tot = {"rays": 0, "ms": 0.0, "k1": 0.0, "bytes": 0, "records": 0}
     per = []
     for bounce in range(5):
@@ -542,7 +547,7 @@ def run_incoherent(api, torch, dev, flush, peak, c4_triangles):
     s = sc.Scene(c4_triangles, seed=0x5EED0001 + 3)
     ctx = api.Context(max_treelet_size=BUDGET, device=dev.index)
     ctx.register(s); ti = ctx.form_treelets()
-    prim = sc.rays_primary(WIDTH, HEIGHT, flags=0)
+    prim = sc.rays_primary(WIDTH, HEIGHT, flags=0, tile=TILE)
     _, _, hits = _timed_batch(ctx, torch, dev, _abi.MODE_TREELET, prim, flush, reps=1)
     rays = s.bounce(prim, hits, 5, 1, 0)
     ms, r, _ = _timed_batch(ctx, torch, dev, _abi.MODE_TREELET, rays, flush)

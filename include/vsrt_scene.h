@@ -52,6 +52,11 @@ int vsrt_arena_validate(const uint8_t* arena, uint64_t size, uint64_t tlas_offse
  * the pixel centres, the others are jittered (hash of the ray id).  Writes rays [first, first+count). */
 void vsrt_rays_primary(uint32_t width, uint32_t height, uint32_t spp, uint64_t seed, uint32_t ray_flags,
                        uint64_t first, uint64_t count, vsrt_ray* out);
+/* The same rays with the ids walking the frame in tile_w x tile_h pixel tiles (row-major tiles, row-major inside a tile): the
+ * order of the reference's raygen launch, whose one-warp CTAs cover 8 x 4 pixels (warp_pixel_mapping WARP_8X4,
+ * vulkan_ray_tracing.cc:3505).  0 x 0, or a tile that does not divide the frame, = scanline order. */
+void vsrt_rays_primary_tiled(uint32_t width, uint32_t height, uint32_t spp, uint64_t seed, uint32_t ray_flags,
+                             uint64_t first, uint64_t count, uint32_t tile_w, uint32_t tile_h, vsrt_ray* out);
 /* Diffuse bounce: for every ray i that hit, a cosine-weighted direction about the geometric normal of the hit
  * point (flipped towards the incoming ray); misses are dropped.  Returns the number of rays written. */
 uint64_t vsrt_rays_bounce(const vsrt_ray* rays, const vsrt_hit* hits, uint64_t n, uint64_t seed, uint32_t bounce,

@@ -72,7 +72,7 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #define VSRT_K1_INNER 2
 #endif
 #ifndef VSRT_K1_INT_T
-#define VSRT_K1_INT_T 20
+#define VSRT_K1_INT_T 16   // 20 until the end of round 2; with the 192 KB L1: 16 / 20 / 24 lanes = 1.823-1.827 / 1.835-1.838 / 1.879 ms (bench), C4 bounce 2.68 / 2.70 ms
 #endif
 // 1 (default) = the stack holds one 16-byte entry per internal node and list -- first child slot, six offset|flag bytes, mask of the
 // still pending hit children, meta -- instead of one 8-byte entry per hit child (0, kept as the A/B variant).  Both reference lists

@@ -815,12 +815,22 @@ int trace_frame_pipelined(vsrt_context* c, uint64_t tlas, int mode, uint64_t n, 
   if (derive && (!c->pool || c->pool->th.size() != threads)) { delete c->pool; c->pool = new HostPool(threads); }
   const std::vector<uint64_t>* const rtab = &c->h_root_of_slot; const int device = c->device;
   auto run_job = [&](const FrameJob& j) {
-    c->pool->submit([j, rtab, addr0, device](unsigned t, unsigned nt) {
+    // the window's records are handed out in pieces of 32,768 from a shared cursor rather than as one equal slice per worker: a
+    // worker whose core is also serving something else (the launching thread, the driver's completion path, another rank) then
+    // takes fewer pieces instead of making the whole window wait for its slice (e2e of one box, one run after the other, with
+    // equal slices: 65 .. 95 M rays/s)
+    std::atomic<uint64_t>* const cursor = &c->pool->next;
+    c->pool->submit([j, rtab, addr0, device, cursor](unsigned, unsigned) {
       cudaSetDevice(device);
       cudaEventSynchronize(j.copied);
-      const uint64_t lo = j.n * t / nt, hi = j.n * (t + 1) / nt;
-      if (j.packed) expand_records(*rtab, addr0, j.packed, const_cast<vsrt_txn*>(j.txns), j.ids, lo, hi);
-      else if (j.ids) derive_ids(*rtab, addr0, j.txns, j.ids, lo, hi);
+      constexpr uint64_t PIECE = 32768;
+      for (;;) {
+        const uint64_t lo = cursor->fetch_add(PIECE, std::memory_order_relaxed);
+        if (lo >= j.n) break;
+        const uint64_t hi = std::min(lo + PIECE, j.n);
+        if (j.packed) expand_records(*rtab, addr0, j.packed, const_cast<vsrt_txn*>(j.txns), j.ids, lo, hi);
+        else if (j.ids) derive_ids(*rtab, addr0, j.txns, j.ids, lo, hi);
+      }
     });
   };
   const uint64_t rec_size = packed ? 4 : sizeof(vsrt_txn);

@@ -4,6 +4,7 @@
 #pragma once
 #include "vsrt_internal.h"
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -32,6 +33,7 @@ template <typename T> struct DevBuf {
 struct HostPool {
   std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
   std::function<void(unsigned, unsigned)> job; uint64_t gen = 0; unsigned running = 0; bool stop = false;
+  std::atomic<uint64_t> next{0};   // work cursor of the current job: the workers take pieces of it as they get to them (reset by submit)
   explicit HostPool(unsigned n) {
     for (unsigned t = 0; t < n; t++) th.emplace_back([this, t, n] {
       uint64_t seen = 0;
@@ -44,7 +46,7 @@ struct HostPool {
     });
   }
   void wait() { std::unique_lock<std::mutex> l(m); cv_done.wait(l, [&] { return running == 0; }); }
-  void submit(std::function<void(unsigned, unsigned)> f) { wait(); { std::lock_guard<std::mutex> l(m); job = std::move(f); running = (unsigned)th.size(); gen++; } cv.notify_all(); }
+  void submit(std::function<void(unsigned, unsigned)> f) { wait(); { std::lock_guard<std::mutex> l(m); job = std::move(f); running = (unsigned)th.size(); next.store(0, std::memory_order_relaxed); gen++; } cv.notify_all(); }
   ~HostPool() { wait(); { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& x : th) x.join(); }
 };
 // Per-batch control words of a context, one device allocation: what a batch reads back (counters, record total, error flags) is

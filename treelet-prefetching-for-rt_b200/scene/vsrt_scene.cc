@@ -437,24 +437,41 @@ static inline void set_ray(vsrt_ray* r, const float o[3], const float d[3], floa
   for (int a = 0; a < 3; a++) { r->origin[a] = o[a]; r->direction[a] = d[a]; }
   r->tmin = tmin; r->tmax = tmax; r->ray_flags = flags; r->cull_mask = 0xff; r->sbt_record_offset = 0; r->sbt_record_stride = 0; r->miss_index = 0;
 }
-extern "C" void vsrt_rays_primary(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint32_t flags, uint64_t first, uint64_t count, vsrt_ray* out) {
+// tile_w x tile_h > 0: ray ids walk the frame in pixel tiles, one tile after the other in row-major tile order and row-major inside
+// a tile -- the order in which the reference's raygen launch hands rays to traceRay: it launches CTAs of one warp that cover
+// 8 x 4 pixels (warp_pixel_mapping mapping = WARP_8X4, vulkan_ray_tracing.cc:3505, :3542-3564), grid x-major.  The rays are
+// the scanline generator's, permuted: jitter is keyed by the pixel's scanline id.  A frame that the tile does not divide
+// falls back to scanlines.
+extern "C" void vsrt_rays_primary_tiled(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint32_t flags, uint64_t first, uint64_t count,
+                                        uint32_t tile_w, uint32_t tile_h, vsrt_ray* out) {
   const float tan_half = tanf(0.5f * 45.0f * 3.14159265f / 180.0f), aspect = (float)W / (float)H;
+  const bool tiled = tile_w && tile_h && W % tile_w == 0 && H % tile_h == 0;
+  const uint64_t frame = (uint64_t)W * H, tile_px = (uint64_t)tile_w * tile_h, tiles_x = tiled ? W / tile_w : 1;
+  (void)spp;
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < (int64_t)count; k++) {
     uint64_t id = first + (uint64_t)k;
-    // ray id = sample * (W*H) + y * W + x: a contiguous block of W*H ids is one full frame of one sample, so ranks
+    // ray id = sample * (W*H) + pixel: a contiguous block of W*H ids is one full frame of one sample, so ranks
     // that take consecutive blocks get statistically identical work
-    uint32_t x = (uint32_t)(id % W); uint64_t r = id / W; uint32_t y = (uint32_t)(r % H); uint32_t sm = (uint32_t)(r / H);
+    const uint64_t sm = id / frame, p = id % frame;
+    uint32_t x, y;
+    if (tiled) {
+      const uint64_t t = p / tile_px, i = p % tile_px;
+      x = (uint32_t)((t % tiles_x) * tile_w + i % tile_w); y = (uint32_t)((t / tiles_x) * tile_h + i / tile_w);
+    } else { x = (uint32_t)(p % W); y = (uint32_t)(p / W); }
+    const uint64_t pid = sm * frame + (uint64_t)y * W + x;      // the ray's id in scanline order: keys the jitter
     float jx = 0.5f, jy = 0.5f;
-    if (sm > 0) { jx = u01(seed, id, 0); jy = u01(seed, id, 1); }   // sample 0 = pixel centres, the others jittered
+    if (sm > 0) { jx = u01(seed, pid, 0); jy = u01(seed, pid, 1); }   // sample 0 = pixel centres, the others jittered
     float px = (((float)x + jx) / (float)W * 2.0f - 1.0f) * tan_half * aspect;
     float py = (1.0f - ((float)y + jy) / (float)H * 2.0f) * tan_half;
     float d[3] = { px, py, -1.0f }; float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     for (int a = 0; a < 3; a++) d[a] /= n;
     float o[3] = { 0.0f, 0.0f, 3.5f };
-    (void)sm;
     set_ray(&out[k], o, d, 1e-3f, 1e30f, flags);
   }
+}
+extern "C" void vsrt_rays_primary(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint32_t flags, uint64_t first, uint64_t count, vsrt_ray* out) {
+  vsrt_rays_primary_tiled(W, H, spp, seed, flags, first, count, 0, 0, out);
 }
 extern "C" void vsrt_rays_random(uint64_t seed, uint32_t flags, uint64_t first, uint64_t count, vsrt_ray* out) {
 #pragma omp parallel for schedule(static)

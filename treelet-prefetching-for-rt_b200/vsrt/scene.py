@@ -43,6 +43,9 @@ def lib():
                                           ctypes.c_uint32]
         L.vsrt_rays_primary.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
                                         ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+        L.vsrt_rays_primary_tiled.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
+                                              ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                              ctypes.c_uint32, ctypes.c_void_p]
         L.vsrt_rays_random.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
                                        ctypes.c_void_p]
         L.vsrt_rays_bounce_scene.argtypes = [ctypes.c_void_p]
@@ -120,11 +123,15 @@ class Scene(Arena):
         return out[:n].copy()
 
 
-def rays_primary(width, height, spp=1, seed=1, flags=0, first=0, count=None):
+def rays_primary(width, height, spp=1, seed=1, flags=0, first=0, count=None, tile=None):
+    """Camera rays [first, first + count) of a width x height x spp frame.  tile=(w, h): ids walk the frame in w x h pixel
+    tiles, the order of the reference's raygen launch (one-warp CTAs of 8 x 4 pixels, vulkan_ray_tracing.cc:3505);
+    None = scanlines.  Either way the same set of rays."""
     total = width * height * spp
     count = total - first if count is None else count
     out = np.zeros(count, dtype=_abi.RAY)
-    lib().vsrt_rays_primary(width, height, spp, seed, flags, first, count, _abi.ptr(out))
+    tw, th = tile if tile else (0, 0)
+    lib().vsrt_rays_primary_tiled(width, height, spp, seed, flags, first, count, tw, th, _abi.ptr(out))
     return out
 
 

@@ -128,6 +128,14 @@ __device__ unsigned long long g_k1_stats[16];   // [0] inner rounds, [1 + state]
 #ifndef VSRT_K1_SMEM_STACK
 #define VSRT_K1_SMEM_STACK 0
 #endif
+// Traversal stack of the hot kernel in GLOBAL memory with the layout [warp][entry][lane], 16 bytes per lane.  Local memory
+// interleaves the lanes of a warp word by word (word w of a lane's array lives in line w of the warp's area), so a 16-byte
+// entry read at lane-dependent depths touches four sectors per lane for 16 useful bytes (ncu, round 2: 1.8 bytes per sector on the
+// local loads and stores of K1, 44 % of all L1 sectors of the kernel, 115 M partial-sector writes through to L2 per launch).
+// Here a lane's entry is one contiguous half-sector.  Space: resident lanes x entries x 16 B (204 MB for 96 entries).
+#ifndef VSRT_K1_GSTACK
+#define VSRT_K1_GSTACK 0
+#endif
 constexpr int PUSH_MAX = VSRT_K1_NODE_ENTRY ? 2 : 6;   // stack entries one internal node can push in TREELET mode: one per list, or one per child
 enum { ST_IDLE = 0, ST_DEFER = 1, ST_FIN = 2, ST_POP = 3, ST_INT = 4, ST_INST = 5, ST_LEAF = 6 };   // lane state (DEFER: the ray is handed to the EXACT pass at the next refill)
 
@@ -171,6 +179,12 @@ __global__ void __launch_bounds__(THREADS, VSRT_K1_MIN_BLOCKS) k_traverse(const 
   __shared__ uint4 s_stk[EXACT ? 1 : VSRT_K1_SMEM_STACK][EXACT ? 1 : THREADS];
   uint4 l_stk[EXACT ? STACK_N : 1];
 #define STK(i_) (*(SMEM ? &s_stk[(i_)][threadIdx.x] : &l_stk[(i_)]))
+#elif VSRT_K1_GSTACK && VSRT_K1_NODE_ENTRY
+  constexpr bool GST = !EXACT;
+  uint4 l_stk[EXACT ? STACK_N : 1];
+  // a 32-bit byte offset in a register, the base stays in the parameter bank: a 64-bit pointer held through the loop costs two registers and spills
+  const uint32_t g_ofs = ((blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * (uint32_t)STACK_N * 32u + (unsigned)lane) * 16u;
+#define STK(i_) (*(GST ? reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.gstack) + (g_ofs + (uint32_t)(i_) * 512u)) : &l_stk[(i_)]))
 #elif VSRT_K1_NODE_ENTRY
   uint4 stk[STACK_N];
 #define STK(i_) stk[(i_)]
@@ -688,6 +702,17 @@ int vsrt_launch_traverse(const TraverseParams& p, uint32_t stack_entries, bool e
   if (stack_entries <= 96) return launch_n<96>(p, exact, trav_layout, st);
   if (stack_entries <= 192) return launch_n<192>(p, exact, trav_layout, st);
   return launch_n<384>(p, exact, trav_layout, st);
+}
+
+// bytes of the global-memory traversal stack (VSRT_K1_GSTACK builds; 0 otherwise): every lane of the largest persistent grid
+size_t vsrt_traverse_gstack_bytes(uint32_t stack_entries) {
+#if VSRT_K1_GSTACK && VSRT_K1_NODE_ENTRY
+  int dev = 0, n_sm = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const size_t sn = stack_entries <= 96 ? 96 : (stack_entries <= 192 ? 192 : 384);
+  return (size_t)n_sm * 16u /* resident CTAs per SM, upper bound */ * THREADS * sn * 16u;
+#else
+  (void)stack_entries; return 0;
+#endif
 }
 
 int vsrt_launch_ray_coherence(const vsrt_ray* rays, uint64_t n, uint32_t* out, cudaStream_t st) {

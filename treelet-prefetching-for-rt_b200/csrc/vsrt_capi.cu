@@ -198,6 +198,9 @@ int run_batch(vsrt_context* c, uint64_t tlas, int mode, const vsrt_ray* d_rays, 
       wf_grid = vsrt_wf_grid(n);
       CUDA_OK(c, c->d_gstack.ensure(vsrt_wf_stack_bytes(wf_grid, stack_entries)));
       tp.gstack = (uint2*)c->d_gstack.p; tp.stack_n = stack_entries;
+    } else if (const size_t gb = vsrt_traverse_gstack_bytes(stack_entries)) {   // VSRT_K1_GSTACK build: the hot kernel's stack lives in global memory
+      CUDA_OK(c, c->d_gstack.ensure(gb));
+      tp.gstack = (uint2*)c->d_gstack.p; tp.stack_n = stack_entries;
     } else { tp.gstack = nullptr; tp.stack_n = stack_entries; }
     CUDA_OK(c, cudaEventRecord(c->ev[0], st));
     if (binned) { tp.perm = nullptr; tp.perm_on = nullptr; rc = vsrt_launch_traverse_tb(tp, c->tb_tables, stack_entries, c->d_tb.p, c->tb_stats, st); }

@@ -162,6 +162,7 @@ int vsrt_launch_radix_sort(uint32_t* kA, uint32_t* iA, uint32_t* kB, uint32_t* i
 // treelet-binned wavefront K1 (traverse_tb.cu): treelet-layout copy of the arena (opaque tables), scratch size, the batch driver
 int vsrt_tb_build_layout(const ArenaView& av, const FormOutputs& fo, uint32_t n_treelets, void** tables_out, cudaStream_t st);
 void vsrt_tb_free_layout(void* tables);
+size_t vsrt_traverse_gstack_bytes(uint32_t stack_entries);   // traverse.cu: global-memory stack of the VSRT_K1_GSTACK build, 0 otherwise
 size_t vsrt_tb_scratch_bytes(uint64_t n_rays, uint32_t stack_n);
 int vsrt_launch_traverse_tb(const TraverseParams& tp, void* tables, uint32_t stack_n, void* scratch, unsigned long long* stats_out, cudaStream_t st);
 

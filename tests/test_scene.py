@@ -61,3 +61,23 @@ def test_ray_generators():
     assert np.array_equal(a, b)       # sharding a frame by ray index gives the same rays
     q = sc.rays_random(100, seed=2, first=10); p = sc.rays_random(110, seed=2)[10:]
     assert np.array_equal(q, p)
+
+
+def test_primary_rays_in_raygen_tile_order():
+    """tile=(8, 4): the frame's ray ids walk the image in 8 x 4 pixel tiles, the order in which the reference's raygen launch reaches
+    traceRay (one-warp CTAs of 8 x 4 pixels, warp_pixel_mapping WARP_8X4, vulkan_ray_tracing.cc:3505).  Same rays as the scanline
+    order, permuted (jitter keyed by the pixel); windows of the id space agree with the whole; a frame the tile does not divide
+    falls back to scanlines."""
+    W, H, spp = 64, 32, 2
+    scan = sc.rays_primary(W, H, spp=spp, seed=3)
+    tiled = sc.rays_primary(W, H, spp=spp, seed=3, tile=(8, 4))
+    ids = np.arange(W * H * spp)
+    sm, p = ids // (W * H), ids % (W * H)
+    t, i = p // 32, p % 32
+    x, y = (t % (W // 8)) * 8 + i % 8, (t // (W // 8)) * 4 + i // 8
+    assert np.array_equal(tiled, scan[sm * W * H + y * W + x])
+    assert not np.array_equal(tiled, scan)
+    # a warp's 32 consecutive ids are one 8 x 4 tile: their directions span 8 pixels in x and 4 in y
+    assert np.array_equal(sc.rays_primary(W, H, spp=spp, seed=3, tile=(8, 4), first=96, count=200), tiled[96:296])
+    assert np.array_equal(sc.rays_primary(60, 30, tile=(8, 4)), sc.rays_primary(60, 30))
+    assert np.array_equal(sc.rays_primary(W, H, tile=(W, 1)), sc.rays_primary(W, H))      # a tile as wide as the frame IS the scanline order
